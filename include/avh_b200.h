@@ -1,0 +1,137 @@
+/* avh_b200.h — C ABI of libavh_b200.so: the sm_100a (B200) implementation of the AV-HuBERT encoder hot path.
+ *
+ * The reference (EnriqueOO97/MultiModalVC) is pure Python/PyTorch and has no FFI of its own; the entry
+ * points below are what a binding for this path replaces, call for call:
+ *
+ *   avh_create / avh_load_tensor / avh_finalize_weights
+ *       <- AVHubertModel.__init__ + nn.Module.load_state_dict(state["model"], strict=False)
+ *          (avhubert/hubert.py:335-433, src/model.py:218-226, avhubert/hubert_asr.py:299-305)
+ *   avh_forward
+ *       <- AVHubertModel.extract_finetune(source={'audio','video'}, padding_mask, output_layer)
+ *          (avhubert/hubert.py:694-745) including ResEncoder.forward (avhubert/resnet.py:156-164) and
+ *          TransformerEncoder.forward (fairseq/fairseq/models/wav2vec/wav2vec2.py:859-902)
+ *   avh_forward_host
+ *       <- the same call preceded by utils.move_to_cuda(sample) (src/eval.py:196) and followed by a
+ *          device->host read of the features: the end-to-end path with HOST buffers
+ *   avh_fbank
+ *       <- logfbank + stacker + audio/video length alignment + per-frame F.layer_norm + collater_audio
+ *          (avhubert/hubert_dataset.py:286-296,351-353,430-456)
+ *   avh_add_noise
+ *       <- AVHubertDataset.add_noise with the noise clip already selected (avhubert/hubert_dataset.py:317-346)
+ *
+ * Conventions: every function returns 0 on success and non-zero on failure; avh_last_error() returns the
+ * message of the last failure on the calling thread.  No exceptions cross the boundary.  All work is
+ * enqueued on the CUDA stream passed in (a cudaStream_t cast to void*; NULL = legacy default stream) with no
+ * device-wide synchronisation.  The caller owns every input/output buffer; the library only borrows the
+ * pointers for the duration of the enqueue and never writes to inputs.  A handle is bound to one device
+ * and is not thread-safe; use one handle per device/thread (one process per GPU in the reference:
+ * fairseq/fairseq/distributed/utils.py:317-350).
+ */
+#ifndef AVH_B200_H_
+#define AVH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVH_ABI_VERSION 1
+#if defined(__GNUC__)
+#define AVH_API __attribute__((visibility("default")))
+#else
+#define AVH_API
+#endif
+
+/* element types of caller-provided buffers */
+enum { AVH_F32 = 0, AVH_F16 = 1, AVH_BF16 = 2 };
+/* arithmetic of the dense contractions */
+enum {
+  AVH_COMPUTE_BF16 = 0, /* bf16 operands, fp32 accumulation (tcgen05 kind::f16) */
+  AVH_COMPUTE_FP32 = 1  /* fp32-faithful: operands split into bf16 hi+mid planes, 3 tcgen05 products, fp32 accumulation */
+};
+enum { AVH_FUSE_CONCAT = 0, AVH_FUSE_ADD = 1 };
+
+/* Mirror of the AVHubertConfig fields that determine shapes on this path (avhubert/hubert.py:64-315). */
+typedef struct avh_config {
+  int32_t encoder_layers;          /* hubert.py:76  */
+  int32_t encoder_embed_dim;       /* hubert.py:79  */
+  int32_t encoder_ffn_embed_dim;   /* hubert.py:82  */
+  int32_t encoder_attention_heads; /* hubert.py:85  (head dim must be 64) */
+  int32_t audio_feat_dim;          /* hubert.py:236 (104 = 4 x 26 stacked log-fbank) */
+  int32_t modality_fuse;           /* hubert.py:238 AVH_FUSE_* */
+  int32_t layer_norm_first;        /* hubert.py:131 */
+  int32_t conv_pos;                /* hubert.py:213 (128) */
+  int32_t conv_pos_groups;         /* hubert.py:217 (16)  */
+  int32_t compute_mode;            /* AVH_COMPUTE_* */
+  int32_t frontend_chunk_frames;   /* video frames per lip-frontend pass; 0 = default */
+  int32_t capture_stages;          /* non-zero: keep copies of intermediate stages for avh_read_stage (tests) */
+  int32_t reserved[4];
+} avh_config;
+
+typedef struct avh_handle avh_handle;
+
+AVH_API int avh_abi_version(void);
+AVH_API const char* avh_last_error(void);
+
+AVH_API int avh_create(const avh_config* cfg, int device, avh_handle** out);
+AVH_API int avh_destroy(avh_handle* h);
+
+/* One state-dict entry, by its reference key name (e.g. "encoder.layers.3.fc1.weight",
+ * "feature_extractor_video.resnet.trunk.layer2.0.downsample.1.running_var").  `data` may be a host or a
+ * device pointer (contiguous, `dtype` elements).  Keys the path never reads (mask_emb, final_proj.*,
+ * label_embs_concat, *.num_batches_tracked) are accepted and ignored.  Unknown keys fail. */
+AVH_API int avh_load_tensor(avh_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim);
+/* Fold eval-mode BatchNorm into conv epilogues, fold weight-norm of pos_conv, fold the q scaling, repack
+ * every weight into the kernels' K-major bf16 layouts and upload.  Fails listing the first missing key. */
+AVH_API int avh_finalize_weights(avh_handle* h);
+
+/* extract_finetune.  All pointers are DEVICE pointers.
+ *   video  [B,1,T,88,88] contiguous, or NULL (zero-filled modality arm, hubert.py:703-704)
+ *   audio  [B,F,T] with element strides audio_strides[3] (the collater hands a transposed view,
+ *          hubert_dataset.py:453), or NULL (hubert.py:705-708)
+ *   padding_mask [B,T] bytes, non-zero = padded frame, or NULL
+ *   output_layer 0 = all layers + final LayerNorm; k>=1 = stop after layer k, no final LayerNorm
+ *          (hubert.py:742, wav2vec2.py:862,892-894)
+ *   out    [B,T,D] contiguous, out_dtype elements */
+AVH_API int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
+                void* out, int out_dtype, void* stream);
+
+/* Same computation with HOST buffers (pinned memory recommended): copies the inputs host->device, runs
+ * avh_forward and copies `out` device->host, all on `stream`; returns after the stream has drained.
+ * `audio` here is contiguous [B,F,T]. */
+AVH_API int avh_forward_host(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                     const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
+                     void* stream);
+
+/* Intermediate taps for stage-level parity tests; names: "resnet" [B*T,512], "fused_ln" [B*T,E],
+ * "enc_in" [B*T,D].  Copies the fp32 value of the last avh_forward into `dst` (device, fp32). */
+AVH_API int avh_read_stage(avh_handle* h, const char* name, float* dst, int64_t capacity_elems, void* stream);
+
+/* Audio frontend.  wav: int16 samples of n_clips clips back to back, clip i = [offsets[i], offsets[i+1]).
+ *   video_len[i] (may be NULL): number of video frames clip i is aligned to (pad with zero rows / trim).
+ *   T: collated length; rows >= the clip's own length are zero and flagged in padding_mask.
+ *   out [n_clips, T, 104] fp32 row-major (the collater's [B,104,T] is the transposed VIEW of this),
+ *   padding_mask [n_clips, T] bytes (may be NULL).  All DEVICE pointers. */
+AVH_API int avh_fbank(const int16_t* wav, const int64_t* offsets, const int32_t* video_len, int n_clips, int T,
+              int normalize, float* out, uint8_t* padding_mask, void* stream);
+
+/* noise: fp32 noise clip (device) tiled/cropped to each clip's length from its start; snr_db as in the
+ * reference; out int16 (device) same layout as wav; scratch: device buffer of >= 4*n_clips doubles. */
+AVH_API int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clips, const float* noise, int64_t noise_len,
+                  float snr_db, int16_t* out, double* scratch, void* stream);
+
+/* Bare tcgen05 GEMM for kernel-level tests and profiling: C[M,N] = A[M,K] * B[N,K]^T (+bias)(gelu)(+R).
+ * A,B bf16 row-major (K contiguous, K % 8 == 0), bias fp32 [N] or NULL, R/C bf16 or fp32 [M,N]. */
+AVH_API int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu,
+                  const void* R, int r_fp32, void* C, int c_fp32, int block_n, void* stream);
+
+/* Counters for bench.py: kernels launched by this library since the last reset. */
+AVH_API int64_t avh_launch_count(void);
+AVH_API void avh_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVH_B200_H_ */

@@ -1,0 +1,1083 @@
+// C ABI of libavh_b200.so (include/avh_b200.h): handle, weight folding/repacking, per-shape execution plans
+// and the forward orchestration of AVHubertModel.extract_finetune (avhubert/hubert.py:694-745) on sm_100a.
+//
+// Data layout in HBM (N = B*T tokens/frames, P = 1 in bf16 mode, 2 (hi|mid bf16 planes) in fp32 mode):
+//   lip frontend activations   NHWC with one shared zero row/column per image: [n, H+1, W+1, C]; a 3x3/s1
+//                              conv is then 9 row-shifted GEMM taps over the flat [n*(H+1)*(W+1), C] matrix
+//                              (TMA out-of-bounds zero fill covers the first/last image)
+//   tokens                     row-major [N, C]; residual stream in fp32, GEMM operands bf16 [N, P*C]
+//   positional-conv input      [B*(T+64), P*D] bf16 with 64 zero rows after every clip (time halo)
+//   weights                    K-major bf16 [out, P*K] (conv: K = (kh,kw,cin); pos-conv: K = (tap, window))
+#include "avh_b200.h"
+#include "common.cuh"
+#include "gemm.h"
+#include "kernels.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_fp16.h>
+
+namespace avh {
+
+static thread_local std::string g_err;
+void set_last_error(const std::string& msg) { g_err = msg; }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int device_sm_count() {
+  static int cached_dev = -1, cached_n = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached_n = n;
+    cached_dev = dev;
+  }
+  return cached_n;
+}
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+  int64_t numel() const { return (int64_t)v.size(); }
+};
+
+// ---------------------------------------------------------------------------- device memory arena
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  int init(size_t bytes) {
+    cap = bytes;
+    AVH_CUDA_OK(cudaMalloc(&base, cap));
+    AVH_CUDA_OK(cudaMemset(base, 0, cap));
+    return 0;
+  }
+  void* take(size_t bytes) {
+    used = (used + 1023) & ~(size_t)1023;
+    void* p = base + used;
+    used += bytes;
+    return used <= cap ? p : nullptr;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+  }
+};
+// two-pass allocation: first pass sizes the arena (base == nullptr), second pass hands out pointers
+struct Sizer {
+  size_t used = 0;
+  void take(size_t bytes) {
+    used = (used + 1023) & ~(size_t)1023;
+    used += bytes;
+  }
+};
+
+inline bf16 f2bf(float x) { return __float2bfloat16_rn(x); }
+inline float bf2f(bf16 x) { return __bfloat162float(x); }
+
+// ---------------------------------------------------------------------------- packed weights
+struct PackedW {          // K-major bf16 [n, P*kpad] on the device
+  bf16* w = nullptr;
+  int n = 0, k = 0, kpad = 0;
+};
+struct ConvUnit {         // conv + folded eval-mode BatchNorm (+ PReLU)
+  PackedW w;
+  float* scale = nullptr;
+  float* bias = nullptr;
+  float* slope = nullptr;
+  int cin = 0, cout = 0, ks = 3, stride = 1;
+};
+struct BlockW {
+  ConvUnit c1, c2, ds;
+  bool has_ds = false;
+  float* slope2 = nullptr;
+};
+struct LinearW {
+  PackedW w;
+  float* bias = nullptr;
+};
+struct LayerW {
+  LinearW qkv, out, fc1, fc2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct Step {
+  std::function<int(cudaStream_t)> run;
+};
+
+struct CallArgs {          // per-call pointers the steps read through the plan
+  const void* video = nullptr;
+  int video_dt = 0;
+  const void* audio = nullptr;
+  int audio_dt = 0;
+  long long as[3] = {0, 0, 0};
+  const unsigned char* mask = nullptr;
+  void* out = nullptr;
+  int out_dt = 0;
+};
+
+struct Plan {
+  int B = 0, T = 0, output_layer = 0;
+  bool has_video = false, has_audio = false, has_mask = false;
+  Arena arena;
+  std::vector<Step> steps;
+  std::vector<GemmPlan*> gemms;
+  std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
+  CallArgs args;
+  ~Plan() {
+    for (GemmPlan* g : gemms) delete g;
+    arena.release();
+  }
+};
+
+}  // namespace
+}  // namespace avh
+
+using namespace avh;
+
+struct avh_handle {
+  avh_config cfg;
+  int device = 0;
+  int P = 1;                       // operand planes: 1 = bf16, 2 = fp32-faithful split
+  bool finalized = false;
+  std::map<std::string, HostTensor> raw;
+  Arena warena;
+  ConvUnit stem;
+  BlockW blocks[4][2];
+  LinearW proj_v, proj_a, post_proj;
+  bool has_post_proj = false;
+  float *fuse_ln_g = nullptr, *fuse_ln_b = nullptr, *enc_ln_g = nullptr, *enc_ln_b = nullptr;
+  PackedW pos_w;
+  float* pos_bias = nullptr;
+  int pos_window = 64;            // input-channel window per 64-column N tile (64 or 128)
+  int* pos_acol = nullptr;        // device [D/64] window start per N tile
+  std::vector<LayerW> layers;
+  std::map<std::string, std::unique_ptr<Plan>> plans;
+  cudaEvent_t host_evt = nullptr;
+  void* h2d_video = nullptr;      // staging for avh_forward_host
+  void* h2d_audio = nullptr;
+  void* h2d_mask = nullptr;
+  void* d_out = nullptr;
+  size_t h2d_video_cap = 0, h2d_audio_cap = 0, h2d_mask_cap = 0, d_out_cap = 0;
+};
+
+namespace avh {
+namespace {
+
+int dtype_size(int dt) { return dt == AVH_F32 ? 4 : 2; }
+
+// ============================================================================ weight folding / packing
+struct Packer {
+  avh_handle* h;
+  Arena* arena;      // null during sizing
+  Sizer sizer;
+  std::string missing;
+
+  const HostTensor* get(const std::string& key) {
+    auto it = h->raw.find(key);
+    if (it == h->raw.end()) {
+      if (missing.empty()) missing = key;
+      return nullptr;
+    }
+    return &it->second;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& host) {
+    const size_t bytes = host.size() * sizeof(T);
+    if (arena == nullptr) {
+      sizer.take(bytes);
+      return nullptr;
+    }
+    T* d = reinterpret_cast<T*>(arena->take(bytes));
+    if (d == nullptr) return nullptr;
+    if (cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return d;
+  }
+  // fp32 [n, kpad] -> bf16 planes [n, P*kpad]
+  PackedW pack(const std::vector<float>& w, int n, int k, int kpad) {
+    const int P = h->P;
+    PackedW out;
+    out.n = n; out.k = k; out.kpad = kpad;
+    if (arena == nullptr) {
+      sizer.take((size_t)n * P * kpad * sizeof(bf16));
+      return out;
+    }
+    std::vector<bf16> host((size_t)n * P * kpad);
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < kpad; ++c) {
+        const float x = w[(size_t)r * kpad + c];
+        const bf16 hi = f2bf(x);
+        host[(size_t)r * P * kpad + c] = hi;
+        if (P > 1) host[(size_t)r * P * kpad + kpad + c] = f2bf(x - bf2f(hi));
+      }
+    out.w = upload(host);
+    return out;
+  }
+  float* upload_f(const std::vector<float>& v) { return upload(v); }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// conv weight [cout, cin, kh, kw] (+ BN) -> K-major [(kh,kw,cin)] + folded scale/bias
+bool pack_conv(Packer& pk, const std::string& wkey, const std::string& bnkey, const std::string& prelu_key,
+               int ks, int stride, ConvUnit* cu) {
+  const HostTensor* w = pk.get(wkey);
+  const HostTensor* g = pk.get(bnkey + ".weight");
+  const HostTensor* b = pk.get(bnkey + ".bias");
+  const HostTensor* m = pk.get(bnkey + ".running_mean");
+  const HostTensor* v = pk.get(bnkey + ".running_var");
+  const HostTensor* s = prelu_key.empty() ? nullptr : pk.get(prelu_key);
+  if (!w || !g || !b || !m || !v || (!prelu_key.empty() && !s)) return false;
+  const int cout = (int)w->shape[0], cin = (int)w->shape[1];
+  cu->cin = cin; cu->cout = cout; cu->ks = ks; cu->stride = stride;
+  const int K = ks * ks * cin;
+  std::vector<float> packed((size_t)cout * K);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < ks * ks; ++t) packed[(size_t)o * K + (size_t)t * cin + c] = w->v[((size_t)o * cin + c) * ks * ks + t];
+  cu->w = pk.pack(packed, cout, K, K);
+  std::vector<float> sc(cout), bi(cout);
+  for (int o = 0; o < cout; ++o) {
+    const float inv = 1.0f / std::sqrt(v->v[o] + 1e-5f);      // nn.BatchNorm eps default
+    sc[o] = g->v[o] * inv;
+    bi[o] = b->v[o] - m->v[o] * sc[o];
+  }
+  cu->scale = pk.upload_f(sc);
+  cu->bias = pk.upload_f(bi);
+  cu->slope = nullptr;
+  if (s) {
+    std::vector<float> sl(cout);
+    for (int o = 0; o < cout; ++o) sl[o] = s->v[s->numel() == 1 ? 0 : o];
+    cu->slope = pk.upload_f(sl);
+  }
+  return true;
+}
+
+bool pack_linear(Packer& pk, const std::string& prefix, LinearW* lw, float wscale = 1.f) {
+  const HostTensor* w = pk.get(prefix + ".weight");
+  const HostTensor* b = pk.get(prefix + ".bias");
+  if (!w || !b) return false;
+  const int n = (int)w->shape[0], k = (int)w->shape[1], kpad = round_up(k, 64);
+  std::vector<float> p((size_t)n * kpad, 0.f);
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < k; ++c) p[(size_t)r * kpad + c] = w->v[(size_t)r * k + c] * wscale;
+  lw->w = pk.pack(p, n, k, kpad);
+  std::vector<float> bb(b->v);
+  for (auto& x : bb) x *= wscale;
+  lw->bias = pk.upload_f(bb);
+  return true;
+}
+
+bool pack_all(Packer& pk) {
+  avh_handle* h = pk.h;
+  const avh_config& c = h->cfg;
+  const int D = c.encoder_embed_dim;
+  const std::string R = "feature_extractor_video.resnet.";
+  bool ok = true;
+  // ---- stem: Conv3d weight [64,1,5,7,7] -> [64, 256] (K = dt*49 + kh*7 + kw, zero padded)
+  {
+    const HostTensor* w = pk.get(R + "frontend3D.0.weight");
+    const HostTensor* g = pk.get(R + "frontend3D.1.weight");
+    const HostTensor* b = pk.get(R + "frontend3D.1.bias");
+    const HostTensor* m = pk.get(R + "frontend3D.1.running_mean");
+    const HostTensor* v = pk.get(R + "frontend3D.1.running_var");
+    const HostTensor* s = pk.get(R + "frontend3D.2.weight");
+    if (w && g && b && m && v && s) {
+      std::vector<float> p((size_t)64 * 256, 0.f);
+      for (int o = 0; o < 64; ++o)
+        for (int k = 0; k < 245; ++k) p[(size_t)o * 256 + k] = w->v[(size_t)o * 245 + k];
+      h->stem.w = pk.pack(p, 64, 245, 256);
+      h->stem.cin = 1; h->stem.cout = 64;
+      std::vector<float> sc(64), bi(64), sl(64);
+      for (int o = 0; o < 64; ++o) {
+        const float inv = 1.0f / std::sqrt(v->v[o] + 1e-5f);
+        sc[o] = g->v[o] * inv;
+        bi[o] = b->v[o] - m->v[o] * sc[o];
+        sl[o] = s->v[s->numel() == 1 ? 0 : o];
+      }
+      h->stem.scale = pk.upload_f(sc);
+      h->stem.bias = pk.upload_f(bi);
+      h->stem.slope = pk.upload_f(sl);
+    } else ok = false;
+  }
+  // ---- ResNet-18 trunk (avhubert/resnet.py:77-129)
+  for (int L = 0; L < 4; ++L)
+    for (int bi = 0; bi < 2; ++bi) {
+      BlockW& bw = h->blocks[L][bi];
+      const std::string pre = R + "trunk.layer" + std::to_string(L + 1) + "." + std::to_string(bi) + ".";
+      const int stride = (L > 0 && bi == 0) ? 2 : 1;
+      ok &= pack_conv(pk, pre + "conv1.weight", pre + "bn1", pre + "relu1.weight", 3, stride, &bw.c1);
+      ok &= pack_conv(pk, pre + "conv2.weight", pre + "bn2", "", 3, 1, &bw.c2);
+      bw.has_ds = (L > 0 && bi == 0);
+      if (bw.has_ds) ok &= pack_conv(pk, pre + "downsample.0.weight", pre + "downsample.1", "", 1, stride, &bw.ds);
+      const HostTensor* s2 = pk.get(pre + "relu2.weight");
+      if (s2) {
+        const int cout = 64 << L;
+        std::vector<float> sl(cout);
+        for (int o = 0; o < cout; ++o) sl[o] = s2->v[s2->numel() == 1 ? 0 : o];
+        bw.slope2 = pk.upload_f(sl);
+      } else ok = false;
+    }
+  // ---- modality projections, fusion LN, post_extract_proj
+  ok &= pack_linear(pk, "feature_extractor_video.proj", &h->proj_v);
+  ok &= pack_linear(pk, "feature_extractor_audio.proj", &h->proj_a);
+  {
+    const HostTensor* g = pk.get("layer_norm.weight");
+    const HostTensor* b = pk.get("layer_norm.bias");
+    if (g && b) { h->fuse_ln_g = pk.upload_f(g->v); h->fuse_ln_b = pk.upload_f(b->v); } else ok = false;
+  }
+  h->has_post_proj = (c.modality_fuse == AVH_FUSE_CONCAT);
+  if (h->has_post_proj) ok &= pack_linear(pk, "post_extract_proj", &h->post_proj);
+  // ---- positional conv: weight-norm(dim=2) fold, grouped -> per-N-tile windowed dense K-major
+  {
+    const HostTensor* wg = pk.get("encoder.pos_conv.0.weight_g");
+    const HostTensor* wv = pk.get("encoder.pos_conv.0.weight_v");
+    const HostTensor* wb = pk.get("encoder.pos_conv.0.bias");
+    if (wg && wv && wb) {
+      const int KT = c.conv_pos, G = c.conv_pos_groups, cg = D / G;    // taps, groups, channels per group
+      // norm over (out, in) per tap (torch.nn.utils.weight_norm dim=2, wav2vec2.py:834)
+      std::vector<double> nrm(KT, 0.0);
+      for (size_t i = 0; i < wv->v.size(); ++i) nrm[i % KT] += (double)wv->v[i] * wv->v[i];
+      std::vector<float> ratio(KT);
+      for (int k = 0; k < KT; ++k) ratio[k] = (float)((double)wg->v[k] / std::sqrt(nrm[k]));
+      const int ntile = D / 64;
+      std::vector<int> acol(ntile);
+      int window = 64;
+      for (int j = 0; j < ntile; ++j) {
+        const int g0 = (64 * j) / cg, g1 = (64 * j + 63) / cg;
+        acol[j] = g0 * cg;
+        const int need = (g1 + 1) * cg - g0 * cg;
+        if (need > window) window = round_up(need, 64);
+      }
+      h->pos_window = window;
+      const int kpad = KT * window;
+      std::vector<float> p((size_t)D * kpad, 0.f);
+      for (int o = 0; o < D; ++o) {
+        const int g = o / cg, j = o / 64;
+        for (int i = 0; i < cg; ++i) {
+          const int col = g * cg + i - acol[j];           // position inside the tile's window
+          for (int k = 0; k < KT; ++k)
+            p[(size_t)o * kpad + (size_t)k * window + col] = wv->v[((size_t)o * cg + i) * KT + k] * ratio[k];
+        }
+      }
+      h->pos_w = pk.pack(p, D, kpad, kpad);
+      h->pos_bias = pk.upload_f(wb->v);
+      h->pos_acol = pk.upload(acol);
+    } else ok = false;
+  }
+  // ---- transformer layers: fused QKV with q scaling folded (multihead_attention.py:60, scaling = hd^-0.5)
+  h->layers.resize(c.encoder_layers);
+  const float qscale = 1.0f / std::sqrt((float)(D / c.encoder_attention_heads));
+  for (int l = 0; l < c.encoder_layers; ++l) {
+    LayerW& lw = h->layers[l];
+    const std::string pre = "encoder.layers." + std::to_string(l) + ".";
+    const HostTensor* qw = pk.get(pre + "self_attn.q_proj.weight");
+    const HostTensor* kw = pk.get(pre + "self_attn.k_proj.weight");
+    const HostTensor* vw = pk.get(pre + "self_attn.v_proj.weight");
+    const HostTensor* qb = pk.get(pre + "self_attn.q_proj.bias");
+    const HostTensor* kb = pk.get(pre + "self_attn.k_proj.bias");
+    const HostTensor* vb = pk.get(pre + "self_attn.v_proj.bias");
+    if (qw && kw && vw && qb && kb && vb) {
+      std::vector<float> w((size_t)3 * D * D), b((size_t)3 * D);
+      for (size_t i = 0; i < (size_t)D * D; ++i) {
+        w[i] = qw->v[i] * qscale;
+        w[(size_t)D * D + i] = kw->v[i];
+        w[(size_t)2 * D * D + i] = vw->v[i];
+      }
+      for (int i = 0; i < D; ++i) { b[i] = qb->v[i] * qscale; b[D + i] = kb->v[i]; b[2 * D + i] = vb->v[i]; }
+      lw.qkv.w = pk.pack(w, 3 * D, D, D);
+      lw.qkv.bias = pk.upload_f(b);
+    } else ok = false;
+    ok &= pack_linear(pk, pre + "self_attn.out_proj", &lw.out);
+    ok &= pack_linear(pk, pre + "fc1", &lw.fc1);
+    ok &= pack_linear(pk, pre + "fc2", &lw.fc2);
+    const HostTensor* g1 = pk.get(pre + "self_attn_layer_norm.weight");
+    const HostTensor* b1 = pk.get(pre + "self_attn_layer_norm.bias");
+    const HostTensor* g2 = pk.get(pre + "final_layer_norm.weight");
+    const HostTensor* b2 = pk.get(pre + "final_layer_norm.bias");
+    if (g1 && b1 && g2 && b2) {
+      lw.ln1_g = pk.upload_f(g1->v); lw.ln1_b = pk.upload_f(b1->v);
+      lw.ln2_g = pk.upload_f(g2->v); lw.ln2_b = pk.upload_f(b2->v);
+    } else ok = false;
+  }
+  {
+    const HostTensor* g = pk.get("encoder.layer_norm.weight");
+    const HostTensor* b = pk.get("encoder.layer_norm.bias");
+    if (g && b) { h->enc_ln_g = pk.upload_f(g->v); h->enc_ln_b = pk.upload_f(b->v); } else ok = false;
+  }
+  return ok;
+}
+
+// ============================================================================ plan construction
+struct Tap {
+  int a_row_off, a_col, b_col;
+};
+
+struct Builder {
+  avh_handle* h;
+  Plan* plan;
+  bool sizing;
+  Sizer sizer;
+  int P;
+  bool f32;      // fp32-faithful mode
+
+  void* alloc(size_t bytes) {
+    if (sizing) {
+      sizer.take(bytes);
+      return reinterpret_cast<void*>(0x1000);   // placeholder, never dereferenced
+    }
+    return plan->arena.take(bytes);
+  }
+  void push(std::function<int(cudaStream_t)> f) {
+    if (!sizing) plan->steps.push_back(Step{std::move(f)});
+  }
+
+  // K-step table for one GEMM: every tap x every 64-wide K chunk (x 3 split-precision products in fp32 mode)
+  const KStep* ktable(const std::vector<Tap>& taps, int chunks, int a_plane_stride, int b_plane_stride,
+                      int* num_kb) {
+    std::vector<KStep> t;
+    const int nprod = f32 ? 3 : 1;
+    static const int PA[3] = {0, 0, 1}, PB[3] = {0, 1, 0};
+    for (int pr = nprod - 1; pr >= 0; --pr)       // small cross terms first, hi*hi last
+      for (const Tap& tp : taps)
+        for (int c = 0; c < chunks; ++c)
+          t.push_back(KStep{tp.a_col + PA[pr] * a_plane_stride + c * 64, tp.a_row_off,
+                            tp.b_col + PB[pr] * b_plane_stride + c * 64, 0});
+    *num_kb = (int)t.size();
+    KStep* d = reinterpret_cast<KStep*>(alloc(t.size() * sizeof(KStep)));
+    if (!sizing) cudaMemcpy(d, t.data(), t.size() * sizeof(KStep), cudaMemcpyHostToDevice);
+    return d;
+  }
+
+  // enqueue one GEMM; returns false on planning failure
+  bool gemm(const void* A, long long a_rows, int a_cols, const PackedW& W, long long M, const std::vector<Tap>& taps,
+            int chunks, int a_plane_stride, Epilogue ep, int block_n = 0, const int* a_col_nblk = nullptr) {
+    GemmProblem pr;
+    pr.A = A; pr.a_rows = a_rows; pr.a_cols = a_cols; pr.lda = a_cols;
+    pr.B = W.w; pr.b_rows = W.n; pr.b_cols = P * W.kpad; pr.ldb = (long long)P * W.kpad;
+    pr.M = M; pr.N = W.n;
+    pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
+    pr.a_col_nblk = a_col_nblk;
+    pr.block_n = block_n ? block_n : gemm_pick_block_n(M, W.n);
+    pr.ep = ep;
+    if (sizing) return true;
+    GemmPlan* gp = new GemmPlan();
+    plan->gemms.push_back(gp);
+    if (gemm_plan(pr, gp)) return false;
+    const bool wants_mask = ep.row_zero != nullptr;     // sentinel: bind the caller's mask at launch
+    Plan* pl = plan;
+    plan->steps.push_back(Step{[gp, pl, wants_mask](cudaStream_t s) {
+      if (wants_mask) gp->prob.ep.row_zero = pl->args.mask;
+      return gemm_launch(*gp, s);
+    }});
+    return true;
+  }
+};
+
+const unsigned char* const MASK_SENTINEL = reinterpret_cast<const unsigned char*>(0x1);
+
+// activation tensor: `data` holds the values ([rows, C], bf16 in bf16 mode / fp32 in fp32 mode); `op` is the
+// GEMM-operand form (bf16 [rows, P*C]); identical to data in bf16 mode.
+struct Act {
+  void* data = nullptr;
+  void* op = nullptr;
+  long long rows = 0;
+  int C = 0;
+};
+
+struct FrontendBufs {
+  void* im2col = nullptr;   // [CF*1936, P*256]
+  void* stem_out = nullptr; // [CF*1936, 64]
+  Act pooled;               // padded 23x23x64
+  Act a[4][4];              // per layer: block0.conv1 out, block0 out, block1.conv1 out, block1 out
+  Act ds[4];                // downsample outputs (layers 2-4)
+  void* col[4] = {nullptr, nullptr, nullptr, nullptr};   // im2col_s2 outputs (layers 2-4)
+};
+
+bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
+  Builder b;
+  b.h = h; b.plan = plan; b.sizing = sizing; b.P = h->P; b.f32 = (h->cfg.compute_mode == AVH_COMPUTE_FP32);
+  const avh_config& c = h->cfg;
+  const int P = b.P;
+  const bool f32 = b.f32;
+  const int B = plan->B, T = plan->T, D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim;
+  const int Hh = c.encoder_attention_heads;
+  const long long N = (long long)B * T;
+  const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
+  const size_t es = f32 ? 4 : 2;            // bytes per activation value
+  const int act_dt = f32 ? DT_F32 : DT_BF16;
+  Plan* pl = plan;
+
+  auto new_act = [&](long long rows, int C) {
+    Act a;
+    a.rows = rows; a.C = C;
+    a.data = b.alloc((size_t)rows * C * es);
+    a.op = f32 ? b.alloc((size_t)rows * C * 2 * P) : a.data;
+    return a;
+  };
+  // fp32 mode: refresh the split bf16 operand planes of an activation
+  auto sync_op = [&](const Act& a) {
+    if (!f32) return;
+    const float* src = reinterpret_cast<const float*>(a.data);
+    void* dst = a.op;
+    const long long rows = a.rows;
+    const int C = a.C, planes = P;
+    b.push([=](cudaStream_t s) { return launch_split_rows(src, C, dst, planes, rows, C, 0, 0, s); });
+  };
+  auto ep_base = [&](void* Cptr, long long ldc) {
+    Epilogue ep;
+    ep.C = Cptr; ep.ldc = ldc; ep.c_fp32 = f32 ? 1 : 0;
+    return ep;
+  };
+
+  // fused token features [N, E]: audio arm in columns [0,D), video arm in [D,2D) (concat) or summed (add)
+  Act fused = new_act(N, E);
+  const int v_off = c.modality_fuse == AVH_FUSE_CONCAT ? D : 0;
+  const int a_off = 0;
+
+  // ========================================================================== lip frontend
+  if (plan->has_video) {
+    int CF = c.frontend_chunk_frames > 0 ? c.frontend_chunk_frames : 480;
+    if (CF > N) CF = (int)N;
+    FrontendBufs fb;
+    fb.im2col = b.alloc((size_t)CF * 1936 * 256 * 2 * P);
+    fb.stem_out = b.alloc((size_t)CF * 1936 * 64 * es);
+    static const int HS[4] = {22, 11, 6, 3};
+    fb.pooled = new_act((long long)CF * 23 * 23, 64);
+    for (int L = 0; L < 4; ++L) {
+      const int S = HS[L] + 1, Cc = 64 << L;
+      for (int i = 0; i < 4; ++i) fb.a[L][i] = new_act((long long)CF * S * S, Cc);
+      if (L > 0) {
+        fb.ds[L] = new_act((long long)CF * S * S, Cc);
+        fb.col[L] = b.alloc((size_t)CF * HS[L] * HS[L] * 9 * (Cc / 2) * P * 2);
+      }
+    }
+    Act pooled_feat = new_act(N, 512);     // avgpool output = ResEncoder output [B*T, 512]
+    if (!sizing) plan->stages["resnet"] = {pooled_feat.data, {act_dt, N * 512}};
+
+    // 3x3 stride-1 conv over the padded layout as 9 shifted taps
+    auto conv3x3_s1 = [&](const Act& in, const ConvUnit& cu, const Act& out, int Himg, int nimg, const float* slope1,
+                          const Act* res, const float* slope2) -> bool {
+      const int S = Himg + 1;
+      std::vector<Tap> taps;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          taps.push_back(Tap{(kh - 1) * S + (kw - 1), 0, (kh * 3 + kw) * cu.cin});
+      Epilogue ep = ep_base(out.data, cu.cout);
+      ep.col_scale = cu.scale; ep.col_bias = cu.bias;
+      if (slope1) { ep.act = ACT_PRELU; ep.slope1 = slope1; }
+      if (res) { ep.R = res->data; ep.ldr = cu.cout; ep.r_fp32 = f32 ? 1 : 0; }
+      ep.slope2 = slope2;
+      ep.map_mode = MAP_2LEVEL; ep.S2 = S * S; ep.S1 = S; ep.H = Himg; ep.W = Himg;
+      ep.O2 = S * S; ep.O1 = S; ep.O0 = 0; ep.invalid_zero = 1;
+      const long long rows = (long long)nimg * S * S;
+      if (!b.gemm(in.op, rows, P * cu.cin, cu.w, rows, taps, cu.cin / 64, cu.cin, ep)) return false;
+      sync_op(out);
+      return true;
+    };
+
+    for (long long f0 = 0; f0 < N; f0 += CF) {
+      const int nf = (int)std::min<long long>(CF, N - f0);
+      // ---- stem: im2col -> GEMM(+BN+PReLU) -> maxpool
+      {
+        void* col = fb.im2col;
+        const int planes = P;
+        b.push([=](cudaStream_t s) {
+          return launch_stem_im2col(pl->args.video, pl->args.video_dt, T, f0, nf, col, planes, s);
+        });
+        Epilogue ep = ep_base(fb.stem_out, 64);
+        ep.col_scale = h->stem.scale; ep.col_bias = h->stem.bias; ep.act = ACT_PRELU; ep.slope1 = h->stem.slope;
+        const long long rows = (long long)nf * 1936;
+        if (!b.gemm(fb.im2col, rows, P * 256, h->stem.w, rows, {Tap{0, 0, 0}}, 4, 256, ep)) return false;
+        void* so = fb.stem_out;
+        void* po = fb.pooled.data;
+        b.push([=](cudaStream_t s) { return launch_maxpool_stem(so, po, nf, f32 ? 1 : 0, s); });
+        Act pv = fb.pooled; pv.rows = (long long)nf * 529;
+        sync_op(pv);
+      }
+      // ---- trunk
+      Act cur = fb.pooled;
+      for (int L = 0; L < 4; ++L) {
+        const int Hn = HS[L], S = Hn + 1, Cc = 64 << L;
+        for (int bi = 0; bi < 2; ++bi) {
+          const BlockW& bw = h->blocks[L][bi];
+          Act mid = fb.a[L][bi * 2], out = fb.a[L][bi * 2 + 1];
+          mid.rows = out.rows = (long long)nf * S * S;
+          const Act* res = &cur;
+          Act dsout;
+          if (bw.has_ds) {
+            // stride-2: explicit im2col of the previous layer's padded map, conv1 and the 1x1 downsample read it
+            const int Hp = HS[L - 1], Cin = Cc / 2;
+            void* col = fb.col[L];
+            const void* src = cur.op;
+            const int CinP = Cin * P;
+            b.push([=](cudaStream_t s) { return launch_im2col_s2(src, col, nf, Hp, Hp, CinP, s); });
+            const long long rows = (long long)nf * Hn * Hn;
+            std::vector<Tap> taps;
+            for (int t = 0; t < 9; ++t) taps.push_back(Tap{0, t * CinP, t * Cin});
+            Epilogue ep = ep_base(mid.data, Cc);
+            ep.col_scale = bw.c1.scale; ep.col_bias = bw.c1.bias; ep.act = ACT_PRELU; ep.slope1 = bw.c1.slope;
+            ep.map_mode = MAP_2LEVEL; ep.S2 = Hn * Hn; ep.S1 = Hn; ep.H = Hn; ep.W = Hn;
+            ep.O2 = S * S; ep.O1 = S; ep.O0 = 0;
+            if (!b.gemm(col, rows, 9 * CinP, bw.c1.w, rows, taps, Cin / 64, Cin, ep)) return false;
+            sync_op(mid);
+            dsout = fb.ds[L];
+            dsout.rows = mid.rows;
+            Epilogue epd = ep_base(dsout.data, Cc);
+            epd.col_scale = bw.ds.scale; epd.col_bias = bw.ds.bias;
+            epd.map_mode = MAP_2LEVEL; epd.S2 = Hn * Hn; epd.S1 = Hn; epd.H = Hn; epd.W = Hn;
+            epd.O2 = S * S; epd.O1 = S; epd.O0 = 0;
+            if (!b.gemm(col, rows, 9 * CinP, bw.ds.w, rows, {Tap{0, 4 * CinP, 0}}, Cin / 64, Cin, epd)) return false;
+            res = &dsout;
+          } else {
+            if (!conv3x3_s1(cur, bw.c1, mid, Hn, nf, bw.c1.slope, nullptr, nullptr)) return false;
+          }
+          if (!conv3x3_s1(mid, bw.c2, out, Hn, nf, nullptr, res, bw.slope2)) return false;
+          cur = out;
+        }
+      }
+      // ---- AdaptiveAvgPool2d(1) -> [nf, 512] rows f0.. of the ResEncoder output
+      {
+        const void* src = cur.data;
+        char* dst = reinterpret_cast<char*>(pooled_feat.data) + (size_t)f0 * 512 * es;
+        b.push([=](cudaStream_t s) { return launch_avgpool(src, dst, nf, 3, 3, 512, f32 ? 1 : 0, s); });
+      }
+    }
+    sync_op(pooled_feat);
+    // ---- SubModel.proj (hubert.py:321,327): Linear 512 -> D into the video columns of the fused buffer
+    {
+      Epilogue ep = ep_base(reinterpret_cast<char*>(fused.data) + (size_t)v_off * es, E);
+      ep.col_bias = h->proj_v.bias;
+      if (!b.gemm(pooled_feat.op, N, P * 512, h->proj_v.w, N, {Tap{0, 0, 0}}, 512 / 64, 512, ep)) return false;
+    }
+  }
+  // ========================================================================== audio arm
+  if (plan->has_audio) {
+    const int Fa = c.audio_feat_dim, Fp = round_up(Fa, 64);
+    Act arows = new_act(N, Fp);       // zero-initialised; only the first Fa columns are ever written
+    {
+      void* dst = arows.data;
+      b.push([=](cudaStream_t s) {
+        return launch_bct_to_rows(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
+                                  B, Fa, T, dst, act_dt, Fp, s);
+      });
+      sync_op(arows);
+    }
+    Epilogue ep = ep_base(reinterpret_cast<char*>(fused.data) + (size_t)a_off * es, E);
+    ep.col_bias = h->proj_a.bias;
+    if (c.modality_fuse == AVH_FUSE_ADD && plan->has_video) {     // features_audio + features_video
+      ep.R = ep.C; ep.ldr = E; ep.r_fp32 = f32 ? 1 : 0;
+    }
+    if (!b.gemm(arows.op, N, P * Fp, h->proj_a.w, N, {Tap{0, 0, 0}}, Fp / 64, Fp, ep)) return false;
+  }
+  // a missing modality contributes zeros [B,D,T] (hubert.py:703-708): with concat its columns stay at the
+  // arena's zero fill (nothing ever writes them for this plan); with add there is nothing to add.
+
+  // ========================================================================== fusion LN + post_extract_proj
+  float* x = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));      // residual stream, fp32
+  Act lnE = new_act(N, E);
+  {
+    const void* src = fused.data;
+    float* of = f32 ? reinterpret_cast<float*>(lnE.data) : nullptr;
+    void* ol = f32 ? nullptr : lnE.data;
+    float* g = h->fuse_ln_g; float* be = h->fuse_ln_b;
+    if (h->has_post_proj) {
+      b.push([=](cudaStream_t s) {
+        return launch_layernorm(src, act_dt, E, g, be, 1e-5f, of, ol, DT_BF16, nullptr, N, E, s);
+      });
+      sync_op(lnE);
+      if (!sizing) plan->stages["fused_ln"] = {lnE.data, {act_dt, N * E}};
+      Epilogue ep;
+      ep.C = x; ep.ldc = D; ep.c_fp32 = 1;
+      ep.col_bias = h->post_proj.bias;
+      if (plan->has_mask) ep.row_zero = MASK_SENTINEL;      // index_put(x, padding_mask, 0), wav2vec2.py:869-870
+      if (!b.gemm(lnE.op, N, P * E, h->post_proj.w, N, {Tap{0, 0, 0}}, E / 64, E, ep)) return false;
+    } else {
+      // no post_extract_proj (embed == D): the LN output is the encoder input; zero padded rows here
+      const bool hm = plan->has_mask;
+      b.push([=](cudaStream_t s) {
+        return launch_layernorm(src, act_dt, E, g, be, 1e-5f, x, nullptr, DT_BF16, hm ? pl->args.mask : nullptr, N, E, s);
+      });
+      if (!sizing) plan->stages["fused_ln"] = {x, {DT_F32, N * E}};
+    }
+  }
+  if (c.capture_stages) {      // x is overwritten in place by the encoder: keep a copy for stage-level tests
+    float* enc_in_copy = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));
+    b.push([=](cudaStream_t s) {
+      return cudaMemcpyAsync(enc_in_copy, x, (size_t)N * D * 4, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
+    });
+    if (!sizing) plan->stages["enc_in"] = {enc_in_copy, {DT_F32, N * D}};
+  }
+
+  // ========================================================================== positional conv + GELU + residual
+  {
+    const int G = 64, Tp = T + G;
+    void* xpad = b.alloc((size_t)B * Tp * P * D * 2);      // bf16 [B*(T+64), P*D], gap rows stay zero
+    const int planes = P;
+    b.push([=](cudaStream_t s) { return launch_split_rows(x, D, xpad, planes, N, D, T, Tp, s); });
+    const int KT = c.conv_pos, win = h->pos_window;
+    std::vector<Tap> taps;
+    for (int k = 0; k < KT; ++k) taps.push_back(Tap{k - KT / 2, 0, k * win});
+    Epilogue ep;
+    ep.C = x; ep.ldc = D; ep.c_fp32 = 1;
+    ep.col_bias = h->pos_bias; ep.act = ACT_GELU;
+    ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+    ep.map_mode = MAP_2LEVEL; ep.S2 = Tp; ep.S1 = Tp; ep.H = 1; ep.W = T; ep.O2 = T; ep.O1 = 0; ep.O0 = 0;
+    if (!b.gemm(xpad, (long long)B * Tp, P * D, h->pos_w, (long long)B * Tp, taps, win / 64, D, ep, 64, h->pos_acol))
+      return false;
+  }
+
+  // ========================================================================== transformer layers
+  Act hbuf = new_act(N, D);          // LayerNorm output / post-LN operand copy of x
+  Act qkv = new_act(N, 3 * D);
+  Act ctx = new_act(N, D);
+  Act ffn = new_act(N, F);
+  float* tmp = c.layer_norm_first ? nullptr : reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));
+  const bool hm = plan->has_mask;
+
+  auto ln_to_h = [&](const float* src, const float* g, const float* be, float* also_f32) {
+    // LN(src) -> hbuf (operand form) and optionally an fp32 copy (post-LN: the new residual stream)
+    float* of = f32 ? reinterpret_cast<float*>(hbuf.data) : also_f32;
+    void* ol = f32 ? nullptr : hbuf.data;
+    b.push([=](cudaStream_t s) { return launch_layernorm(src, DT_F32, D, g, be, 1e-5f, of, ol, DT_BF16, nullptr, N, D, s); });
+    if (f32 && also_f32 != nullptr) {
+      float* hd = reinterpret_cast<float*>(hbuf.data);
+      b.push([=](cudaStream_t s) {
+        return cudaMemcpyAsync(also_f32, hd, (size_t)N * D * 4, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
+      });
+    }
+    sync_op(hbuf);
+  };
+  auto x_to_h = [&]() {   // operand copy of the residual stream (post-LN blocks read x itself)
+    void* dst = hbuf.op;
+    const int planes = P;
+    b.push([=](cudaStream_t s) { return launch_split_rows(x, D, dst, planes, N, D, 0, 0, s); });
+  };
+
+  if (!c.layer_norm_first) {
+    // encoder-level LayerNorm right after the positional conv (wav2vec2.py:876-877)
+    float* g = h->enc_ln_g; float* be = h->enc_ln_b;
+    b.push([=](cudaStream_t s) { return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
+    x_to_h();
+  }
+  const int n_layers = plan->output_layer > 0 ? std::min(plan->output_layer, c.encoder_layers) : c.encoder_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    const LayerW& lw = h->layers[l];
+    if (c.layer_norm_first) ln_to_h(x, lw.ln1_g, lw.ln1_b, nullptr);
+    {   // fused QKV projection
+      Epilogue ep = ep_base(qkv.data, 3 * D);
+      ep.col_bias = lw.qkv.bias;
+      if (!b.gemm(hbuf.op, N, P * D, lw.qkv.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+    }
+    {
+      const void* q = qkv.data; void* o = ctx.data;
+      b.push([=](cudaStream_t s) {
+        return launch_attention(q, hm ? pl->args.mask : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
+      });
+      sync_op(ctx);
+    }
+    {   // out_proj + residual
+      Epilogue ep;
+      ep.C = c.layer_norm_first ? x : tmp; ep.ldc = D; ep.c_fp32 = 1;
+      ep.col_bias = lw.out.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+      if (!b.gemm(ctx.op, N, P * D, lw.out.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+    }
+    if (c.layer_norm_first) ln_to_h(x, lw.ln2_g, lw.ln2_b, nullptr);
+    else {
+      float* g = lw.ln1_g; float* be = lw.ln1_b;
+      b.push([=](cudaStream_t s) { return launch_layernorm(tmp, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
+      x_to_h();
+    }
+    {   // fc1 + GELU (erf form, fp32: fairseq/fairseq/modules/gelu.py:95-96)
+      Epilogue ep = ep_base(ffn.data, F);
+      ep.col_bias = lw.fc1.bias; ep.act = ACT_GELU;
+      if (!b.gemm(hbuf.op, N, P * D, lw.fc1.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      sync_op(ffn);
+    }
+    {   // fc2 + residual
+      Epilogue ep;
+      ep.C = c.layer_norm_first ? x : tmp; ep.ldc = D; ep.c_fp32 = 1;
+      ep.col_bias = lw.fc2.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+      if (!b.gemm(ffn.op, N, P * F, lw.fc2.w, N, {Tap{0, 0, 0}}, F / 64, F, ep)) return false;
+    }
+    if (!c.layer_norm_first) {
+      float* g = lw.ln2_g; float* be = lw.ln2_b;
+      b.push([=](cudaStream_t s) { return launch_layernorm(tmp, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
+      if (l + 1 < n_layers) x_to_h();
+    }
+  }
+  // ========================================================================== output
+  if (c.layer_norm_first && plan->output_layer == 0) {
+    float* g = h->enc_ln_g; float* be = h->enc_ln_b;
+    b.push([=](cudaStream_t s) {
+      return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, nullptr, pl->args.out, pl->args.out_dt, nullptr, N, D, s);
+    });
+  } else {
+    b.push([=](cudaStream_t s) { return launch_convert(x, DT_F32, pl->args.out, pl->args.out_dt, N * D, s); });
+  }
+  if (bytes_out) *bytes_out = b.sizer.used;
+  return true;
+}
+
+Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer) {
+  const std::string key = std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
+                          (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer);
+  auto it = h->plans.find(key);
+  if (it != h->plans.end()) return it->second.get();
+  if (h->plans.size() >= 8) h->plans.clear();      // bound workspace growth for ragged shape streams
+  std::unique_ptr<Plan> p(new Plan());
+  p->B = B; p->T = T; p->has_video = has_video; p->has_audio = has_audio; p->has_mask = has_mask;
+  p->output_layer = output_layer;
+  size_t bytes = 0;
+  if (!build_plan(h, p.get(), true, &bytes)) return nullptr;
+  if (p->arena.init(bytes + (1 << 20))) return nullptr;
+  if (!build_plan(h, p.get(), false, nullptr)) return nullptr;
+  Plan* raw = p.get();
+  h->plans[key] = std::move(p);
+  return raw;
+}
+
+int ensure_cap(void** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  AVH_CUDA_OK(cudaMalloc(p, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+bool ignorable_key(const std::string& k) {
+  if (k == "mask_emb" || k == "label_embs_concat") return true;
+  if (k.rfind("final_proj.", 0) == 0) return true;
+  const std::string suf = "num_batches_tracked";
+  return k.size() >= suf.size() && k.compare(k.size() - suf.size(), suf.size(), suf) == 0;
+}
+bool known_prefix(const std::string& k) {
+  static const char* pre[] = {"feature_extractor_video.", "feature_extractor_audio.", "layer_norm.",
+                              "post_extract_proj.", "encoder."};
+  for (const char* p : pre)
+    if (k.rfind(p, 0) == 0) return true;
+  return false;
+}
+
+}  // namespace
+}  // namespace avh
+
+// ============================================================================ extern "C"
+extern "C" {
+
+int avh_abi_version(void) { return AVH_ABI_VERSION; }
+const char* avh_last_error(void) { return avh::g_err.c_str(); }
+int64_t avh_launch_count(void) { return avh::g_launches.load(); }
+void avh_reset_launch_count(void) { avh::g_launches.store(0); }
+
+int avh_create(const avh_config* cfg, int device, avh_handle** out) {
+  AVH_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  AVH_CHECK(cfg->encoder_layers >= 1 && cfg->encoder_embed_dim >= 64, "bad encoder shape");
+  AVH_CHECK(cfg->encoder_embed_dim % 64 == 0 && cfg->encoder_ffn_embed_dim % 64 == 0, "dims must be multiples of 64");
+  AVH_CHECK(cfg->encoder_attention_heads * 64 == cfg->encoder_embed_dim, "head dim must be 64");
+  AVH_CHECK(cfg->conv_pos >= 2 && cfg->conv_pos % 2 == 0 && cfg->conv_pos <= 128, "conv_pos must be even and <= 128");
+  AVH_CHECK(cfg->conv_pos_groups >= 1 && cfg->encoder_embed_dim % cfg->conv_pos_groups == 0, "bad conv_pos_groups");
+  AVH_CHECK(cfg->audio_feat_dim >= 1 && cfg->audio_feat_dim <= 1024, "bad audio_feat_dim");
+  AVH_CHECK(cfg->modality_fuse == AVH_FUSE_CONCAT || cfg->modality_fuse == AVH_FUSE_ADD, "bad modality_fuse");
+  AVH_CHECK(cfg->compute_mode == AVH_COMPUTE_BF16 || cfg->compute_mode == AVH_COMPUTE_FP32, "bad compute_mode");
+  int ndev = 0;
+  AVH_CUDA_OK(cudaGetDeviceCount(&ndev));
+  AVH_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+  cudaDeviceProp prop;
+  AVH_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  AVH_CHECK(prop.major == 10, "libavh_b200 contains sm_100a code only; this device is not a B200-class GPU");
+  AVH_CUDA_OK(cudaSetDevice(device));
+  avh_handle* h = new avh_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->P = cfg->compute_mode == AVH_COMPUTE_FP32 ? 2 : 1;
+  *out = h;
+  return 0;
+}
+
+int avh_destroy(avh_handle* h) {
+  if (h == nullptr) return 0;
+  cudaSetDevice(h->device);
+  h->plans.clear();
+  h->warena.release();
+  if (h->h2d_video) cudaFree(h->h2d_video);
+  if (h->h2d_audio) cudaFree(h->h2d_audio);
+  if (h->h2d_mask) cudaFree(h->h2d_mask);
+  if (h->d_out) cudaFree(h->d_out);
+  delete h;
+  return 0;
+}
+
+int avh_load_tensor(avh_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+  AVH_CHECK(h != nullptr && key != nullptr && data != nullptr, "null argument");
+  AVH_CHECK(ndim >= 0 && ndim <= 8, "bad ndim");
+  AVH_CHECK(dtype == AVH_F32 || dtype == AVH_F16 || dtype == AVH_BF16, "bad dtype");
+  const std::string k(key);
+  if (avh::ignorable_key(k)) return 0;
+  AVH_CHECK(avh::known_prefix(k), "unexpected state-dict key: " + k);
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  AVH_CHECK(n >= 0 && n < (1ll << 31), "tensor too large");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  std::vector<uint8_t> rawb((size_t)n * avh::dtype_size(dtype));
+  AVH_CUDA_OK(cudaMemcpy(rawb.data(), data, rawb.size(), cudaMemcpyDefault));
+  avh::HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.v.resize((size_t)n);
+  if (dtype == AVH_F32) std::memcpy(t.v.data(), rawb.data(), rawb.size());
+  else if (dtype == AVH_F16) {
+    const __half* p = reinterpret_cast<const __half*>(rawb.data());
+    for (int64_t i = 0; i < n; ++i) t.v[i] = __half2float(p[i]);
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(rawb.data());
+    for (int64_t i = 0; i < n; ++i) t.v[i] = __bfloat162float(p[i]);
+  }
+  h->raw[k] = std::move(t);
+  h->finalized = false;
+  return 0;
+}
+
+int avh_finalize_weights(avh_handle* h) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  h->plans.clear();
+  h->warena.release();
+  h->warena = avh::Arena();
+  avh::Packer sizer{h, nullptr, avh::Sizer(), ""};
+  const bool ok = avh::pack_all(sizer);
+  AVH_CHECK(ok, "missing state-dict key: " + sizer.missing);
+  if (h->warena.init(sizer.sizer.used + (1 << 20))) return 1;
+  avh::Packer pk{h, &h->warena, avh::Sizer(), ""};
+  AVH_CHECK(avh::pack_all(pk), "weight upload failed");
+  AVH_CHECK(h->warena.used <= h->warena.cap, "weight arena overflow");
+  AVH_CUDA_OK(cudaDeviceSynchronize());
+  h->finalized = true;
+  return 0;
+}
+
+int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
+                void* out, int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
+  AVH_CHECK(B >= 1 && T >= 1, "empty batch");
+  AVH_CHECK((long long)B * T < (1ll << 24), "batch too large");
+  AVH_CHECK(out != nullptr, "null output");
+  AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
+  AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer);
+  if (p == nullptr) return 1;
+  p->args.video = video; p->args.video_dt = video_dtype;
+  p->args.audio = audio; p->args.audio_dt = audio_dtype;
+  if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
+  p->args.mask = padding_mask;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  for (auto& st : p->steps)
+    if (st.run(s)) {
+      if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
+      return 1;
+    }
+  return 0;
+}
+
+int avh_forward_host(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                     const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
+                     void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int D = h->cfg.encoder_embed_dim, Fa = h->cfg.audio_feat_dim;
+  const size_t vbytes = (size_t)B * T * 88 * 88 * avh::dtype_size(video_dtype);
+  const size_t abytes = (size_t)B * T * Fa * avh::dtype_size(audio_dtype);
+  const size_t obytes = (size_t)B * T * D * avh::dtype_size(out_dtype);
+  if (video) {
+    if (avh::ensure_cap(&h->h2d_video, &h->h2d_video_cap, vbytes)) return 1;
+    AVH_CUDA_OK(cudaMemcpyAsync(h->h2d_video, video, vbytes, cudaMemcpyHostToDevice, s));
+  }
+  if (audio) {
+    if (avh::ensure_cap(&h->h2d_audio, &h->h2d_audio_cap, abytes)) return 1;
+    AVH_CUDA_OK(cudaMemcpyAsync(h->h2d_audio, audio, abytes, cudaMemcpyHostToDevice, s));
+  }
+  if (padding_mask) {
+    if (avh::ensure_cap(&h->h2d_mask, &h->h2d_mask_cap, (size_t)B * T)) return 1;
+    AVH_CUDA_OK(cudaMemcpyAsync(h->h2d_mask, padding_mask, (size_t)B * T, cudaMemcpyHostToDevice, s));
+  }
+  if (avh::ensure_cap(&h->d_out, &h->d_out_cap, obytes)) return 1;
+  const int64_t as[3] = {(int64_t)Fa * T, T, 1};
+  if (avh_forward(h, video ? h->h2d_video : nullptr, video_dtype, audio ? h->h2d_audio : nullptr, audio_dtype, as,
+                  padding_mask ? reinterpret_cast<const uint8_t*>(h->h2d_mask) : nullptr, B, T, output_layer,
+                  h->d_out, out_dtype, stream))
+    return 1;
+  AVH_CUDA_OK(cudaMemcpyAsync(out, h->d_out, obytes, cudaMemcpyDeviceToHost, s));
+  AVH_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int avh_read_stage(avh_handle* h, const char* name, float* dst, int64_t capacity_elems, void* stream) {
+  AVH_CHECK(h != nullptr && name != nullptr && dst != nullptr, "null argument");
+  for (auto& kv : h->plans) {
+    auto it = kv.second->stages.find(name);
+    if (it == kv.second->stages.end()) continue;
+    const long long n = it->second.second.second;
+    AVH_CHECK(n <= capacity_elems, "destination too small");
+    return avh::launch_convert(it->second.first, it->second.second.first, dst, avh::DT_F32, n,
+                               reinterpret_cast<cudaStream_t>(stream));
+  }
+  avh::set_last_error(std::string("no such stage in any cached plan: ") + name);
+  return 1;
+}
+
+int avh_fbank(const int16_t* wav, const int64_t* offsets, const int32_t* video_len, int n_clips, int T,
+              int normalize, float* out, uint8_t* padding_mask, void* stream) {
+  avh::FbankArgs a;
+  a.wav = wav;
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  a.video_len = video_len;
+  a.n_clips = n_clips;
+  a.T = T;
+  a.normalize = normalize;
+  a.out = out;
+  a.padding_mask = padding_mask;
+  return avh::launch_fbank(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clips, const float* noise, int64_t noise_len,
+                  float snr_db, int16_t* out, double* scratch, void* stream) {
+  return avh::launch_add_noise(wav, reinterpret_cast<const long long*>(offsets), n_clips, noise, noise_len, snr_db,
+                               out, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu, const void* R,
+                  int r_fp32, void* C, int c_fp32, int block_n, void* stream) {
+  AVH_CHECK(A && B && C, "null pointer");
+  AVH_CHECK(K % 8 == 0 && N % 32 == 0, "K must be a multiple of 8 and N of 32");
+  avh::GemmProblem pr;
+  pr.A = A; pr.a_rows = M; pr.a_cols = K; pr.lda = K;
+  pr.B = B; pr.b_rows = N; pr.b_cols = K; pr.ldb = K;
+  pr.M = M; pr.N = N; pr.num_kb = (K + 63) / 64;
+  pr.block_n = block_n ? block_n : avh::gemm_pick_block_n(M, N);
+  pr.ep.C = C; pr.ep.ldc = N; pr.ep.c_fp32 = c_fp32;
+  pr.ep.col_bias = bias;
+  pr.ep.act = gelu ? avh::ACT_GELU : avh::ACT_NONE;
+  pr.ep.R = R; pr.ep.ldr = N; pr.ep.r_fp32 = r_fp32;
+  avh::GemmPlan plan;
+  if (avh::gemm_plan(pr, &plan)) return 1;
+  return avh::gemm_launch(plan, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

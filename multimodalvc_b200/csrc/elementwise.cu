@@ -1,0 +1,383 @@
+// HBM/L2-bound helper kernels of the AV-HuBERT hot path: LayerNorm, layout changes, the explicit
+// im2col gathers that feed the tcgen05 GEMM (round-1 lip frontend), pooling and precision splitting.
+// All loads/stores are 16-byte vectors along the channel (innermost) dimension where the layout allows.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cuda_fp16.h>
+
+namespace avh {
+namespace {
+
+__device__ __forceinline__ float load_any(const void* p, int dt, long long i) {
+  if (dt == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  if (dt == DT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void store_lp(void* out, int dt, long long i, float v) {
+  if (dt == DT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  else if (dt == DT_F16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+  else reinterpret_cast<float*>(out)[i] = v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------- LayerNorm
+// one warp per row; two-pass mean/variance in fp32 (rows are <= 8 KB and stay in L1 between passes).
+// Reference: torch.nn.LayerNorm via fairseq/fairseq/modules/layer_norm.py:51-56, eps 1e-5.
+__global__ void layernorm_kernel(const void* __restrict__ in, int in_dt, long long ld_in,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 float* __restrict__ out_f32, void* __restrict__ out_lp, int lp_dt,
+                                 const unsigned char* __restrict__ row_zero, long long rows, int C) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long base = row * ld_in;
+  const bool zero = row_zero != nullptr && row_zero[row] != 0;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += load_any(in, in_dt, base + c);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = load_any(in, in_dt, base + c) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  for (int c = lane; c < C; c += 32) {
+    float v = (load_any(in, in_dt, base + c) - mean) * rstd;
+    if (gamma != nullptr) v = v * gamma[c] + beta[c];
+    if (zero) v = 0.f;
+    if (out_f32 != nullptr) out_f32[row * C + c] = v;
+    if (out_lp != nullptr) store_lp(out_lp, lp_dt, row * C + c, v);
+  }
+}
+
+// fp32 rows with C % 128 == 0: float4 loads, row cached in registers (C <= 2048)
+template <int VEC>
+__global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long ld_in,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float eps, float* __restrict__ out_f32, void* __restrict__ out_lp,
+                                         int lp_dt, const unsigned char* __restrict__ row_zero, long long rows) {
+  constexpr int C = VEC * 128;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bool zero = row_zero != nullptr && row_zero[row] != 0;
+  const float4* x = reinterpret_cast<const float4*>(in + row * ld_in);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = x[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gamma != nullptr) {
+      g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    }
+    float4 o;
+    o.x = v[i].x * rstd * g.x + b.x;
+    o.y = v[i].y * rstd * g.y + b.y;
+    o.z = v[i].z * rstd * g.z + b.z;
+    o.w = v[i].w * rstd * g.w + b.w;
+    if (zero) o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * C)[c4] = o;
+    if (out_lp != nullptr) {
+      if (lp_dt == DT_BF16) {
+        uint2 u = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_lp) + row * C)[c4] = u;
+      } else if (lp_dt == DT_F16) {
+        __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+        uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_lp) + row * C)[c4] = u;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out_lp) + row * C)[c4] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- layout / dtype
+__global__ void bct_to_rows_kernel(const void* __restrict__ in, int in_dt, long long sb, long long sc, long long st,
+                                   int B, int C, int T, void* __restrict__ out, int out_dt, long long ldo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * T * C) return;
+  const int c = (int)(i % C);
+  const long long bt = i / C;
+  const int t = (int)(bt % T);
+  const int b = (int)(bt / T);
+  store_lp(out, out_dt, bt * ldo + c, load_any(in, in_dt, b * sb + c * sc + t * st));
+}
+
+__global__ void convert_kernel(const void* __restrict__ in, int in_dt, void* __restrict__ out, int out_dt,
+                               long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) store_lp(out, out_dt, i, load_any(in, in_dt, i));
+}
+
+// 4 consecutive columns per thread
+__global__ void split_rows_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
+                                  int planes, long long rows, int cols, int T, int Tpad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = cols >> 2;
+  if (i >= rows * c4n) return;
+  const long long r = i / c4n;
+  const int c = (int)(i - r * c4n) * 4;
+  const float4 x = *reinterpret_cast<const float4*>(in + r * ld + c);
+  const long long orow = T > 0 ? (r / T) * Tpad + (r % T) : r;
+  __nv_bfloat16* o = out + orow * ((long long)planes * cols) + c;
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+  uint2 u = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(o) = u;
+  if (planes > 1) {
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    uint2 m = make_uint2(pack_bf16(x.x - f0.x, x.y - f0.y), pack_bf16(x.z - f1.x, x.w - f1.y));
+    *reinterpret_cast<uint2*>(o + cols) = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------- lip frontend
+// Conv3d(1,64,(5,7,7),s(1,2,2),p(2,3,3)) as GEMM rows (avhubert/resnet.py:138).
+__global__ void stem_im2col_kernel(const void* __restrict__ video, int in_dt, int T, long long f0, int nf,
+                                   __nv_bfloat16* __restrict__ out, int planes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-element chunk each
+  const long long total = (long long)nf * 1936 * 32;
+  if (i >= total) return;
+  const int chunk = (int)(i & 31);
+  const long long row = i >> 5;
+  const int pix = (int)(row % 1936);
+  const long long f = f0 + row / 1936;
+  const int ho = pix / 44, wo = pix - ho * 44;
+  const int t = (int)(f % T);
+  const long long clip0 = (f - t) * 7744;      // first frame of this clip
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float x = 0.f;
+    if (k < 245) {
+      const int dt = k / 49, r = k - dt * 49, kh = r / 7, kw = r - kh * 7;
+      const int tt = t + dt - 2, hh = 2 * ho + kh - 3, ww = 2 * wo + kw - 3;
+      if (tt >= 0 && tt < T && hh >= 0 && hh < 88 && ww >= 0 && ww < 88)
+        x = load_any(video, in_dt, clip0 + (long long)tt * 7744 + hh * 88 + ww);
+    }
+    v[j] = x;
+  }
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  uint4* orow = reinterpret_cast<uint4*>(out + row * (256ll * planes));
+  orow[chunk] = *reinterpret_cast<uint4*>(h);
+  if (planes > 1) {
+    uint4 m;
+    uint32_t* mp = reinterpret_cast<uint32_t*>(&m);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f2 = __bfloat1622float2(h[j]);
+      mp[j] = pack_bf16(v[2 * j] - f2.x, v[2 * j + 1] - f2.y);
+    }
+    orow[32 + chunk] = m;
+  }
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+__device__ __forceinline__ float4 f32x4_max(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (avhubert/resnet.py:141): [nf,44,44,64] -> padded [nf,23,23,64].
+// VT = uint4 (8 bf16) or float4 (4 fp32); CV = vectors per pixel.
+template <typename VT, int CV, bool F32>
+__global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ out, int nf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nf * 484 * CV) return;
+  const int cv = (int)(i % CV);
+  const long long p = i / CV;
+  const int pix = (int)(p % 484);
+  const long long n = p / 484;
+  const int ho = pix / 22, wo = pix - ho * 22;
+  VT m;
+  bool first = true;
+  for (int dh = -1; dh <= 1; ++dh) {
+    const int h = 2 * ho + dh;
+    if (h < 0 || h >= 44) continue;
+    for (int dw = -1; dw <= 1; ++dw) {
+      const int w = 2 * wo + dw;
+      if (w < 0 || w >= 44) continue;
+      const VT v = __ldg(in + ((n * 44 + h) * 44 + w) * CV + cv);
+      if (first) m = v;
+      else {
+        if constexpr (F32) m = f32x4_max(m, v);
+        else m = bf16x8_max(m, v);
+      }
+      first = false;
+    }
+  }
+  out[((n * 23 + ho) * 23 + wo) * CV + cv] = m;
+}
+
+// 3x3 stride-2 pad-1 im2col from the zero-padded layout [n,H+1,W+1,C] (avhubert/resnet.py:15-17 with stride 2)
+__global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int H, int W, int C8) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * Ho * Wo * 9 * C8;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  long long r = i / C8;
+  const int tap = (int)(r % 9);
+  r /= 9;
+  const int wo = (int)(r % Wo);
+  r /= Wo;
+  const int ho = (int)(r % Ho);
+  const long long img = r / Ho;
+  const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(in + ((img * (H + 1) + h) * (W + 1) + w) * C8 + c8);
+  out[i] = v;
+}
+
+// AdaptiveAvgPool2d(1) (avhubert/resnet.py:90,127) over the valid pixels of the padded layout
+__global__ void avgpool_kernel(const void* __restrict__ in, void* __restrict__ out, int dt, int n, int H, int W,
+                               int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * C) return;
+  const int c = (int)(i % C);
+  const long long img = i / C;
+  float s = 0.f;
+  for (int h = 0; h < H; ++h)
+    for (int w = 0; w < W; ++w) s += load_any(in, dt, ((img * (H + 1) + h) * (W + 1) + w) * C + c);
+  store_lp(out, dt, i, s / (float)(H * W));
+}
+
+inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace
+
+int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* gamma, const float* beta, float eps,
+                     float* out_f32, void* out_lp, int lp_dt, const unsigned char* row_zero, long long rows, int C,
+                     cudaStream_t stream) {
+  const int wpb = 8;
+  if (rows <= 0) return 0;
+  const int grid = blocks_for(rows, wpb);
+  const bool vec_ok = in_dt == DT_F32 && C % 128 == 0 && ld_in % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+#define AVH_LN_VEC(V)                                                                                            \
+  layernorm_f32_vec_kernel<V><<<grid, wpb * 32, 0, stream>>>(reinterpret_cast<const float*>(in), ld_in, gamma, \
+                                                             beta, eps, out_f32, out_lp, lp_dt, row_zero, rows)
+  if (vec_ok && C == 768) AVH_LN_VEC(6);
+  else if (vec_ok && C == 1024) AVH_LN_VEC(8);
+  else if (vec_ok && C == 1536) AVH_LN_VEC(12);
+  else if (vec_ok && C == 2048) AVH_LN_VEC(16);
+  else if (vec_ok && C == 256) AVH_LN_VEC(2);
+  else if (vec_ok && C == 128) AVH_LN_VEC(1);
+  else
+    layernorm_kernel<<<grid, wpb * 32, 0, stream>>>(in, in_dt, ld_in, gamma, beta, eps, out_f32, out_lp, lp_dt,
+                                                    row_zero, rows, C);
+#undef AVH_LN_VEC
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_bct_to_rows(const void* in, int in_dt, long long sb, long long sc, long long st, int B, int C, int T,
+                       void* out, int out_dt, long long ldo, cudaStream_t stream) {
+  const long long n = (long long)B * C * T;
+  if (n <= 0) return 0;
+  bct_to_rows_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, in_dt, sb, sc, st, B, C, T, out, out_dt, ldo);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_convert(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  convert_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, in_dt, out, out_dt, n);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_split_rows(const float* in, long long ld, void* out, int planes, long long rows, int cols, int T,
+                      int Tpad, cudaStream_t stream) {
+  AVH_CHECK(cols % 4 == 0 && ld % 4 == 0, "split_rows needs 4-column granularity");
+  const long long n = rows * (cols / 4);
+  if (n <= 0) return 0;
+  split_rows_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, ld, reinterpret_cast<__nv_bfloat16*>(out), planes,
+                                                            rows, cols, T, Tpad);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_stem_im2col(const void* video, int in_dt, int T, long long f0, int nf, void* out, int planes,
+                       cudaStream_t stream) {
+  const long long n = (long long)nf * 1936 * 32;
+  if (n <= 0) return 0;
+  stem_im2col_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(video, in_dt, T, f0, nf,
+                                                             reinterpret_cast<__nv_bfloat16*>(out), planes);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_maxpool_stem(const void* in, void* out, int nf, int fp32, cudaStream_t stream) {
+  if (nf <= 0) return 0;
+  if (fp32) {
+    const long long n = (long long)nf * 484 * 16;
+    maxpool_stem_kernel<float4, 16, true><<<blocks_for(n, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), nf);
+  } else {
+    const long long n = (long long)nf * 484 * 8;
+    maxpool_stem_kernel<uint4, 8, false><<<blocks_for(n, 256), 256, 0, stream>>>(
+        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), nf);
+  }
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)n * Ho * Wo * 9 * (C / 8);
+  if (total <= 0) return 0;
+  im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in),
+                                                               reinterpret_cast<uint4*>(out), n, H, W, C / 8);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int fp32, cudaStream_t stream) {
+  const long long total = (long long)n * C;
+  if (total <= 0) return 0;
+  avgpool_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(in, out, fp32 ? DT_F32 : DT_BF16, n, H, W, C);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace avh

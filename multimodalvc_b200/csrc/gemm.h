@@ -1,0 +1,73 @@
+// Internal C++ interface of the tcgen05 GEMM ("shifted-row multi-tap GEMM") used by every dense
+// contraction on the AV-HuBERT path: Linear layers, the grouped positional conv, 3x3/1x1 convs of the
+// lip ResNet (implicit GEMM over a zero-padded NHWC layout) and the bf16x3 split-precision fp32 mode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace avh {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_PRELU = 2 };
+enum { MAP_IDENTITY = 0, MAP_2LEVEL = 1 };
+
+// out = rowmask( act2( act1( acc * col_scale + col_bias ) + R ) ), written as bf16 or fp32.
+struct Epilogue {
+  void* C = nullptr;
+  long long ldc = 0;
+  int c_fp32 = 0;
+  const float* col_scale = nullptr;
+  const float* col_bias = nullptr;
+  int act = ACT_NONE;
+  const float* slope1 = nullptr;        // PReLU slopes (per column) for act
+  const void* R = nullptr;              // residual, same row mapping as C
+  long long ldr = 0;
+  int r_fp32 = 0;
+  const float* slope2 = nullptr;        // PReLU applied after the residual add
+  const unsigned char* row_zero = nullptr;  // [out rows] 1 -> row forced to 0 (key-padding mask)
+  // tile row r -> output row.  MAP_2LEVEL: n=r/S2, rem=r%S2, h=rem/S1, w=rem%S1,
+  // valid = h<H && w<W, out_row = n*O2 + h*O1 + w + O0.
+  int map_mode = MAP_IDENTITY;
+  int S1 = 1, S2 = 1, H = 1, W = 1;
+  long long O0 = 0, O1 = 0, O2 = 0;
+  int invalid_zero = 0;                 // invalid rows: 1 -> store zeros, 0 -> skip
+};
+
+// One K-block (64 bf16 along K) of the contraction: A box at (col, m0 + row_off), B box at (col, n0 + row_off).
+struct KStep {
+  int a_col, a_row_off, b_col, b_row_off;
+};
+
+struct GemmProblem {
+  const void* A = nullptr;  // bf16 [a_rows, a_cols], row stride lda (elements, multiple of 8)
+  long long a_rows = 0;
+  int a_cols = 0;
+  long long lda = 0;
+  const void* B = nullptr;  // bf16 [b_rows, b_cols], row stride ldb
+  long long b_rows = 0;
+  int b_cols = 0;
+  long long ldb = 0;
+  long long M = 0;          // tile-row space size
+  int N = 0;                // output columns (multiple of 32)
+  int num_kb = 0;           // number of K blocks
+  const KStep* ktable = nullptr;  // device pointer, num_kb entries; null -> a_col=b_col=kb*64, offsets 0
+  int a_col_per_nblk = 0;   // grouped conv: A column offset added per N tile
+  const int* a_col_nblk = nullptr;  // device table [num N tiles] of A column offsets (overrides a_col_per_nblk)
+  int block_n = 128;        // 64 / 128 / 256
+  Epilogue ep;
+};
+
+struct GemmPlan {
+  CUtensorMap tma_a, tma_b;
+  GemmProblem prob;
+  int grid = 0;
+  size_t smem = 0;
+};
+
+constexpr int GEMM_MAX_KSTEPS = 768;
+
+int gemm_plan(const GemmProblem& prob, GemmPlan* plan);       // builds tensor maps; 0 on success
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);  // enqueue; 0 on success
+int gemm_pick_block_n(long long M, int N);                    // tile heuristic
+
+}  // namespace avh

@@ -1,0 +1,65 @@
+// Internal launchers for the non-GEMM kernels of the AV-HuBERT hot path (all enqueue on `stream`,
+// return 0 on success / 1 with avh::set_last_error on failure).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace avh {
+
+enum { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+
+// Self-attention core on the fused QKV projection [B*T, 3*D] -> context [B*T, D]; bf16 or fp32 I/O.
+int launch_attention(const void* qkv, const unsigned char* kpm, void* out, int B, int T, int D, int H, int fp32,
+                     cudaStream_t stream);
+
+// LayerNorm over the last dim C of [rows, C] (row stride ld_in); optional fp32 and low-precision outputs
+// (both dense [rows, C]); rows flagged in row_zero (may be null) are written as zeros.
+int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* gamma, const float* beta, float eps,
+                     float* out_f32, void* out_lp, int lp_dt, const unsigned char* row_zero, long long rows, int C,
+                     cudaStream_t stream);
+
+// generic strided [B, C, T] (any float dtype) -> row-major [B*T, ldo] (fp32/fp16/bf16): the
+// x.transpose(1,2) in SubModel.forward (avhubert/hubert.py:327)
+int launch_bct_to_rows(const void* in, int in_dt, long long sb, long long sc, long long st, int B, int C, int T,
+                       void* out, int out_dt, long long ldo, cudaStream_t stream);
+
+// flat element-wise dtype conversion
+int launch_convert(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t stream);
+
+// fp32 [rows, cols] (row stride ld) -> bf16 [rows', planes*cols]: plane 0 = round-to-nearest bf16 ("hi"),
+// plane 1 = bf16 of the residual ("mid").  Optional time padding: out row = (r / T) * Tpad + r % T (T = 0:
+// identity) — the zero-gapped token layout the positional convolution reads.
+int launch_split_rows(const float* in, long long ld, void* out, int planes, long long rows, int cols, int T,
+                      int Tpad, cudaStream_t stream);
+
+// ---- lip frontend helpers (avhubert/resnet.py) ----------------------------------------------------
+// explicit im2col of the 5x7x7/stride(1,2,2)/pad(2,3,3) stem for frames [f0, f0+nf) of the flattened
+// (b,t) axis: out bf16 [nf*44*44, planes*256], K index = dt*49 + kh*7 + kw, columns 245..255 zero;
+// planes = 2 adds the bf16 residual plane (fp32-faithful mode).
+int launch_stem_im2col(const void* video, int in_dt, int T, long long f0, int nf, void* out, int planes,
+                       cudaStream_t stream);
+// MaxPool (1,3,3)/(1,2,2)/(0,1,1): dense NHWC [nf,44,44,64] -> zero-padded layout [nf,23,23,64] (bf16 or fp32)
+int launch_maxpool_stem(const void* in, void* out, int nf, int fp32, cudaStream_t stream);
+// im2col for 3x3 stride-2 pad-1 convs reading the zero-padded bf16 layout [n,H+1,W+1,C] -> dense
+// [n*Ho*Wo, 9*C] (K index = (kh*3+kw)*C + c)
+int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream);
+// mean over the H*W valid pixels of the padded layout [n,H+1,W+1,C] -> [n, C] (bf16 or fp32 in and out)
+int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int fp32, cudaStream_t stream);
+
+// ---- audio frontend ---------------------------------------------------------------------------------
+struct FbankArgs {
+  const int16_t* wav;          // concatenated clips
+  const long long* offsets;    // [n_clips+1] sample offsets (device)
+  const int* video_len;        // [n_clips] frames to align to, or null (use own stacked length)
+  int n_clips;
+  int T;                       // output rows per clip (collated size)
+  int normalize;               // per-row LayerNorm over the 104 features
+  float* out;                  // [n_clips, T, 104]
+  unsigned char* padding_mask; // [n_clips, T] or null
+};
+int launch_fbank(const FbankArgs& a, cudaStream_t stream);
+// hubert_dataset.py:317-346 on device: mixed int16 = trunc(clip_rescale(clean + noise * scale))
+int launch_add_noise(const int16_t* clean, const long long* offsets, int n_clips, const float* noise,
+                     long long noise_len, float snr_db, int16_t* out, double* scratch, cudaStream_t stream);
+
+}  // namespace avh

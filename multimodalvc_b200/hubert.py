@@ -1,0 +1,401 @@
+"""Host-side mirror of the reference's ``AVHubertModel`` for the encoder hot path (avhubert/hubert.py:334-779).
+
+Same constructor shape (``AVHubertModel(cfg, task_cfg, dictionaries)`` / ``build_model(cfg, task)``), same
+state-dict key names (so ``load_state_dict(state["model"], strict=False)`` from a reference checkpoint works:
+src/model.py:223-224, avhubert/hubert_asr.py:303), same ``extract_finetune`` signature, tensor layouts,
+padding-mask semantics and ``[B,T,D]`` output (avhubert/hubert.py:694-745).  The torch modules below are
+*parameter containers only* — their ``forward`` is never called.  All arithmetic happens in
+``libavh_b200.so`` (hand-written sm_100a kernels) through the C ABI in ``include/avh_b200.h``; there is no
+PyTorch or CPU fallback, and calls fail loudly when the extension is missing or the tensors are not on a
+B200-class device.
+"""
+import ctypes
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.AVH_F32, torch.float16: _lib.AVH_F16, torch.bfloat16: _lib.AVH_BF16}
+
+
+@dataclass
+class AVHubertConfig:
+    """The fields of the reference ``AVHubertConfig`` (avhubert/hubert.py:64-315) that shape this path, with the
+    reference defaults.  Pretraining-only fields are accepted (kept as attributes) and ignored."""
+    label_rate: int = 25
+    encoder_layers: int = 12
+    encoder_embed_dim: int = 768
+    encoder_ffn_embed_dim: int = 3072
+    encoder_attention_heads: int = 12
+    activation_fn: str = "gelu"
+    dropout: float = 0.1
+    attention_dropout: float = 0.1
+    activation_dropout: float = 0.0
+    encoder_layerdrop: float = 0.0
+    dropout_input: float = 0.0
+    dropout_features: float = 0.0
+    final_dim: int = 0
+    untie_final_proj: bool = False
+    layer_norm_first: bool = False
+    feature_grad_mult: float = 1.0
+    conv_pos: int = 128
+    conv_pos_groups: int = 16
+    resnet_relu_type: str = "prelu"
+    resnet_weights: Optional[str] = None
+    sub_encoder_layers: int = 0
+    audio_feat_dim: int = -1
+    modality_dropout: float = 0.0
+    audio_dropout: float = 0.0
+    modality_fuse: str = "concat"
+    masking_type: str = "input"
+    # --- B200 build options (not in the reference) ---
+    compute_dtype: str = "auto"        # "auto": fp32 module -> fp32-faithful mode, half/bf16 module -> bf16 mode
+    frontend_chunk_frames: int = 0     # 0 = library default
+    capture_stages: bool = False       # keep intermediate stages readable (tests)
+
+    @staticmethod
+    def named(size, **kw):
+        """Shipped shapes: Base (avhubert/conf/pretrain/base_vox_iter5.yaml:70-97) and Large
+        (large_vox_iter5.yaml:70-101); `tiny` is a test-sized shape with the same structure."""
+        shape = dict(base=(12, 768, 3072, 12), large=(24, 1024, 4096, 16), tiny=(2, 128, 256, 2))[size]
+        cfg = AVHubertConfig(encoder_layers=shape[0], encoder_embed_dim=shape[1], encoder_ffn_embed_dim=shape[2],
+                             encoder_attention_heads=shape[3], audio_feat_dim=104, layer_norm_first=True)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        return cfg
+
+
+# ----------------------------------------------------------------------------- parameter containers
+class _BasicBlockParams(nn.Module):      # avhubert/resnet.py:35-74
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu1 = nn.PReLU(num_parameters=cout)
+        self.relu2 = nn.PReLU(num_parameters=cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:   # downsample_basic_block, resnet.py:20-24
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+
+class _TrunkParams(nn.Module):           # avhubert/resnet.py:77-129, layers [2,2,2,2]
+    def __init__(self):
+        super().__init__()
+        cin = 64
+        for i, w in enumerate([64, 128, 256, 512]):
+            stride = 1 if i == 0 else 2
+            setattr(self, f"layer{i + 1}", nn.Sequential(_BasicBlockParams(cin, w, stride), _BasicBlockParams(w, w, 1)))
+            cin = w
+        for m in self.modules():         # resnet.py:92-98
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+
+
+class _ResEncoderParams(nn.Module):      # avhubert/resnet.py:131-142
+    backend_out = 512
+
+    def __init__(self):
+        super().__init__()
+        self.frontend3D = nn.Sequential(
+            nn.Conv3d(1, 64, (5, 7, 7), (1, 2, 2), (2, 3, 3), bias=False), nn.BatchNorm3d(64), nn.PReLU(num_parameters=64),
+            nn.MaxPool3d((1, 3, 3), (1, 2, 2), (0, 1, 1)))
+        self.trunk = _TrunkParams()
+
+
+class _SubModelParams(nn.Module):        # avhubert/hubert.py:317-332 (sub_encoder_layers == 0)
+    def __init__(self, resnet, input_dim, dim):
+        super().__init__()
+        self.resnet = resnet
+        self.proj = nn.Linear(input_dim, dim)
+        self.encoder = None
+
+
+class _PosConvParams(nn.Module):         # weight_norm(Conv1d, dim=2): wav2vec2.py:822-834
+    def __init__(self, dim, k, groups):
+        super().__init__()
+        std = math.sqrt(4.0 / (k * dim))
+        v = torch.randn(dim, dim // groups, k) * std
+        self.weight_g = nn.Parameter(v.norm(dim=(0, 1), keepdim=True).clone())
+        self.weight_v = nn.Parameter(v)
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class _SelfAttnParams(nn.Module):        # fairseq/fairseq/modules/multihead_attention.py:64-77
+    def __init__(self, dim):
+        super().__init__()
+        self.k_proj = nn.Linear(dim, dim)
+        self.v_proj = nn.Linear(dim, dim)
+        self.q_proj = nn.Linear(dim, dim)
+        self.out_proj = nn.Linear(dim, dim)
+
+
+class _LayerParams(nn.Module):           # wav2vec2.py:907-958
+    def __init__(self, dim, ffn):
+        super().__init__()
+        self.self_attn = _SelfAttnParams(dim)
+        self.self_attn_layer_norm = nn.LayerNorm(dim)
+        self.fc1 = nn.Linear(dim, ffn)
+        self.fc2 = nn.Linear(ffn, dim)
+        self.final_layer_norm = nn.LayerNorm(dim)
+
+
+class _EncoderParams(nn.Module):         # wav2vec2.py:816-857
+    def __init__(self, cfg):
+        super().__init__()
+        D = cfg.encoder_embed_dim
+        self.embedding_dim = D
+        self.layer_norm_first = cfg.layer_norm_first
+        self.pos_conv = nn.Sequential(_PosConvParams(D, cfg.conv_pos, cfg.conv_pos_groups))
+        self.layers = nn.ModuleList([_LayerParams(D, cfg.encoder_ffn_embed_dim) for _ in range(cfg.encoder_layers)])
+        self.layer_norm = nn.LayerNorm(D)
+        for m in self.modules():         # init_bert_params
+            if isinstance(m, nn.Linear):
+                m.weight.data.normal_(0.0, 0.02)
+                m.bias.data.zero_()
+
+
+class AVHubertModel(nn.Module):
+    """Drop-in for the reference ``AVHubertModel`` on the ``extract_finetune`` path."""
+
+    def __init__(self, cfg: AVHubertConfig, task_cfg=None, dictionaries=(None,), **kwargs):
+        super().__init__()
+        if cfg.activation_fn != "gelu":
+            raise NotImplementedError("only activation_fn='gelu' (every shipped AV-HuBERT config) is implemented")
+        if cfg.sub_encoder_layers != 0:
+            raise NotImplementedError("sub_encoder_layers > 0 is not used by any shipped config")
+        if cfg.resnet_relu_type != "prelu":
+            raise NotImplementedError("only resnet_relu_type='prelu' is implemented")
+        if cfg.modality_fuse not in ("concat", "add"):
+            raise ValueError(f"unknown modality_fuse {cfg.modality_fuse}")
+        if cfg.audio_feat_dim <= 0:
+            raise ValueError("audio_feat_dim must be set (104 for 4x26 stacked log-fbank)")
+        self.cfg = cfg
+        D = cfg.encoder_embed_dim
+        self.encoder_embed_dim = D
+        self.modality_fuse = cfg.modality_fuse
+        self.embed = 2 * D if cfg.modality_fuse == "concat" else D
+        self.feature_extractor_audio = _SubModelParams(None, cfg.audio_feat_dim, D)
+        self.feature_extractor_video = _SubModelParams(_ResEncoderParams(), _ResEncoderParams.backend_out, D)
+        self.post_extract_proj = nn.Linear(self.embed, D) if self.embed != D else None
+        self.mask_emb = nn.Parameter(
+            torch.FloatTensor(cfg.audio_feat_dim if cfg.masking_type == "input" else D).uniform_())
+        self.encoder = _EncoderParams(cfg)
+        self.layer_norm = nn.LayerNorm(self.embed)
+        final_dim = cfg.final_dim if cfg.final_dim > 0 else D
+        self.final_proj = nn.Linear(D, final_dim)      # pretraining head; dropped by remove_pretraining_modules
+        self._handle = None
+        self._handle_key = None
+        self._dirty = True
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
+
+    # ------------------------------------------------------------------ reference API surface
+    @classmethod
+    def build_model(cls, cfg: AVHubertConfig, task=None):
+        """avhubert/hubert.py:434-440"""
+        return cls(cfg, getattr(task, "cfg", None), getattr(task, "dictionaries", (None,)))
+
+    def upgrade_state_dict_named(self, state_dict, name):
+        return state_dict
+
+    def remove_pretraining_modules(self):
+        """avhubert/hubert.py:757-759"""
+        self.target_glu = None
+        self.final_proj = None
+
+    @staticmethod
+    def forward_padding_mask(features_len: int, padding_mask: torch.Tensor) -> torch.Tensor:
+        """avhubert/hubert.py:564-574 (identity when the mask already has one entry per frame)."""
+        extra = padding_mask.size(1) % features_len
+        if extra > 0:
+            padding_mask = padding_mask[:, :-extra]
+        padding_mask = padding_mask.view(padding_mask.size(0), features_len, -1)
+        return padding_mask.all(-1)
+
+    # ------------------------------------------------------------------ weights -> device library
+    def _mark_dirty(self):
+        self._dirty = True
+
+    def _apply(self, fn, *args, **kwargs):       # .cuda() / .half() / .to(): packed copies become stale
+        out = super()._apply(fn, *args, **kwargs)
+        self._dirty = True
+        return out
+
+    def refresh_weights(self):
+        """Call after modifying parameters in place (optimizer step, manual edits)."""
+        self._dirty = True
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            _lib.load().avh_destroy(self._handle)
+            self._handle = None
+            self._handle_key = None
+
+    def __del__(self):
+        try:
+            self._destroy_handle()
+        except Exception:
+            pass
+
+    def _compute_mode(self, dtype):
+        cd = self.cfg.compute_dtype
+        if cd == "auto":
+            return _lib.AVH_COMPUTE_FP32 if dtype == torch.float32 else _lib.AVH_COMPUTE_BF16
+        if cd in ("bf16", "bfloat16"):
+            return _lib.AVH_COMPUTE_BF16
+        if cd in ("fp32", "float32"):
+            return _lib.AVH_COMPUTE_FP32
+        raise ValueError(f"compute_dtype must be auto|bf16|fp32, got {cd}")
+
+    def _ensure_handle(self):
+        p = self.encoder.layer_norm.weight
+        if p.device.type != "cuda":
+            raise RuntimeError("multimodalvc_b200.AVHubertModel computes on a B200 only: move the module to a CUDA "
+                               "device (there is no CPU path)")
+        key = (p.device.index if p.device.index is not None else torch.cuda.current_device(),
+               self._compute_mode(p.dtype))
+        if self._handle is not None and key == self._handle_key and not self._dirty:
+            return self._handle
+        lib = _lib.load()
+        if self._handle is None or key != self._handle_key:
+            self._destroy_handle()
+            c = self.cfg
+            cc = _lib.AvhConfig(
+                encoder_layers=c.encoder_layers, encoder_embed_dim=c.encoder_embed_dim,
+                encoder_ffn_embed_dim=c.encoder_ffn_embed_dim, encoder_attention_heads=c.encoder_attention_heads,
+                audio_feat_dim=c.audio_feat_dim,
+                modality_fuse=_lib.AVH_FUSE_CONCAT if c.modality_fuse == "concat" else _lib.AVH_FUSE_ADD,
+                layer_norm_first=int(bool(c.layer_norm_first)), conv_pos=c.conv_pos, conv_pos_groups=c.conv_pos_groups,
+                compute_mode=key[1], frontend_chunk_frames=int(c.frontend_chunk_frames),
+                capture_stages=int(bool(c.capture_stages)))
+            hp = ctypes.c_void_p()
+            _lib.check(lib.avh_create(ctypes.byref(cc), key[0], ctypes.byref(hp)))
+            self._handle, self._handle_key = hp, key
+        with torch.no_grad():
+            for name, t in self.state_dict().items():
+                if name == "mask_emb" or name.startswith("final_proj.") or name.endswith("num_batches_tracked"):
+                    continue
+                if not t.is_floating_point():
+                    continue
+                t = t.detach().contiguous()
+                if t.dtype not in _DTYPES:
+                    t = t.float()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(lib.avh_load_tensor(self._handle, name.encode(), ctypes.c_void_p(t.data_ptr()),
+                                               _DTYPES[t.dtype], shape, t.dim()))
+            torch.cuda.synchronize(p.device)
+        _lib.check(lib.avh_finalize_weights(self._handle))
+        self._dirty = False
+        return self._handle
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
+        """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
+        padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask)."""
+        if mask:
+            raise NotImplementedError("apply_input_mask (mask=True) is off in every shipped fine-tune/inference "
+                                      "config and is not implemented on the device path")
+        if self.training:
+            raise RuntimeError("training-mode forward (batch-statistics BatchNorm, dropout, LayerDrop) is not "
+                               "implemented; call .eval() — the encoder is frozen on every inference path")
+        src_audio, src_video = source["audio"], source["video"]
+        if src_audio is None and src_video is None:
+            raise ValueError("both modalities are None")
+        handle = self._ensure_handle()
+        dev = self.encoder.layer_norm.weight.device
+        ref = src_video if src_video is not None else src_audio
+        if ref.device != dev:
+            raise RuntimeError(f"inputs are on {ref.device} but the module is on {dev}")
+        B = ref.size(0)
+        if src_video is not None:
+            if src_video.dim() != 5 or src_video.size(1) != 1 or tuple(src_video.shape[3:]) != (88, 88):
+                raise ValueError(f"video must be [B,1,T,88,88], got {tuple(src_video.shape)}")
+            T = src_video.size(2)
+            src_video = src_video.contiguous()
+            if src_video.dtype not in _DTYPES:
+                src_video = src_video.float()
+        if src_audio is not None:
+            if src_audio.dim() != 3 or src_audio.size(1) != self.cfg.audio_feat_dim:
+                raise ValueError(f"audio must be [B,{self.cfg.audio_feat_dim},T], got {tuple(src_audio.shape)}")
+            if src_video is not None and (src_audio.size(2) != T or src_audio.size(0) != B):
+                raise ValueError("audio and video disagree on batch/time")
+            T = src_audio.size(2)
+            if src_audio.dtype not in _DTYPES:
+                src_audio = src_audio.float()
+        pm_u8 = None
+        if padding_mask is not None:
+            if padding_mask.size(1) != T:
+                padding_mask = self.forward_padding_mask(T, padding_mask)
+            pm_u8 = padding_mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
+        out_dtype = self.encoder.layer_norm.weight.dtype
+        if out_dtype not in _DTYPES:
+            out_dtype = torch.float32
+        out = torch.empty(B, T, self.encoder_embed_dim, device=dev, dtype=out_dtype)
+        strides = None
+        if src_audio is not None:
+            strides = (ctypes.c_int64 * 3)(*src_audio.stride())
+        ol = 0 if output_layer is None else int(output_layer)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_forward(
+                handle,
+                ctypes.c_void_p(src_video.data_ptr()) if src_video is not None else None,
+                _DTYPES[src_video.dtype] if src_video is not None else 0,
+                ctypes.c_void_p(src_audio.data_ptr()) if src_audio is not None else None,
+                _DTYPES[src_audio.dtype] if src_audio is not None else 0,
+                strides,
+                ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None,
+                B, T, ol, ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
+        return out, padding_mask
+
+    def extract_finetune_host(self, video, audio, padding_mask=None, output_layer=None, out=None):
+        """End-to-end call with HOST tensors (pinned recommended): H2D copies, forward and the D2H read of the
+        features all happen inside ``avh_forward_host``.  video [B,1,T,88,88] / audio [B,F,T] contiguous CPU
+        tensors (either may be None); returns a CPU tensor [B,T,D]."""
+        handle = self._ensure_handle()
+        dev = self.encoder.layer_norm.weight.device
+        ref = video if video is not None else audio
+        B = ref.size(0)
+        T = video.size(2) if video is not None else audio.size(2)
+        out_dtype = self.encoder.layer_norm.weight.dtype
+        if out is None:
+            out = torch.empty(B, T, self.encoder_embed_dim, dtype=out_dtype).pin_memory()
+        pm = None
+        if padding_mask is not None:
+            pm = padding_mask.contiguous().view(torch.uint8)
+        for t in (video, audio):
+            if t is not None and (t.device.type != "cpu" or not t.is_contiguous()):
+                raise ValueError("extract_finetune_host takes contiguous CPU tensors")
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_forward_host(
+                handle,
+                ctypes.c_void_p(video.data_ptr()) if video is not None else None,
+                _DTYPES[video.dtype] if video is not None else 0,
+                ctypes.c_void_p(audio.data_ptr()) if audio is not None else None,
+                _DTYPES[audio.dtype] if audio is not None else 0,
+                ctypes.c_void_p(pm.data_ptr()) if pm is not None else None,
+                B, T, 0 if output_layer is None else int(output_layer),
+                ctypes.c_void_p(out.data_ptr()), _DTYPES[out.dtype], ctypes.c_void_p(stream)))
+        return out
+
+    def read_stage(self, name, numel):
+        """Intermediate tensor of the last forward (needs cfg.capture_stages=True): 'resnet', 'fused_ln', 'enc_in'."""
+        dev = self.encoder.layer_norm.weight.device
+        dst = torch.empty(numel, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_read_stage(self._handle, name.encode(), ctypes.c_void_p(dst.data_ptr()),
+                                                  numel, ctypes.c_void_p(stream)))
+        return dst
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("the pretraining forward (masked prediction, avhubert/hubert.py:591-674) is out "
+                                  "of scope; use extract_finetune")

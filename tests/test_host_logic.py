@@ -1,0 +1,101 @@
+"""Host-side logic that needs no GPU: frame arithmetic, sharding, and the N>1 partition under gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from multimodalvc_b200 import audio, sharding
+from oracle import fbank_oracle as fo
+
+
+@pytest.mark.parametrize("n", [1, 399, 400, 401, 559, 560, 561, 32000, 96000, 384000, 12345])
+def test_num_frames_matches_oracle(n):
+    assert audio.num_frames(n) == fo.num_frames(n)
+    assert audio.stacked_len(n) == len(fo.stacker(__import__("numpy").zeros((fo.num_frames(n), 26)), 4))
+
+
+def test_contiguous_shard_partitions_exactly():
+    for n in (0, 1, 7, 16, 64):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                seen += list(sharding.contiguous_shard(n, r, world))
+            assert seen == list(range(n))
+            sizes = [len(sharding.contiguous_shard(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_shards_cover_and_balance():
+    g = torch.Generator().manual_seed(7)
+    lengths = torch.randint(25, 601, (64,), generator=g).tolist()          # BASELINE config 3
+    for world in (2, 4, 8):
+        shards = sharding.balanced_shards(lengths, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(64))
+        loads = [sum(sharding.clip_cost(lengths[i]) for i in s) for s in shards]
+        assert max(loads) / (sum(loads) / world) < 1.10
+        for s in shards:
+            assert [lengths[i] for i in s] == sorted((lengths[i] for i in s), reverse=True)
+
+
+def test_length_buckets_bound_padding():
+    g = torch.Generator().manual_seed(7)
+    lengths = torch.randint(25, 601, (64,), generator=g).tolist()
+    buckets = sharding.length_buckets(range(64), lengths, max_pad_frac=0.15)
+    assert sorted(i for b in buckets for i in b) == list(range(64))
+    for b in buckets:
+        tmax = max(lengths[i] for i in b)
+        assert 1 - sum(lengths[i] for i in b) / (tmax * len(b)) <= 0.15 + 1e-9
+
+
+def test_clip_cost_matches_baseline_numbers():
+    # one 6 s Large clip = 95 495 731 200 MAC
+    assert sharding.clip_cost(150) == pytest.approx(95_495_731_200, rel=1e-9)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, lengths, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.balanced_shards(lengths, world)[rank]
+    # every rank "processes" its clips: here, a per-clip checksum; no data-path collective is needed.
+    part = torch.zeros(len(lengths), dtype=torch.int64)
+    for i in mine:
+        part[i] = lengths[i] * 31 + 7
+    # bench.py-style bookkeeping: units processed and max-over-ranks time
+    units = torch.tensor([len(mine)], dtype=torch.int64)
+    dist.all_reduce(units)
+    dist.all_reduce(part)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((units.item(), part.tolist(), t.item()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_run_under_gloo():
+    lengths = [150, 30, 600, 75, 320, 25, 410, 90]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lengths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    units, part, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert units == len(lengths)
+    assert part == [n * 31 + 7 for n in lengths]          # every clip processed exactly once
+    assert tmax == 2.0
