@@ -1,0 +1,165 @@
+"""End-to-end parity of AVHubertModel.extract_finetune on a B200 against (a) the golden outputs of the REAL
+reference (tests/golden/enc_*.npz) and (b) the fp32 CPU oracle on the same seeded inputs.
+
+Gates: fp32 mode <= 2e-3 relative (max|y - y_ref| / max|y_ref|), bf16 mode cosine >= 0.999,
+padding masks bit-exact.  Dense mode: padded positions are compared too."""
+import pytest
+import torch
+
+from multimodalvc_b200 import HubertEncoderWrapper
+
+from helpers import cosine, load_encoder_case, make_device_model, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-3
+BF16_COS = 0.999
+TINY = ["tiny_av_ragged", "tiny_video_only", "tiny_audio_only", "tiny_layer1", "tiny_postln", "tiny_add"]
+
+
+def run_case(name, dtype, **cfg_kw):
+    c = load_encoder_case(name)
+    m = make_device_model(c["oracle"], c["over"], c["size"], dtype, **cfg_kw)
+    src, pm = to_dev(c["src"], c["pm"], dtype=dtype)
+    y, pm_out = m.extract_finetune(src, pm, output_layer=c["output_layer"])
+    torch.cuda.synchronize()
+    assert y.dtype == dtype and y.shape == c["y_ref"].shape
+    assert torch.isfinite(y).all()
+    if pm is not None:
+        assert torch.equal(pm_out.cpu(), torch.from_numpy(c["pm_ref"]))
+    return y.float().cpu(), c, m
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_fp32_mode_matches_reference_golden_tiny(name):
+    y, c, _ = run_case(name, torch.float32)
+    assert rel_err(y, c["y_ref"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_bf16_mode_matches_reference_golden_tiny(name):
+    y, c, _ = run_case(name, torch.bfloat16)
+    assert cosine(y, c["y_ref"]) > BF16_COS
+
+
+def test_fp16_module_like_reference_eval():
+    # src/eval.py:155-156,200: model.half(), video cast to fp16
+    y, c, _ = run_case("tiny_av_ragged", torch.float16)
+    assert cosine(y, c["y_ref"]) > BF16_COS
+
+
+def test_base_config1_fp32_and_bf16():
+    # BASELINE config 1: Base, B=1, T=50
+    y, c, _ = run_case("base_b1_t50", torch.float32)
+    assert rel_err(y, c["y_ref"]) < FP32_TOL
+    y, c, _ = run_case("base_b1_t50", torch.bfloat16)
+    assert cosine(y, c["y_ref"]) > BF16_COS
+
+
+def test_large_ragged_fp32_and_bf16():
+    y, c, _ = run_case("large_b2_t40", torch.float32)
+    assert rel_err(y, c["y_ref"]) < FP32_TOL
+    y, c, _ = run_case("large_b2_t40", torch.bfloat16)
+    assert cosine(y, c["y_ref"]) > BF16_COS
+
+
+def test_stage_level_parity_fp32():
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32, capture_stages=True)
+    src, pm = to_dev(c["src"], c["pm"])
+    m.extract_finetune(src, pm)
+    with torch.no_grad():
+        stages, _ = c["oracle"].stage_outputs(c["src"], c["pm"])
+    B, T = c["pm"].shape
+    res = m.read_stage("resnet", B * T * 512).view(B, T, 512).cpu()
+    assert rel_err(res, stages["resnet"].transpose(1, 2)) < 1e-3
+    fl = m.read_stage("fused_ln", B * T * 256).view(B, T, 256).cpu()
+    assert rel_err(fl, stages["fused_ln"]) < 1e-3
+    ei = m.read_stage("enc_in", B * T * 128).view(B, T, 128).cpu()
+    ref = stages["enc_in"].masked_fill(c["pm"].unsqueeze(-1), 0.0)       # device copy is taken after pad zeroing
+    assert rel_err(ei, ref) < 1e-3
+
+
+def test_frontend_chunking_is_invisible():
+    c = load_encoder_case("tiny_av_ragged")
+    src, pm = to_dev(c["src"], c["pm"])
+    ys = []
+    for chunk in (0, 7, 60):
+        m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32, frontend_chunk_frames=chunk)
+        ys.append(m.extract_finetune(src, pm)[0].cpu())
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
+
+
+def test_inputs_are_not_modified_and_views_are_accepted():
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32)
+    src, pm = to_dev(c["src"], c["pm"])
+    assert not src["audio"].is_contiguous()          # collater hands a transposed view
+    keep = {k: v.clone() for k, v in src.items()}
+    pm_keep = pm.clone()
+    y1, _ = m.extract_finetune(src, pm)
+    y2, _ = m.extract_finetune({"audio": src["audio"].contiguous(), "video": src["video"]}, pm)
+    assert torch.equal(src["audio"], keep["audio"]) and torch.equal(src["video"], keep["video"])
+    assert torch.equal(pm, pm_keep)
+    assert torch.equal(y1, y2)
+
+
+def test_wrapper_output_dict_and_layout():
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32)
+    src, pm = to_dev(c["src"], c["pm"])
+    out = HubertEncoderWrapper(m)(source=src, padding_mask=pm)
+    assert out["encoder_out"].shape == (c["y_ref"].shape[1], c["y_ref"].shape[0], c["y_ref"].shape[2])
+    assert rel_err(out["encoder_out"].transpose(0, 1).cpu(), c["y_ref"]) < FP32_TOL
+    assert out["encoder_padding_mask"] is out["padding_mask"]
+
+
+def test_host_buffer_entry_point_matches_device_call():
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32)
+    src, pm = to_dev(c["src"], c["pm"])
+    y_dev, _ = m.extract_finetune(src, pm)
+    y_host = m.extract_finetune_host(c["src"]["video"].contiguous().pin_memory(),
+                                     c["src"]["audio"].contiguous().pin_memory(), c["pm"])
+    assert torch.equal(y_dev.cpu(), y_host)
+
+
+def test_reload_after_weight_change_and_dtype_change():
+    c = load_encoder_case("tiny_video_only")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32)
+    src, pm = to_dev(c["src"], c["pm"])
+    y0, _ = m.extract_finetune(src, pm)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["encoder.layer_norm.bias"] += 1.0
+    m.load_state_dict(sd)
+    y1, _ = m.extract_finetune(src, pm)
+    assert (y1 - y0 - 1.0).abs().max().item() < 1e-5
+    m = m.bfloat16()
+    y2, _ = m.extract_finetune({"audio": None, "video": src["video"].bfloat16()}, pm)
+    assert y2.dtype == torch.bfloat16 and cosine(y2.float().cpu(), y1.cpu()) > BF16_COS
+
+
+def test_large_b16_t150_properties():
+    """BASELINE config 2 at full size: too slow for the CPU oracle in a test, so size-independent properties:
+    (1) batch independence — clip i alone equals clip i inside the batch; (2) zero padding invisibility for
+    valid frames; (3) determinism."""
+    from oracle import avhubert_oracle as ao
+    oracle = ao.build_oracle("large", seed=1234)
+    m = make_device_model(oracle, {}, "large", torch.bfloat16)
+    src, _ = ao.synthetic_inputs(16, 150, seed=21)
+    src, _ = to_dev(src, None, dtype=torch.bfloat16)
+    y, _ = m.extract_finetune(src, None)
+    y_again, _ = m.extract_finetune(src, None)
+    assert torch.equal(y, y_again)
+    one = {"audio": src["audio"][3:4], "video": src["video"][3:4]}
+    y1, _ = m.extract_finetune(one, None)
+    assert cosine(y1.float().cpu(), y[3:4].float().cpu()) > 0.9999
+    # pad clip 3 to T=180 with zeros + mask: valid frames unchanged
+    v = torch.zeros(1, 1, 180, 88, 88, device="cuda", dtype=torch.bfloat16)
+    v[:, :, :150] = one["video"]
+    a = torch.zeros(1, 104, 180, device="cuda", dtype=torch.bfloat16)
+    a[:, :, :150] = one["audio"]
+    pm = torch.zeros(1, 180, dtype=torch.bool, device="cuda")
+    pm[:, 150:] = True
+    yp, _ = m.extract_finetune({"audio": a, "video": v}, pm)
+    assert cosine(yp[:, :150].float().cpu(), y1.float().cpu()) > 0.9995

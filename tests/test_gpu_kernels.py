@@ -1,0 +1,146 @@
+"""Kernel-level parity on a B200, through the C ABI: the tcgen05 GEMM (all tile widths, ragged M/K, fused
+epilogues) and the audio kernels against the float64 oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from multimodalvc_b200 import _lib, audio
+from oracle import fbank_oracle as fo
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gemm(A, B, bias=None, gelu=False, R=None, c_fp32=True, block_n=0):
+    M, K = A.shape
+    N = B.shape[0]
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if c_fp32 else torch.bfloat16)
+    vp = ctypes.c_void_p
+    _lib.check(_lib.load().avh_gemm_bf16(
+        vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()) if bias is not None else None, int(gelu),
+        vp(R.data_ptr()) if R is not None else None, int(R is not None and R.dtype == torch.float32),
+        vp(C.data_ptr()), int(c_fp32), block_n, vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return C
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 64, 64, 64), (128, 128, 64, 128), (128, 256, 64, 256),          # single tile, single K block
+    (256, 128, 512, 128), (300, 192, 320, 64), (1000, 384, 1024, 128),     # ragged M, several K blocks
+    (2400, 1024, 1024, 0), (2400, 3072, 1024, 0), (2400, 4096, 1024, 256), (2400, 1024, 4096, 128),   # c2 shapes
+    (77, 64, 104, 64), (20000, 64, 256, 64),                                # K tail (OOB zero fill), many tiles
+])
+def test_gemm_matches_fp32_reference(M, N, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    C = gemm(A, B, block_n=bn)
+    ref = A.float() @ B.float().t()
+    assert torch.isfinite(C).all()
+    tol = 1e-4 * (K ** 0.5) * 0.05 * 4 + 1e-5          # fp32 accumulation error only
+    assert (C - ref).abs().max().item() < max(tol, 2e-3 * ref.abs().max().item() * 1e-2 + tol)
+
+
+def test_gemm_fused_epilogue_bias_gelu_residual_bf16_out():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 515, 256, 384
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g)
+    ref = torch.nn.functional.gelu(A.float() @ B.float().t() + bias) + R
+    C = gemm(A, B, bias=bias, gelu=True, R=R, c_fp32=True)
+    assert (C - ref).abs().max().item() < 2e-4
+    Rb = R.bfloat16()
+    Cb = gemm(A, B, bias=bias, gelu=True, R=Rb, c_fp32=False)
+    refb = (torch.nn.functional.gelu(A.float() @ B.float().t() + bias) + Rb.float())
+    assert (Cb.float() - refb).abs().max().item() < 3e-2      # bf16 output rounding
+
+
+def test_gemm_many_tiles_per_cta_exercises_both_accumulator_stages():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, N, K = 148 * 128 * 3 + 50, 128, 128            # > 3 tiles per CTA: TMEM double buffering + phase flips
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
+    C = gemm(A, B, block_n=128)
+    ref = A.float() @ B.float().t()
+    assert (C - ref).abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------- audio
+def _fbank_dev(wavs, video_lens=None, normalize=True, max_sample_size=None):
+    a, pm = audio.logfbank_stack_collate([torch.from_numpy(w) for w in wavs], video_lens=video_lens,
+                                         normalize=normalize, max_sample_size=max_sample_size)
+    torch.cuda.synchronize()
+    return a.transpose(1, 2).cpu().numpy(), pm.cpu().numpy()      # [B,T,104]
+
+
+def test_logfbank_within_1e4_of_oracle_and_stacking_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "audio_fbank.npz"))
+    names = [k[4:] for k in z.files if k.startswith("wav_")]
+    wavs = [z["wav_" + n] for n in names]
+    feats, pm = _fbank_dev(wavs, normalize=False)
+    T = feats.shape[1]
+    for i, n in enumerate(names):
+        ref = fo.stacker(z["fbank_" + n].astype(np.float32), 4)          # [T_i, 104]
+        Ti = ref.shape[0]
+        assert np.abs(feats[i, :Ti] - ref).max() < 1e-4, n              # gate: 1e-4 abs vs the restatement
+        # stacking / zero rows / collation padding are copies: exact zeros where the oracle has zeros
+        assert np.array_equal(feats[i, :Ti] == 0, ref == 0), n
+        assert not feats[i, Ti:].any()
+        assert np.array_equal(pm[i], np.arange(T) >= Ti)               # padding mask bit-exact
+
+
+def test_logfbank_layernorm_alignment_and_crop():
+    z = np.load(os.path.join(GOLDEN, "audio_fbank.npz"))
+    wavs = [z["wav_noise_6s"], z["wav_noise_ragged"], z["wav_tone_1k"]]
+    vlen = [148, 25, 30]                 # trim by 2, pad by several, pad by 5
+    feats, pm = _fbank_dev(wavs, video_lens=vlen, normalize=True, max_sample_size=100)
+    assert feats.shape == (3, 100, 104)
+    for i, w in enumerate(wavs):
+        ref = fo.featurize_clip(w, n_video=vlen[i], normalize=True)
+        out, mask = fo.collater_audio([ref], 100)
+        assert np.abs(feats[i] - out[0]).max() < 1e-4
+        assert np.array_equal(pm[i], mask[0])
+
+
+def test_logfbank_empty_and_single_frame_inputs():
+    feats, pm = _fbank_dev([np.zeros(1, dtype=np.int16), fo.synthetic_wave(400, 1), fo.synthetic_wave(401, 2)],
+                           normalize=False)
+    assert feats.shape == (3, 1, 104)
+    assert np.allclose(feats[0, 0, :26], np.log(np.finfo(float).eps), atol=1e-4)      # all-zero frame -> log(eps)
+    assert not feats[0, 0, 26:].any() and not pm.any()
+    for i, w in [(1, fo.synthetic_wave(400, 1)), (2, fo.synthetic_wave(401, 2))]:
+        ref = fo.stacker(fo.logfbank(w).astype(np.float32), 4)
+        assert np.abs(feats[i, :1] - ref).max() < 1e-4
+
+
+def test_logfbank_full_size_batch_properties():
+    # BASELINE config sizes: 32 x 24 s clips; checked through size-independent properties
+    wavs = [fo.synthetic_wave(384000, 100 + i) for i in range(4)] * 8
+    feats, pm = _fbank_dev(wavs, video_lens=[600] * 32, normalize=True)
+    assert feats.shape == (32, 600, 104) and not pm.any()
+    assert np.abs(feats.mean(-1)).max() < 1e-4 and np.abs(feats.var(-1) - 1).max() < 1e-3     # per-row LN
+    assert np.array_equal(feats[:4], feats[4:8])                                              # deterministic
+    ref = fo.featurize_clip(wavs[0], n_video=600)
+    assert np.abs(feats[0] - ref).max() < 1e-4
+
+
+def test_add_noise_matches_reference_within_one_lsb():
+    z = np.load(os.path.join(GOLDEN, "audio_reference.npz"))
+    clean, noise = torch.from_numpy(z["clean"]), torch.from_numpy(z["noise"])
+    for snr, key in [(-5, "mix_snr_m5"), (0, "mix_snr_0"), (5, "mix_snr_5"), (40, "mix_snr_40")]:
+        out = audio.add_noise([clean, clean[:20000]], noise, snr)
+        torch.cuda.synchronize()
+        d = np.abs(out[0].cpu().numpy().astype(np.int32) - z[key].astype(np.int32))
+        assert d.max() <= 1, (snr, d.max())                 # stated tolerance: +-1 LSB (fp32 RMS summation order)
+        assert (d != 0).mean() < 0.02
+        ref2 = fo.add_noise(z["clean"][:20000], z["noise"], snr)
+        d2 = np.abs(out[1].cpu().numpy().astype(np.int32) - ref2.astype(np.int32))
+        assert d2.max() <= 1
+    loud = torch.from_numpy(z["loud"])
+    out = audio.add_noise([loud], noise, -5)[0].cpu().numpy().astype(np.int32)
+    assert np.abs(out - z["mix_loud"].astype(np.int32)).max() <= 1
