@@ -127,6 +127,12 @@ AVH_API int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clip
 AVH_API int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu,
                   const void* R, int r_fp32, void* C, int c_fp32, int block_n, void* stream);
 
+/* Per-kernel-class timing of one forward for bench.py / profiles: with profiling on, avh_forward brackets
+ * every launch with CUDA events on the launching stream; avh_profile_json waits for them and writes
+ * {"class": {"launches": n, "ms": t, "tc_flops": executed tensor-core FLOPs}, ...} for the last forward. */
+AVH_API int avh_set_profiling(avh_handle* h, int on);
+AVH_API int avh_profile_json(avh_handle* h, char* buf, int64_t cap);
+
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 AVH_API int64_t avh_launch_count(void);
 AVH_API void avh_reset_launch_count(void);

@@ -13,6 +13,7 @@
 #include "gemm.h"
 #include "kernels.h"
 
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -114,6 +115,8 @@ struct LayerW {
 
 struct Step {
   std::function<int(cudaStream_t)> run;
+  std::string name;       // kernel class for avh_profile_json
+  double flops = 0;       // executed tensor-core FLOPs (GEMM steps)
 };
 
 struct CallArgs {          // per-call pointers the steps read through the plan
@@ -164,7 +167,9 @@ struct avh_handle {
   int* pos_acol = nullptr;        // device [D/64] window start per N tile
   std::vector<LayerW> layers;
   std::map<std::string, std::unique_ptr<Plan>> plans;
-  cudaEvent_t host_evt = nullptr;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;      // 2 per step of the last profiled forward
+  Plan* prof_plan = nullptr;
   void* h2d_video = nullptr;      // staging for avh_forward_host
   void* h2d_audio = nullptr;
   void* h2d_mask = nullptr;
@@ -439,8 +444,9 @@ struct Builder {
     }
     return plan->arena.take(bytes);
   }
+  std::string tag = "misc";     // name given to the steps pushed next
   void push(std::function<int(cudaStream_t)> f) {
-    if (!sizing) plan->steps.push_back(Step{std::move(f)});
+    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, 0.0});
   }
 
   // K-step table for one GEMM: every tap x every 64-wide K chunk (x 3 split-precision products in fp32 mode)
@@ -480,7 +486,7 @@ struct Builder {
     plan->steps.push_back(Step{[gp, pl, wants_mask](cudaStream_t s) {
       if (wants_mask) gp->prob.ep.row_zero = pl->args.mask;
       return gemm_launch(*gp, s);
-    }});
+    }, tag, 2.0 * (double)M * (double)W.n * 64.0 * (double)pr.num_kb});
     return true;
   }
 };
@@ -533,7 +539,10 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     void* dst = a.op;
     const long long rows = a.rows;
     const int C = a.C, planes = P;
+    const std::string keep = b.tag;
+    b.tag = "split";
     b.push([=](cudaStream_t s) { return launch_split_rows(src, C, dst, planes, rows, C, 0, 0, s); });
+    b.tag = keep;
   };
   auto ep_base = [&](void* Cptr, long long ldc) {
     Epilogue ep;
@@ -582,6 +591,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       ep.map_mode = MAP_2LEVEL; ep.S2 = S * S; ep.S1 = S; ep.H = Himg; ep.W = Himg;
       ep.O2 = S * S; ep.O1 = S; ep.O0 = 0; ep.invalid_zero = 1;
       const long long rows = (long long)nimg * S * S;
+      b.tag = "conv3x3_c" + std::to_string(cu.cin);
       if (!b.gemm(in.op, rows, P * cu.cin, cu.w, rows, taps, cu.cin / 64, cu.cin, ep)) return false;
       sync_op(out);
       return true;
@@ -593,15 +603,18 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       {
         void* col = fb.im2col;
         const int planes = P;
+        b.tag = "stem_im2col";
         b.push([=](cudaStream_t s) {
           return launch_stem_im2col(pl->args.video, pl->args.video_dt, T, f0, nf, col, planes, s);
         });
         Epilogue ep = ep_base(fb.stem_out, 64);
         ep.col_scale = h->stem.scale; ep.col_bias = h->stem.bias; ep.act = ACT_PRELU; ep.slope1 = h->stem.slope;
         const long long rows = (long long)nf * 1936;
+        b.tag = "stem_gemm";
         if (!b.gemm(fb.im2col, rows, P * 256, h->stem.w, rows, {Tap{0, 0, 0}}, 4, 256, ep)) return false;
         void* so = fb.stem_out;
         void* po = fb.pooled.data;
+        b.tag = "maxpool";
         b.push([=](cudaStream_t s) { return launch_maxpool_stem(so, po, nf, f32 ? 1 : 0, s); });
         Act pv = fb.pooled; pv.rows = (long long)nf * 529;
         sync_op(pv);
@@ -622,6 +635,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             void* col = fb.col[L];
             const void* src = cur.op;
             const int CinP = Cin * P;
+            b.tag = "im2col_s2";
             b.push([=](cudaStream_t s) { return launch_im2col_s2(src, col, nf, Hp, Hp, CinP, s); });
             const long long rows = (long long)nf * Hn * Hn;
             std::vector<Tap> taps;
@@ -630,6 +644,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             ep.col_scale = bw.c1.scale; ep.col_bias = bw.c1.bias; ep.act = ACT_PRELU; ep.slope1 = bw.c1.slope;
             ep.map_mode = MAP_2LEVEL; ep.S2 = Hn * Hn; ep.S1 = Hn; ep.H = Hn; ep.W = Hn;
             ep.O2 = S * S; ep.O1 = S; ep.O0 = 0;
+            b.tag = "conv_s2_c" + std::to_string(Cin);
             if (!b.gemm(col, rows, 9 * CinP, bw.c1.w, rows, taps, Cin / 64, Cin, ep)) return false;
             sync_op(mid);
             dsout = fb.ds[L];
@@ -638,6 +653,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             epd.col_scale = bw.ds.scale; epd.col_bias = bw.ds.bias;
             epd.map_mode = MAP_2LEVEL; epd.S2 = Hn * Hn; epd.S1 = Hn; epd.H = Hn; epd.W = Hn;
             epd.O2 = S * S; epd.O1 = S; epd.O0 = 0;
+            b.tag = "downsample";
             if (!b.gemm(col, rows, 9 * CinP, bw.ds.w, rows, {Tap{0, 4 * CinP, 0}}, Cin / 64, Cin, epd)) return false;
             res = &dsout;
           } else {
@@ -651,6 +667,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       {
         const void* src = cur.data;
         char* dst = reinterpret_cast<char*>(pooled_feat.data) + (size_t)f0 * 512 * es;
+        b.tag = "avgpool";
         b.push([=](cudaStream_t s) { return launch_avgpool(src, dst, nf, 3, 3, 512, f32 ? 1 : 0, s); });
       }
     }
@@ -659,6 +676,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     {
       Epilogue ep = ep_base(reinterpret_cast<char*>(fused.data) + (size_t)v_off * es, E);
       ep.col_bias = h->proj_v.bias;
+      b.tag = "proj_video";
       if (!b.gemm(pooled_feat.op, N, P * 512, h->proj_v.w, N, {Tap{0, 0, 0}}, 512 / 64, 512, ep)) return false;
     }
   }
@@ -668,6 +686,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     Act arows = new_act(N, Fp);       // zero-initialised; only the first Fa columns are ever written
     {
       void* dst = arows.data;
+      b.tag = "audio_rows";
       b.push([=](cudaStream_t s) {
         return launch_bct_to_rows(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
                                   B, Fa, T, dst, act_dt, Fp, s);
@@ -679,6 +698,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     if (c.modality_fuse == AVH_FUSE_ADD && plan->has_video) {     // features_audio + features_video
       ep.R = ep.C; ep.ldr = E; ep.r_fp32 = f32 ? 1 : 0;
     }
+    b.tag = "proj_audio";
     if (!b.gemm(arows.op, N, P * Fp, h->proj_a.w, N, {Tap{0, 0, 0}}, Fp / 64, Fp, ep)) return false;
   }
   // a missing modality contributes zeros [B,D,T] (hubert.py:703-708): with concat its columns stay at the
@@ -692,6 +712,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     float* of = f32 ? reinterpret_cast<float*>(lnE.data) : nullptr;
     void* ol = f32 ? nullptr : lnE.data;
     float* g = h->fuse_ln_g; float* be = h->fuse_ln_b;
+    b.tag = "fuse_ln";
     if (h->has_post_proj) {
       b.push([=](cudaStream_t s) {
         return launch_layernorm(src, act_dt, E, g, be, 1e-5f, of, ol, DT_BF16, nullptr, N, E, s);
@@ -702,6 +723,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       ep.C = x; ep.ldc = D; ep.c_fp32 = 1;
       ep.col_bias = h->post_proj.bias;
       if (plan->has_mask) ep.row_zero = MASK_SENTINEL;      // index_put(x, padding_mask, 0), wav2vec2.py:869-870
+      b.tag = "post_extract_proj";
       if (!b.gemm(lnE.op, N, P * E, h->post_proj.w, N, {Tap{0, 0, 0}}, E / 64, E, ep)) return false;
     } else {
       // no post_extract_proj (embed == D): the LN output is the encoder input; zero padded rows here
@@ -713,6 +735,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     }
   }
   if (c.capture_stages) {      // x is overwritten in place by the encoder: keep a copy for stage-level tests
+    b.tag = "stage_copy";
     float* enc_in_copy = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));
     b.push([=](cudaStream_t s) {
       return cudaMemcpyAsync(enc_in_copy, x, (size_t)N * D * 4, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
@@ -725,7 +748,9 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     const int G = 64, Tp = T + G;
     void* xpad = b.alloc((size_t)B * Tp * P * D * 2);      // bf16 [B*(T+64), P*D], gap rows stay zero
     const int planes = P;
+    b.tag = "pos_pad";
     b.push([=](cudaStream_t s) { return launch_split_rows(x, D, xpad, planes, N, D, T, Tp, s); });
+    b.tag = "pos_conv";
     const int KT = c.conv_pos, win = h->pos_window;
     std::vector<Tap> taps;
     for (int k = 0; k < KT; ++k) taps.push_back(Tap{k - KT / 2, 0, k * win});
@@ -750,6 +775,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     // LN(src) -> hbuf (operand form) and optionally an fp32 copy (post-LN: the new residual stream)
     float* of = f32 ? reinterpret_cast<float*>(hbuf.data) : also_f32;
     void* ol = f32 ? nullptr : hbuf.data;
+    b.tag = "layer_ln";
     b.push([=](cudaStream_t s) { return launch_layernorm(src, DT_F32, D, g, be, 1e-5f, of, ol, DT_BF16, nullptr, N, D, s); });
     if (f32 && also_f32 != nullptr) {
       float* hd = reinterpret_cast<float*>(hbuf.data);
@@ -762,12 +788,14 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   auto x_to_h = [&]() {   // operand copy of the residual stream (post-LN blocks read x itself)
     void* dst = hbuf.op;
     const int planes = P;
+    b.tag = "split";
     b.push([=](cudaStream_t s) { return launch_split_rows(x, D, dst, planes, N, D, 0, 0, s); });
   };
 
   if (!c.layer_norm_first) {
     // encoder-level LayerNorm right after the positional conv (wav2vec2.py:876-877)
     float* g = h->enc_ln_g; float* be = h->enc_ln_b;
+    b.tag = "layer_ln";
     b.push([=](cudaStream_t s) { return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
     x_to_h();
   }
@@ -778,10 +806,12 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     {   // fused QKV projection
       Epilogue ep = ep_base(qkv.data, 3 * D);
       ep.col_bias = lw.qkv.bias;
+      b.tag = "qkv_proj";
       if (!b.gemm(hbuf.op, N, P * D, lw.qkv.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
     }
     {
       const void* q = qkv.data; void* o = ctx.data;
+      b.tag = "attention";
       b.push([=](cudaStream_t s) {
         return launch_attention(q, hm ? pl->args.mask : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
       });
@@ -791,17 +821,20 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       Epilogue ep;
       ep.C = c.layer_norm_first ? x : tmp; ep.ldc = D; ep.c_fp32 = 1;
       ep.col_bias = lw.out.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+      b.tag = "out_proj";
       if (!b.gemm(ctx.op, N, P * D, lw.out.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
     }
     if (c.layer_norm_first) ln_to_h(x, lw.ln2_g, lw.ln2_b, nullptr);
     else {
       float* g = lw.ln1_g; float* be = lw.ln1_b;
+      b.tag = "layer_ln";
       b.push([=](cudaStream_t s) { return launch_layernorm(tmp, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
       x_to_h();
     }
     {   // fc1 + GELU (erf form, fp32: fairseq/fairseq/modules/gelu.py:95-96)
       Epilogue ep = ep_base(ffn.data, F);
       ep.col_bias = lw.fc1.bias; ep.act = ACT_GELU;
+      b.tag = "fc1";
       if (!b.gemm(hbuf.op, N, P * D, lw.fc1.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
       sync_op(ffn);
     }
@@ -809,15 +842,18 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       Epilogue ep;
       ep.C = c.layer_norm_first ? x : tmp; ep.ldc = D; ep.c_fp32 = 1;
       ep.col_bias = lw.fc2.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+      b.tag = "fc2";
       if (!b.gemm(ffn.op, N, P * F, lw.fc2.w, N, {Tap{0, 0, 0}}, F / 64, F, ep)) return false;
     }
     if (!c.layer_norm_first) {
       float* g = lw.ln2_g; float* be = lw.ln2_b;
+      b.tag = "layer_ln";
       b.push([=](cudaStream_t s) { return launch_layernorm(tmp, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
       if (l + 1 < n_layers) x_to_h();
     }
   }
   // ========================================================================== output
+  b.tag = "final_ln";
   if (c.layer_norm_first && plan->output_layer == 0) {
     float* g = h->enc_ln_g; float* be = h->enc_ln_b;
     b.push([=](cudaStream_t s) {
@@ -916,6 +952,7 @@ int avh_destroy(avh_handle* h) {
   if (h->h2d_audio) cudaFree(h->h2d_audio);
   if (h->h2d_mask) cudaFree(h->h2d_mask);
   if (h->d_out) cudaFree(h->d_out);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -987,11 +1024,59 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   p->args.mask = padding_mask;
   p->args.out = out; p->args.out_dt = out_dtype;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  for (auto& st : p->steps)
+  if (h->profiling) {
+    while (h->prof_events.size() < 2 * p->steps.size()) {
+      cudaEvent_t e;
+      AVH_CUDA_OK(cudaEventCreate(&e));
+      h->prof_events.push_back(e);
+    }
+    h->prof_plan = p;
+  }
+  size_t i = 0;
+  for (auto& st : p->steps) {
+    if (h->profiling) cudaEventRecord(h->prof_events[2 * i], s);
     if (st.run(s)) {
       if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
       return 1;
     }
+    if (h->profiling) cudaEventRecord(h->prof_events[2 * i + 1], s);
+    ++i;
+  }
+  return 0;
+}
+
+int avh_set_profiling(avh_handle* h, int on) {
+  AVH_CHECK(h != nullptr, "null handle");
+  h->profiling = on != 0;
+  h->prof_plan = nullptr;
+  return 0;
+}
+
+int avh_profile_json(avh_handle* h, char* buf, int64_t cap) {
+  AVH_CHECK(h != nullptr && buf != nullptr && cap > 2, "bad argument");
+  AVH_CHECK(h->prof_plan != nullptr, "no profiled forward recorded (avh_set_profiling(h,1) then avh_forward)");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  avh::Plan* p = h->prof_plan;
+  std::map<std::string, std::array<double, 3>> agg;     // name -> launches, ms, flops
+  for (size_t i = 0; i < p->steps.size(); ++i) {
+    AVH_CUDA_OK(cudaEventSynchronize(h->prof_events[2 * i + 1]));
+    float ms = 0.f;
+    AVH_CUDA_OK(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+    auto& a = agg[p->steps[i].name];
+    a[0] += 1; a[1] += ms; a[2] += p->steps[i].flops;
+  }
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %.0f, \"ms\": %.6f, \"tc_flops\": %.0f}", first ? "" : ", ",
+             kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2]);
+    out += tmp;
+    first = false;
+  }
+  out += "}";
+  AVH_CHECK((int64_t)out.size() + 1 <= cap, "profile buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
   return 0;
 }
 

@@ -396,6 +396,20 @@ class AVHubertModel(nn.Module):
                                                   numel, ctypes.c_void_p(stream)))
         return dst
 
+    def profile_forward(self, source, padding_mask=None, output_layer=None):
+        """One forward with CUDA events around every launch; returns {class: {launches, ms, tc_flops}}."""
+        import json
+        handle = self._ensure_handle()
+        lib = _lib.load()
+        _lib.check(lib.avh_set_profiling(handle, 1))
+        try:
+            self.extract_finetune(source, padding_mask, output_layer=output_layer)
+            buf = ctypes.create_string_buffer(1 << 16)
+            _lib.check(lib.avh_profile_json(handle, buf, len(buf)))
+        finally:
+            lib.avh_set_profiling(handle, 0)
+        return json.loads(buf.value.decode())
+
     def forward(self, *args, **kwargs):
         raise NotImplementedError("the pretraining forward (masked prediction, avhubert/hubert.py:591-674) is out "
                                   "of scope; use extract_finetune")
