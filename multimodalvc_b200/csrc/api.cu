@@ -290,7 +290,7 @@ bool pack_all(Packer& pk) {
   const int D = c.encoder_embed_dim;
   const std::string R = "feature_extractor_video.resnet.";
   bool ok = true;
-  // ---- stem: Conv3d weight [64,1,5,7,7] -> [64, 256] (K = dt*49 + kh*7 + kw, zero padded)
+  // ---- stem: Conv3d weight [64,1,5,7,7] -> [64, 5*64]
   {
     const HostTensor* w = pk.get(R + "frontend3D.0.weight");
     const HostTensor* g = pk.get(R + "frontend3D.1.weight");
@@ -299,10 +299,11 @@ bool pack_all(Packer& pk) {
     const HostTensor* v = pk.get(R + "frontend3D.1.running_var");
     const HostTensor* s = pk.get(R + "frontend3D.2.weight");
     if (w && g && b && m && v && s) {
-      std::vector<float> p((size_t)64 * 256, 0.f);
+      std::vector<float> p((size_t)64 * 320, 0.f);      // K = dt*64 + kh*7 + kw (49..63 of each tap zero)
       for (int o = 0; o < 64; ++o)
-        for (int k = 0; k < 245; ++k) p[(size_t)o * 256 + k] = w->v[(size_t)o * 245 + k];
-      h->stem.w = pk.pack(p, 64, 245, 256);
+        for (int dt = 0; dt < 5; ++dt)
+          for (int k = 0; k < 49; ++k) p[(size_t)o * 320 + dt * 64 + k] = w->v[(size_t)o * 245 + dt * 49 + k];
+      h->stem.w = pk.pack(p, 64, 245, 320);
       h->stem.cin = 1; h->stem.cout = 64;
       std::vector<float> sc(64), bi(64), sl(64);
       for (int o = 0; o < 64; ++o) {
@@ -503,7 +504,7 @@ struct Act {
 };
 
 struct FrontendBufs {
-  void* im2col = nullptr;   // [CF*1936, P*256]
+  void* im2col = nullptr;   // stem (kh,kw) patches [CB*(T+2)*1936, P*64]
   void* stem_out = nullptr; // [CF*1936, 64]
   Act pooled;               // padded 23x23x64
   Act a[4][4];              // per layer: block0.conv1 out, block0 out, block1.conv1 out, block1 out
@@ -557,10 +558,13 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 
   // ========================================================================== lip frontend
   if (plan->has_video) {
-    int CF = c.frontend_chunk_frames > 0 ? c.frontend_chunk_frames : 480;
-    if (CF > N) CF = (int)N;
+    // chunks of whole clips (the stem's temporal taps are row shifts inside a clip-padded layout)
+    const int target = c.frontend_chunk_frames > 0 ? c.frontend_chunk_frames : 640;
+    int CB = std::max(1, target / T);
+    CB = (B + ((B + CB - 1) / CB) - 1) / ((B + CB - 1) / CB);       // even split over ceil(B/CB) chunks
+    const int CF = CB * T;
     FrontendBufs fb;
-    fb.im2col = b.alloc((size_t)CF * 1936 * 256 * 2 * P);
+    fb.im2col = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * 2 * P);
     fb.stem_out = b.alloc((size_t)CF * 1936 * 64 * es);
     static const int HS[4] = {22, 11, 6, 3};
     fb.pooled = new_act((long long)CF * 23 * 23, 64);
@@ -597,21 +601,27 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       return true;
     };
 
-    for (long long f0 = 0; f0 < N; f0 += CF) {
-      const int nf = (int)std::min<long long>(CF, N - f0);
-      // ---- stem: im2col -> GEMM(+BN+PReLU) -> maxpool
+    for (int b0 = 0; b0 < B; b0 += CB) {
+      const int nb = std::min(CB, B - b0);
+      const int nf = nb * T;
+      const long long f0 = (long long)b0 * T;
+      // ---- stem: (kh,kw) patches -> GEMM over 5 temporal row-shift taps (+BN+PReLU) -> maxpool
       {
         void* col = fb.im2col;
         const int planes = P;
-        b.tag = "stem_im2col";
+        b.tag = "stem_patches";
         b.push([=](cudaStream_t s) {
-          return launch_stem_im2col(pl->args.video, pl->args.video_dt, T, f0, nf, col, planes, s);
+          return launch_stem_patches(pl->args.video, pl->args.video_dt, T, b0, nb, col, planes, s);
         });
         Epilogue ep = ep_base(fb.stem_out, 64);
         ep.col_scale = h->stem.scale; ep.col_bias = h->stem.bias; ep.act = ACT_PRELU; ep.slope1 = h->stem.slope;
-        const long long rows = (long long)nf * 1936;
+        const long long rows = (long long)nb * (T + 2) * 1936;       // tile rows include the gap frames
+        ep.map_mode = MAP_2LEVEL; ep.S2 = (T + 2) * 1936; ep.S1 = ep.S2; ep.H = 1; ep.W = T * 1936;
+        ep.O2 = (long long)T * 1936; ep.O1 = 0; ep.O0 = 0;
+        std::vector<Tap> taps;
+        for (int dt = 0; dt < 5; ++dt) taps.push_back(Tap{(dt - 2) * 1936, 0, dt * 64});
         b.tag = "stem_gemm";
-        if (!b.gemm(fb.im2col, rows, P * 256, h->stem.w, rows, {Tap{0, 0, 0}}, 4, 256, ep)) return false;
+        if (!b.gemm(fb.im2col, rows, P * 64, h->stem.w, rows, taps, 1, 64, ep)) return false;
         void* so = fb.stem_out;
         void* po = fb.pooled.data;
         b.tag = "maxpool";

@@ -153,37 +153,41 @@ __global__ void split_rows_kernel(const float* __restrict__ in, long long ld, __
 }
 
 // ------------------------------------------------------------------------------------- lip frontend
-// Conv3d(1,64,(5,7,7),s(1,2,2),p(2,3,3)) as GEMM rows (avhubert/resnet.py:138).
-__global__ void stem_im2col_kernel(const void* __restrict__ video, int in_dt, int T, long long f0, int nf,
-                                   __nv_bfloat16* __restrict__ out, int planes) {
+// Spatial (kh,kw) patches of the Conv3d(1,64,(5,7,7),s(1,2,2),p(2,3,3)) stem (avhubert/resnet.py:138): for
+// clip-local frame (bl,t) and output pixel (ho,wo), out row ((bl*(T+2)+t)*1936 + ho*44+wo) holds the 49 taps
+// x[t, 2ho+kh-3, 2wo+kw-3] at column kh*7+kw (columns 49..63 zero).  The 5 temporal taps are then row shifts
+// of +-1936 rows in the tcgen05 GEMM; the two gap frames after every clip are never written and stay zero.
+__global__ void stem_patches_kernel(const void* __restrict__ video, int in_dt, int T, int b0, int nb,
+                                    __nv_bfloat16* __restrict__ out, int planes) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-element chunk each
-  const long long total = (long long)nf * 1936 * 32;
+  const long long total = (long long)nb * T * 1936 * 8;
   if (i >= total) return;
-  const int chunk = (int)(i & 31);
-  const long long row = i >> 5;
+  const int chunk = (int)(i & 7);
+  const long long row = i >> 3;
   const int pix = (int)(row % 1936);
-  const long long f = f0 + row / 1936;
+  const long long ft = row / 1936;
+  const int t = (int)(ft % T);
+  const int bl = (int)(ft / T);
   const int ho = pix / 44, wo = pix - ho * 44;
-  const int t = (int)(f % T);
-  const long long clip0 = (f - t) * 7744;      // first frame of this clip
+  const long long src = ((long long)(b0 + bl) * T + t) * 7744;
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = chunk * 8 + j;
     float x = 0.f;
-    if (k < 245) {
-      const int dt = k / 49, r = k - dt * 49, kh = r / 7, kw = r - kh * 7;
-      const int tt = t + dt - 2, hh = 2 * ho + kh - 3, ww = 2 * wo + kw - 3;
-      if (tt >= 0 && tt < T && hh >= 0 && hh < 88 && ww >= 0 && ww < 88)
-        x = load_any(video, in_dt, clip0 + (long long)tt * 7744 + hh * 88 + ww);
+    if (k < 49) {
+      const int kh = k / 7, kw = k - kh * 7;
+      const int hh = 2 * ho + kh - 3, ww = 2 * wo + kw - 3;
+      if (hh >= 0 && hh < 88 && ww >= 0 && ww < 88) x = load_any(video, in_dt, src + hh * 88 + ww);
     }
     v[j] = x;
   }
   __nv_bfloat162 h[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-  uint4* orow = reinterpret_cast<uint4*>(out + row * (256ll * planes));
-  orow[chunk] = *reinterpret_cast<uint4*>(h);
+  const long long orow = ((long long)bl * (T + 2) + t) * 1936 + pix;
+  uint4* o = reinterpret_cast<uint4*>(out + orow * (64ll * planes));
+  o[chunk] = *reinterpret_cast<uint4*>(h);
   if (planes > 1) {
     uint4 m;
     uint32_t* mp = reinterpret_cast<uint32_t*>(&m);
@@ -192,7 +196,7 @@ __global__ void stem_im2col_kernel(const void* __restrict__ video, int in_dt, in
       const float2 f2 = __bfloat1622float2(h[j]);
       mp[j] = pack_bf16(v[2 * j] - f2.x, v[2 * j + 1] - f2.y);
     }
-    orow[32 + chunk] = m;
+    o[8 + chunk] = m;
   }
 }
 
@@ -333,12 +337,12 @@ int launch_split_rows(const float* in, long long ld, void* out, int planes, long
   return 0;
 }
 
-int launch_stem_im2col(const void* video, int in_dt, int T, long long f0, int nf, void* out, int planes,
-                       cudaStream_t stream) {
-  const long long n = (long long)nf * 1936 * 32;
+int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, void* out, int planes,
+                        cudaStream_t stream) {
+  const long long n = (long long)nb * T * 1936 * 8;
   if (n <= 0) return 0;
-  stem_im2col_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(video, in_dt, T, f0, nf,
-                                                             reinterpret_cast<__nv_bfloat16*>(out), planes);
+  stem_patches_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(video, in_dt, T, b0, nb,
+                                                              reinterpret_cast<__nv_bfloat16*>(out), planes);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

@@ -33,11 +33,11 @@ int launch_split_rows(const float* in, long long ld, void* out, int planes, long
                       int Tpad, cudaStream_t stream);
 
 // ---- lip frontend helpers (avhubert/resnet.py) ----------------------------------------------------
-// explicit im2col of the 5x7x7/stride(1,2,2)/pad(2,3,3) stem for frames [f0, f0+nf) of the flattened
-// (b,t) axis: out bf16 [nf*44*44, planes*256], K index = dt*49 + kh*7 + kw, columns 245..255 zero;
-// planes = 2 adds the bf16 residual plane (fp32-faithful mode).
-int launch_stem_im2col(const void* video, int in_dt, int T, long long f0, int nf, void* out, int planes,
-                       cudaStream_t stream);
+// spatial (kh,kw) patches of the 5x7x7/stride(1,2,2)/pad(2,3,3) stem for clips [b0, b0+nb): out bf16
+// [nb*(T+2)*1936, planes*64], row = (bl*(T+2)+t)*1936 + pixel, column = kh*7+kw (49..63 zero; the two gap
+// frames after each clip are left untouched = zero); planes = 2 adds the bf16 residual plane.
+int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, void* out, int planes,
+                        cudaStream_t stream);
 // MaxPool (1,3,3)/(1,2,2)/(0,1,1): dense NHWC [nf,44,44,64] -> zero-padded layout [nf,23,23,64] (bf16 or fp32)
 int launch_maxpool_stem(const void* in, void* out, int nf, int fp32, cudaStream_t stream);
 // im2col for 3x3 stride-2 pad-1 convs reading the zero-padded bf16 layout [n,H+1,W+1,C] -> dense
