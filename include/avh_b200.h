@@ -123,9 +123,14 @@ AVH_API int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clip
                   float snr_db, int16_t* out, double* scratch, void* stream);
 
 /* Bare tcgen05 GEMM for kernel-level tests and profiling: C[M,N] = A[M,K] * B[N,K]^T (+bias)(gelu)(+R).
- * A,B bf16 row-major (K contiguous, K % 8 == 0), bias fp32 [N] or NULL, R/C bf16 or fp32 [M,N]. */
+ * A,B bf16 row-major (K contiguous, K % 8 == 0), bias fp32 [N] or NULL, R/C bf16 or fp32 [M,N].
+ * block_n: 0 = auto, else a multiple of 32 <= 256; pair: 0 = default, 1 = single-CTA tiles, 2 = CTA-pair tiles. */
 AVH_API int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu,
-                  const void* R, int r_fp32, void* C, int c_fp32, int block_n, void* stream);
+                  const void* R, int r_fp32, void* C, int c_fp32, int block_n, int pair, void* stream);
+
+/* Debug: when dev_buf (device, >= 16*grid u64) is non-NULL every GEMM launch stamps %globaltimer at its
+ * pipeline milestones per CTA; NULL switches it off. */
+AVH_API int avh_gemm_set_trace(void* dev_buf);
 
 /* Per-kernel-class timing of one forward for bench.py / profiles: with profiling on, avh_forward brackets
  * every launch with CUDA events on the launching stream; avh_profile_json waits for them and writes

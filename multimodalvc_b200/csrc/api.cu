@@ -16,6 +16,7 @@
 #include <array>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -476,7 +477,7 @@ struct Builder {
     pr.M = M; pr.N = W.n;
     pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
     pr.a_col_nblk = a_col_nblk;
-    pr.block_n = block_n ? block_n : gemm_pick_block_n(M, W.n);
+    pr.block_n = block_n;
     pr.ep = ep;
     if (sizing) return true;
     GemmPlan* gp = new GemmPlan();
@@ -565,7 +566,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     const int CF = CB * T;
     FrontendBufs fb;
     fb.im2col = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * 2 * P);
-    fb.stem_out = b.alloc((size_t)CF * 1936 * 64 * es);
+    fb.stem_out = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * es);      // same clip-padded row space as the patches
     static const int HS[4] = {22, 11, 6, 3};
     fb.pooled = new_act((long long)CF * 23 * 23, 64);
     for (int L = 0; L < 4; ++L) {
@@ -616,8 +617,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         Epilogue ep = ep_base(fb.stem_out, 64);
         ep.col_scale = h->stem.scale; ep.col_bias = h->stem.bias; ep.act = ACT_PRELU; ep.slope1 = h->stem.slope;
         const long long rows = (long long)nb * (T + 2) * 1936;       // tile rows include the gap frames
-        ep.map_mode = MAP_2LEVEL; ep.S2 = (T + 2) * 1936; ep.S1 = ep.S2; ep.H = 1; ep.W = T * 1936;
-        ep.O2 = (long long)T * 1936; ep.O1 = 0; ep.O0 = 0;
+        // rows map 1:1 (TMA-store epilogue); rows of the gap frames hold don't-care values nobody reads
         std::vector<Tap> taps;
         for (int dt = 0; dt < 5; ++dt) taps.push_back(Tap{(dt - 2) * 1936, 0, dt * 64});
         b.tag = "stem_gemm";
@@ -625,7 +625,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         void* so = fb.stem_out;
         void* po = fb.pooled.data;
         b.tag = "maxpool";
-        b.push([=](cudaStream_t s) { return launch_maxpool_stem(so, po, nf, f32 ? 1 : 0, s); });
+        b.push([=](cudaStream_t s) { return launch_maxpool_stem(so, po, nf, T, f32 ? 1 : 0, s); });
         Act pv = fb.pooled; pv.rows = (long long)nf * 529;
         sync_op(pv);
       }
@@ -1157,15 +1157,34 @@ int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clips, const
                                out, scratch, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int avh_gemm_set_trace(void* dev_buf) {
+  avh::gemm_set_trace(reinterpret_cast<unsigned long long*>(dev_buf));
+  return 0;
+}
+
 int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu, const void* R,
-                  int r_fp32, void* C, int c_fp32, int block_n, void* stream) {
+                  int r_fp32, void* C, int c_fp32, int block_n, int pair, void* stream) {
   AVH_CHECK(A && B && C, "null pointer");
   AVH_CHECK(K % 8 == 0 && N % 32 == 0, "K must be a multiple of 8 and N of 32");
   avh::GemmProblem pr;
   pr.A = A; pr.a_rows = M; pr.a_cols = K; pr.lda = K;
   pr.B = B; pr.b_rows = N; pr.b_cols = K; pr.ldb = K;
   pr.M = M; pr.N = N; pr.num_kb = (K + 63) / 64;
-  pr.block_n = block_n ? block_n : avh::gemm_pick_block_n(M, N);
+  // debug (tools/gemm_sweep.py): AVH_GEMM_KREPEAT=r walks the K range r times (L2-resident long main loops)
+  static void* d_ktab = nullptr;
+  const char* rep = std::getenv("AVH_GEMM_KREPEAT");
+  if (rep != nullptr && std::atoi(rep) > 1) {
+    const int r = std::atoi(rep), kb0 = pr.num_kb;
+    AVH_CHECK(kb0 * r <= avh::GEMM_MAX_KSTEPS, "k repeat too large");
+    std::vector<avh::KStep> t;
+    for (int i = 0; i < kb0 * r; ++i) t.push_back(avh::KStep{(i % kb0) * 64, 0, (i % kb0) * 64, 0});
+    if (d_ktab == nullptr) AVH_CUDA_OK(cudaMalloc(&d_ktab, avh::GEMM_MAX_KSTEPS * sizeof(avh::KStep)));
+    AVH_CUDA_OK(cudaMemcpy(d_ktab, t.data(), t.size() * sizeof(avh::KStep), cudaMemcpyHostToDevice));
+    pr.ktable = reinterpret_cast<const avh::KStep*>(d_ktab);
+    pr.num_kb = kb0 * r;
+  }
+  pr.block_n = block_n;
+  pr.pair = pair;
   pr.ep.C = C; pr.ep.ldc = N; pr.ep.c_fp32 = c_fp32;
   pr.ep.col_bias = bias;
   pr.ep.act = gelu ? avh::ACT_GELU : avh::ACT_NONE;

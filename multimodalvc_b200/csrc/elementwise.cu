@@ -216,7 +216,7 @@ __device__ __forceinline__ float4 f32x4_max(float4 a, float4 b) {
 // MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (avhubert/resnet.py:141): [nf,44,44,64] -> padded [nf,23,23,64].
 // VT = uint4 (8 bf16) or float4 (4 fp32); CV = vectors per pixel.
 template <typename VT, int CV, bool F32>
-__global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ out, int nf) {
+__global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ out, int nf, int T) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)nf * 484 * CV) return;
   const int cv = (int)(i % CV);
@@ -224,6 +224,7 @@ __global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ 
   const int pix = (int)(p % 484);
   const long long n = p / 484;
   const int ho = pix / 22, wo = pix - ho * 22;
+  const long long ns = (n / T) * (T + 2) + (n % T);      // source frame index in the clip-padded stem output
   VT m;
   bool first = true;
   for (int dh = -1; dh <= 1; ++dh) {
@@ -232,7 +233,7 @@ __global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ 
     for (int dw = -1; dw <= 1; ++dw) {
       const int w = 2 * wo + dw;
       if (w < 0 || w >= 44) continue;
-      const VT v = __ldg(in + ((n * 44 + h) * 44 + w) * CV + cv);
+      const VT v = __ldg(in + ((ns * 44 + h) * 44 + w) * CV + cv);
       if (first) m = v;
       else {
         if constexpr (F32) m = f32x4_max(m, v);
@@ -348,16 +349,16 @@ int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, voi
   return 0;
 }
 
-int launch_maxpool_stem(const void* in, void* out, int nf, int fp32, cudaStream_t stream) {
+int launch_maxpool_stem(const void* in, void* out, int nf, int T, int fp32, cudaStream_t stream) {
   if (nf <= 0) return 0;
   if (fp32) {
     const long long n = (long long)nf * 484 * 16;
     maxpool_stem_kernel<float4, 16, true><<<blocks_for(n, 256), 256, 0, stream>>>(
-        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), nf);
+        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), nf, T);
   } else {
     const long long n = (long long)nf * 484 * 8;
     maxpool_stem_kernel<uint4, 8, false><<<blocks_for(n, 256), 256, 0, stream>>>(
-        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), nf);
+        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), nf, T);
   }
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);

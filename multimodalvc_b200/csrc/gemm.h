@@ -53,14 +53,18 @@ struct GemmProblem {
   const KStep* ktable = nullptr;  // device pointer, num_kb entries; null -> a_col=b_col=kb*64, offsets 0
   int a_col_per_nblk = 0;   // grouped conv: A column offset added per N tile
   const int* a_col_nblk = nullptr;  // device table [num N tiles] of A column offsets (overrides a_col_per_nblk)
-  int block_n = 128;        // 64 / 128 / 256
+  int block_n = 0;          // output-tile width: multiple of 32, <= 256; 0 = chosen by gemm_plan (wave fitting)
+  int pair = 0;             // 0 = default (CTA pairs, tcgen05 cta_group::2), 1 = single-CTA form, 2 = pairs
   Epilogue ep;
 };
 
 struct GemmPlan {
-  CUtensorMap tma_a, tma_b;
+  CUtensorMap tma_a, tma_b, tma_c;
+  int c_mode = 0;
   GemmProblem prob;
   int grid = 0;
+  int stages = 0;
+  int ktab_bytes = 0;
   size_t smem = 0;
 };
 
@@ -68,6 +72,7 @@ constexpr int GEMM_MAX_KSTEPS = 768;
 
 int gemm_plan(const GemmProblem& prob, GemmPlan* plan);       // builds tensor maps; 0 on success
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);  // enqueue; 0 on success
-int gemm_pick_block_n(long long M, int N);                    // tile heuristic
+int gemm_pick_block_n(long long M, int N);
+void gemm_set_trace(unsigned long long* dev_buf);             // debug: per-CTA globaltimer stamps [grid][16]                    // tile heuristic
 
 }  // namespace avh

@@ -1,77 +1,106 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a (B200): C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 in, fp32 accumulate.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread issues
-// tcgen05.mma, accumulators live in TMEM, two accumulator stages so the epilogue of tile i overlaps the
-// main loop of tile i+1), warp 2 = TMEM allocator, warps 4..7 = epilogue (tcgen05.ld -> fused
-// scale/bias/activation/residual/mask -> global).  A and B tiles are K-major, 128-byte swizzled, moved
-// by TMA with out-of-bounds zero fill; the K loop walks a table of (A column, A row shift, B column,
-// B row shift) so that one kernel serves plain Linear layers, shifted-row implicit-GEMM convolutions
-// and split-precision products.
+// Persistent and warp-specialised.  Work unit: a (PAIR*128) x BN output tile owned by a cluster of PAIR CTAs
+// (PAIR = 1: single-CTA 128 x BN tiles, the default; PAIR = 2: one CTA pair on the two SMs of a TPC drives ONE
+// tcgen05.mma.cta_group::2 of shape 256 x BN x 16, each CTA staging its own 128 rows of A and HALF of B).
+//   warp 0      TMA producer (one lane): A/B k-blocks into a ring of 128-byte-swizzled K-major smem stages,
+//               out-of-bounds rows/columns zero-filled by TMA
+//   warp 1      MMA issuer (one lane, leader CTA only): tcgen05.mma into TMEM, two accumulator stages of 256
+//               columns so the epilogue of tile i overlaps the main loop of tile i+1; tcgen05.commit (multicast
+//               to both CTAs in pair mode) frees smem stages and publishes finished accumulators
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue.  Fast path, thread = row: tcgen05.ld -> fused per-column scale/bias, PReLU /
+//               erf-GELU, residual add, second PReLU, row masking -> 128-byte-swizzled smem box -> TMA store,
+//               or TMA reduce-add straight into the fp32 residual stream (x += acc + bias without loading x).
+//               Re-mapped outputs (stride-2 conv rows, positional conv) take a per-thread path that transposes
+//               32x32 chunks through smem so that global accesses are row-contiguous.
+// BN is a run-time multiple of 32 (<= 256) chosen per problem by a measured cost model (whole waves over the
+// 148 SMs; one k-block costs ~max(4*92, 2*BN) + 170 clk whatever the tile width).  The K loop walks a table of
+// (A column, A row shift, B column) steps, so the same kernel runs plain Linear layers, shifted-row
+// implicit-GEMM convolutions (3x3 trunk convs, the 5 temporal taps of the stem, the 128 taps of the grouped
+// positional conv) and split-precision (bf16 hi/mid plane) fp32-faithful products.  The epilogue variant is a
+// template parameter: predicated-off options are not free in the 8 epilogue warps (the fully dynamic form
+// issues ~1500 instructions per 32x32 chunk) and the epilogue is what bounds short-K GEMMs.
 //
 // Replaces on the reference path (all cuBLAS/cuDNN library calls there): nn.Linear in
 // avhubert/hubert.py:321,360-364, fairseq/fairseq/models/wav2vec/wav2vec2.py:955-956,
-// multihead_attention.py:64-77; nn.Conv1d pos_conv wav2vec2.py:822-835; nn.Conv2d avhubert/resnet.py:15-24.
+// multihead_attention.py:64-77; nn.Conv1d pos_conv wav2vec2.py:822-835; nn.Conv2d / Conv3d avhubert/resnet.py:15-24,138.
 #include "common.cuh"
 #include "gemm.h"
+
+#include <cstdlib>
+#include <mutex>
+#include <set>
 
 namespace avh {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_THREADS = 256;
-
-template <int BN>
-struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int KTABLE_BYTES = GEMM_MAX_KSTEPS * 16;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + KTABLE_BYTES + BAR_BYTES;
-};
+constexpr int BM = 128;                       // rows per CTA
+constexpr int BK = 64;                        // K elements per stage (one 128-byte swizzle row)
+constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
+constexpr int NUM_THREADS = 384;              // 12 warps: producer, mma, alloc, spare, 8 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;               // TMEM columns per accumulator stage
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;          // per-warp 32 rows x 128 B staging boxes (32 KB)
+constexpr int COLVEC_BYTES = 2 * 4 * 256 * 4;              // per-tile bias/scale/slope vectors, double-buffered (8 KB)
+constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct KernelParams {
   long long M;
   int N;
   int num_kb;
-  int num_m_blk, num_n_blk;
+  int num_m_blk, num_n_blk;     // m blocks in units of PAIR*128 rows
+  int block_n;
+  int stages;
+  int ktab_bytes;               // smem reserved for the K-step table (multiple of 1024; 0 without a table)
   int a_col_per_nblk;
   const int* a_col_nblk;
   const int4* ktable;
+  int c_mode;                   // 0 = per-thread global stores, 1 = TMA store of C, 2 = TMA reduce-add into C (= R)
+  unsigned long long* trace;    // debug: [grid][16] SM clock stamps (null in production)
   Epilogue ep;
 };
 
-__device__ __forceinline__ void load8(const float* p, float* v) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
-    v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
+#define AVH_TRACE(slot)                                                                            \
+  do {                                                                                             \
+    if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
 
-template <int BN>
+// ACT (ACT_*), RES (residual add), S2 (second PReLU), SCALE (per-column scale) and OUTF32 (fp32 output and
+// residual, else bf16) are compile-time when >= 0 and read from the Epilogue struct when -1.
+template <int PAIR, int ACT, int RES, int S2, int SCALE, int OUTF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const KernelParams p) {
-  using C = Cfg<BN>;
+            const __grid_constant__ CUtensorMap tma_c, const KernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int BN = p.block_n;
+  const int STAGES = p.stages;
+  const int b_stage_bytes = (BN / PAIR) * BK * 2;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
-  int4* ktab = reinterpret_cast<int4*>(smem_b + C::STAGES * C::B_STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ktab) + C::KTABLE_BYTES);
-  uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* epi_stage = smem_b + STAGES * b_stage_bytes;
+  float* colvec = reinterpret_cast<float*>(epi_stage + EPI_STAGE_BYTES);
+  int4* ktab = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(colvec) + COLVEC_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ktab) + p.ktab_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = PAIR == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / PAIR;                 // cluster index
+  const int num_units = gridDim.x / PAIR;
   const int num_tiles = p.num_m_blk * p.num_n_blk;
+  if (threadIdx.x == 0) AVH_TRACE(0);
 
   if (p.ktable != nullptr) {
     for (int i = threadIdx.x; i < p.num_kb; i += NUM_THREADS) ktab[i] = __ldg(p.ktable + i);
@@ -79,87 +108,113 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (p.c_mode != 0) tma_prefetch_desc(&tma_c);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], PAIR * EPI_WARPS);
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) AVH_TRACE(1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int m_blk = tile % p.num_m_blk;
         const int n_blk = tile / p.num_m_blk;
-        const int m0 = m_blk * BM;
-        const int n0 = n_blk * BN;
+        const int m0 = (m_blk * PAIR + cta_rank) * BM;
+        const int n0 = n_blk * BN + cta_rank * (BN / PAIR);
         const int a_col_base = p.a_col_nblk != nullptr ? __ldg(p.a_col_nblk + n_blk) : n_blk * p.a_col_per_nblk;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           int4 e;
           if (p.ktable != nullptr) e = ktab[kb];
           else e = make_int4(kb * BK, 0, kb * BK, 0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
-          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
-          tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &tma_b, &full_bar[stage], e.z, n0 + e.w);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+          if (PAIR == 2) {
+            tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
+            tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
+          } else {
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
+            tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
+          }
+          if (tile == unit && kb == 0) AVH_TRACE(2);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(BM * PAIR, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) AVH_TRACE(3);
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (PAIR == 2) umma_commit_pair(&empty_bar[stage]);   // smem slot reusable in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+        if (PAIR == 2) umma_commit_pair(&tmem_full[acc]);        // accumulator complete -> both epilogues
+        else umma_commit(&tmem_full[acc]);
+        if (it == 0) AVH_TRACE(4);
+        AVH_TRACE(5);
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (both CTAs)
     const Epilogue& ep = p.ep;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;     // which interleaved set of column boxes this warp handles
+    const int act = ACT >= 0 ? ACT : ep.act;
+    const bool has_s2 = S2 >= 0 ? S2 != 0 : ep.slope2 != nullptr;
+    const bool has_scale = SCALE >= 0 ? SCALE != 0 : ep.col_scale != nullptr;
+    const bool out_f32 = OUTF32 >= 0 ? OUTF32 != 0 : ep.c_fp32 != 0;
+    const bool res_any = RES >= 0 ? RES != 0 : ep.R != nullptr;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m_blk = tile % p.num_m_blk;
       const int n_blk = tile / p.num_m_blk;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const long long r = (long long)m_blk * BM + q * 32 + lane;
+      const int row0 = (m_blk * PAIR + cta_rank) * BM + q * 32;     // first row of this warp's quarter
+      const long long r = (long long)row0 + lane;
       bool store = r < p.M;
       bool zero = false;
       long long orow = r;
@@ -174,100 +229,277 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
       if (store && ep.row_zero != nullptr && ep.row_zero[orow]) zero = true;
+      // per-column epilogue vectors of this tile -> smem while the main loop runs: every CTA reads the same few
+      // cache lines at the same moment; from global inside the box loop that costs ~1 us of L2 queueing per box
+      float* cv = colvec + acc * 1024;
+      {
+        const int c = threadIdx.x - 128;
+        const int gc = n_blk * BN + c;
+        const bool ok = c < BN && gc < p.N;
+        cv[c] = (ok && ep.col_bias != nullptr) ? __ldg(ep.col_bias + gc) : 0.f;
+        cv[256 + c] = (ok && ep.col_scale != nullptr) ? __ldg(ep.col_scale + gc) : 1.f;
+        cv[512 + c] = (ok && ep.slope1 != nullptr) ? __ldg(ep.slope1 + gc) : 1.f;
+        cv[768 + c] = (ok && ep.slope2 != nullptr) ? __ldg(ep.slope2 + gc) : 1.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (warp == 4 && lane == 0) {
+        if (it == 0) AVH_TRACE(6);
+        AVH_TRACE(8);
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+      uint8_t* stg = epi_stage + (warp - 4) * 4096;
+
+      if (p.c_mode != 0) {
+        // ---- thread = row: TMEM -> registers -> fused math -> 128-byte-swizzled smem box -> TMA store / reduce-add
+        const bool has_res = res_any && p.c_mode != 2;
+        const int box_cols = out_f32 ? 32 : 64;
+        const bool live = store && !zero;
+        const int nboxes = (BN + box_cols - 1) / box_cols;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        __syncwarp();
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + ch * 32, raw);
-        tmem_ld_wait();
-        if (ch == BN / 32 - 1) {
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);     // accumulator stage drained
-        }
-        const int col0 = n_blk * BN + ch * 32;
-        if (store && col0 < p.N) {
-        float v[32];
+        for (int bx = half; bx < nboxes; bx += 2) {
+          const int cbase = bx * box_cols;                 // column offset inside the tile
+          uint32_t packed[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (zero) {
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub == 1 && out_f32) break;
+            const int c0 = cbase + sub * 32;
+            const int col0 = n_blk * BN + c0;
+            uint32_t rawv[32];
+            if (c0 < BN) tmem_ld_32x32(taddr + c0, rawv);
+            // residual row segment (32 columns) straight from global while the TMEM load is in flight
+            uint4 rres[8];
+            if (has_res && live && col0 < p.N) {
+              if (out_f32) {
+                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.R) + orow * ep.ldr + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        } else {
-          float t[32];
-          if (ep.col_scale != nullptr) {
-            load8(ep.col_scale + col0, t);
+                for (int j = 0; j < 8; ++j) rres[j] = __ldg(rp + j);
+              } else {
+                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.R) + orow * ep.ldr + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= t[j];
-          }
-          if (ep.col_bias != nullptr) {
-            load8(ep.col_bias + col0, t);
+                for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
+              }
+            }
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += t[j];
-          }
-          if (ep.act == ACT_GELU) {
+            for (int j = 0; j < 32; ++j) v[j] = (c0 < BN) ? __uint_as_float(rawv[j]) : 0.f;
+            if (col0 < p.N) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (ep.act == ACT_PRELU) {
-            load8(ep.slope1 + col0, t);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bi = *reinterpret_cast<const float4*>(cv + c0 + 4 * j);
+                if (has_scale) {
+                  const float4 sc = *reinterpret_cast<const float4*>(cv + 256 + c0 + 4 * j);
+                  v[4 * j] = fmaf(v[4 * j], sc.x, bi.x); v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, bi.y);
+                  v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, bi.z); v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, bi.w);
+                } else {
+                  v[4 * j] += bi.x; v[4 * j + 1] += bi.y; v[4 * j + 2] += bi.z; v[4 * j + 3] += bi.w;
+                }
+              }
+              if (act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * t[j];
-          }
-          if (ep.R != nullptr) {
-            if (ep.r_fp32) {
-              load8(reinterpret_cast<const float*>(ep.R) + orow * ep.ldr + col0, t);
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+              } else if (act == ACT_PRELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += t[j];
+                for (int j = 0; j < 8; ++j) {
+                  const float4 s1 = *reinterpret_cast<const float4*>(cv + 512 + c0 + 4 * j);
+                  v[4 * j] = v[4 * j] > 0.f ? v[4 * j] : v[4 * j] * s1.x;
+                  v[4 * j + 1] = v[4 * j + 1] > 0.f ? v[4 * j + 1] : v[4 * j + 1] * s1.y;
+                  v[4 * j + 2] = v[4 * j + 2] > 0.f ? v[4 * j + 2] : v[4 * j + 2] * s1.z;
+                  v[4 * j + 3] = v[4 * j + 3] > 0.f ? v[4 * j + 3] : v[4 * j + 3] * s1.w;
+                }
+              }
+              if (has_res && live) {
+                if (out_f32) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    v[4 * j] += __uint_as_float(rres[j].x); v[4 * j + 1] += __uint_as_float(rres[j].y);
+                    v[4 * j + 2] += __uint_as_float(rres[j].z); v[4 * j + 3] += __uint_as_float(rres[j].w);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const float2 f = __bfloat1622float2(h2[k]);
+                      v[8 * j + 2 * k] += f.x;
+                      v[8 * j + 2 * k + 1] += f.y;
+                    }
+                  }
+                }
+              }
+              if (has_s2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 s2 = *reinterpret_cast<const float4*>(cv + 768 + c0 + 4 * j);
+                  v[4 * j] = v[4 * j] > 0.f ? v[4 * j] : v[4 * j] * s2.x;
+                  v[4 * j + 1] = v[4 * j + 1] > 0.f ? v[4 * j + 1] : v[4 * j + 1] * s2.y;
+                  v[4 * j + 2] = v[4 * j + 2] > 0.f ? v[4 * j + 2] : v[4 * j + 2] * s2.z;
+                  v[4 * j + 3] = v[4 * j + 3] > 0.f ? v[4 * j + 3] : v[4 * j + 3] * s2.w;
+                }
+              }
+            }
+            if (zero) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (out_f32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) packed[j] = __float_as_uint(v[j]);
             } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const __nv_bfloat16*>(ep.R) + orow * ep.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[sub * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            }
+          }
+          if (bx + 2 >= nboxes) {
+            // this warp's last TMEM read of the accumulator stage: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+          // the previous box of this warp must have been read out of smem before it is overwritten
+          if (lane == 0) tma_wait_group_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            if (p.c_mode == 2) tma_reduce_add_2d(&tma_c, stg, n_blk * BN + cbase, row0);
+            else tma_store_2d(&tma_c, stg, n_blk * BN + cbase, row0);
+            tma_commit_group();
+          }
+        }
+        if (half >= nboxes) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
+        }
+      } else {
+        // ---- re-mapped rows: transpose 32x32 chunks through smem, then row-contiguous global accesses
+        const uint32_t store_mask = __ballot_sync(0xffffffffu, store);
+        const uint32_t zero_mask = __ballot_sync(0xffffffffu, zero);
+        const int my_orow = (int)orow;
+        float* stf = reinterpret_cast<float*>(stg);
+        const int c4 = lane & 7, rsub = lane >> 3;
+        const int nchunks = BN / 32;
+#pragma unroll 1
+        for (int ch = half; ch < nchunks; ch += 2) {
+          uint32_t rawv[32];
+          tmem_ld_32x32(taddr + ch * 32, rawv);
+          tmem_ld_wait();
+          if (ch + 2 >= nchunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_uint4(rawv[4 * j], rawv[4 * j + 1], rawv[4 * j + 2], rawv[4 * j + 3]);
+          __syncwarp();
+          const int col0 = n_blk * BN + ch * 32;
+          if (col0 < p.N) {
+            const int col = col0 + c4 * 4;
+            const int cc = ch * 32 + c4 * 4;
+            const float4 bi = *reinterpret_cast<const float4*>(cv + cc);
+            const float4 sc = *reinterpret_cast<const float4*>(cv + 256 + cc);
+            const float4 s1 = *reinterpret_cast<const float4*>(cv + 512 + cc);
+            const float4 s2 = *reinterpret_cast<const float4*>(cv + 768 + cc);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {          // two groups of four rows: residual loads of a group in flight together
+              long long orow4[4];
+              float4 res[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                uint4 u = __ldg(rp + i);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                const int rr = (g * 4 + i) * 4 + rsub;
+                orow4[i] = (long long)__shfl_sync(0xffffffffu, my_orow, rr);
+                res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (res_any && ((store_mask & ~zero_mask) >> rr) & 1u) {
+                  const long long off = orow4[i] * ep.ldr + col;
+                  if (out_f32) res[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.R) + off));
+                  else {
+                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(ep.R) + off));
+                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+                    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                    res[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                  }
+                }
+              }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 f = __bfloat1622float2(h2[j]);
-                  v[8 * i + 2 * j] += f.x;
-                  v[8 * i + 2 * j + 1] += f.y;
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (g * 4 + i) * 4 + rsub;
+                float4 v = *reinterpret_cast<const float4*>(stf + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                if (has_scale) {
+                  v.x = fmaf(v.x, sc.x, bi.x); v.y = fmaf(v.y, sc.y, bi.y);
+                  v.z = fmaf(v.z, sc.z, bi.z); v.w = fmaf(v.w, sc.w, bi.w);
+                } else {
+                  v.x += bi.x; v.y += bi.y; v.z += bi.z; v.w += bi.w;
+                }
+                if (act == ACT_GELU) {
+                  v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+                } else if (act == ACT_PRELU) {
+                  v.x = v.x > 0.f ? v.x : v.x * s1.x; v.y = v.y > 0.f ? v.y : v.y * s1.y;
+                  v.z = v.z > 0.f ? v.z : v.z * s1.z; v.w = v.w > 0.f ? v.w : v.w * s1.w;
+                }
+                if (res_any) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                if (has_s2) {
+                  v.x = v.x > 0.f ? v.x : v.x * s2.x; v.y = v.y > 0.f ? v.y : v.y * s2.y;
+                  v.z = v.z > 0.f ? v.z : v.z * s2.z; v.w = v.w > 0.f ? v.w : v.w * s2.w;
+                }
+                if ((zero_mask >> rr) & 1u) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((store_mask >> rr) & 1u) {
+                  const long long off = orow4[i] * ep.ldc + col;
+                  if (out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + off) = v;
+                  else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + off) =
+                           make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
                 }
               }
             }
           }
-          if (ep.slope2 != nullptr) {
-            load8(ep.slope2 + col0, t);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * t[j];
-          }
+          __syncwarp();      // staging buffer is rewritten by the next chunk
         }
-        if (ep.c_fp32) {
-          float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + orow * ep.ldc + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + orow * ep.ldc + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-            cp[i] = u;
+        if (half >= nchunks) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+            else mbar_arrive(&tmem_empty[acc]);
           }
-        }
         }
       }
+      if (warp == 4 && lane == 0) {
+        if (it == 0) AVH_TRACE(7);
+        AVH_TRACE(9);
+      }
     }
+    if (lane == 0 && p.c_mode != 0) tma_wait_group0();     // bulk stores of this thread are complete
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (threadIdx.x == 0) AVH_TRACE(10);
+  if (warp == 2) {
+    if (PAIR == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+    if (lane == 0) AVH_TRACE(11);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -284,6 +516,23 @@ EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+// output tensor map: [rows, cols] fp32 or bf16, box = 128 bytes of columns x 32 rows, 128B swizzle
+int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32) {
+  EncodeTiledFn fn = get_encode_fn();
+  AVH_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const int es = fp32 ? 4 : 2;
+  AVH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * es) % 16 == 0, "TMA store alignment");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (C) failed (code " + std::to_string((int)r) + ")");
+  return 0;
 }
 
 // 2-D bf16 row-major tensor [rows, cols] (row stride ld elements), box = 64 cols x box_rows, 128B swizzle.
@@ -303,71 +552,163 @@ int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long
   return 0;
 }
 
-template <int BN>
-int launch_t(const GemmPlan& plan, const KernelParams& kp, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)Cfg<BN>::SMEM));
-    configured = true;
+unsigned long long* g_trace = nullptr;
+
+int default_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("AVH_GEMM_PAIR");
+    v = (e != nullptr && e[0] == '2') ? 2 : 1;
   }
-  gemm_kernel<BN><<<plan.grid, NUM_THREADS, Cfg<BN>::SMEM, stream>>>(plan.tma_a, plan.tma_b, kp);
-  AVH_CUDA_OK(cudaGetLastError());
-  count_launch(1);
-  return 0;
+  return v;
+}
+
+// modelled cycles of one launch (measured on B200, tools/micro/mma_bench.cu + tools/gemm_sweep.py): one
+// tcgen05.mma (128 rows per CTA, K = 16) costs max(92, BN/2) clk from a single issuing thread, a k-block of four
+// costs that plus ~170 clk of barrier handling; tiles run in whole waves over the work units.
+double model_cycles(long long M, int N, int num_kb, int bn, int pair, int sms) {
+  const long long mt = (M + (long long)BM * pair - 1) / ((long long)BM * pair);
+  const long long nt = (N + bn - 1) / bn;
+  const long long units = sms / pair;
+  const long long rounds = (mt * nt + units - 1) / units;
+  const double mma = bn / 2.0 > 92.0 ? bn / 2.0 : 92.0;
+  const double per_tile = num_kb * (4.0 * mma + 170.0) + 400.0;
+  return rounds * per_tile + 8.0 * bn + 2500.0;          // + exposed last epilogue + launch
 }
 
 }  // namespace
 
-int gemm_pick_block_n(long long M, int N) {
-  // Prefer the widest tile that still yields at least ~one wave of CTAs (148 SMs).
-  const long long mt = (M + BM - 1) / BM;
-  const int sms = device_sm_count();
-  for (int bn : {256, 128}) {
-    if (N % bn == 0 || N > 4 * bn) {
-      long long tiles = mt * ((N + bn - 1) / bn);
-      if (tiles >= sms) return bn;
-    }
-  }
-  return (N % 128 == 0 && mt * (N / 128) >= sms / 2) ? 128 : 64;
-}
+void gemm_set_trace(unsigned long long* dev_buf) { g_trace = dev_buf; }
+
+int gemm_pick_block_n(long long M, int N) { return 0; (void)M; (void)N; }      // 0 = let gemm_plan choose
 
 int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
-  AVH_CHECK(pr.block_n == 64 || pr.block_n == 128 || pr.block_n == 256, "block_n must be 64/128/256");
   AVH_CHECK(pr.N % 32 == 0, "N must be a multiple of 32");
   AVH_CHECK(pr.num_kb >= 1, "num_kb must be >= 1");
   AVH_CHECK(pr.ktable == nullptr || pr.num_kb <= GEMM_MAX_KSTEPS, "too many K steps for the smem table");
-  AVH_CHECK(pr.M >= 1 && pr.M < (1ll << 31) - BM, "M out of range");
+  AVH_CHECK(pr.M >= 1 && pr.M < (1ll << 31) - 2 * BM, "M out of range");
   AVH_CHECK(pr.ep.C != nullptr, "output pointer is null");
+  AVH_CHECK(pr.block_n >= 0 && pr.block_n <= 256 && pr.block_n % 32 == 0, "block_n must be a multiple of 32, <= 256");
+  AVH_CHECK(pr.ep.R == nullptr || pr.ep.r_fp32 == pr.ep.c_fp32, "residual and output dtypes must match");
   plan->prob = pr;
-  if (encode_2d(&plan->tma_a, pr.A, pr.a_rows, pr.a_cols, pr.lda, BM)) return 1;
-  if (encode_2d(&plan->tma_b, pr.B, pr.b_rows, pr.b_cols, pr.ldb, pr.block_n)) return 1;
-  const long long mt = (pr.M + BM - 1) / BM;
-  const long long nt = (pr.N + pr.block_n - 1) / pr.block_n;
-  const long long tiles = mt * nt;
   const int sms = device_sm_count();
-  plan->grid = (int)(tiles < sms ? tiles : sms);
-  plan->smem = pr.block_n == 256 ? Cfg<256>::SMEM : pr.block_n == 128 ? Cfg<128>::SMEM : Cfg<64>::SMEM;
+  int pair = pr.pair ? pr.pair : default_pair();
+  if (sms < 2) pair = 1;
+  int bn = pr.block_n;
+  if (bn == 0) {
+    double best = 1e30;
+    const int step = pr.ep.c_fp32 ? 32 : 64;      // the TMA epilogue stores 128-byte boxes
+    for (int c = step; c <= 256; c += step) {
+      if (c > ((pr.N + step - 1) / step) * step) break;
+      const double t = model_cycles(pr.M, pr.N, pr.num_kb, c, pair, sms);
+      if (t < best) { best = t; bn = c; }
+    }
+  }
+  plan->prob.block_n = bn;
+  plan->prob.pair = pair;
+  if (encode_2d(&plan->tma_a, pr.A, pr.a_rows, pr.a_cols, pr.lda, BM)) return 1;
+  if (encode_2d(&plan->tma_b, pr.B, pr.b_rows, pr.b_cols, pr.ldb, bn / pair)) return 1;
+  // TMA epilogue whenever tile rows map 1:1 onto output rows (Linear layers, implicit 3x3 convs, stem): plain
+  // box stores, or reduce-add when the residual is the output itself (x += ...) and nothing follows the add
+  {
+    const Epilogue& e = pr.ep;
+    const bool identity = e.map_mode != MAP_2LEVEL || (e.O2 == e.S2 && e.O1 == e.S1 && e.O0 == 0 && e.invalid_zero);
+    int mode = 0;
+    if (identity && (bn % (e.c_fp32 ? 32 : 64) == 0 || pr.N <= bn)) {
+      mode = 1;
+      if (e.R != nullptr && e.R == e.C) {
+        // in-place residual: a reduce-add when nothing follows the add, else the per-thread path
+        mode = (e.ldr == e.ldc && e.c_fp32 && e.slope2 == nullptr && e.row_zero == nullptr) ? 2 : 0;
+      }
+    }
+    static int force = -1;
+    if (force < 0) { const char* ev = std::getenv("AVH_GEMM_CMODE"); force = ev ? std::atoi(ev) : 9; }
+    if (force == 0) mode = 0;
+    plan->c_mode = mode;
+    if (mode != 0) {
+      if (encode_c(&plan->tma_c, e.C, pr.M, pr.N, e.ldc, e.c_fp32)) return 1;
+    } else {
+      plan->tma_c = plan->tma_a;
+    }
+  }
+  const long long mt = (pr.M + (long long)BM * pair - 1) / ((long long)BM * pair);
+  const long long nt = (pr.N + bn - 1) / bn;
+  const long long tiles = mt * nt;
+  const long long units = sms / pair;
+  plan->grid = (int)(tiles < units ? tiles : units) * pair;
+  const int stage_bytes = A_STAGE_BYTES + (bn / pair) * BK * 2;
+  const int ktab_bytes = pr.ktable != nullptr ? ((pr.num_kb * 16 + 1023) / 1024) * 1024 : 0;
+  int stages = (SMEM_LIMIT - 1024 - EPI_STAGE_BYTES - COLVEC_BYTES - ktab_bytes - BAR_BYTES) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  AVH_CHECK(stages >= 2, "tile too large for shared memory");
+  plan->stages = stages;
+  plan->ktab_bytes = ktab_bytes;
+  plan->smem = 1024 + (size_t)stages * stage_bytes + EPI_STAGE_BYTES + COLVEC_BYTES + ktab_bytes + BAR_BYTES;
   return 0;
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   const GemmProblem& pr = plan.prob;
+  const int pair = pr.pair;
   KernelParams kp;
   kp.M = pr.M;
   kp.N = pr.N;
   kp.num_kb = pr.num_kb;
-  kp.num_m_blk = (int)((pr.M + BM - 1) / BM);
+  kp.num_m_blk = (int)((pr.M + (long long)BM * pair - 1) / ((long long)BM * pair));
   kp.num_n_blk = (pr.N + pr.block_n - 1) / pr.block_n;
+  kp.block_n = pr.block_n;
+  kp.stages = plan.stages;
+  kp.ktab_bytes = plan.ktab_bytes;
   kp.a_col_per_nblk = pr.a_col_per_nblk;
   kp.a_col_nblk = pr.a_col_nblk;
   kp.ktable = reinterpret_cast<const int4*>(pr.ktable);
+  kp.c_mode = plan.c_mode;
+  kp.trace = g_trace;
   kp.ep = pr.ep;
-  switch (pr.block_n) {
-    case 256: return launch_t<256>(plan, kp, stream);
-    case 128: return launch_t<128>(plan, kp, stream);
-    default: return launch_t<64>(plan, kp, stream);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const Epilogue& e = pr.ep;
+  const int act = e.act, res = e.R != nullptr, s2 = e.slope2 != nullptr, scl = e.col_scale != nullptr, f32 = e.c_fp32;
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, KernelParams);
+  KernelFn fn = nullptr;
+#define AVH_SPEC(A, R, S, C, F) \
+  if (fn == nullptr && pair == 1 && act == A && res == R && s2 == S && scl == C && f32 == F) fn = gemm_kernel<1, A, R, S, C, F>;
+  AVH_SPEC(ACT_NONE, 0, 0, 0, 0)      // Linear + bias -> bf16                  (qkv, modality projections)
+  AVH_SPEC(ACT_NONE, 0, 0, 0, 1)      // Linear + bias -> fp32                  (post_extract_proj, fp32 mode)
+  AVH_SPEC(ACT_GELU, 0, 0, 0, 0)      // Linear + bias + GELU -> bf16           (fc1)
+  AVH_SPEC(ACT_GELU, 0, 0, 0, 1)      //                                        (fc1, fp32 mode)
+  AVH_SPEC(ACT_NONE, 1, 0, 0, 1)      // Linear + bias + residual -> fp32       (out_proj, fc2)
+  AVH_SPEC(ACT_GELU, 1, 0, 0, 1)      // conv + bias + GELU + residual -> fp32  (positional conv)
+  AVH_SPEC(ACT_PRELU, 0, 0, 1, 0)     // conv + BN + PReLU -> bf16              (stem, block conv1)
+  AVH_SPEC(ACT_PRELU, 0, 0, 1, 1)
+  AVH_SPEC(ACT_NONE, 1, 1, 1, 0)      // conv + BN + residual + PReLU -> bf16   (block conv2)
+  AVH_SPEC(ACT_NONE, 1, 1, 1, 1)
+  AVH_SPEC(ACT_NONE, 0, 0, 1, 0)      // conv + BN -> bf16                      (downsample)
+  AVH_SPEC(ACT_NONE, 0, 0, 1, 1)
+#undef AVH_SPEC
+  if (fn == nullptr) fn = pair == 2 ? gemm_kernel<2, -1, -1, -1, -1, -1> : gemm_kernel<1, -1, -1, -1, -1, -1>;
+  static std::mutex mu;
+  static std::set<const void*> configured;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (configured.find(reinterpret_cast<const void*>(fn)) == configured.end()) {
+      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured.insert(reinterpret_cast<const void*>(fn));
+    }
   }
+  AVH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, plan.tma_a, plan.tma_b, plan.tma_c, kp));
+  count_launch(1);
+  return 0;
 }
 
 }  // namespace avh

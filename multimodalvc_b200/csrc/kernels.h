@@ -38,8 +38,9 @@ int launch_split_rows(const float* in, long long ld, void* out, int planes, long
 // frames after each clip are left untouched = zero); planes = 2 adds the bf16 residual plane.
 int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, void* out, int planes,
                         cudaStream_t stream);
-// MaxPool (1,3,3)/(1,2,2)/(0,1,1): dense NHWC [nf,44,44,64] -> zero-padded layout [nf,23,23,64] (bf16 or fp32)
-int launch_maxpool_stem(const void* in, void* out, int nf, int fp32, cudaStream_t stream);
+// MaxPool (1,3,3)/(1,2,2)/(0,1,1): NHWC frames [.,44,44,64] stored with two gap frames after every T frames
+// (frame f at index (f/T)*(T+2) + f%T) -> zero-padded layout [nf,23,23,64] (bf16 or fp32)
+int launch_maxpool_stem(const void* in, void* out, int nf, int T, int fp32, cudaStream_t stream);
 // im2col for 3x3 stride-2 pad-1 convs reading the zero-padded bf16 layout [n,H+1,W+1,C] -> dense
 // [n*Ho*Wo, 9*C] (K index = (kh*3+kw)*C + c)
 int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream);

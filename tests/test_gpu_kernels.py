@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def gemm(A, B, bias=None, gelu=False, R=None, c_fp32=True, block_n=0):
+def gemm(A, B, bias=None, gelu=False, R=None, c_fp32=True, block_n=0, pair=0):
     M, K = A.shape
     N = B.shape[0]
     C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if c_fp32 else torch.bfloat16)
@@ -22,22 +22,24 @@ def gemm(A, B, bias=None, gelu=False, R=None, c_fp32=True, block_n=0):
     _lib.check(_lib.load().avh_gemm_bf16(
         vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()) if bias is not None else None, int(gelu),
         vp(R.data_ptr()) if R is not None else None, int(R is not None and R.dtype == torch.float32),
-        vp(C.data_ptr()), int(c_fp32), block_n, vp(torch.cuda.current_stream().cuda_stream)))
+        vp(C.data_ptr()), int(c_fp32), block_n, pair, vp(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     return C
 
 
+@pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("M,N,K,bn", [
-    (128, 64, 64, 64), (128, 128, 64, 128), (128, 256, 64, 256),          # single tile, single K block
-    (256, 128, 512, 128), (300, 192, 320, 64), (1000, 384, 1024, 128),     # ragged M, several K blocks
-    (2400, 1024, 1024, 0), (2400, 3072, 1024, 0), (2400, 4096, 1024, 256), (2400, 1024, 4096, 128),   # c2 shapes
+    (128, 64, 64, 64), (128, 128, 64, 128), (128, 256, 64, 256), (256, 32, 64, 32),   # single tile, single K block
+    (256, 128, 512, 128), (300, 192, 320, 64), (1000, 384, 1024, 160),     # ragged M/N tiles, several K blocks
+    (2400, 1024, 1024, 0), (2400, 3072, 1024, 0), (2400, 4096, 1024, 0), (2400, 1024, 4096, 0),   # c2 shapes
+    (2400, 4096, 1024, 224), (2400, 1024, 4096, 96),
     (77, 64, 104, 64), (20000, 64, 256, 64),                                # K tail (OOB zero fill), many tiles
 ])
-def test_gemm_matches_fp32_reference(M, N, K, bn):
+def test_gemm_matches_fp32_reference(M, N, K, bn, pair):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
-    C = gemm(A, B, block_n=bn)
+    C = gemm(A, B, block_n=bn, pair=pair)
     ref = A.float() @ B.float().t()
     assert torch.isfinite(C).all()
     tol = 1e-4 * (K ** 0.5) * 0.05 * 4 + 1e-5          # fp32 accumulation error only
@@ -54,6 +56,8 @@ def test_gemm_fused_epilogue_bias_gelu_residual_bf16_out():
     ref = torch.nn.functional.gelu(A.float() @ B.float().t() + bias) + R
     C = gemm(A, B, bias=bias, gelu=True, R=R, c_fp32=True)
     assert (C - ref).abs().max().item() < 2e-4
+    C1 = gemm(A, B, bias=bias, gelu=True, R=R, c_fp32=True, pair=1)
+    assert torch.equal(C, C1)                                 # pair and single-CTA tiles: same arithmetic
     Rb = R.bfloat16()
     Cb = gemm(A, B, bias=bias, gelu=True, R=Rb, c_fp32=False)
     refb = (torch.nn.functional.gelu(A.float() @ B.float().t() + bias) + Rb.float())
@@ -65,9 +69,10 @@ def test_gemm_many_tiles_per_cta_exercises_both_accumulator_stages():
     M, N, K = 148 * 128 * 3 + 50, 128, 128            # > 3 tiles per CTA: TMEM double buffering + phase flips
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     B = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
-    C = gemm(A, B, block_n=128)
     ref = A.float() @ B.float().t()
-    assert (C - ref).abs().max().item() < 1e-3
+    for pair in (1, 2):
+        C = gemm(A, B, block_n=128, pair=pair)
+        assert (C - ref).abs().max().item() < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------- audio

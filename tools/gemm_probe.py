@@ -10,13 +10,14 @@ SHAPES = [  # name, M, N, K, block_n, gelu, residual(fp32), c_fp32
     ("fc2", 2400, 1024, 4096, 0, 0, 1, 1),
     ("qkv", 2400, 3072, 1024, 0, 0, 0, 0),
     ("out", 2400, 1024, 1024, 0, 0, 1, 1),
-    ("big", 8192, 8192, 8192, 256, 0, 0, 0),
-    ("n64", 300000, 64, 576, 64, 0, 0, 0),
+    ("big", 8192, 8192, 8192, 0, 0, 0, 0),
+    ("n64", 300000, 64, 576, 0, 0, 0, 0),
 ]
 
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    pair = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     lib = _lib.load()
     vp = ctypes.c_void_p
     st = torch.cuda.current_stream().cuda_stream
@@ -28,7 +29,7 @@ def main():
         C = torch.empty(M, N, device="cuda", dtype=torch.float32 if cf else torch.bfloat16)
         def run():
             _lib.check(lib.avh_gemm_bf16(vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()), gelu,
-                                         vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, vp(st)))
+                                         vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, vp(st)))
         for _ in range(2):
             run()
         torch.cuda.synchronize()
