@@ -6,8 +6,8 @@
 // Input is the fused QKV projection [B*T, 3*D] (q pre-scaled by head_dim^-0.5 at weight-fold time),
 // output is the per-head context [B*T, D] ready for out_proj.
 //
-// Round-1 version: warp-level mma.sync (m16n8k16) tiles; attention is ~2.4 % of the layer FLOPs at
-// T=150.  The tcgen05 version is tracked in DESIGN.md "next".
+// Warp-level mma.sync (m16n8k16) tiles: attention is ~1.2 % of the path's FLOPs at T=150 and the (b,h) problems
+// are tiny (150x150x64), so one CTA per head with Q/K/V resident in smem beats a tcgen05 pipeline's fixed costs.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -15,8 +15,6 @@ namespace avh {
 namespace {
 
 constexpr int HD = 64;       // head dim
-constexpr int BQ = 64;       // queries per CTA (4 warps x 16)
-constexpr int BKV = 64;      // keys per inner tile
 constexpr int PITCH = 72;    // smem row pitch in bf16 (144 B) -> conflict-free ldmatrix
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -33,25 +31,40 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const int sz = valid ? 16 : 0;      // src-size 0 -> 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// copy a [64 x 64] bf16 tile (rows row0.., global row stride ld) into smem [64][PITCH]; rows >= nrows -> 0
-__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int row0,
-                                          int nrows) {
-  for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+// asynchronous copy of a [ROWS x 64] bf16 tile (rows row0.., global row stride ld) into smem [ROWS][PITCH];
+// rows >= nrows are zero-filled
+template <int ROWS, int NT>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int row0,
+                                                int nrows) {
+  for (int i = threadIdx.x; i < ROWS * 8; i += NT) {
     const int r = i >> 3, c = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row0 + r < nrows) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(row0 + r) * ld) + c);
-    *reinterpret_cast<uint4*>(dst + r * PITCH + c * 8) = v;
+    const bool ok = row0 + r < nrows;
+    cp_async16(dst + r * PITCH + c * 8, src + (long long)(ok ? row0 + r : 0) * ld + c * 8, ok);
   }
 }
 
-__global__ void __launch_bounds__(128)
+// One CTA = NW warps x 16 query rows of one (batch, head); keys/values stream through smem in chunks of BKV with
+// an online softmax, so a 6 s clip (T = 150) is ONE chunk: Q, K and V of the head are read from L2 exactly once.
+template <int NW, int BKV>
+__global__ void __launch_bounds__(NW * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __restrict__ kpm,
                  __nv_bfloat16* __restrict__ out, int T, int D) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[BQ * PITCH];
-  __shared__ __align__(16) __nv_bfloat16 sK[BKV * PITCH];
-  __shared__ __align__(16) __nv_bfloat16 sV[BKV * PITCH];
-  __shared__ float sMask[BKV];
+  constexpr int BQ = NW * 16;
+  constexpr int NT = NW * 32;
+  constexpr int NJ = BKV / 8;        // 8-key score tiles per chunk
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sK = sQ + BQ * PITCH;
+  __nv_bfloat16* sV = sK + BKV * PITCH;
+  float* sMask = reinterpret_cast<float*>(sV + BKV * PITCH);
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,12 +72,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * HD;
   const int q0 = qt * BQ;
 
-  load_tile(sQ, base, ld, q0, T);
-  __syncthreads();
-  uint32_t qf[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
-    ldsm_x4(qf[kk], sQ + (warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + kk * 16 + 8 * (lane >> 4));
+  load_tile_async<BQ, NT>(sQ, base, ld, q0, T);
+  load_tile_async<BKV, NT>(sK, base + D, ld, 0, T);
+  load_tile_async<BKV, NT>(sV, base + 2 * D, ld, 0, T);
+  cp_async_commit();
 
   float o[8][4];
 #pragma unroll
@@ -72,23 +83,33 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
   constexpr float LOG2E = 1.4426950408889634f;
+  uint32_t qf[4][4];
 
   for (int k0 = 0; k0 < T; k0 += BKV) {
-    __syncthreads();   // previous tile fully consumed
-    load_tile(sK, base + D, ld, k0, T);
-    load_tile(sV, base + 2 * D, ld, k0, T);
-    if (threadIdx.x < BKV) {
-      const int k = k0 + threadIdx.x;
-      const bool dead = (k >= T) || (kpm != nullptr && kpm[(long long)b * T + k] != 0);
-      sMask[threadIdx.x] = dead ? -INFINITY : 0.f;
+    if (k0 > 0) {
+      __syncthreads();   // previous chunk fully consumed
+      load_tile_async<BKV, NT>(sK, base + D, ld, k0, T);
+      load_tile_async<BKV, NT>(sV, base + 2 * D, ld, k0, T);
+      cp_async_commit();
     }
+    for (int i = threadIdx.x; i < BKV; i += NT) {
+      const int k = k0 + i;
+      const bool dead = (k >= T) || (kpm != nullptr && kpm[(long long)b * T + k] != 0);
+      sMask[i] = dead ? -INFINITY : 0.f;
+    }
+    cp_async_wait_all();
     __syncthreads();
+    if (k0 == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        ldsm_x4(qf[kk], sQ + (warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + kk * 16 + 8 * (lane >> 4));
+    }
 
-    float s[8][4];
+    float s[NJ][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    for (int j = 0; j < NJ; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {          // 8 key n-tiles
+    for (int j = 0; j < NJ; ++j) {          // 8-key n-tiles
 #pragma unroll
       for (int kp = 0; kp < 2; ++kp) {     // two pairs of k-steps (dims 0-31, 32-63)
         uint32_t kf[4];
@@ -100,9 +121,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
     // mask + online softmax (rows: lane/4 and lane/4+8; this thread's keys: j*8 + 2*(lane%4) + {0,1})
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float mk0 = sMask[j * 8 + 2 * (lane & 3)], mk1 = sMask[j * 8 + 2 * (lane & 3) + 1];
-      s[j][0] += mk0; s[j][1] += mk1; s[j][2] += mk0; s[j][3] += mk1;
+    for (int j = 0; j < NJ; ++j) {
+      const float2 mk = *reinterpret_cast<const float2*>(sMask + j * 8 + 2 * (lane & 3));
+      s[j][0] += mk.x; s[j][1] += mk.y; s[j][2] += mk.x; s[j][3] += mk.y;
       mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
       mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
     }
@@ -115,24 +136,27 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
       const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
       scale[r] = exp2f((m_run[r] - msafe) * LOG2E);     // m_run=-inf -> 0
       m_run[r] = mnew[r];
-      mnew[r] = msafe;
+      mnew[r] = msafe * LOG2E;
     }
     float rs[2] = {0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f((s[j][0] - mnew[0]) * LOG2E);
-      s[j][1] = exp2f((s[j][1] - mnew[0]) * LOG2E);
-      s[j][2] = exp2f((s[j][2] - mnew[1]) * LOG2E);
-      s[j][3] = exp2f((s[j][3] - mnew[1]) * LOG2E);
+    for (int j = 0; j < NJ; ++j) {
+      s[j][0] = exp2f(fmaf(s[j][0], LOG2E, -mnew[0]));
+      s[j][1] = exp2f(fmaf(s[j][1], LOG2E, -mnew[0]));
+      s[j][2] = exp2f(fmaf(s[j][2], LOG2E, -mnew[1]));
+      s[j][3] = exp2f(fmaf(s[j][3], LOG2E, -mnew[1]));
       rs[0] += s[j][0] + s[j][1];
       rs[1] += s[j][2] + s[j][3];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       o[j][0] *= scale[0]; o[j][1] *= scale[0]; o[j][2] *= scale[1]; o[j][3] *= scale[1];
     }
     l_run[0] = l_run[0] * scale[0] + rs[0];
     l_run[1] = l_run[1] * scale[1] + rs[1];
     // O += P V
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {       // 16 keys per step
+    for (int kk = 0; kk < BKV / 16; ++kk) {       // 16 keys per step
       uint32_t pf[4];
       pf[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
       pf[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
@@ -164,6 +188,22 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
     if (row0 + 8 < T)
       *reinterpret_cast<uint32_t*>(ob + (long long)(row0 + 8) * D + j * 8) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
   }
+}
+
+template <int NW, int BKV>
+int launch_att_t(const void* qkv, const unsigned char* kpm, void* out, int B, int T, int D, int H, cudaStream_t stream) {
+  constexpr int BQ = NW * 16;
+  const size_t smem = (size_t)(BQ + 2 * BKV) * PITCH * 2 + BKV * 4;
+  static bool configured = false;
+  if (!configured) {
+    AVH_CUDA_OK(cudaFuncSetAttribute(attention_kernel<NW, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((T + BQ - 1) / BQ, H, B);
+  attention_kernel<NW, BKV><<<grid, NW * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), kpm,
+                                                            reinterpret_cast<__nv_bfloat16*>(out), T, D);
+  AVH_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // fp32 reference-precision attention for the split-precision (fp32) mode: one warp per query row.
@@ -222,9 +262,13 @@ int launch_attention(const void* qkv, const unsigned char* kpm, void* out, int B
     attention_f32_kernel<<<grid, nw * 32, smem, stream>>>(reinterpret_cast<const float*>(qkv), kpm,
                                                          reinterpret_cast<float*>(out), T, D, H);
   } else {
-    dim3 grid((T + BQ - 1) / BQ, H, B);
-    attention_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), kpm,
-                                               reinterpret_cast<__nv_bfloat16*>(out), T, D);
+    // tile shapes: whole-clip tiles for short clips (T <= 160: one CTA per (batch, head)), else 128 x 128
+    int rc;
+    if (T <= 64) rc = launch_att_t<4, 64>(qkv, kpm, out, B, T, D, H, stream);
+    else if (T <= 96) rc = launch_att_t<6, 96>(qkv, kpm, out, B, T, D, H, stream);
+    else if (T <= 160) rc = launch_att_t<10, 160>(qkv, kpm, out, B, T, D, H, stream);
+    else rc = launch_att_t<8, 128>(qkv, kpm, out, B, T, D, H, stream);
+    if (rc) return rc;
   }
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
