@@ -105,6 +105,13 @@ AVH_API int avh_forward_host(avh_handle* h, const void* video, int video_dtype, 
                      const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
                      void* stream);
 
+/* avh_forward_host without the final wait: everything is enqueued on `stream` (H2D, kernels, D2H) and the call
+ * returns; `out` and the input buffers must stay valid until the caller has synchronised the stream.  Work
+ * enqueued on different streams uses separate workspaces, so several batches can be in flight per device. */
+AVH_API int avh_forward_host_async(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                           const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
+                           void* stream);
+
 /* Intermediate taps for stage-level parity tests; names: "resnet" [B*T,512], "fused_ln" [B*T,E],
  * "enc_in" [B*T,D].  Copies the fp32 value of the last avh_forward into `dst` (device, fp32). */
 AVH_API int avh_read_stage(avh_handle* h, const char* name, float* dst, int64_t capacity_elems, void* stream);

@@ -15,7 +15,7 @@ AVH_FUSE_CONCAT, AVH_FUSE_ADD = 0, 1
 
 EXPORTS = [
     "avh_abi_version", "avh_last_error", "avh_create", "avh_destroy", "avh_load_tensor", "avh_finalize_weights",
-    "avh_forward", "avh_forward_host", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
+    "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
     "avh_gemm_set_trace",
 ]
@@ -61,6 +61,7 @@ def load():
     lib.avh_finalize_weights.argtypes = [vp]
     lib.avh_forward.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]
+    lib.avh_forward_host_async.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_read_stage.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]
     lib.avh_fbank.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.avh_add_noise.argtypes = [vp, vp, i32, vp, i64, ctypes.c_float, vp, vp, vp]

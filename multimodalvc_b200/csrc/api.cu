@@ -171,11 +171,11 @@ struct avh_handle {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // 2 per step of the last profiled forward
   Plan* prof_plan = nullptr;
-  void* h2d_video = nullptr;      // staging for avh_forward_host
-  void* h2d_audio = nullptr;
-  void* h2d_mask = nullptr;
-  void* d_out = nullptr;
-  size_t h2d_video_cap = 0, h2d_audio_cap = 0, h2d_mask_cap = 0, d_out_cap = 0;
+  struct Staging {                // device staging of avh_forward_host, one set per stream
+    void* video = nullptr; void* audio = nullptr; void* mask = nullptr; void* out = nullptr;
+    size_t video_cap = 0, audio_cap = 0, mask_cap = 0, out_cap = 0;
+  };
+  std::map<void*, Staging> staging;
 };
 
 namespace avh {
@@ -876,9 +876,13 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   return true;
 }
 
-Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer) {
+// One plan (= workspace + launch list) per shape AND per CUDA stream: forwards enqueued on different streams
+// never share scratch memory, so a caller can keep several batches in flight on one device.
+Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
+               cudaStream_t stream) {
   const std::string key = std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
-                          (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer);
+                          (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
+                          std::to_string(reinterpret_cast<uintptr_t>(stream));
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   if (h->plans.size() >= 8) h->plans.clear();      // bound workspace growth for ragged shape streams
@@ -958,10 +962,12 @@ int avh_destroy(avh_handle* h) {
   cudaSetDevice(h->device);
   h->plans.clear();
   h->warena.release();
-  if (h->h2d_video) cudaFree(h->h2d_video);
-  if (h->h2d_audio) cudaFree(h->h2d_audio);
-  if (h->h2d_mask) cudaFree(h->h2d_mask);
-  if (h->d_out) cudaFree(h->d_out);
+  for (auto& kv : h->staging) {
+    if (kv.second.video) cudaFree(kv.second.video);
+    if (kv.second.audio) cudaFree(kv.second.audio);
+    if (kv.second.mask) cudaFree(kv.second.mask);
+    if (kv.second.out) cudaFree(kv.second.out);
+  }
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
   return 0;
@@ -1026,7 +1032,8 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
   AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
   AVH_CUDA_OK(cudaSetDevice(h->device));
-  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer);
+  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer,
+                               reinterpret_cast<cudaStream_t>(stream));
   if (p == nullptr) return 1;
   p->args.video = video; p->args.video_dt = video_dtype;
   p->args.audio = audio; p->args.audio_dt = audio_dtype;
@@ -1090,36 +1097,46 @@ int avh_profile_json(avh_handle* h, char* buf, int64_t cap) {
   return 0;
 }
 
-int avh_forward_host(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
-                     const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
-                     void* stream) {
+int avh_forward_host_async(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                           const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
+                           void* stream) {
   AVH_CHECK(h != nullptr, "null handle");
   AVH_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  avh_handle::Staging& st = h->staging[stream];
   const int D = h->cfg.encoder_embed_dim, Fa = h->cfg.audio_feat_dim;
   const size_t vbytes = (size_t)B * T * 88 * 88 * avh::dtype_size(video_dtype);
   const size_t abytes = (size_t)B * T * Fa * avh::dtype_size(audio_dtype);
   const size_t obytes = (size_t)B * T * D * avh::dtype_size(out_dtype);
   if (video) {
-    if (avh::ensure_cap(&h->h2d_video, &h->h2d_video_cap, vbytes)) return 1;
-    AVH_CUDA_OK(cudaMemcpyAsync(h->h2d_video, video, vbytes, cudaMemcpyHostToDevice, s));
+    if (avh::ensure_cap(&st.video, &st.video_cap, vbytes)) return 1;
+    AVH_CUDA_OK(cudaMemcpyAsync(st.video, video, vbytes, cudaMemcpyHostToDevice, s));
   }
   if (audio) {
-    if (avh::ensure_cap(&h->h2d_audio, &h->h2d_audio_cap, abytes)) return 1;
-    AVH_CUDA_OK(cudaMemcpyAsync(h->h2d_audio, audio, abytes, cudaMemcpyHostToDevice, s));
+    if (avh::ensure_cap(&st.audio, &st.audio_cap, abytes)) return 1;
+    AVH_CUDA_OK(cudaMemcpyAsync(st.audio, audio, abytes, cudaMemcpyHostToDevice, s));
   }
   if (padding_mask) {
-    if (avh::ensure_cap(&h->h2d_mask, &h->h2d_mask_cap, (size_t)B * T)) return 1;
-    AVH_CUDA_OK(cudaMemcpyAsync(h->h2d_mask, padding_mask, (size_t)B * T, cudaMemcpyHostToDevice, s));
+    if (avh::ensure_cap(&st.mask, &st.mask_cap, (size_t)B * T)) return 1;
+    AVH_CUDA_OK(cudaMemcpyAsync(st.mask, padding_mask, (size_t)B * T, cudaMemcpyHostToDevice, s));
   }
-  if (avh::ensure_cap(&h->d_out, &h->d_out_cap, obytes)) return 1;
+  if (avh::ensure_cap(&st.out, &st.out_cap, obytes)) return 1;
   const int64_t as[3] = {(int64_t)Fa * T, T, 1};
-  if (avh_forward(h, video ? h->h2d_video : nullptr, video_dtype, audio ? h->h2d_audio : nullptr, audio_dtype, as,
-                  padding_mask ? reinterpret_cast<const uint8_t*>(h->h2d_mask) : nullptr, B, T, output_layer,
-                  h->d_out, out_dtype, stream))
+  if (avh_forward(h, video ? st.video : nullptr, video_dtype, audio ? st.audio : nullptr, audio_dtype, as,
+                  padding_mask ? reinterpret_cast<const uint8_t*>(st.mask) : nullptr, B, T, output_layer, st.out,
+                  out_dtype, stream))
     return 1;
-  AVH_CUDA_OK(cudaMemcpyAsync(out, h->d_out, obytes, cudaMemcpyDeviceToHost, s));
-  AVH_CUDA_OK(cudaStreamSynchronize(s));
+  AVH_CUDA_OK(cudaMemcpyAsync(out, st.out, obytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+int avh_forward_host(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                     const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
+                     void* stream) {
+  if (avh_forward_host_async(h, video, video_dtype, audio, audio_dtype, padding_mask, B, T, output_layer, out,
+                             out_dtype, stream))
+    return 1;
+  AVH_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -355,10 +355,12 @@ class AVHubertModel(nn.Module):
                 B, T, ol, ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
         return out, padding_mask
 
-    def extract_finetune_host(self, video, audio, padding_mask=None, output_layer=None, out=None):
+    def extract_finetune_host(self, video, audio, padding_mask=None, output_layer=None, out=None, wait=True):
         """End-to-end call with HOST tensors (pinned recommended): H2D copies, forward and the D2H read of the
         features all happen inside ``avh_forward_host``.  video [B,1,T,88,88] / audio [B,F,T] contiguous CPU
-        tensors (either may be None); returns a CPU tensor [B,T,D]."""
+        tensors (either may be None); returns a CPU tensor [B,T,D].  ``wait=False`` only enqueues on the current
+        stream (the caller synchronises it before reading ``out``), which lets several batches be in flight on
+        different streams."""
         handle = self._ensure_handle()
         dev = self.encoder.layer_norm.weight.device
         ref = video if video is not None else audio
@@ -375,7 +377,8 @@ class AVHubertModel(nn.Module):
                 raise ValueError("extract_finetune_host takes contiguous CPU tensors")
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.load().avh_forward_host(
+            lib = _lib.load()
+            _lib.check((lib.avh_forward_host if wait else lib.avh_forward_host_async)(
                 handle,
                 ctypes.c_void_p(video.data_ptr()) if video is not None else None,
                 _DTYPES[video.dtype] if video is not None else 0,
