@@ -131,9 +131,10 @@ AVH_API int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clip
 
 /* Bare tcgen05 GEMM for kernel-level tests and profiling: C[M,N] = A[M,K] * B[N,K]^T (+bias)(gelu)(+R).
  * A,B bf16 row-major (K contiguous, K % 8 == 0), bias fp32 [N] or NULL, R/C bf16 or fp32 [M,N].
- * block_n: 0 = auto, else a multiple of 32 <= 256; pair: 0 = default, 1 = single-CTA tiles, 2 = CTA-pair tiles. */
+ * block_n: 0 = auto, else a multiple of 32 <= 256; pair: 0 = default, 1 = single-CTA tiles, 2 = CTA-pair tiles;
+ * occ: 0 = auto, 1 = one CTA per SM, 2 = two CTAs per SM (block_n <= 128). */
 AVH_API int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu,
-                  const void* R, int r_fp32, void* C, int c_fp32, int block_n, int pair, void* stream);
+                  const void* R, int r_fp32, void* C, int c_fp32, int block_n, int pair, int occ, void* stream);
 
 /* Debug: when dev_buf (device, >= 16*grid u64) is non-NULL every GEMM launch stamps %globaltimer at its
  * pipeline milestones per CTA; NULL switches it off. */

@@ -65,7 +65,7 @@ def load():
     lib.avh_read_stage.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]
     lib.avh_fbank.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.avh_add_noise.argtypes = [vp, vp, i32, vp, i64, ctypes.c_float, vp, vp, vp]
-    lib.avh_gemm_bf16.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp]
+    lib.avh_gemm_bf16.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
     lib.avh_gemm_set_trace.argtypes = [vp]
     lib.avh_set_profiling.argtypes = [vp, i32]
     lib.avh_profile_json.argtypes = [vp, ctypes.c_char_p, i64]

@@ -1180,7 +1180,7 @@ int avh_gemm_set_trace(void* dev_buf) {
 }
 
 int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const float* bias, int gelu, const void* R,
-                  int r_fp32, void* C, int c_fp32, int block_n, int pair, void* stream) {
+                  int r_fp32, void* C, int c_fp32, int block_n, int pair, int occ, void* stream) {
   AVH_CHECK(A && B && C, "null pointer");
   AVH_CHECK(K % 8 == 0 && N % 32 == 0, "K must be a multiple of 8 and N of 32");
   avh::GemmProblem pr;
@@ -1202,6 +1202,7 @@ int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const f
   }
   pr.block_n = block_n;
   pr.pair = pair;
+  pr.occ = occ;
   pr.ep.C = C; pr.ep.ldc = N; pr.ep.c_fp32 = c_fp32;
   pr.ep.col_bias = bias;
   pr.ep.act = gelu ? avh::ACT_GELU : avh::ACT_NONE;

@@ -54,6 +54,7 @@ struct GemmProblem {
   int a_col_per_nblk = 0;   // grouped conv: A column offset added per N tile
   const int* a_col_nblk = nullptr;  // device table [num N tiles] of A column offsets (overrides a_col_per_nblk)
   int block_n = 0;          // output-tile width: multiple of 32, <= 256; 0 = chosen by gemm_plan (wave fitting)
+  int occ = 0;              // CTAs per SM: 0 = chosen by gemm_plan, 1, or 2 (block_n <= 128 only)
   int pair = 0;             // 0 = default (CTA pairs, tcgen05 cta_group::2), 1 = single-CTA form, 2 = pairs
   Epilogue ep;
 };

@@ -39,15 +39,25 @@ namespace {
 constexpr int BM = 128;                       // rows per CTA
 constexpr int BK = 64;                        // K elements per stage (one 128-byte swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
-constexpr int NUM_THREADS = 384;              // 12 warps: producer, mma, alloc, spare, 8 epilogue
-constexpr int EPI_WARPS = 8;
 constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;               // TMEM columns per accumulator stage
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;          // per-warp 32 rows x 128 B staging boxes (32 KB)
 constexpr int COLVEC_BYTES = 2 * 4 * 256 * 4;              // per-tile bias/scale/slope vectors, double-buffered (8 KB)
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
-constexpr int SMEM_LIMIT = 227 * 1024;
+
+// OCC = CTAs resident per SM.  OCC 1: 8 epilogue warps, all 512 TMEM columns (BN <= 256), 227 KB of smem.
+// OCC 2: two independent CTAs per SM, each with its own TMA producer and MMA-issuing thread, 4 epilogue warps,
+// 256 TMEM columns (BN <= 128) and <= 113 KB of smem.  A single thread sustains one tcgen05.mma per ~92 clk
+// whatever its N (tools/micro/mma_bench.cu), so narrow tiles (N = 64/128 convolutions) only fill the tensor pipe
+// with two issuers per SM.
+template <int OCC>
+struct Occ {
+  static constexpr int EPI_WARPS = OCC == 2 ? 4 : 8;
+  static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;    // producer, mma, alloc, spare + epilogue warps
+  static constexpr int TMEM_COLS = 512 / OCC;
+  static constexpr int ACC_STRIDE = 256 / OCC;                // TMEM columns per accumulator stage
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;    // per-warp 32 rows x 128 B staging boxes
+  static constexpr int SMEM_LIMIT = OCC == 2 ? 113 * 1024 : 227 * 1024;
+  static constexpr int HSTRIDE = EPI_WARPS / 4;               // column-box interleave between epilogue warp sets
+};
 
 struct KernelParams {
   long long M;
@@ -72,10 +82,16 @@ struct KernelParams {
 
 // ACT (ACT_*), RES (residual add), S2 (second PReLU), SCALE (per-column scale) and OUTF32 (fp32 output and
 // residual, else bf16) are compile-time when >= 0 and read from the Epilogue struct when -1.
-template <int PAIR, int ACT, int RES, int S2, int SCALE, int OUTF32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int PAIR, int OCC, int ACT, int RES, int S2, int SCALE, int OUTF32>
+__global__ void __launch_bounds__(Occ<OCC>::NUM_THREADS, OCC)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, const KernelParams p) {
+  constexpr int EPI_WARPS = Occ<OCC>::EPI_WARPS;
+  constexpr int NUM_THREADS = Occ<OCC>::NUM_THREADS;
+  constexpr int TMEM_COLS = Occ<OCC>::TMEM_COLS;
+  constexpr int ACC_STRIDE = Occ<OCC>::ACC_STRIDE;
+  constexpr int EPI_STAGE_BYTES = Occ<OCC>::EPI_STAGE_BYTES;
+  constexpr int HSTRIDE = Occ<OCC>::HSTRIDE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -232,16 +248,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // per-column epilogue vectors of this tile -> smem while the main loop runs: every CTA reads the same few
       // cache lines at the same moment; from global inside the box loop that costs ~1 us of L2 queueing per box
       float* cv = colvec + acc * 1024;
-      {
-        const int c = threadIdx.x - 128;
+      for (int c = threadIdx.x - 128; c < 256; c += 32 * EPI_WARPS) {
         const int gc = n_blk * BN + c;
         const bool ok = c < BN && gc < p.N;
         cv[c] = (ok && ep.col_bias != nullptr) ? __ldg(ep.col_bias + gc) : 0.f;
         cv[256 + c] = (ok && ep.col_scale != nullptr) ? __ldg(ep.col_scale + gc) : 1.f;
         cv[512 + c] = (ok && ep.slope1 != nullptr) ? __ldg(ep.slope1 + gc) : 1.f;
         cv[768 + c] = (ok && ep.slope2 != nullptr) ? __ldg(ep.slope2 + gc) : 1.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -259,7 +274,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const bool live = store && !zero;
         const int nboxes = (BN + box_cols - 1) / box_cols;
 #pragma unroll 1
-        for (int bx = half; bx < nboxes; bx += 2) {
+        for (int bx = half; bx < nboxes; bx += HSTRIDE) {
           const int cbase = bx * box_cols;                 // column offset inside the tile
           uint32_t packed[32];
 #pragma unroll
@@ -354,7 +369,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               for (int j = 0; j < 16; ++j) packed[sub * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
             }
           }
-          if (bx + 2 >= nboxes) {
+          if (bx + HSTRIDE >= nboxes) {
             // this warp's last TMEM read of the accumulator stage: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
@@ -395,11 +410,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int c4 = lane & 7, rsub = lane >> 3;
         const int nchunks = BN / 32;
 #pragma unroll 1
-        for (int ch = half; ch < nchunks; ch += 2) {
+        for (int ch = half; ch < nchunks; ch += HSTRIDE) {
           uint32_t rawv[32];
           tmem_ld_32x32(taddr + ch * 32, rawv);
           tmem_ld_wait();
-          if (ch + 2 >= nchunks) {
+          if (ch + HSTRIDE >= nchunks) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -565,14 +580,20 @@ int default_pair() {
 
 // modelled cycles of one launch (measured on B200, tools/micro/mma_bench.cu + tools/gemm_sweep.py): one
 // tcgen05.mma (128 rows per CTA, K = 16) costs max(92, BN/2) clk from a single issuing thread, a k-block of four
-// costs that plus ~170 clk of barrier handling; tiles run in whole waves over the work units.
-double model_cycles(long long M, int N, int num_kb, int bn, int pair, int sms) {
+// costs that plus ~170 clk of barrier handling; `occ` CTAs on an SM issue independently but share the tensor
+// pipe (4 * BN/2 clk per k-block each) and the L2->SM operand stream (~53 B/clk/SM).  Tiles run in whole waves.
+double model_cycles(long long M, int N, int num_kb, int bn, int pair, int occ, int sms) {
   const long long mt = (M + (long long)BM * pair - 1) / ((long long)BM * pair);
   const long long nt = (N + bn - 1) / bn;
-  const long long units = sms / pair;
+  const long long units = (long long)sms * occ / pair;
   const long long rounds = (mt * nt + units - 1) / units;
   const double mma = bn / 2.0 > 92.0 ? bn / 2.0 : 92.0;
-  const double per_tile = num_kb * (4.0 * mma + 170.0) + 400.0;
+  double kblock = 4.0 * mma + 170.0;
+  const double pipe = occ * 4.0 * (bn / 2.0);
+  const double l2 = occ * (double)(A_STAGE_BYTES + (bn / pair) * BK * 2) / 80.0;
+  if (pipe > kblock) kblock = pipe;
+  if (l2 > kblock) kblock = l2;
+  const double per_tile = num_kb * kblock + 400.0;
   return rounds * per_tile + 8.0 * bn + 2500.0;          // + exposed last epilogue + launch
 }
 
@@ -595,17 +616,32 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
   int pair = pr.pair ? pr.pair : default_pair();
   if (sms < 2) pair = 1;
   int bn = pr.block_n;
-  if (bn == 0) {
+  int occ = pr.occ;
+  static int occ_env = -1;
+  if (occ_env < 0) { const char* ev = std::getenv("AVH_GEMM_OCC"); occ_env = ev ? std::atoi(ev) : 0; }
+  if (occ == 0) occ = occ_env;
+  if (pair == 2) occ = 1;
+  {
     double best = 1e30;
+    int best_bn = bn, best_occ = occ ? occ : 1;
     const int step = pr.ep.c_fp32 ? 32 : 64;      // the TMA epilogue stores 128-byte boxes
-    for (int c = step; c <= 256; c += step) {
-      if (c > ((pr.N + step - 1) / step) * step) break;
-      const double t = model_cycles(pr.M, pr.N, pr.num_kb, c, pair, sms);
-      if (t < best) { best = t; bn = c; }
+    for (int oc = 1; oc <= 2; ++oc) {
+      if (occ != 0 && oc != occ) continue;
+      if (oc == 2 && pair == 2) continue;
+      for (int c = step; c <= 256 / oc; c += step) {
+        if (bn != 0 && c != bn) continue;
+        if (bn == 0 && c > ((pr.N + step - 1) / step) * step) break;
+        const double t = model_cycles(pr.M, pr.N, pr.num_kb, c, pair, oc, sms);
+        if (t < best) { best = t; best_bn = c; best_occ = oc; }
+      }
     }
+    if (bn == 0) bn = best_bn;
+    occ = (bn <= 128) ? best_occ : 1;
+    if (bn == 0) { bn = 64; occ = 1; }
   }
   plan->prob.block_n = bn;
   plan->prob.pair = pair;
+  plan->prob.occ = occ;
   if (encode_2d(&plan->tma_a, pr.A, pr.a_rows, pr.a_cols, pr.lda, BM)) return 1;
   if (encode_2d(&plan->tma_b, pr.B, pr.b_rows, pr.b_cols, pr.ldb, bn / pair)) return 1;
   // TMA epilogue whenever tile rows map 1:1 onto output rows (Linear layers, implicit 3x3 convs, stem): plain
@@ -634,16 +670,18 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
   const long long mt = (pr.M + (long long)BM * pair - 1) / ((long long)BM * pair);
   const long long nt = (pr.N + bn - 1) / bn;
   const long long tiles = mt * nt;
-  const long long units = sms / pair;
+  const long long units = (long long)sms * occ / pair;
   plan->grid = (int)(tiles < units ? tiles : units) * pair;
   const int stage_bytes = A_STAGE_BYTES + (bn / pair) * BK * 2;
   const int ktab_bytes = pr.ktable != nullptr ? ((pr.num_kb * 16 + 1023) / 1024) * 1024 : 0;
-  int stages = (SMEM_LIMIT - 1024 - EPI_STAGE_BYTES - COLVEC_BYTES - ktab_bytes - BAR_BYTES) / stage_bytes;
+  const int smem_limit = occ == 2 ? Occ<2>::SMEM_LIMIT : Occ<1>::SMEM_LIMIT;
+  const int epi_bytes = occ == 2 ? Occ<2>::EPI_STAGE_BYTES : Occ<1>::EPI_STAGE_BYTES;
+  int stages = (smem_limit - 1024 - epi_bytes - COLVEC_BYTES - ktab_bytes - BAR_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   AVH_CHECK(stages >= 2, "tile too large for shared memory");
   plan->stages = stages;
   plan->ktab_bytes = ktab_bytes;
-  plan->smem = 1024 + (size_t)stages * stage_bytes + EPI_STAGE_BYTES + COLVEC_BYTES + ktab_bytes + BAR_BYTES;
+  plan->smem = 1024 + (size_t)stages * stage_bytes + epi_bytes + COLVEC_BYTES + ktab_bytes + BAR_BYTES;
   return 0;
 }
 
@@ -667,7 +705,8 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   kp.ep = pr.ep;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  const int occ = pr.occ == 2 ? 2 : 1;
+  cfg.blockDim = dim3(occ == 2 ? Occ<2>::NUM_THREADS : Occ<1>::NUM_THREADS);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -681,28 +720,40 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   const int act = e.act, res = e.R != nullptr, s2 = e.slope2 != nullptr, scl = e.col_scale != nullptr, f32 = e.c_fp32;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, KernelParams);
   KernelFn fn = nullptr;
-#define AVH_SPEC(A, R, S, C, F) \
-  if (fn == nullptr && pair == 1 && act == A && res == R && s2 == S && scl == C && f32 == F) fn = gemm_kernel<1, A, R, S, C, F>;
-  AVH_SPEC(ACT_NONE, 0, 0, 0, 0)      // Linear + bias -> bf16                  (qkv, modality projections)
-  AVH_SPEC(ACT_NONE, 0, 0, 0, 1)      // Linear + bias -> fp32                  (post_extract_proj, fp32 mode)
-  AVH_SPEC(ACT_GELU, 0, 0, 0, 0)      // Linear + bias + GELU -> bf16           (fc1)
-  AVH_SPEC(ACT_GELU, 0, 0, 0, 1)      //                                        (fc1, fp32 mode)
-  AVH_SPEC(ACT_NONE, 1, 0, 0, 1)      // Linear + bias + residual -> fp32       (out_proj, fc2)
-  AVH_SPEC(ACT_GELU, 1, 0, 0, 1)      // conv + bias + GELU + residual -> fp32  (positional conv)
-  AVH_SPEC(ACT_PRELU, 0, 0, 1, 0)     // conv + BN + PReLU -> bf16              (stem, block conv1)
-  AVH_SPEC(ACT_PRELU, 0, 0, 1, 1)
-  AVH_SPEC(ACT_NONE, 1, 1, 1, 0)      // conv + BN + residual + PReLU -> bf16   (block conv2)
-  AVH_SPEC(ACT_NONE, 1, 1, 1, 1)
-  AVH_SPEC(ACT_NONE, 0, 0, 1, 0)      // conv + BN -> bf16                      (downsample)
-  AVH_SPEC(ACT_NONE, 0, 0, 1, 1)
+#define AVH_SPEC(O, A, R, S, C, F)                                                                     \
+  if (fn == nullptr && pair == 1 && occ == O && act == A && res == R && s2 == S && scl == C && f32 == F) \
+    fn = gemm_kernel<1, O, A, R, S, C, F>;
+  AVH_SPEC(1, ACT_NONE, 0, 0, 0, 0)      // Linear + bias -> bf16                  (qkv, modality projections)
+  AVH_SPEC(1, ACT_NONE, 0, 0, 0, 1)      // Linear + bias -> fp32                  (post_extract_proj, fp32 mode)
+  AVH_SPEC(1, ACT_GELU, 0, 0, 0, 0)      // Linear + bias + GELU -> bf16           (fc1)
+  AVH_SPEC(1, ACT_GELU, 0, 0, 0, 1)      //                                        (fc1, fp32 mode)
+  AVH_SPEC(1, ACT_NONE, 1, 0, 0, 1)      // Linear + bias + residual -> fp32       (out_proj, fc2)
+  AVH_SPEC(1, ACT_GELU, 1, 0, 0, 1)      // conv + bias + GELU + residual -> fp32  (positional conv)
+  AVH_SPEC(1, ACT_PRELU, 0, 0, 1, 0)     // conv + BN + PReLU -> bf16              (stem, block conv1)
+  AVH_SPEC(1, ACT_PRELU, 0, 0, 1, 1)
+  AVH_SPEC(1, ACT_NONE, 1, 1, 1, 0)      // conv + BN + residual + PReLU -> bf16   (block conv2)
+  AVH_SPEC(1, ACT_NONE, 1, 1, 1, 1)
+  AVH_SPEC(1, ACT_NONE, 0, 0, 1, 0)      // conv + BN -> bf16                      (downsample)
+  AVH_SPEC(1, ACT_NONE, 0, 0, 1, 1)
+  AVH_SPEC(2, ACT_NONE, 0, 0, 0, 0)      // two CTAs per SM: narrow tiles
+  AVH_SPEC(2, ACT_NONE, 1, 0, 0, 1)
+  AVH_SPEC(2, ACT_GELU, 1, 0, 0, 1)
+  AVH_SPEC(2, ACT_PRELU, 0, 0, 1, 0)
+  AVH_SPEC(2, ACT_NONE, 1, 1, 1, 0)
+  AVH_SPEC(2, ACT_NONE, 0, 0, 1, 0)
 #undef AVH_SPEC
-  if (fn == nullptr) fn = pair == 2 ? gemm_kernel<2, -1, -1, -1, -1, -1> : gemm_kernel<1, -1, -1, -1, -1, -1>;
+  if (fn == nullptr) {
+    if (pair == 2) fn = gemm_kernel<2, 1, -1, -1, -1, -1, -1>;
+    else if (occ == 2) fn = gemm_kernel<1, 2, -1, -1, -1, -1, -1>;
+    else fn = gemm_kernel<1, 1, -1, -1, -1, -1, -1>;
+  }
   static std::mutex mu;
   static std::set<const void*> configured;
   {
     std::lock_guard<std::mutex> lk(mu);
     if (configured.find(reinterpret_cast<const void*>(fn)) == configured.end()) {
-      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       occ == 2 ? Occ<2>::SMEM_LIMIT : Occ<1>::SMEM_LIMIT));
       configured.insert(reinterpret_cast<const void*>(fn));
     }
   }

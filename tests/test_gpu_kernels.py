@@ -14,15 +14,18 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def gemm(A, B, bias=None, gelu=False, R=None, c_fp32=True, block_n=0, pair=0):
+def gemm(A, B, bias=None, gelu=False, R=None, c_fp32=True, block_n=0, pair=0, occ=0, inplace=False):
     M, K = A.shape
     N = B.shape[0]
     C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if c_fp32 else torch.bfloat16)
+    if inplace:          # x += A B^T + bias: residual and output are the same buffer (TMA reduce-add epilogue)
+        C = R.clone()
+        R = C
     vp = ctypes.c_void_p
     _lib.check(_lib.load().avh_gemm_bf16(
         vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()) if bias is not None else None, int(gelu),
         vp(R.data_ptr()) if R is not None else None, int(R is not None and R.dtype == torch.float32),
-        vp(C.data_ptr()), int(c_fp32), block_n, pair, vp(torch.cuda.current_stream().cuda_stream)))
+        vp(C.data_ptr()), int(c_fp32), block_n, pair, occ, vp(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     return C
 
@@ -62,6 +65,36 @@ def test_gemm_fused_epilogue_bias_gelu_residual_bf16_out():
     Cb = gemm(A, B, bias=bias, gelu=True, R=Rb, c_fp32=False)
     refb = (torch.nn.functional.gelu(A.float() @ B.float().t() + bias) + Rb.float())
     assert (Cb.float() - refb).abs().max().item() < 3e-2      # bf16 output rounding
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (1000, 128, 576, 64), (40000, 64, 576, 64), (30000, 128, 1152, 128),
+                                      (2400, 1024, 1024, 128), (500, 96, 320, 32)])
+def test_gemm_two_ctas_per_sm(M, N, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.float() @ B.float().t() + bias
+    C1 = gemm(A, B, bias=bias, block_n=bn, pair=1, occ=1)
+    C2 = gemm(A, B, bias=bias, block_n=bn, pair=1, occ=2)
+    assert (C1 - ref).abs().max().item() < 2e-3
+    assert torch.equal(C1, C2)
+    Cb = gemm(A, B, bias=bias, block_n=bn, pair=1, occ=2, c_fp32=False)
+    assert (Cb.float() - ref).abs().max().item() < ref.abs().max().item() * 2 ** -8 + 1e-3      # bf16 output rounding
+
+
+def test_gemm_inplace_residual_uses_reduce_add():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 2400, 1024, 512
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + A.float() @ B.float().t() + bias
+    for occ in (1, 2):
+        out = gemm(A, B, bias=bias, R=x, c_fp32=True, inplace=True, occ=occ, block_n=128 if occ == 2 else 0)
+        assert (out - ref).abs().max().item() < 2e-4
+    assert (gemm(A, B, bias=bias, R=x, c_fp32=True) - ref).abs().max().item() < 2e-4      # out-of-place residual
 
 
 def test_gemm_many_tiles_per_cta_exercises_both_accumulator_stages():

@@ -1,6 +1,7 @@
 """One encoder-shaped tcgen05 GEMM launch, repeated (ncu target): python gemm_one.py <name> [pair] [reps]"""
 import ctypes, sys, os
 import torch
+OCC = int(__import__("os").environ.get("PROBE_OCC", "0"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multimodalvc_b200 import _lib
 from gemm_probe import SHAPES
@@ -13,6 +14,6 @@ for nm, M, N, K, bn, gelu, res, cf in SHAPES:
     C = torch.empty(M, N, device="cuda", dtype=torch.float32 if cf else torch.bfloat16)
     for _ in range(reps):
         _lib.check(lib.avh_gemm_bf16(vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()), gelu,
-                                     vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, vp(st)))
+                                     vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, OCC, vp(st)))
     torch.cuda.synchronize()
     print("done", nm)

@@ -2,6 +2,7 @@
 import ctypes
 import sys
 import torch
+OCC = int(__import__("os").environ.get("PROBE_OCC", "0"))
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from multimodalvc_b200 import _lib
 
@@ -29,7 +30,7 @@ def main():
         C = torch.empty(M, N, device="cuda", dtype=torch.float32 if cf else torch.bfloat16)
         def run():
             _lib.check(lib.avh_gemm_bf16(vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()), gelu,
-                                         vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, vp(st)))
+                                         vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, OCC, vp(st)))
         for _ in range(2):
             run()
         torch.cuda.synchronize()

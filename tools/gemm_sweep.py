@@ -27,7 +27,7 @@ def main():
             C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
             def run():
                 _lib.check(lib.avh_gemm_bf16(vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, None, 0, None, 0,
-                                             vp(C.data_ptr()), 0, bn, pair, vp(st)))
+                                             vp(C.data_ptr()), 0, bn, pair, 0, vp(st)))
             for _ in range(3): run()
             torch.cuda.synchronize()
             lib.avh_gemm_set_trace(vp(trace.data_ptr())); trace.zero_(); run(); torch.cuda.synchronize()

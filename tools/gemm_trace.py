@@ -1,6 +1,7 @@
 """Device-side timeline of one tcgen05 GEMM launch (globaltimer stamps per CTA)."""
 import ctypes, sys, os
 import torch
+OCC = int(__import__("os").environ.get("PROBE_OCC", "0"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multimodalvc_b200 import _lib
 from gemm_probe import SHAPES
@@ -23,7 +24,7 @@ def main():
         C = torch.empty(M, N, device="cuda", dtype=torch.float32 if cf else torch.bfloat16)
         def run():
             _lib.check(lib.avh_gemm_bf16(vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()) if use_bias else None, gelu,
-                                         vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, vp(st)))
+                                         vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, OCC, vp(st)))
         for _ in range(3): run()
         torch.cuda.synchronize()
         lib.avh_gemm_set_trace(vp(trace.data_ptr()))
