@@ -164,7 +164,7 @@ def main():
 
     # ---- model: random-init Large weights (same seed on every rank), bf16 compute
     torch.manual_seed(1234)
-    model = AVHubertModel(AVHubertConfig.named("large"))
+    model = AVHubertModel(AVHubertConfig.named("large", frontend_chunk_frames=int(os.environ.get("AVH_BENCH_CHUNK", "0"))))
     model.remove_pretraining_modules()
     model = model.to(dev, torch.bfloat16).eval()
 

@@ -560,7 +560,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   // ========================================================================== lip frontend
   if (plan->has_video) {
     // chunks of whole clips (the stem's temporal taps are row shifts inside a clip-padded layout)
-    const int target = c.frontend_chunk_frames > 0 ? c.frontend_chunk_frames : 640;
+    const int target = c.frontend_chunk_frames > 0 ? c.frontend_chunk_frames : 2400;
     int CB = std::max(1, target / T);
     CB = (B + ((B + CB - 1) / CB) - 1) / ((B + CB - 1) / CB);       // even split over ceil(B/CB) chunks
     const int CF = CB * T;

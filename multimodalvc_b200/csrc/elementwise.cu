@@ -157,46 +157,56 @@ __global__ void split_rows_kernel(const float* __restrict__ in, long long ld, __
 // clip-local frame (bl,t) and output pixel (ho,wo), out row ((bl*(T+2)+t)*1936 + ho*44+wo) holds the 49 taps
 // x[t, 2ho+kh-3, 2wo+kw-3] at column kh*7+kw (columns 49..63 zero).  The 5 temporal taps are then row shifts
 // of +-1936 rows in the tcgen05 GEMM; the two gap frames after every clip are never written and stay zero.
-__global__ void stem_patches_kernel(const void* __restrict__ video, int in_dt, int T, int b0, int nb,
-                                    __nv_bfloat16* __restrict__ out, int planes) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-element chunk each
-  const long long total = (long long)nb * T * 1936 * 8;
-  if (i >= total) return;
-  const int chunk = (int)(i & 7);
-  const long long row = i >> 3;
-  const int pix = (int)(row % 1936);
-  const long long ft = row / 1936;
+// One CTA = one frame x 4 output rows (176 pixels): the 13 input rows it needs are staged in smem (zero borders
+// included, so the gather has no bounds checks), then every thread assembles 16-byte chunks of 8 taps.
+constexpr int SP_ROWS = 4;                 // output rows per CTA
+constexpr int SP_IN_ROWS = 2 * SP_ROWS + 5;   // 13 input rows
+constexpr int SP_PITCH = 96;               // 88 columns + 3 zero columns left + 5 right
+__global__ void __launch_bounds__(256)
+stem_patches_kernel(const void* __restrict__ video, int in_dt, int T, int b0, int nb,
+                    __nv_bfloat16* __restrict__ out, int planes) {
+  __shared__ float sIn[SP_IN_ROWS][SP_PITCH];
+  const int rg = blockIdx.x % 11;                       // row group: output rows 4*rg .. 4*rg+3
+  const long long ft = blockIdx.x / 11;                 // clip-local frame index over the chunk
   const int t = (int)(ft % T);
   const int bl = (int)(ft / T);
-  const int ho = pix / 44, wo = pix - ho * 44;
   const long long src = ((long long)(b0 + bl) * T + t) * 7744;
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = chunk * 8 + j;
+  const int h0 = 2 * (rg * SP_ROWS) - 3;                // first input row staged
+  for (int i = threadIdx.x; i < SP_IN_ROWS * SP_PITCH; i += 256) {
+    const int r = i / SP_PITCH, c = i - r * SP_PITCH;
+    const int hh = h0 + r, ww = c - 3;
     float x = 0.f;
-    if (k < 49) {
-      const int kh = k / 7, kw = k - kh * 7;
-      const int hh = 2 * ho + kh - 3, ww = 2 * wo + kw - 3;
-      if (hh >= 0 && hh < 88 && ww >= 0 && ww < 88) x = load_any(video, in_dt, src + hh * 88 + ww);
-    }
-    v[j] = x;
+    if (hh >= 0 && hh < 88 && ww >= 0 && ww < 88) x = load_any(video, in_dt, src + hh * 88 + ww);
+    sIn[r][c] = x;
   }
-  __nv_bfloat162 h[4];
+  __syncthreads();
+  const long long orow0 = ((long long)bl * (T + 2) + t) * 1936 + (long long)rg * SP_ROWS * 44;
+  for (int i = threadIdx.x; i < SP_ROWS * 44 * 8; i += 256) {
+    const int chunk = i & 7;
+    const int pl = i >> 3;                              // pixel inside the CTA's 4 rows
+    const int hol = pl / 44, wo = pl - hol * 44;
+    float v[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-  const long long orow = ((long long)bl * (T + 2) + t) * 1936 + pix;
-  uint4* o = reinterpret_cast<uint4*>(out + orow * (64ll * planes));
-  o[chunk] = *reinterpret_cast<uint4*>(h);
-  if (planes > 1) {
-    uint4 m;
-    uint32_t* mp = reinterpret_cast<uint32_t*>(&m);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f2 = __bfloat1622float2(h[j]);
-      mp[j] = pack_bf16(v[2 * j] - f2.x, v[2 * j + 1] - f2.y);
+    for (int j = 0; j < 8; ++j) {
+      const int k = chunk * 8 + j;
+      const int kh = k / 7, kw = k - kh * 7;
+      v[j] = k < 49 ? sIn[2 * hol + kh][2 * wo + kw] : 0.f;
     }
-    o[8 + chunk] = m;
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    uint4* o = reinterpret_cast<uint4*>(out + (orow0 + pl) * (64ll * planes));
+    o[chunk] = *reinterpret_cast<uint4*>(h);
+    if (planes > 1) {
+      uint4 m;
+      uint32_t* mp = reinterpret_cast<uint32_t*>(&m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f2 = __bfloat1622float2(h[j]);
+        mp[j] = pack_bf16(v[2 * j] - f2.x, v[2 * j + 1] - f2.y);
+      }
+      o[8 + chunk] = m;
+    }
   }
 }
 
@@ -340,10 +350,10 @@ int launch_split_rows(const float* in, long long ld, void* out, int planes, long
 
 int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, void* out, int planes,
                         cudaStream_t stream) {
-  const long long n = (long long)nb * T * 1936 * 8;
-  if (n <= 0) return 0;
-  stem_patches_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(video, in_dt, T, b0, nb,
-                                                              reinterpret_cast<__nv_bfloat16*>(out), planes);
+  const long long nblk = (long long)nb * T * 11;
+  if (nblk <= 0) return 0;
+  stem_patches_kernel<<<(unsigned)nblk, 256, 0, stream>>>(video, in_dt, T, b0, nb,
+                                                          reinterpret_cast<__nv_bfloat16*>(out), planes);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

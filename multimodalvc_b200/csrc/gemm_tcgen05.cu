@@ -15,7 +15,7 @@
 //               Re-mapped outputs (stride-2 conv rows, positional conv) take a per-thread path that transposes
 //               32x32 chunks through smem so that global accesses are row-contiguous.
 // BN is a run-time multiple of 32 (<= 256) chosen per problem by a measured cost model (whole waves over the
-// 148 SMs; one k-block costs ~max(4*92, 2*BN) + 170 clk whatever the tile width).  The K loop walks a table of
+// 148 SMs; one k-block costs ~max(4*55, 2*BN) + 170 clk).  The K loop walks a table of
 // (A column, A row shift, B column) steps, so the same kernel runs plain Linear layers, shifted-row
 // implicit-GEMM convolutions (3x3 trunk convs, the 5 temporal taps of the stem, the 128 taps of the grouped
 // positional conv) and split-precision (bf16 hi/mid plane) fp32-faithful products.  The epilogue variant is a
@@ -45,9 +45,9 @@ constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 16;
 
 // OCC = CTAs resident per SM.  OCC 1: 8 epilogue warps, all 512 TMEM columns (BN <= 256), 227 KB of smem.
 // OCC 2: two independent CTAs per SM, each with its own TMA producer and MMA-issuing thread, 4 epilogue warps,
-// 256 TMEM columns (BN <= 128) and <= 113 KB of smem.  A single thread sustains one tcgen05.mma per ~92 clk
-// whatever its N (tools/micro/mma_bench.cu), so narrow tiles (N = 64/128 convolutions) only fill the tensor pipe
-// with two issuers per SM.
+// 256 TMEM columns (BN <= 128) and <= 113 KB of smem.  One elected lane sustains one tcgen05.mma per ~53 clk
+// (tools/micro/mma_bench.cu), i.e. it saturates the tensor pipe for N >= 128 but only 59 % of it for N = 64:
+// narrow tiles (stem, layer1 convolutions) want two issuers per SM.
 template <int OCC>
 struct Occ {
   static constexpr int EPI_WARPS = OCC == 2 ? 4 : 8;
@@ -148,23 +148,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) AVH_TRACE(1);
 
+  // Producer and MMA warps run their loops with ALL lanes (warp-uniform operands stay in uniform registers) and
+  // elect one lane only for the issue itself.  A loop entered by a single lane makes the compiler wrap every
+  // UTCHMMA / UTMALDG in an ELECT/BRA.U.ANY "uniformisation" loop: ~105 clk per tcgen05.mma instead of ~53
+  // (tools/micro/mma_bench.cu modes 0 vs 6), which capped every tile narrower than 256 columns.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int m_blk = tile % p.num_m_blk;
-        const int n_blk = tile / p.num_m_blk;
-        const int m0 = (m_blk * PAIR + cta_rank) * BM;
-        const int n0 = n_blk * BN + cta_rank * (BN / PAIR);
-        const int a_col_base = p.a_col_nblk != nullptr ? __ldg(p.a_col_nblk + n_blk) : n_blk * p.a_col_per_nblk;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          int4 e;
-          if (p.ktable != nullptr) e = ktab[kb];
-          else e = make_int4(kb * BK, 0, kb * BK, 0);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const int m_blk = tile % p.num_m_blk;
+      const int n_blk = tile / p.num_m_blk;
+      const int m0 = (m_blk * PAIR + cta_rank) * BM;
+      const int n0 = n_blk * BN + cta_rank * (BN / PAIR);
+      const int a_col_base = p.a_col_nblk != nullptr ? __ldg(p.a_col_nblk + n_blk) : n_blk * p.a_col_per_nblk;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        int4 e;
+        if (p.ktable != nullptr) e = ktab[kb];
+        else e = make_int4(kb * BK, 0, kb * BK, 0);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
           if (PAIR == 2) {
             tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
@@ -174,13 +178,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
           }
           if (tile == unit && kb == 0) AVH_TRACE(2);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (leader) {
       const uint32_t idesc = umma_idesc_bf16(BM * PAIR, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -194,23 +199,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (it == 0 && kb == 0) AVH_TRACE(3);
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
+          if (elect_one()) {
+            if (it == 0 && kb == 0) AVH_TRACE(3);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-            if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+              if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (PAIR == 2) umma_commit_pair(&empty_bar[stage]);   // smem slot reusable in BOTH CTAs
+            else umma_commit(&empty_bar[stage]);
           }
-          if (PAIR == 2) umma_commit_pair(&empty_bar[stage]);   // smem slot reusable in BOTH CTAs
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (PAIR == 2) umma_commit_pair(&tmem_full[acc]);        // accumulator complete -> both epilogues
-        else umma_commit(&tmem_full[acc]);
-        if (it == 0) AVH_TRACE(4);
-        AVH_TRACE(5);
+        if (elect_one()) {
+          if (PAIR == 2) umma_commit_pair(&tmem_full[acc]);        // accumulator complete -> both epilogues
+          else umma_commit(&tmem_full[acc]);
+          if (it == 0) AVH_TRACE(4);
+          AVH_TRACE(5);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -578,17 +589,17 @@ int default_pair() {
   return v;
 }
 
-// modelled cycles of one launch (measured on B200, tools/micro/mma_bench.cu + tools/gemm_sweep.py): one
-// tcgen05.mma (128 rows per CTA, K = 16) costs max(92, BN/2) clk from a single issuing thread, a k-block of four
-// costs that plus ~170 clk of barrier handling; `occ` CTAs on an SM issue independently but share the tensor
-// pipe (4 * BN/2 clk per k-block each) and the L2->SM operand stream (~53 B/clk/SM).  Tiles run in whole waves.
+// modelled cycles of one launch (measured on B200, tools/micro/mma_bench.cu + tools/gemm_sweep.py): a k-block
+// (4 tcgen05.mma of 128 x BN x 16 + barrier handling) costs max(415, 2*BN) clk — 98 % of the tensor pipe at
+// BN >= 224; `occ` CTAs on an SM issue independently but share the tensor pipe and the L2->SM operand stream
+// (~80 B/clk/SM).  Tiles run in whole waves.
 double model_cycles(long long M, int N, int num_kb, int bn, int pair, int occ, int sms) {
   const long long mt = (M + (long long)BM * pair - 1) / ((long long)BM * pair);
   const long long nt = (N + bn - 1) / bn;
   const long long units = (long long)sms * occ / pair;
   const long long rounds = (mt * nt + units - 1) / units;
-  const double mma = bn / 2.0 > 92.0 ? bn / 2.0 : 92.0;
-  double kblock = 4.0 * mma + 170.0;
+  double kblock = 415.0;                                   // issue + barrier handling floor of one k-block
+  if (2.0 * bn > kblock) kblock = 2.0 * bn;                // tensor pipe: 4 MMAs of BN/2 clk
   const double pipe = occ * 4.0 * (bn / 2.0);
   const double l2 = occ * (double)(A_STAGE_BYTES + (bn / pair) * BK * 2) / 80.0;
   if (pipe > kblock) kblock = pipe;
@@ -701,6 +712,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   kp.a_col_nblk = pr.a_col_nblk;
   kp.ktable = reinterpret_cast<const int4*>(pr.ktable);
   kp.c_mode = plan.c_mode;
+
   kp.trace = g_trace;
   kp.ep = pr.ep;
   cudaLaunchConfig_t cfg = {};

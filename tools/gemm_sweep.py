@@ -35,11 +35,11 @@ def main():
             lib.avh_gemm_set_trace(None)
             t = trace.view(148, 16).cpu()
             lead = t[:, 3] > 0
-            ml = (t[lead, 5] - t[lead, 3]).double().mean().item() / (REP * K // 64)
-            span = (t[t[:, 0] > 0].max() - t[t[:, 0] > 0, 0].min()).item() / 1e3
+            ml = (t[lead, 5] - t[lead, 3]).double().mean().item() / (REP * K // 64)      # SM clocks per k-block
+            ghz = float(c) / 1e3 if c.replace(".", "").isdigit() else 1.9
             fl = 2.0 * 128 * pair * bn * 64
-            print(f"pair={pair} BN={bn}: {ml:.1f} ns/k-block  -> {fl/ml/1e3:.2f} TFLOP/s per unit, "
-                  f"{fl/ml/1e3*148/pair:.0f} TFLOP/s chip; span {span:.0f} us; sm clock {c} MHz", flush=True)
+            print(f"pair={pair} BN={bn}: {ml:.0f} clk/k-block ({ml/ghz:.0f} ns at {c} MHz) -> "
+                  f"{fl/(ml/ghz)/1e3*148/pair:.0f} TFLOP/s chip, {100*2.0*bn/ml:.0f}% of the tensor pipe", flush=True)
 
 if __name__ == "__main__":
     main()

@@ -55,6 +55,27 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int mode, int iters, long
       const long long t1 = clock64();
       if (w == 0) out[blockIdx.x] = (t1 - t0) / 2;     // two issuers: report clk per MMA of the pair
     }
+  } else if (mode == 6 || mode == 7) {
+    // canonical form: the WHOLE warp runs the loop with warp-uniform operands, one elected lane issues
+    if (warp == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(128 * PAIR, N);
+      const uint32_t a = smem_u32(smem), b = smem_u32(smem + 16384);
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+        const uint64_t ad = umma_desc_sw128(a), bd = umma_desc_sw128(b);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, 1);
+          if (mode == 7) umma_commit(&bar);       // a commit per k-block, like the GEMM (barrier never waited here)
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+      if (mode == 6) mbar_wait(&bar, 0);
+      const long long t1 = clock64();
+      if (lane == 0) out[blockIdx.x] = t1 - t0;
+    }
   } else if (warp == 0 && lane == 0 && leader) {
     const uint32_t idesc = umma_idesc_bf16(128 * PAIR, N);
     const uint32_t a = smem_u32(smem), b = smem_u32(smem + 16384);
@@ -107,7 +128,7 @@ int main() {
   long long* d_out;
   cudaMalloc(&d_out, 148 * 8);
   const int iters = 4096;
-  for (int mode : {0, 4, 5})
+  for (int mode : {0, 6})
     for (int N : {32, 64, 128, 160, 192, 256}) run<1>(N, mode, iters, d_out);
   return 0;
 }
