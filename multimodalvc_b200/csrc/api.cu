@@ -33,6 +33,15 @@ void set_last_error(const std::string& msg) { g_err = msg; }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("AVH_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 int device_sm_count() {
   static int cached_dev = -1, cached_n = 148;
   int dev = 0;

@@ -60,6 +60,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   constexpr int BQ = NW * 16;
   constexpr int NT = NW * 32;
   constexpr int NJ = BKV / 8;        // 8-key score tiles per chunk
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem_att[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sK = sQ + BQ * PITCH;
@@ -200,15 +202,16 @@ int launch_att_t(const void* qkv, const unsigned char* kpm, void* out, int B, in
     configured = true;
   }
   dim3 grid((T + BQ - 1) / BQ, H, B);
-  attention_kernel<NW, BKV><<<grid, NW * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), kpm,
-                                                            reinterpret_cast<__nv_bfloat16*>(out), T, D);
-  AVH_CUDA_OK(cudaGetLastError());
+  AVH_CUDA_OK(launch_pdl(attention_kernel<NW, BKV>, grid, dim3(NW * 32), smem, stream,
+                         reinterpret_cast<const __nv_bfloat16*>(qkv), kpm, reinterpret_cast<__nv_bfloat16*>(out), T, D));
   return 0;
 }
 
 // fp32 reference-precision attention for the split-precision (fp32) mode: one warp per query row.
 __global__ void attention_f32_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ kpm,
                                      float* __restrict__ out, int T, int D, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sp[];                 // [warps][T] probabilities
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -259,8 +262,8 @@ int launch_attention(const void* qkv, const unsigned char* kpm, void* out, int B
     dim3 grid((T + nw - 1) / nw, H, B);
     const size_t smem = (size_t)nw * T * sizeof(float);
     AVH_CHECK(smem <= 48 * 1024, "sequence too long for the fp32 attention kernel");
-    attention_f32_kernel<<<grid, nw * 32, smem, stream>>>(reinterpret_cast<const float*>(qkv), kpm,
-                                                         reinterpret_cast<float*>(out), T, D, H);
+    AVH_CUDA_OK(launch_pdl(attention_f32_kernel, grid, dim3(nw * 32), smem, stream,
+                           reinterpret_cast<const float*>(qkv), kpm, reinterpret_cast<float*>(out), T, D, H));
   } else {
     // tile shapes: whole-clip tiles for short clips (T <= 160: one CTA per (batch, head)), else 128 x 128
     int rc;

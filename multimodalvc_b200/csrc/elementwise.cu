@@ -33,6 +33,8 @@ __global__ void layernorm_kernel(const void* __restrict__ in, int in_dt, long lo
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  float* __restrict__ out_f32, void* __restrict__ out_lp, int lp_dt,
                                  const unsigned char* __restrict__ row_zero, long long rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -62,6 +64,8 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float eps, float* __restrict__ out_f32, void* __restrict__ out_lp,
                                          int lp_dt, const unsigned char* __restrict__ row_zero, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int C = VEC * 128;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -71,10 +75,25 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
   float4 v[VEC];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i] = x[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < VEC; ++i) v[i] = x[lane + 32 * i];
+  // affine parameters in flight together with the row (they are needed last; fetching them in the output loop
+  // added a second exposed L2 round trip per launch)
+  float4 g[VEC], b[VEC];
+  if (gamma != nullptr) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+      b[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      g[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) * (1.f / C);
   float q = 0.f;
 #pragma unroll
@@ -86,16 +105,11 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int c4 = lane + 32 * i;
-    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gamma != nullptr) {
-      g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-      b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-    }
     float4 o;
-    o.x = v[i].x * rstd * g.x + b.x;
-    o.y = v[i].y * rstd * g.y + b.y;
-    o.z = v[i].z * rstd * g.z + b.z;
-    o.w = v[i].w * rstd * g.w + b.w;
+    o.x = v[i].x * rstd * g[i].x + b[i].x;
+    o.y = v[i].y * rstd * g[i].y + b[i].y;
+    o.z = v[i].z * rstd * g[i].z + b[i].z;
+    o.w = v[i].w * rstd * g[i].w + b[i].w;
     if (zero) o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * C)[c4] = o;
     if (out_lp != nullptr) {
@@ -116,6 +130,8 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
 // ------------------------------------------------------------------------------------- layout / dtype
 __global__ void bct_to_rows_kernel(const void* __restrict__ in, int in_dt, long long sb, long long sc, long long st,
                                    int B, int C, int T, void* __restrict__ out, int out_dt, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * T * C) return;
   const int c = (int)(i % C);
@@ -127,6 +143,8 @@ __global__ void bct_to_rows_kernel(const void* __restrict__ in, int in_dt, long 
 
 __global__ void convert_kernel(const void* __restrict__ in, int in_dt, void* __restrict__ out, int out_dt,
                                long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) store_lp(out, out_dt, i, load_any(in, in_dt, i));
 }
@@ -134,6 +152,8 @@ __global__ void convert_kernel(const void* __restrict__ in, int in_dt, void* __r
 // 4 consecutive columns per thread
 __global__ void split_rows_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
                                   int planes, long long rows, int cols, int T, int Tpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c4n = cols >> 2;
   if (i >= rows * c4n) return;
@@ -165,6 +185,8 @@ constexpr int SP_PITCH = 96;               // 88 columns + 3 zero columns left +
 __global__ void __launch_bounds__(256)
 stem_patches_kernel(const void* __restrict__ video, int in_dt, int T, int b0, int nb,
                     __nv_bfloat16* __restrict__ out, int planes) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sIn[SP_IN_ROWS][SP_PITCH];
   const int rg = blockIdx.x % 11;                       // row group: output rows 4*rg .. 4*rg+3
   const long long ft = blockIdx.x / 11;                 // clip-local frame index over the chunk
@@ -227,6 +249,8 @@ __device__ __forceinline__ float4 f32x4_max(float4 a, float4 b) {
 // VT = uint4 (8 bf16) or float4 (4 fp32); CV = vectors per pixel.
 template <typename VT, int CV, bool F32>
 __global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ out, int nf, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)nf * 484 * CV) return;
   const int cv = (int)(i % CV);
@@ -257,6 +281,8 @@ __global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ 
 
 // 3x3 stride-2 pad-1 im2col from the zero-padded layout [n,H+1,W+1,C] (avhubert/resnet.py:15-17 with stride 2)
 __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int H, int W, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)n * Ho * Wo * 9 * C8;
@@ -278,6 +304,8 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict
 // AdaptiveAvgPool2d(1) (avhubert/resnet.py:90,127) over the valid pixels of the padded layout
 __global__ void avgpool_kernel(const void* __restrict__ in, void* __restrict__ out, int dt, int n, int H, int W,
                                int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * C) return;
   const int c = (int)(i % C);
@@ -295,14 +323,14 @@ inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per);
 int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* gamma, const float* beta, float eps,
                      float* out_f32, void* out_lp, int lp_dt, const unsigned char* row_zero, long long rows, int C,
                      cudaStream_t stream) {
-  const int wpb = 8;
+  const int wpb = 4;
   if (rows <= 0) return 0;
   const int grid = blocks_for(rows, wpb);
   const bool vec_ok = in_dt == DT_F32 && C % 128 == 0 && ld_in % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(in) & 15) == 0;
 #define AVH_LN_VEC(V)                                                                                            \
-  layernorm_f32_vec_kernel<V><<<grid, wpb * 32, 0, stream>>>(reinterpret_cast<const float*>(in), ld_in, gamma, \
-                                                             beta, eps, out_f32, out_lp, lp_dt, row_zero, rows)
+  AVH_CUDA_OK(launch_pdl(layernorm_f32_vec_kernel<V>, dim3(grid), dim3(wpb * 32), 0, stream,                    \
+                         reinterpret_cast<const float*>(in), ld_in, gamma, beta, eps, out_f32, out_lp, lp_dt, row_zero, rows))
   if (vec_ok && C == 768) AVH_LN_VEC(6);
   else if (vec_ok && C == 1024) AVH_LN_VEC(8);
   else if (vec_ok && C == 1536) AVH_LN_VEC(12);
@@ -310,8 +338,8 @@ int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* ga
   else if (vec_ok && C == 256) AVH_LN_VEC(2);
   else if (vec_ok && C == 128) AVH_LN_VEC(1);
   else
-    layernorm_kernel<<<grid, wpb * 32, 0, stream>>>(in, in_dt, ld_in, gamma, beta, eps, out_f32, out_lp, lp_dt,
-                                                    row_zero, rows, C);
+    AVH_CUDA_OK(launch_pdl(layernorm_kernel, dim3(grid), dim3(wpb * 32), 0, stream, in, in_dt, ld_in, gamma, beta, eps,
+                           out_f32, out_lp, lp_dt, row_zero, rows, C));
 #undef AVH_LN_VEC
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
@@ -322,7 +350,8 @@ int launch_bct_to_rows(const void* in, int in_dt, long long sb, long long sc, lo
                        void* out, int out_dt, long long ldo, cudaStream_t stream) {
   const long long n = (long long)B * C * T;
   if (n <= 0) return 0;
-  bct_to_rows_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, in_dt, sb, sc, st, B, C, T, out, out_dt, ldo);
+  AVH_CUDA_OK(launch_pdl(bct_to_rows_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, in_dt, sb, sc, st, B, C,
+                         T, out, out_dt, ldo));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -330,7 +359,7 @@ int launch_bct_to_rows(const void* in, int in_dt, long long sb, long long sc, lo
 
 int launch_convert(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
-  convert_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, in_dt, out, out_dt, n);
+  AVH_CUDA_OK(launch_pdl(convert_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, in_dt, out, out_dt, n));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -341,8 +370,8 @@ int launch_split_rows(const float* in, long long ld, void* out, int planes, long
   AVH_CHECK(cols % 4 == 0 && ld % 4 == 0, "split_rows needs 4-column granularity");
   const long long n = rows * (cols / 4);
   if (n <= 0) return 0;
-  split_rows_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, ld, reinterpret_cast<__nv_bfloat16*>(out), planes,
-                                                            rows, cols, T, Tpad);
+  AVH_CUDA_OK(launch_pdl(split_rows_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, ld,
+                         reinterpret_cast<__nv_bfloat16*>(out), planes, rows, cols, T, Tpad));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -352,8 +381,8 @@ int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, voi
                         cudaStream_t stream) {
   const long long nblk = (long long)nb * T * 11;
   if (nblk <= 0) return 0;
-  stem_patches_kernel<<<(unsigned)nblk, 256, 0, stream>>>(video, in_dt, T, b0, nb,
-                                                          reinterpret_cast<__nv_bfloat16*>(out), planes);
+  AVH_CUDA_OK(launch_pdl(stem_patches_kernel, dim3((unsigned)nblk), dim3(256), 0, stream, video, in_dt, T, b0, nb,
+                         reinterpret_cast<__nv_bfloat16*>(out), planes));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -363,12 +392,12 @@ int launch_maxpool_stem(const void* in, void* out, int nf, int T, int fp32, cuda
   if (nf <= 0) return 0;
   if (fp32) {
     const long long n = (long long)nf * 484 * 16;
-    maxpool_stem_kernel<float4, 16, true><<<blocks_for(n, 256), 256, 0, stream>>>(
-        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), nf, T);
+    AVH_CUDA_OK(launch_pdl(maxpool_stem_kernel<float4, 16, true>, dim3(blocks_for(n, 256)), dim3(256), 0, stream,
+                           reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), nf, T));
   } else {
     const long long n = (long long)nf * 484 * 8;
-    maxpool_stem_kernel<uint4, 8, false><<<blocks_for(n, 256), 256, 0, stream>>>(
-        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), nf, T);
+    AVH_CUDA_OK(launch_pdl(maxpool_stem_kernel<uint4, 8, false>, dim3(blocks_for(n, 256)), dim3(256), 0, stream,
+                           reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), nf, T));
   }
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
@@ -379,8 +408,8 @@ int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cuda
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = (long long)n * Ho * Wo * 9 * (C / 8);
   if (total <= 0) return 0;
-  im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in),
-                                                               reinterpret_cast<uint4*>(out), n, H, W, C / 8);
+  AVH_CUDA_OK(launch_pdl(im2col_s2_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream,
+                         reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n, H, W, C / 8));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -389,7 +418,8 @@ int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cuda
 int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int fp32, cudaStream_t stream) {
   const long long total = (long long)n * C;
   if (total <= 0) return 0;
-  avgpool_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(in, out, fp32 ? DT_F32 : DT_BF16, n, H, W, C);
+  AVH_CUDA_OK(launch_pdl(avgpool_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream, in, out,
+                         fp32 ? DT_F32 : DT_BF16, n, H, W, C));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

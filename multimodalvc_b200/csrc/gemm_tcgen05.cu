@@ -116,6 +116,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int unit = blockIdx.x / PAIR;                 // cluster index
   const int num_units = gridDim.x / PAIR;
   const int num_tiles = p.num_m_blk * p.num_n_blk;
+  pdl_launch_dependents();            // the next kernel of the stream may start its own prologue
   if (threadIdx.x == 0) AVH_TRACE(0);
 
   if (p.ktable != nullptr) {
@@ -146,6 +147,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (K table, barrier init, TMEM allocation, descriptor prefetch) touched only launch-constant
+  // data; from here on the kernel reads and writes activations of its predecessors
+  pdl_wait();
   if (threadIdx.x == 0) AVH_TRACE(1);
 
   // Producer and MMA warps run their loops with ALL lanes (warp-uniform operands stay in uniform registers) and
@@ -721,13 +725,15 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(occ == 2 ? Occ<2>::NUM_THREADS : Occ<1>::NUM_THREADS);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)pair;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const Epilogue& e = pr.ep;
   const int act = e.act, res = e.R != nullptr, s2 = e.slope2 != nullptr, scl = e.col_scale != nullptr, f32 = e.c_fp32;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, KernelParams);
