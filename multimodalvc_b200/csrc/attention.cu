@@ -53,8 +53,8 @@ __device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_b
 
 // One CTA = NW warps x 16 query rows of one (batch, head); keys/values stream through smem in chunks of BKV with
 // an online softmax, so a 6 s clip (T = 150) is ONE chunk: Q, K and V of the head are read from L2 exactly once.
-template <int NW, int BKV>
-__global__ void __launch_bounds__(NW * 32)
+template <int NW, int BKV, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __restrict__ kpm,
                  __nv_bfloat16* __restrict__ out, int T, int D) {
   constexpr int BQ = NW * 16;
@@ -192,17 +192,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   }
 }
 
-template <int NW, int BKV>
+template <int NW, int BKV, int MINB>
 int launch_att_t(const void* qkv, const unsigned char* kpm, void* out, int B, int T, int D, int H, cudaStream_t stream) {
   constexpr int BQ = NW * 16;
   const size_t smem = (size_t)(BQ + 2 * BKV) * PITCH * 2 + BKV * 4;
   static bool configured = false;
   if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(attention_kernel<NW, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AVH_CUDA_OK(cudaFuncSetAttribute(attention_kernel<NW, BKV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid((T + BQ - 1) / BQ, H, B);
-  AVH_CUDA_OK(launch_pdl(attention_kernel<NW, BKV>, grid, dim3(NW * 32), smem, stream,
+  AVH_CUDA_OK(launch_pdl(attention_kernel<NW, BKV, MINB>, grid, dim3(NW * 32), smem, stream,
                          reinterpret_cast<const __nv_bfloat16*>(qkv), kpm, reinterpret_cast<__nv_bfloat16*>(out), T, D));
   return 0;
 }
@@ -267,10 +267,12 @@ int launch_attention(const void* qkv, const unsigned char* kpm, void* out, int B
   } else {
     // tile shapes: whole-clip tiles for short clips (T <= 160: one CTA per (batch, head)), else 128 x 128
     int rc;
-    if (T <= 64) rc = launch_att_t<4, 64>(qkv, kpm, out, B, T, D, H, stream);
-    else if (T <= 96) rc = launch_att_t<6, 96>(qkv, kpm, out, B, T, D, H, stream);
-    else if (T <= 160) rc = launch_att_t<10, 160>(qkv, kpm, out, B, T, D, H, stream);
-    else rc = launch_att_t<8, 128>(qkv, kpm, out, B, T, D, H, stream);
+    // (a 160-key chunk needs 80 score registers per thread and drops to one CTA per SM: 256 heads on 148 SMs
+    //  = two waves; 80-key chunks with the online softmax fit two CTAs per SM and finish in one wave)
+    if (T <= 64) rc = launch_att_t<4, 64, 2>(qkv, kpm, out, B, T, D, H, stream);
+    else if (T <= 96) rc = launch_att_t<6, 96, 2>(qkv, kpm, out, B, T, D, H, stream);
+    else if (T <= 160) rc = launch_att_t<10, 80, 2>(qkv, kpm, out, B, T, D, H, stream);
+    else rc = launch_att_t<8, 128, 2>(qkv, kpm, out, B, T, D, H, stream);
     if (rc) return rc;
   }
   AVH_CUDA_OK(cudaGetLastError());
