@@ -251,12 +251,12 @@ template <typename VT, int CV, bool F32>
 __global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ out, int nf, int T) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)nf * 484 * CV) return;
+  // one CTA row of threads per frame (blockIdx.y), 32-bit index math inside the frame
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 484u * CV) return;
   const int cv = (int)(i % CV);
-  const long long p = i / CV;
-  const int pix = (int)(p % 484);
-  const long long n = p / 484;
+  const int pix = (int)(i / CV);
+  const long long n = blockIdx.y;
   const int ho = pix / 22, wo = pix - ho * 22;
   const long long ns = (n / T) * (T + 2) + (n % T);      // source frame index in the clip-padded stem output
   VT m;
@@ -280,24 +280,26 @@ __global__ void maxpool_stem_kernel(const VT* __restrict__ in, VT* __restrict__ 
 }
 
 // 3x3 stride-2 pad-1 im2col from the zero-padded layout [n,H+1,W+1,C] (avhubert/resnet.py:15-17 with stride 2)
+template <typename IdxT>
 __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int H, int W, int C8) {
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n * Ho * Wo * 9 * C8;
+  const IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+  const IdxT total = (IdxT)n * Ho * Wo * 9 * C8;
   if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  long long r = i / C8;
-  const int tap = (int)(r % 9);
-  r /= 9;
-  const int wo = (int)(r % Wo);
-  r /= Wo;
-  const int ho = (int)(r % Ho);
-  const long long img = r / Ho;
-  const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+  // 32-bit index arithmetic whenever the problem allows it: the 64-bit divisions were most of this kernel's time
+  const IdxT per_row = (IdxT)(9 * C8);
+  const IdxT row = i / per_row;
+  const unsigned rem = (unsigned)(i - row * per_row);
+  const unsigned tap = rem / (unsigned)C8, c8 = rem - tap * (unsigned)C8;
+  const IdxT img = row / (IdxT)(Ho * Wo);
+  const unsigned pix = (unsigned)(row - img * (IdxT)(Ho * Wo));
+  const int ho = (int)(pix / (unsigned)Wo), wo = (int)(pix - (unsigned)ho * (unsigned)Wo);
+  const int h = 2 * ho + (int)(tap / 3) - 1, w = 2 * wo + (int)(tap % 3) - 1;
   uint4 v = make_uint4(0, 0, 0, 0);
-  if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(in + ((img * (H + 1) + h) * (W + 1) + w) * C8 + c8);
+  if (h >= 0 && h < H && w >= 0 && w < W)
+    v = __ldg(in + (((long long)img * (H + 1) + h) * (W + 1) + w) * C8 + c8);
   out[i] = v;
 }
 
@@ -391,12 +393,10 @@ int launch_stem_patches(const void* video, int in_dt, int T, int b0, int nb, voi
 int launch_maxpool_stem(const void* in, void* out, int nf, int T, int fp32, cudaStream_t stream) {
   if (nf <= 0) return 0;
   if (fp32) {
-    const long long n = (long long)nf * 484 * 16;
-    AVH_CUDA_OK(launch_pdl(maxpool_stem_kernel<float4, 16, true>, dim3(blocks_for(n, 256)), dim3(256), 0, stream,
+    AVH_CUDA_OK(launch_pdl(maxpool_stem_kernel<float4, 16, true>, dim3(blocks_for(484 * 16, 256), nf), dim3(256), 0, stream,
                            reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), nf, T));
   } else {
-    const long long n = (long long)nf * 484 * 8;
-    AVH_CUDA_OK(launch_pdl(maxpool_stem_kernel<uint4, 8, false>, dim3(blocks_for(n, 256)), dim3(256), 0, stream,
+    AVH_CUDA_OK(launch_pdl(maxpool_stem_kernel<uint4, 8, false>, dim3(blocks_for(484 * 8, 256), nf), dim3(256), 0, stream,
                            reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), nf, T));
   }
   AVH_CUDA_OK(cudaGetLastError());
@@ -408,8 +408,12 @@ int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cuda
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = (long long)n * Ho * Wo * 9 * (C / 8);
   if (total <= 0) return 0;
-  AVH_CUDA_OK(launch_pdl(im2col_s2_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream,
-                         reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n, H, W, C / 8));
+  if (total < (1ll << 31))
+    AVH_CUDA_OK(launch_pdl(im2col_s2_kernel<unsigned>, dim3(blocks_for(total, 256)), dim3(256), 0, stream,
+                           reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n, H, W, C / 8));
+  else
+    AVH_CUDA_OK(launch_pdl(im2col_s2_kernel<long long>, dim3(blocks_for(total, 256)), dim3(256), 0, stream,
+                           reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n, H, W, C / 8));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

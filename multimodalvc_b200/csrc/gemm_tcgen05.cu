@@ -754,6 +754,8 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   AVH_SPEC(1, ACT_NONE, 0, 0, 1, 0)      // conv + BN -> bf16                      (downsample)
   AVH_SPEC(1, ACT_NONE, 0, 0, 1, 1)
   AVH_SPEC(2, ACT_NONE, 0, 0, 0, 0)      // two CTAs per SM: narrow tiles
+  AVH_SPEC(2, ACT_NONE, 0, 0, 0, 1)
+  AVH_SPEC(2, ACT_GELU, 0, 0, 0, 0)
   AVH_SPEC(2, ACT_NONE, 1, 0, 0, 1)
   AVH_SPEC(2, ACT_GELU, 1, 0, 0, 1)
   AVH_SPEC(2, ACT_PRELU, 0, 0, 1, 0)

@@ -22,6 +22,8 @@ def main():
         A = torch.randn(M, K, device="cuda").bfloat16(); B = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
         bias = torch.randn(N, device="cuda"); R = torch.randn(M, N, device="cuda") if res else None
         C = torch.empty(M, N, device="cuda", dtype=torch.float32 if cf else torch.bfloat16)
+        if res and os.environ.get("TRACE_INPLACE", "1") == "1":
+            C = R              # x += A B^T + bias: the TMA reduce-add epilogue, as in the model
         def run():
             _lib.check(lib.avh_gemm_bf16(vp(A.data_ptr()), vp(B.data_ptr()), M, N, K, vp(bias.data_ptr()) if use_bias else None, gelu,
                                          vp(R.data_ptr()) if res else None, 1, vp(C.data_ptr()), cf, bn, pair, OCC, vp(st)))
