@@ -146,10 +146,12 @@ struct Plan {
   Arena arena;
   std::vector<Step> steps;
   std::vector<GemmPlan*> gemms;
+  std::vector<ConvWinPlan*> convwins;
   std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
   CallArgs args;
   ~Plan() {
     for (GemmPlan* g : gemms) delete g;
+    for (ConvWinPlan* g : convwins) delete g;
     arena.release();
   }
 };
@@ -593,6 +595,23 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     auto conv3x3_s1 = [&](const Act& in, const ConvUnit& cu, const Act& out, int Himg, int nimg, const float* slope1,
                           const Act* res, const float* slope2) -> bool {
       const int S = Himg + 1;
+      static int win_env = -1;
+      if (win_env < 0) { const char* ev = std::getenv("AVH_CONV_WINDOW"); win_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
+      if (!f32 && win_env && cu.cin == 64 && cu.cout == 64) {
+        // layer1: operand window resident in smem, nine taps as descriptor row offsets (conv_window.cu)
+        b.tag = "conv3x3_c64";
+        if (sizing) return true;
+        ConvWinProblem wp;
+        wp.A = in.op; wp.B = cu.w.w; wp.rows = (long long)nimg * S * S; wp.S = S;
+        wp.scale = cu.scale; wp.bias = cu.bias; wp.slope1 = slope1;
+        wp.R = res ? res->data : nullptr; wp.slope2 = slope2; wp.C = out.data;
+        ConvWinPlan* cp = new ConvWinPlan();
+        plan->convwins.push_back(cp);
+        if (conv_window_plan(wp, cp)) return false;
+        const double fl = 2.0 * (double)wp.rows * 64.0 * 576.0;
+        plan->steps.push_back(Step{[cp](cudaStream_t s) { return conv_window_launch(*cp, s); }, b.tag, fl});
+        return true;
+      }
       std::vector<Tap> taps;
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw)

@@ -69,6 +69,35 @@ struct GemmPlan {
   size_t smem = 0;
 };
 
+// ---- 3x3 / stride-1 / 64 -> 64 channel convolution over the shared-zero-padded NHWC layout with the operand
+// window resident in smem: ONE TMA load of 128 + 2(S+1) rows per tile, the nine taps are tcgen05.mma operand
+// descriptors that start at different ROWS of that window (the 128-byte swizzle is a function of the absolute
+// smem address, so a descriptor may start at any row: tools/micro/desc_offset.cu), all 9 x 64 x 64 weights stay
+// resident in smem.  Cuts the L2->SM operand stream of the layer1 convolutions ~9x.
+struct ConvWinProblem {
+  const void* A = nullptr;        // bf16 [rows, 64] padded layout, flat
+  const void* B = nullptr;        // bf16 [64, 9*64] K-major weights, K = (tap, cin)
+  long long rows = 0;             // n * S * S
+  int S = 0;                      // padded image pitch (H + 1); H = W = S - 1 valid rows/columns
+  const float* scale = nullptr;   // folded BatchNorm
+  const float* bias = nullptr;
+  const float* slope1 = nullptr;  // PReLU before the residual (conv1) or null
+  const void* R = nullptr;        // bf16 residual [rows, 64] or null
+  const float* slope2 = nullptr;  // PReLU after the residual (conv2) or null
+  void* C = nullptr;              // bf16 [rows, 64]
+};
+struct ConvWinPlan {
+  CUtensorMap tma_a, tma_b, tma_c;
+  ConvWinProblem prob;
+  int grid = 0, stages = 0, win_rows = 0;
+  size_t smem = 0;
+};
+int conv_window_plan(const ConvWinProblem& prob, ConvWinPlan* plan);
+int conv_window_launch(const ConvWinPlan& plan, cudaStream_t stream);
+// tensor-map helpers shared by the GEMM kernels (gemm_tcgen05.cu)
+int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows);
+int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32);
+
 constexpr int GEMM_MAX_KSTEPS = 768;
 
 int gemm_plan(const GemmProblem& prob, GemmPlan* plan);       // builds tensor maps; 0 on success

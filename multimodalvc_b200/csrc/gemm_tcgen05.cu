@@ -548,6 +548,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 // output tensor map: [rows, cols] fp32 or bf16, box = 128 bytes of columns x 32 rows, 128B swizzle
 int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32) {
   EncodeTiledFn fn = get_encode_fn();
@@ -581,6 +583,8 @@ int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long
   AVH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
   return 0;
 }
+
+namespace {
 
 unsigned long long* g_trace = nullptr;
 
