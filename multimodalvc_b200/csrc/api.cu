@@ -147,11 +147,13 @@ struct Plan {
   std::vector<Step> steps;
   std::vector<GemmPlan*> gemms;
   std::vector<ConvWinPlan*> convwins;
+  std::vector<ConvFramePlan*> convframes;
   std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
   CallArgs args;
   ~Plan() {
     for (GemmPlan* g : gemms) delete g;
     for (ConvWinPlan* g : convwins) delete g;
+    for (ConvFramePlan* g : convframes) delete g;
     arena.release();
   }
 };
@@ -630,6 +632,34 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       return true;
     };
 
+    // bf16 mode, layers 2-4: one frame per GEMM row, dense [frames, H*H*C] maps, in-image taps only (conv_frame.cu)
+    static int frame_env = -1;
+    if (frame_env < 0) { const char* ev = std::getenv("AVH_CONV_FRAME"); frame_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
+    const bool frame_mode = !f32 && frame_env != 0;
+    auto conv_frame = [&](const void* in, int Hin, int Sin, int Cin, const ConvUnit& cu, void* out, int Hout, int nimg,
+                          const float* slope1, const void* res, const float* slope2, const std::string& tg) -> bool {
+      ConvFrameProblem fp;
+      fp.A = in; fp.frames = nimg; fp.Hin = Hin; fp.Sin = Sin; fp.Pin = Sin * Sin; fp.Cin = Cin;
+      fp.B = cu.w.w; fp.Cout = cu.cout; fp.ks = cu.ks; fp.stride = cu.stride;
+      fp.Hout = Hout; fp.Sout = Hout; fp.Pout = Hout * Hout;
+      fp.scale = cu.scale; fp.bias = cu.bias; fp.slope1 = slope1; fp.R = res; fp.slope2 = slope2; fp.C = out;
+      b.tag = tg;
+      void* table = b.alloc(conv_frame_table_bytes(fp));
+      if (sizing) return true;
+      ConvFramePlan* cp = new ConvFramePlan();
+      plan->convframes.push_back(cp);
+      if (conv_frame_plan(fp, cp) || conv_frame_bind_table(cp, table)) return false;
+      double taps = 0;
+      for (int oy = 0; oy < Hout; ++oy)
+        for (int k = 0; k < cu.ks; ++k) {
+          const int iy = oy * cu.stride + k - (cu.ks == 3 ? 1 : 0);
+          taps += (iy >= 0 && iy < Hin) ? 1 : 0;
+        }
+      const double fl = 2.0 * (double)nimg * taps * taps * (double)Cin * (double)cu.cout;
+      plan->steps.push_back(Step{[cp](cudaStream_t s) { return conv_frame_launch(*cp, s); }, b.tag, fl});
+      return true;
+    };
+
     for (int b0 = 0; b0 < B; b0 += CB) {
       const int nb = std::min(CB, B - b0);
       const int nf = nb * T;
@@ -667,6 +697,23 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
           mid.rows = out.rows = (long long)nf * S * S;
           const Act* res = &cur;
           Act dsout;
+          if (frame_mode && L > 0) {
+            const int Hp = bi == 0 ? HS[L - 1] : Hn, Sp = (bi == 0 && L == 1) ? Hp + 1 : Hp, Cin = bi == 0 ? Cc / 2 : Cc;
+            const void* resp = cur.data;
+            if (bw.has_ds) {
+              if (!conv_frame(cur.op, Hp, Sp, Cin, bw.ds, fb.ds[L].data, Hn, nf, nullptr, nullptr, nullptr, "downsample"))
+                return false;
+              resp = fb.ds[L].data;
+            }
+            if (!conv_frame(cur.op, Hp, Sp, Cin, bw.c1, mid.data, Hn, nf, bw.c1.slope, nullptr, nullptr,
+                            (bi == 0 ? "conv_s2_c" : "conv3x3_c") + std::to_string(Cin)))
+              return false;
+            if (!conv_frame(mid.data, Hn, Hn, Cc, bw.c2, out.data, Hn, nf, nullptr, resp, bw.slope2,
+                            "conv3x3_c" + std::to_string(Cc)))
+              return false;
+            cur = out;
+            continue;
+          }
           if (bw.has_ds) {
             // stride-2: explicit im2col of the previous layer's padded map, conv1 and the 1x1 downsample read it
             const int Hp = HS[L - 1], Cin = Cc / 2;
@@ -706,7 +753,8 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         const void* src = cur.data;
         char* dst = reinterpret_cast<char*>(pooled_feat.data) + (size_t)f0 * 512 * es;
         b.tag = "avgpool";
-        b.push([=](cudaStream_t s) { return launch_avgpool(src, dst, nf, 3, 3, 512, f32 ? 1 : 0, s); });
+        const int pitch = frame_mode ? 3 : 4;
+        b.push([=](cudaStream_t s) { return launch_avgpool(src, dst, nf, 3, 3, 512, pitch, f32 ? 1 : 0, s); });
       }
     }
     sync_op(pooled_feat);

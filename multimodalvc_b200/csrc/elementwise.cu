@@ -303,9 +303,9 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict
   out[i] = v;
 }
 
-// AdaptiveAvgPool2d(1) (avhubert/resnet.py:90,127) over the valid pixels of the padded layout
+// AdaptiveAvgPool2d(1) (avhubert/resnet.py:90,127) over the valid pixels of a layout with pixel pitch S
 __global__ void avgpool_kernel(const void* __restrict__ in, void* __restrict__ out, int dt, int n, int H, int W,
-                               int C) {
+                               int C, int S) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -314,7 +314,7 @@ __global__ void avgpool_kernel(const void* __restrict__ in, void* __restrict__ o
   const long long img = i / C;
   float s = 0.f;
   for (int h = 0; h < H; ++h)
-    for (int w = 0; w < W; ++w) s += load_any(in, dt, ((img * (H + 1) + h) * (W + 1) + w) * C + c);
+    for (int w = 0; w < W; ++w) s += load_any(in, dt, ((img * S + h) * S + w) * C + c);
   store_lp(out, dt, i, s / (float)(H * W));
 }
 
@@ -419,11 +419,11 @@ int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cuda
   return 0;
 }
 
-int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int fp32, cudaStream_t stream) {
+int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int pitch, int fp32, cudaStream_t stream) {
   const long long total = (long long)n * C;
   if (total <= 0) return 0;
   AVH_CUDA_OK(launch_pdl(avgpool_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream, in, out,
-                         fp32 ? DT_F32 : DT_BF16, n, H, W, C));
+                         fp32 ? DT_F32 : DT_BF16, n, H, W, C, pitch));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace avh {
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_PRELU = 2 };
@@ -94,6 +96,35 @@ struct ConvWinPlan {
 };
 int conv_window_plan(const ConvWinProblem& prob, ConvWinPlan* plan);
 int conv_window_launch(const ConvWinPlan& plan, cudaStream_t stream);
+// ---- convolutions of the small maps (layers 2-4) with one frame per GEMM row: activations [frames, P*C],
+// tile = 128 frames x block_n channels of one output pixel, K loop = in-image taps only (conv_frame.cu).
+struct ConvFrameProblem {
+  const void* A = nullptr;        // bf16 [frames, Pin*Cin]
+  long long frames = 0;
+  int Hin = 0, Sin = 0, Pin = 0, Cin = 0;      // input image H = W, pixel pitch, pixels per frame row, channels
+  const void* B = nullptr;        // bf16 [Cout, ks*ks*Cin] K-major weights, K = (tap, cin)
+  int Cout = 0, ks = 3, stride = 1;            // padding = 1 for ks 3, 0 for ks 1
+  int Hout = 0, Sout = 0, Pout = 0;            // output image, pitch, pixels per frame row
+  const float* scale = nullptr;   // folded BatchNorm
+  const float* bias = nullptr;
+  const float* slope1 = nullptr;  // PReLU (conv1 form) or null
+  const void* R = nullptr;        // bf16 residual in the output layout (conv2 form) or null
+  const float* slope2 = nullptr;  // PReLU after the residual add
+  void* C = nullptr;              // bf16 [frames, Pout*Cout]
+  int block_n = 0, occ = 0;       // 0 = chosen by conv_frame_plan
+};
+struct ConvFramePlan {
+  CUtensorMap tma_a, tma_b, tma_c;
+  ConvFrameProblem prob;
+  int grid = 0, stages = 0;
+  size_t smem = 0;
+  std::vector<int> tiles_host;    // [grid+1] offsets + per-CTA tile lists
+  const int* tiles_dev = nullptr;
+};
+int conv_frame_plan(const ConvFrameProblem& prob, ConvFramePlan* plan);
+size_t conv_frame_table_bytes(const ConvFrameProblem& prob);        // device bytes to reserve for the tile table
+int conv_frame_bind_table(ConvFramePlan* plan, void* dev_table);    // uploads the table (synchronous copy)
+int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream);
 // tensor-map helpers shared by the GEMM kernels (gemm_tcgen05.cu)
 int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows);
 int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32);
