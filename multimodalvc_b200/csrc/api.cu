@@ -148,6 +148,7 @@ struct Plan {
   std::vector<GemmPlan*> gemms;
   std::vector<ConvWinPlan*> convwins;
   std::vector<ConvFramePlan*> convframes;
+  StemFusedPlan stemf;
   std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
   CallArgs args;
   ~Plan() {
@@ -171,6 +172,7 @@ struct avh_handle {
   std::map<std::string, HostTensor> raw;
   Arena warena;
   ConvUnit stem;
+  PackedW stem_wf;          // stem weights in the K order of the fused kernel (stem_fused.cu)
   BlockW blocks[4][2];
   LinearW proj_v, proj_a, post_proj;
   bool has_post_proj = false;
@@ -318,6 +320,13 @@ bool pack_all(Packer& pk) {
         for (int dt = 0; dt < 5; ++dt)
           for (int k = 0; k < 49; ++k) p[(size_t)o * 320 + dt * 64 + k] = w->v[(size_t)o * 245 + dt * 49 + k];
       h->stem.w = pk.pack(p, 64, 245, 320);
+      std::vector<float> pf((size_t)64 * 320, 0.f);     // fused stem kernel: K = dt*64 + kh*8 + kw
+      for (int o = 0; o < 64; ++o)
+        for (int dt = 0; dt < 5; ++dt)
+          for (int kh = 0; kh < 7; ++kh)
+            for (int kw = 0; kw < 7; ++kw)
+              pf[(size_t)o * 320 + dt * 64 + kh * 8 + kw] = w->v[(size_t)o * 245 + dt * 49 + kh * 7 + kw];
+      h->stem_wf = pk.pack(pf, 64, 320, 320);
       h->stem.cin = 1; h->stem.cout = 64;
       std::vector<float> sc(64), bi(64), sl(64);
       for (int o = 0; o < 64; ++o) {
@@ -664,7 +673,21 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       const int nb = std::min(CB, B - b0);
       const int nf = nb * T;
       const long long f0 = (long long)b0 * T;
-      // ---- stem: (kh,kw) patches -> GEMM over 5 temporal row-shift taps (+BN+PReLU) -> maxpool
+      // ---- stem: one fused kernel in bf16 mode (stem_fused.cu) ...
+      static int stemf_env = -1;
+      if (stemf_env < 0) { const char* ev = std::getenv("AVH_STEM_FUSED"); stemf_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
+      if (!f32 && stemf_env) {
+        if (!sizing && b0 == 0 && stem_fused_plan(h->stem_wf.w, &plan->stemf)) return false;
+        void* po = fb.pooled.data;
+        b.tag = "stem_fused";
+        const double fl = 2.0 * (double)nf * 1936.0 * 64.0 * 245.0;
+        if (!sizing)
+          plan->steps.push_back(Step{[=](cudaStream_t s) {
+            return stem_fused_launch(pl->stemf, pl->args.video, pl->args.video_dt, T, b0, nb, h->stem.scale, h->stem.bias,
+                                     h->stem.slope, po, s);
+          }, b.tag, fl});
+      } else
+      // ---- ... else (kh,kw) patches -> GEMM over 5 temporal row-shift taps (+BN+PReLU) -> maxpool
       {
         void* col = fb.im2col;
         const int planes = P;

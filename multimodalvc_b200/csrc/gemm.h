@@ -125,6 +125,13 @@ int conv_frame_plan(const ConvFrameProblem& prob, ConvFramePlan* plan);
 size_t conv_frame_table_bytes(const ConvFrameProblem& prob);        // device bytes to reserve for the tile table
 int conv_frame_bind_table(ConvFramePlan* plan, void* dev_table);    // uploads the table (synchronous copy)
 int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream);
+// ---- fused lip-frontend stem: Conv3d 5x7x7 + BN + PReLU + MaxPool in one kernel (stem_fused.cu)
+struct StemFusedPlan {
+  CUtensorMap tma_w;              // weights bf16 [64, 5*64], K = dt*64 + kh*8 + kw (kw = 7 and k >= 56 zero)
+};
+int stem_fused_plan(const void* w_packed, StemFusedPlan* plan);
+int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, int T, int b0, int nb, const float* scale,
+                      const float* bias, const float* slope, void* pooled_out, cudaStream_t stream);
 // tensor-map helpers shared by the GEMM kernels (gemm_tcgen05.cu)
 int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows);
 int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32);
