@@ -127,7 +127,7 @@ int conv_frame_bind_table(ConvFramePlan* plan, void* dev_table);    // uploads t
 int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream);
 // ---- fused lip-frontend stem: Conv3d 5x7x7 + BN + PReLU + MaxPool in one kernel (stem_fused.cu)
 struct StemFusedPlan {
-  CUtensorMap tma_w;              // weights bf16 [64, 5*64], K = dt*64 + kh*8 + kw (kw = 7 and k >= 56 zero)
+  const void* w = nullptr;        // weights bf16 [64, 5*64], K = dt*64 + kh*8 + kw (kw = 7 and k >= 56 zero)
 };
 int stem_fused_plan(const void* w_packed, StemFusedPlan* plan);
 int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, int T, int b0, int nb, const float* scale,

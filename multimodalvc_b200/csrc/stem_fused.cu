@@ -3,18 +3,28 @@
 // shared-zero-padded NHWC layout [frames, 23*23, 64] that the layer1 convolutions read (conv_window.cu).
 //
 // The unfused chain (patch matrix -> tcgen05 GEMM -> pool) moved 4 x 600 MB through HBM per 2400 frames and was bound
-// by it.  Here the only HBM traffic is the video (15.5 KB per frame) and the pooled maps (66 KB per frame):
-//   * work item = (clip, band of 2 pooled rows, time segment).  A band needs 5 stem rows x 44 columns = 220 stem
-//     pixels (one halo row shared with the band above) = two 128-row MMA blocks, and 15 input rows.
-//   * builder warps turn the input rows of ONE frame into the band's patch tile (220 x 64 bf16, K = kh*8 + kw so
-//     that a 16-byte chunk is 8 consecutive input pixels; 128-byte-swizzled K-major, written with generic stores +
-//     fence.proxy.async) in a ring of 5 frame slots.  The CTA walks time, so every patch tile is built once and used
-//     by the 5 temporal taps of 5 consecutive output frames.
-//   * one elected lane issues, per output frame, 2 blocks x <=5 taps x 4 tcgen05.mma (128 x 64 x 16) against the
-//     weights resident in smem (5 x 8 KB) into a double-buffered TMEM accumulator; out-of-clip taps are skipped.
-//   * 8 epilogue warps (thread = stem pixel): tcgen05.ld -> BN scale/bias -> PReLU -> bf16 -> smem, 16 channels at a
-//     time; then the 3x3/stride-2 max over the staged band and 8-byte stores of the 2 x 22 pooled pixels.
-// Out-of-image pool taps (stem row/column -1) are skipped, as nn.MaxPool3d pads with -inf.
+// by it.  Here the only HBM traffic is the video (15.5 KB per frame) and the pooled maps (66 KB per frame).
+//
+//   * work item = (clip, band of 2 pooled rows, time segment).  A band needs 5 stem rows x 44 columns of stem pixels
+//     (one halo row shared with the band above) and 15 input rows.
+//   * builder warps turn the input rows of ONE frame into the band's patch tile (pixel rows x 64 bf16, K = kh*8 + kw
+//     so that a 16-byte chunk is 8 consecutive input pixels; 128-byte-swizzled K-major, generic stores +
+//     fence.proxy.async) in a ring of 7 frame slots.  The CTA walks time: every patch tile is built once and used by
+//     the temporal taps of 5 consecutive output frames.
+//   * the GEMM is TRANSPOSED: D[channel, pixel] = W[channel, k] * P[pixel, k]^T with the WEIGHTS as the A operand
+//     resident in TENSOR MEMORY (tcgen05.mma with A in TMEM) and the patch tile as B.  A 64-channel A would use half
+//     the 128-row datapath, so TWO consecutive output frames are stacked: for the pair (t, t+1) and input frame
+//     f = t-2+i, A_i = [W_i ; W_(i-1)] (W_-1 = W_5 = 0) — 6 variants x 32 TMEM columns.  Per pair: <= 6 frames x 4
+//     K-steps per pixel half, every MMA 128 x N x 16 at the full tensor rate, and the only shared-memory operand
+//     traffic is the patch tile (the first version, pixels as M and N = 64, re-read its A tile for 64 output columns
+//     and was shared-memory-bandwidth bound at 3300 clk per frame).
+//   * pixels are split into two halves by column (x <= 21 | x >= 21, column 21 in both) so that every pooling window
+//     lies inside one half; the halves are the two accumulator stages (N = 112 and 128): the epilogue of one overlaps
+//     the MMAs of the other.
+//   * 8 epilogue warps, thread = (frame of the pair, channel): tcgen05.ld of the three stem rows of one pooled row ->
+//     BN scale/bias + PReLU with per-thread constants -> 3x3/stride-2 max entirely in registers -> bf16 stores
+//     (a warp writes 64 contiguous bytes per pooled pixel).  Out-of-image pool taps are replaced by a duplicate of
+//     an in-window tap (nn.MaxPool3d pads with -inf).
 #include "common.cuh"
 #include "gemm.h"
 #include "kernels.h"
@@ -26,19 +36,18 @@
 namespace avh {
 namespace {
 
-constexpr int NT = 512;                     // 16 warps: 0 weights, 1 MMA, 2 TMEM, 3 spare, 4-11 epilogue, 12-15 builders
-constexpr int RING = 5;
-constexpr int BLK_BYTES = 128 * 128;        // one 128-row A block
-constexpr int SLOT_BYTES = 224 * 128;       // 220 pixels (+4 zero rows); the second block's MMA reads 32 rows past the
-                                            // slot (next slot / weights): those accumulator rows are never used
-constexpr int W_TAP_BYTES = 64 * 128;       // [64 cout][64 k] per temporal tap
-constexpr int W_BYTES = 5 * W_TAP_BYTES;
-constexpr int NPIX = 220;                   // 5 stem rows x 44
-constexpr int STAGE_BUF = 14336;            // 220 x 64 B (32 channels) rounded up
+constexpr int NT = 512;                     // 16 warps: 0, 2 MMA issuers, 1 TMEM alloc, 3 spare, 4-11 epilogue, 12-15 builders
+constexpr int RING = 7;
+constexpr int H0_ROWS = 112;                // half 0: 5 x 22 pixels (x 0..21) + 2 zero rows
+constexpr int H1_ROWS = 128;                // half 1: 5 x 23 pixels (x 21..43) + 13 zero rows
+constexpr int SLOT_BYTES = (H0_ROWS + H1_ROWS) * 128;     // 30 KB
+constexpr int H1_OFF = H0_ROWS * 128;
+constexpr int NBUILD = 110 + 115;           // patch rows built per frame
 constexpr int SIN_PITCH = 96;               // 3 zero columns + 88 + 5 zero columns
 constexpr int SIN_ROWS = 15;
 constexpr int SIN_BYTES = 3072;
-constexpr size_t SMEM_BYTES = 1024 + RING * SLOT_BYTES + W_BYTES + 2 * STAGE_BUF + SIN_BYTES + 3 * 64 * 4 + 256;
+constexpr size_t SMEM_BYTES = 1024 + RING * SLOT_BYTES + SIN_BYTES + 256;
+constexpr uint32_t TM_A = 0, TM_D0 = 192, TM_D1 = 320;      // TMEM columns: 6 x 32 weights | D half 0 | D half 1
 
 struct StemParams {
   const void* video;
@@ -46,6 +55,7 @@ struct StemParams {
   int T, b0, nb;
   int nseg, seglen, num_items;
   __nv_bfloat16* out;          // [nb*T, 529, 64]
+  const __nv_bfloat16* w;      // [64, 5*64], K = dt*64 + kh*8 + kw
   const float* scale;
   const float* bias;
   const float* slope;
@@ -76,22 +86,54 @@ __device__ __forceinline__ Item decode_item(const StemParams& p, int item) {
   return it;
 }
 
+// One pixel half of one frame pair for this thread's (frame, channel): three stem rows of pooled row `prow`.
+template <int HALF>
+__device__ __forceinline__ void epilogue_half(uint32_t taddr, int prow, bool skip_top, float sc, float bi, float sl,
+                                              __nv_bfloat16* obase, bool do_store, uint64_t* empty_bar, int lane) {
+  constexpr int W = HALF ? 23 : 22;
+  const uint32_t ta = taddr + 2 * prow * W;
+  uint32_t r0[32], r1[32], r2[8];
+  tmem_ld_32x32(ta, r0);
+  tmem_ld_32x32(ta + 32, r1);
+  tmem_ld_32x8(ta + 64, r2);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);       // accumulator half is free for the next pair
+  float v[3 * W];
+#pragma unroll
+  for (int i = 0; i < 3 * W; ++i) {
+    const uint32_t u = i < 32 ? r0[i] : (i < 64 ? r1[i - 32] : r2[i - 64]);
+    const float x = fmaf(__uint_as_float(u), sc, bi);
+    v[i] = x > 0.f ? x : x * sl;
+  }
+#pragma unroll
+  for (int pl = 0; pl < 11; ++pl) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      int lc = 2 * pl + d + (HALF ? 0 : -1);
+      if (lc < 0) lc = 0;                      // column -1: duplicate of column 0
+      const float top = skip_top ? v[W + lc] : v[lc];      // stem row -1 (band 0): duplicate of the row below
+      m = fmaxf(m, fmaxf(top, fmaxf(v[W + lc], v[2 * W + lc])));
+    }
+    if (do_store) obase[pl * 64] = __float2bfloat16_rn(m);
+  }
+}
+
 __global__ void __launch_bounds__(NT, 1)
-stem_fused_kernel(const __grid_constant__ CUtensorMap tma_w, const StemParams p) {
+stem_fused_kernel(const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* ring = smem;
-  uint8_t* smem_w = ring + RING * SLOT_BYTES;
-  uint8_t* stage = smem_w + W_BYTES;
-  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(stage + 2 * STAGE_BUF);
-  float* colvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sIn) + SIN_BYTES);
-  uint64_t* patch_full = reinterpret_cast<uint64_t*>(colvec + 3 * 64);
+  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(ring + RING * SLOT_BYTES);
+  uint64_t* patch_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sIn) + SIN_BYTES);
   uint64_t* slot_free = patch_full + RING;
-  uint64_t* w_full = slot_free + RING;
-  uint64_t* tmem_full = w_full + 1;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* d_full = slot_free + RING;
+  uint64_t* d_empty = d_full + 2;
+  uint64_t* a_ready = d_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,174 +141,125 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tma_w, const StemParams p)
   const long long k_start = clock64();
   long long st0 = 0, st1 = 0;
 
-  // launch-constant setup: zero the ring (K columns 56..63 and rows >= 220 stay zero for good) and the input pads
+  // launch-constant setup: zero the ring (K columns 56..63 and the pad rows stay zero for good) and the input pads
   for (int i = threadIdx.x; i < RING * SLOT_BYTES / 16; i += NT) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < SIN_BYTES / 4; i += NT) reinterpret_cast<uint32_t*>(sIn)[i] = 0u;
-  if (threadIdx.x < 64) {
-    colvec[threadIdx.x] = __ldg(p.scale + threadIdx.x);
-    colvec[64 + threadIdx.x] = __ldg(p.bias + threadIdx.x);
-    colvec[128 + threadIdx.x] = __ldg(p.slope + threadIdx.x);
-  }
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     for (int s = 0; s < RING; ++s) {
       mbar_init(&patch_full[s], 128);
-      mbar_init(&slot_free[s], 1);
+      mbar_init(&slot_free[s], 2);        // one commit per MMA-issuing warp
     }
-    mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&d_full[s], 1);
+      mbar_init(&d_empty[s], 8);
     }
+    mbar_init(a_ready, 128);
     mbar_fence_init();
   }
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tma_w);
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();          // the zero-filled ring is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ weights: resident for the whole kernel
-    if (elect_one()) {
-      mbar_expect_tx(w_full, W_BYTES);
-      for (int dt = 0; dt < 5; ++dt) tma_load_2d(smem_w + dt * W_TAP_BYTES, &tma_w, w_full, dt * 64, 0);
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-    mbar_wait(w_full, 0);
-    int n0 = 0, waited = 0, it = 0;
-    const uint32_t ring_base = smem_u32(ring), w_base = smem_u32(smem_w);
+  if (warp == 0 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers: warp 0 -> pixel half 0, warp 2 ->
+    // half 1.  One elected lane needs ~430 clk per block of 4 MMAs (issue + barrier handling); with one issuer the 12
+    // blocks of a frame pair took 5100 clk against 3400 clk of tensor-pipe time.
+    const int h = warp >> 1;
+    const uint32_t idesc = h ? umma_idesc_bf16(128, H1_ROWS) : umma_idesc_bf16(128, H0_ROWS);
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    int n0 = 0, waited = 0, pc = 0;
+    const uint32_t ring_base = smem_u32(ring);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item im = decode_item(p, item);
-      for (int t = im.t0; t < im.t1; ++t, ++it) {
-        const int acc = it & 1;
-        wait_acc(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, p.dbg, st1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 128;
-        const int lo = max(t - 2, 0), hi = min(t + 2, p.T - 1);
-        for (int f = lo; f <= hi; ++f) {          // oldest frame first: the newest one may still be under construction
-          const int m = n0 + f - im.f_first;
-          while (waited <= m) {
-            wait_acc(&patch_full[waited % RING], (waited / RING) & 1, p.dbg, st0);
-            ++waited;
-          }
+      int next_free = im.f_first;
+      for (int t = im.t0; t < im.t1; t += 2, ++pc) {
+        const bool two = t + 1 < im.t1;
+        const int lo = max(t - 2, 0), hi = min(t + (two ? 3 : 2), p.T - 1);
+        {
+          wait_acc(&d_empty[h], (pc & 1) ^ 1, p.dbg, st1);
           tc_fence_after();
-          const uint32_t a0 = ring_base + (m % RING) * SLOT_BYTES;
-          const uint32_t b0 = w_base + (f - t + 2) * W_TAP_BYTES;
-          if (elect_one()) {
-#pragma unroll
-            for (int blk = 0; blk < 2; ++blk) {
-              const uint64_t adesc = umma_desc_sw128(a0 + blk * BLK_BYTES);
-              const uint64_t bdesc = umma_desc_sw128(b0);
+          const uint32_t tmem_d = tmem_base + (h ? TM_D1 : TM_D0);
+          for (int f = lo; f <= hi; ++f) {        // oldest frame first: the newest one may still be under construction
+            const int m = n0 + f - im.f_first;
+            while (waited <= m) {
+              wait_acc(&patch_full[waited % RING], (waited / RING) & 1, p.dbg, st0);
+              ++waited;
+            }
+            tc_fence_after();
+            const uint32_t b_addr = ring_base + (m % RING) * SLOT_BYTES + h * H1_OFF;
+            const uint32_t a_addr = tmem_base + TM_A + 32 * (f - t + 2);
+            const uint64_t bdesc = umma_desc_sw128(b_addr);
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_d + blk * 64, adesc + 2 * k, bdesc + 2 * k, idesc, (f != lo) || (k != 0));
+                umma_bf16_ts(tmem_d, a_addr + 8 * k, bdesc + 2 * k, idesc, (f != lo) || (k != 0));
             }
+            __syncwarp();
           }
+          if (elect_one()) umma_commit(&d_full[h]);
           __syncwarp();
         }
-        if (elect_one()) {
-          umma_commit(&tmem_full[acc]);
-          if (t - 2 >= im.f_first) umma_commit(&slot_free[(n0 + t - 2 - im.f_first) % RING]);
-          if (t == im.t1 - 1)
-            for (int f = max(im.f_first, t - 1); f <= im.f_last; ++f) umma_commit(&slot_free[(n0 + f - im.f_first) % RING]);
+        // frames below the next pair's window are dead; at the end of the item everything is
+        const int upto = (t + 2 >= im.t1) ? im.f_last + 1 : t;
+        while (next_free < upto) {
+          if (elect_one()) umma_commit(&slot_free[(n0 + next_free - im.f_first) % RING]);
+          __syncwarp();
+          ++next_free;
         }
-        __syncwarp();
       }
       n0 += im.f_last - im.f_first + 1;
     }
-    if (p.dbg != nullptr && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = st0; p.dbg[blockIdx.x * 8 + 3] = st1; }
+    if (p.dbg != nullptr && lane == 0 && h == 0) { p.dbg[blockIdx.x * 8 + 2] = st0; p.dbg[blockIdx.x * 8 + 3] = st1; }
   } else if (warp >= 4 && warp < 12) {
-    // ------------------------------------------------------------------ epilogue: BN + PReLU + 3x3/2 max pool
-    const int e = warp - 4;
-    const int blk = e >> 2, q = e & 3;
-    const int pix = blk * 128 + q * 32 + lane;             // stem pixel of this thread inside the band
-    const int et = threadIdx.x - 128;                      // 0..255
-    const int pp = et >> 2, qd = et & 3;                   // pooled pixel (0..43 valid), 8-channel group inside a chunk
-    const int prow = pp / 22, px = pp - prow * 22;
-    const float4* cv4 = reinterpret_cast<const float4*>(colvec);
-    const int psw = (pix >> 1) & 3;                        // 16-byte-unit swizzle of the staged pixel records
-    int it = 0, buf = 0;
+    // ------------------------------------------------------------------ weights -> TMEM (once), then the epilogue
+    const int q = warp & 3;                                // TMEM lane quarter
+    const int prow = (warp - 4) >> 2;                      // pooled row of the band handled by this warp
+    const int lane_m = q * 32 + lane;                      // accumulator row: frame of the pair * 64 + channel
+    const int fp = lane_m >> 6, ch = lane_m & 63;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (prow == 0) {
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const int dt = i - fp;
+        uint32_t r[32];
+        if (dt >= 0 && dt <= 4) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.w + ch * 320 + dt * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldg(src + c);
+            r[4 * c] = u.x; r[4 * c + 1] = u.y; r[4 * c + 2] = u.z; r[4 * c + 3] = u.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = 0u;
+        }
+        tmem_st_32x32(lane_base + TM_A + 32 * i, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    }
+    const float sc = __ldg(p.scale + ch), bi = __ldg(p.bias + ch), sl = __ldg(p.slope + ch);
+    int pc = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item im = decode_item(p, item);
-      // pool taps of this thread: band rows 2*prow + {0,1,2}, columns 2*px + {-1,0,1}; taps outside the image (stem
-      // row -1 in band 0, column -1) are replaced by a duplicate of a tap inside the window (max is idempotent)
-      int toff[9];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int ry = max(2 * prow + dy, im.j == 0 ? 1 : 0);
-          const int x = max(2 * px + dx - 1, 0);
-          const int pi = ry * 44 + x;
-          toff[dy * 3 + dx] = pi * 64 + ((qd ^ ((pi >> 1) & 3)) << 4);
-        }
-      for (int t = im.t0; t < im.t1; ++t, ++it) {
-        const int acc = it & 1;
-        wait_acc(&tmem_full[acc], (it >> 1) & 1, p.dbg, st0);
+      const bool skip_top = im.j == 0 && prow == 0;
+      for (int t = im.t0; t < im.t1; t += 2, ++pc) {
+        const bool do_store = t + fp < im.t1;
+        __nv_bfloat16* orow = p.out + (((long long)(im.bl * p.T + t + fp) * 23 + (2 * im.j + prow)) * 23) * 64 + ch;
+        wait_acc(&d_full[0], pc & 1, p.dbg, st0);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + blk * 64;
-        __nv_bfloat16* orow = p.out + (((long long)(im.bl * p.T + t) * 23 + (2 * im.j + prow)) * 23 + px) * 64 + qd * 8;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t rawv[32];
-          tmem_ld_32x32(taddr + c * 32, rawv);
-          tmem_ld_wait();
-          if (c == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 sc = cv4[c * 8 + i], bi = cv4[16 + c * 8 + i], sl = cv4[32 + c * 8 + i];
-            float v0 = fmaf(__uint_as_float(rawv[4 * i]), sc.x, bi.x);
-            float v1 = fmaf(__uint_as_float(rawv[4 * i + 1]), sc.y, bi.y);
-            float v2 = fmaf(__uint_as_float(rawv[4 * i + 2]), sc.z, bi.z);
-            float v3 = fmaf(__uint_as_float(rawv[4 * i + 3]), sc.w, bi.w);
-            v0 = v0 > 0.f ? v0 : v0 * sl.x;
-            v1 = v1 > 0.f ? v1 : v1 * sl.y;
-            v2 = v2 > 0.f ? v2 : v2 * sl.z;
-            v3 = v3 > 0.f ? v3 : v3 * sl.w;
-            pk[2 * i] = pack_bf16(v0, v1);
-            pk[2 * i + 1] = pack_bf16(v2, v3);
-          }
-          uint8_t* sb = stage + buf * STAGE_BUF;
-          if (pix < NPIX) {
-            uint8_t* d = sb + pix * 64;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<uint4*>(d + ((u ^ psw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-          }
-          if (p.dbg != nullptr) {
-            const long long c0 = clock64();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            st1 += clock64() - c0;
-          } else {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-          }
-          if (pp < 44) {
-            uint4 m = *reinterpret_cast<const uint4*>(sb + toff[0]);
-            __nv_bfloat162* mh = reinterpret_cast<__nv_bfloat162*>(&m);
-#pragma unroll
-            for (int k = 1; k < 9; ++k) {
-              const uint4 u = *reinterpret_cast<const uint4*>(sb + toff[k]);
-              const __nv_bfloat162* uh = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int h2 = 0; h2 < 4; ++h2) mh[h2] = __hmax2(mh[h2], uh[h2]);
-            }
-            *reinterpret_cast<uint4*>(orow + c * 32) = m;
-          }
-          buf ^= 1;
-        }
+        epilogue_half<0>(lane_base + TM_D0, prow, skip_top, sc, bi, sl, orow, do_store, &d_empty[0], lane);
+        wait_acc(&d_full[1], pc & 1, p.dbg, st1);
+        tc_fence_after();
+        epilogue_half<1>(lane_base + TM_D1, prow, skip_top, sc, bi, sl, orow + 11 * 64, do_store, &d_empty[1], lane);
       }
     }
-    if (p.dbg != nullptr && et == 0) { p.dbg[blockIdx.x * 8 + 4] = st0; p.dbg[blockIdx.x * 8 + 5] = st1; }
+    if (p.dbg != nullptr && threadIdx.x == 128) { p.dbg[blockIdx.x * 8 + 4] = st0; p.dbg[blockIdx.x * 8 + 5] = st1; }
   } else if (warp >= 12) {
     // ------------------------------------------------------------------ builders: input rows -> patch tiles
     const int bt = threadIdx.x - 384;                      // 0..127
@@ -306,6 +299,15 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tma_w, const StemParams p)
         }
       }
     };
+    // patch rows of this thread: row slot rs -> (stem row of the band, stem column, row of the tile)
+    int b_ry[2], b_x[2], b_row[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int rs = bt + 128 * k;
+      if (rs < 110) { b_ry[k] = rs / 22; b_x[k] = rs - b_ry[k] * 22; b_row[k] = rs; }
+      else { const int u = rs - 110; b_ry[k] = u / 23; b_x[k] = 21 + u - b_ry[k] * 23; b_row[k] = H0_ROWS + u; }
+    }
+    const bool second = bt + 128 < NBUILD;
     pdl_wait();                                            // the video may be produced by the previous kernel
     if (valid) prefetch(im, f);
     int n = 0;
@@ -348,15 +350,17 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tma_w, const StemParams p)
       const int slot = n % RING;
       wait_acc(&slot_free[slot], ((n / RING) & 1) ^ 1, p.dbg, st0);
       uint8_t* tile = ring + slot * SLOT_BYTES;
-#pragma unroll 1
-      for (int pix = bt; pix < NPIX; pix += 128) {
-        const int ry = pix / 44, x = pix - ry * 44;
-        uint8_t* rowp = tile + (pix >> 7) * BLK_BYTES + (pix & 127) * 128;
-        const int sw = pix & 7;
 #pragma unroll
-        for (int kh = 0; kh < 7; ++kh) {
-          const uint32_t* s = reinterpret_cast<const uint32_t*>(sIn + (2 * ry + kh) * SIN_PITCH + 2 * x);
-          *reinterpret_cast<uint4*>(rowp + ((kh ^ sw) << 4)) = make_uint4(s[0], s[1], s[2], s[3]);
+      for (int k = 0; k < 2; ++k) {
+        if (k == 0 || second) {
+          uint8_t* rowp = tile + b_row[k] * 128;
+          const int sw = b_row[k] & 7;
+          const uint32_t* s0 = reinterpret_cast<const uint32_t*>(sIn + (2 * b_ry[k]) * SIN_PITCH + 2 * b_x[k]);
+#pragma unroll
+          for (int kh = 0; kh < 7; ++kh) {
+            const uint32_t* s = s0 + kh * (SIN_PITCH / 2);
+            *reinterpret_cast<uint4*>(rowp + ((kh ^ sw) << 4)) = make_uint4(s[0], s[1], s[2], s[3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -372,15 +376,15 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tma_w, const StemParams p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
   if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8] = clock64() - k_start;
 }
 
 }  // namespace
 
 int stem_fused_plan(const void* w_packed, StemFusedPlan* plan) {
-  AVH_CHECK(w_packed != nullptr, "null weight pointer");
-  if (encode_2d(&plan->tma_w, w_packed, 64, 320, 320, 64)) return 1;
+  AVH_CHECK(w_packed != nullptr && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "stem weights must be 16-byte aligned");
+  plan->w = w_packed;
   return 0;
 }
 
@@ -390,23 +394,28 @@ int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, i
   AVH_CHECK(in_dt == DT_BF16 || in_dt == DT_F16 || in_dt == DT_F32, "unsupported video dtype");
   AVH_CHECK(in_dt != DT_BF16 || (reinterpret_cast<uintptr_t>(video) & 15) == 0, "video must be 16-byte aligned");
   const int sms = device_sm_count();
-  // time segments: enough items to fill whole waves; every segment re-builds 2 + 2 boundary frames
+  // time segments (even lengths: frames are processed in pairs): enough items to fill whole waves; every segment
+  // re-builds 2 + 2 boundary frames
   int best_seg = 1;
   double best = 1e30;
   for (int ns = 1; ns <= T && ns <= 32; ++ns) {
-    const int len = (T + ns - 1) / ns;
+    int len = (T + ns - 1) / ns;
+    len += len & 1;
     const int real = (T + len - 1) / len;               // segments that actually hold frames
     if (real != ns) continue;
     const long long items = (long long)nb * 11 * ns;
     const long long rounds = (items + sms - 1) / sms;
-    const double cost = (double)rounds * (len + 2.0);
+    const double cost = (double)rounds * (len + 3.0);
     if (cost < best) { best = cost; best_seg = ns; }
   }
   StemParams p;
   p.video = video; p.in_dt = in_dt; p.T = T; p.b0 = b0; p.nb = nb;
-  p.nseg = best_seg; p.seglen = (T + best_seg - 1) / best_seg;
+  p.nseg = best_seg;
+  p.seglen = (T + best_seg - 1) / best_seg;
+  p.seglen += p.seglen & 1;
   p.num_items = nb * 11 * best_seg;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(plan.w);
   p.scale = scale; p.bias = bias; p.slope = slope;
   static bool configured = false;
   if (!configured) {
@@ -424,13 +433,13 @@ int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, i
     AVH_CUDA_OK(cudaMalloc(&d, (size_t)grid * 64));
     AVH_CUDA_OK(cudaMemset(d, 0, (size_t)grid * 64));
     p.dbg = d;
-    AVH_CUDA_OK(launch_pdl(stem_fused_kernel, dim3(grid), dim3(NT), SMEM_BYTES, stream, plan.tma_w, p));
+    AVH_CUDA_OK(launch_pdl(stem_fused_kernel, dim3(grid), dim3(NT), SMEM_BYTES, stream, p));
     AVH_CUDA_OK(cudaStreamSynchronize(stream));
     std::vector<unsigned long long> hst((size_t)grid * 8);
     AVH_CUDA_OK(cudaMemcpy(hst.data(), d, (size_t)grid * 64, cudaMemcpyDeviceToHost));
     cudaFree(d);
-    static const char* names[8] = {"total", "frames_built", "mma_wait_patch", "mma_wait_tmem_empty", "epi_wait_tmem_full",
-                                   "epi_in_barrier", "build_wait_slot", "build_busy"};
+    static const char* names[8] = {"total", "frames_built", "mma_wait_patch", "mma_wait_d_empty", "epi_wait_d0_full",
+                                   "epi_wait_d1_full", "build_wait_slot", "build_busy"};
     for (int c : {0, grid / 2, grid - 1}) {
       std::fprintf(stderr, "[stem_fused dbg] cta %d (nseg %d seglen %d items %d):", c, p.nseg, p.seglen, p.num_items);
       for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %s=%llu", names[i], hst[(size_t)c * 8 + i]);
@@ -439,7 +448,7 @@ int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, i
     count_launch(1);
     return 0;
   }
-  AVH_CUDA_OK(launch_pdl(stem_fused_kernel, dim3(grid), dim3(NT), SMEM_BYTES, stream, plan.tma_w, p));
+  AVH_CUDA_OK(launch_pdl(stem_fused_kernel, dim3(grid), dim3(NT), SMEM_BYTES, stream, p));
   count_launch(1);
   return 0;
 }

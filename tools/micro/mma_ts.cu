@@ -10,19 +10,11 @@
 namespace avh { void set_last_error(const std::string&) {} int device_sm_count() { return 148; } void count_launch(int) {} }
 using namespace avh;
 
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, int acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __host__ __device__ inline int aval(int m, int k) { return (m * 3 + k * 5) % 7 - 3; }
 __host__ __device__ inline int bval(int n, int k) { return (n + 2 * k) % 5 - 2; }
@@ -102,13 +94,18 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int mode, int iters, long 
   if (warp == 0) {
     const uint32_t idesc = umma_idesc_bf16(mode == 1 ? 64 : 128, N);
     const uint32_t a = smem_u32(smem), b = smem_u32(smem + 16384);
+    const uint64_t ad = umma_desc_sw128(a), bd = umma_desc_sw128(b);
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const int k = i & 3;
-      const uint64_t ad = umma_desc_sw128(a) + 2 * k, bd = umma_desc_sw128(b) + 2 * k;
+    for (int i = 0; i < iters; i += 4) {
+      // a k-block as the real kernels issue it: 4 MMAs back to back inside one elected section; alternate between
+      // two accumulators (mode >= 3) or keep one
+      const uint32_t d = tmem + ((mode >= 3 && (i & 4)) ? 128 : 0);
       if (elect_one()) {
-        if (mode == 2) umma_bf16_ts(tmem, tmem + 256 + 8 * k, bd, idesc, 1);
-        else umma_bf16(tmem, ad, bd, idesc, 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (mode == 2 || mode == 3) umma_bf16_ts(d, tmem + 256 + 8 * k, bd + 2 * k, idesc, 1);
+          else umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, 1);
+        }
       }
       __syncwarp();
     }
@@ -150,14 +147,15 @@ int main() {
   long long* d_t;
   cudaMalloc(&d_t, 8 * sizeof(long long));
   const int iters = 4000;
-  for (int mode : {0, 1, 2})
+  for (int mode : {0, 1, 2, 3, 4})
     for (int N : {64, 112, 128, 224, 256}) {
+      if (mode >= 3 && N > 128) continue;
       rate<<<1, 128, 80 * 1024>>>(N, mode, iters, d_t);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("rate mode %d N=%d failed: %s\n", mode, N, cudaGetErrorString(e)); return 1; }
       long long t;
       cudaMemcpy(&t, d_t, sizeof(t), cudaMemcpyDeviceToHost);
-      const char* names[3] = {"SS M=128", "SS M=64", "TS M=128"};
+      const char* names[5] = {"SS M=128", "SS M=64", "TS M=128", "TS M=128 2acc", "SS M=128 2acc"};
       printf("%s N=%3d: %.1f clk/MMA (M=128 pipe ideal %d)\n", names[mode], N, (double)t / iters, N / 2);
     }
   return 0;
