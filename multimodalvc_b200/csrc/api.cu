@@ -49,6 +49,9 @@ int device_sm_count() {
   if (dev != cached_dev) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached_n = n;
+    // experiment knob: persistent kernels size their grids for this many SMs (e.g. half the chip per CUDA stream)
+    const char* ev = std::getenv("AVH_SM_LIMIT");
+    if (ev != nullptr && std::atoi(ev) > 0 && std::atoi(ev) < cached_n) cached_n = std::atoi(ev);
     cached_dev = dev;
   }
   return cached_n;

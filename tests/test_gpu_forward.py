@@ -80,6 +80,45 @@ def test_stage_level_parity_fp32():
     assert rel_err(ei, ref) < 1e-3
 
 
+def test_stage_level_parity_bf16_frontend_kernels():
+    """bf16 mode runs its own frontend kernels (fused stem on TS-MMA, window conv, frame-row convs): check the
+    ResEncoder output directly against the fp32 oracle.  Tolerance: 17 convolutions on bf16 activations,
+    max-normalised error <= 2e-2 (bf16 has 8 mantissa bits), and cosine >= 0.9995."""
+    c = load_encoder_case("tiny_av_ragged")
+    with torch.no_grad():
+        stages, _ = c["oracle"].stage_outputs(c["src"], c["pm"])
+    B, T = c["pm"].shape
+    ref = stages["resnet"].transpose(1, 2)
+    for chunk in (0, 7):                                   # one launch / several frontend chunks (b0 > 0 paths)
+        m = make_device_model(c["oracle"], c["over"], c["size"], torch.bfloat16, capture_stages=True,
+                              frontend_chunk_frames=chunk)
+        src, pm = to_dev(c["src"], c["pm"], dtype=torch.bfloat16)
+        m.extract_finetune(src, pm)
+        res = m.read_stage("resnet", B * T * 512).view(B, T, 512).float().cpu()
+        assert rel_err(res, ref) < 2e-2 and cosine(res, ref) > 0.9995
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 31])
+def test_bf16_frontend_short_and_odd_clips(T):
+    """The fused stem walks time in frame pairs with a 5-frame ring: clips shorter than the temporal kernel, odd
+    lengths (unpaired last frame) and fp32 / fp16 video inputs (generic loader path) against the fp32 oracle."""
+    from oracle import avhubert_oracle as ao
+    oracle = ao.build_oracle("tiny", seed=77)
+    src, _ = ao.synthetic_inputs(2, T, seed=T)
+    with torch.no_grad():
+        stages, _ = oracle.stage_outputs(src, None)
+    ref = stages["resnet"].transpose(1, 2)
+    m = make_device_model(oracle, {}, "tiny", torch.bfloat16, capture_stages=True)
+    outs = []
+    for vdt in (torch.bfloat16, torch.float32, torch.float16):
+        s = {"audio": src["audio"].cuda().to(torch.bfloat16), "video": src["video"].cuda().to(vdt)}
+        m.extract_finetune(s, None)
+        res = m.read_stage("resnet", 2 * T * 512).view(2, T, 512).float().cpu()
+        assert torch.isfinite(res).all()
+        assert rel_err(res, ref) < 2e-2 and cosine(res, ref) > 0.9995, (T, vdt)
+        outs.append(res)
+
+
 def test_frontend_chunking_is_invisible():
     c = load_encoder_case("tiny_av_ragged")
     src, pm = to_dev(c["src"], c["pm"])
