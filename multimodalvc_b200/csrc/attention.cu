@@ -38,6 +38,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // asynchronous copy of a [ROWS x 64] bf16 tile (rows row0.., global row stride ld) into smem [ROWS][PITCH];
 // rows >= nrows are zero-filled
@@ -51,9 +53,11 @@ __device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_b
   }
 }
 
-// One CTA = NW warps x 16 query rows of one (batch, head); keys/values stream through smem in chunks of BKV with
-// an online softmax, so a 6 s clip (T = 150) is ONE chunk: Q, K and V of the head are read from L2 exactly once.
-template <int NW, int BKV, int MINB>
+// One CTA = NW warps x 16 query rows of one (batch, head); keys/values go through smem in chunks of BKV keys with an
+// online softmax.  NRES = 1: chunks stream through one buffer (any T).  NRES = 2 (T <= 2 * BKV, the 6 s clip): both
+// chunks are requested up front into their own buffers, so the second chunk's L2 latency hides behind the first
+// chunk's math instead of sitting between two __syncthreads.
+template <int NW, int BKV, int MINB, int NRES>
 __global__ void __launch_bounds__(NW * 32, MINB)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __restrict__ kpm,
                  __nv_bfloat16* __restrict__ out, int T, int D) {
@@ -65,8 +69,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   extern __shared__ __align__(16) uint8_t smem_att[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
   __nv_bfloat16* sK = sQ + BQ * PITCH;
-  __nv_bfloat16* sV = sK + BKV * PITCH;
-  float* sMask = reinterpret_cast<float*>(sV + BKV * PITCH);
+  __nv_bfloat16* sV = sK + NRES * BKV * PITCH;
+  float* sMask = reinterpret_cast<float*>(sV + NRES * BKV * PITCH);
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,6 +82,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   load_tile_async<BKV, NT>(sK, base + D, ld, 0, T);
   load_tile_async<BKV, NT>(sV, base + 2 * D, ld, 0, T);
   cp_async_commit();
+  if (NRES == 2) {
+    load_tile_async<BKV, NT>(sK + BKV * PITCH, base + D, ld, BKV, T);
+    load_tile_async<BKV, NT>(sV + BKV * PITCH, base + 2 * D, ld, BKV, T);
+    cp_async_commit();
+  }
 
   float o[8][4];
 #pragma unroll
@@ -88,18 +97,24 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   uint32_t qf[4][4];
 
   for (int k0 = 0; k0 < T; k0 += BKV) {
-    if (k0 > 0) {
+    if (NRES == 1 && k0 > 0) {
       __syncthreads();   // previous chunk fully consumed
       load_tile_async<BKV, NT>(sK, base + D, ld, k0, T);
       load_tile_async<BKV, NT>(sV, base + 2 * D, ld, k0, T);
       cp_async_commit();
+    }
+    if (NRES == 2 && k0 > 0) {
+      __syncthreads();   // mask of the previous chunk consumed
+      sK += BKV * PITCH;
+      sV += BKV * PITCH;
     }
     for (int i = threadIdx.x; i < BKV; i += NT) {
       const int k = k0 + i;
       const bool dead = (k >= T) || (kpm != nullptr && kpm[(long long)b * T + k] != 0);
       sMask[i] = dead ? -INFINITY : 0.f;
     }
-    cp_async_wait_all();
+    if (NRES == 2 && k0 == 0) cp_async_wait_group<1>();
+    else cp_async_wait_all();
     __syncthreads();
     if (k0 == 0) {
 #pragma unroll
@@ -192,17 +207,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __r
   }
 }
 
-template <int NW, int BKV, int MINB>
+template <int NW, int BKV, int MINB, int NRES>
 int launch_att_t(const void* qkv, const unsigned char* kpm, void* out, int B, int T, int D, int H, cudaStream_t stream) {
   constexpr int BQ = NW * 16;
-  const size_t smem = (size_t)(BQ + 2 * BKV) * PITCH * 2 + BKV * 4;
+  const size_t smem = (size_t)(BQ + 2 * NRES * BKV) * PITCH * 2 + BKV * 4;
   static bool configured = false;
   if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(attention_kernel<NW, BKV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AVH_CUDA_OK(cudaFuncSetAttribute(attention_kernel<NW, BKV, MINB, NRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid((T + BQ - 1) / BQ, H, B);
-  AVH_CUDA_OK(launch_pdl(attention_kernel<NW, BKV, MINB>, grid, dim3(NW * 32), smem, stream,
+  AVH_CUDA_OK(launch_pdl(attention_kernel<NW, BKV, MINB, NRES>, grid, dim3(NW * 32), smem, stream,
                          reinterpret_cast<const __nv_bfloat16*>(qkv), kpm, reinterpret_cast<__nv_bfloat16*>(out), T, D));
   return 0;
 }
@@ -269,10 +284,10 @@ int launch_attention(const void* qkv, const unsigned char* kpm, void* out, int B
     int rc;
     // (a 160-key chunk needs 80 score registers per thread and drops to one CTA per SM: 256 heads on 148 SMs
     //  = two waves; 80-key chunks with the online softmax fit two CTAs per SM and finish in one wave)
-    if (T <= 64) rc = launch_att_t<4, 64, 2>(qkv, kpm, out, B, T, D, H, stream);
-    else if (T <= 96) rc = launch_att_t<6, 96, 2>(qkv, kpm, out, B, T, D, H, stream);
-    else if (T <= 160) rc = launch_att_t<10, 80, 2>(qkv, kpm, out, B, T, D, H, stream);
-    else rc = launch_att_t<8, 128, 2>(qkv, kpm, out, B, T, D, H, stream);
+    if (T <= 64) rc = launch_att_t<4, 64, 2, 1>(qkv, kpm, out, B, T, D, H, stream);
+    else if (T <= 96) rc = launch_att_t<6, 96, 2, 1>(qkv, kpm, out, B, T, D, H, stream);
+    else if (T <= 160) rc = launch_att_t<10, 80, 2, 2>(qkv, kpm, out, B, T, D, H, stream);
+    else rc = launch_att_t<8, 128, 2, 1>(qkv, kpm, out, B, T, D, H, stream);
     if (rc) return rc;
   }
   AVH_CUDA_OK(cudaGetLastError());

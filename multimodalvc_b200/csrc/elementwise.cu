@@ -65,19 +65,10 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
                                          float eps, float* __restrict__ out_f32, void* __restrict__ out_lp,
                                          int lp_dt, const unsigned char* __restrict__ row_zero, long long rows) {
   pdl_launch_dependents();
-  pdl_wait();
   constexpr int C = VEC * 128;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const bool zero = row_zero != nullptr && row_zero[row] != 0;
-  const float4* x = reinterpret_cast<const float4*>(in + row * ld_in);
-  float4 v[VEC];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) v[i] = x[lane + 32 * i];
-  // affine parameters in flight together with the row (they are needed last; fetching them in the output loop
-  // added a second exposed L2 round trip per launch)
+  // affine parameters are launch constants: fetch them while the producer of the rows is still running
   float4 g[VEC], b[VEC];
   if (gamma != nullptr) {
 #pragma unroll
@@ -92,6 +83,14 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
       b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  pdl_wait();
+  if (row >= rows) return;
+  const bool zero = row_zero != nullptr && row_zero[row] != 0;
+  const float4* x = reinterpret_cast<const float4*>(in + row * ld_in);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = x[lane + 32 * i];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) * (1.f / C);
