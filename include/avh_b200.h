@@ -18,6 +18,10 @@
  *          (avhubert/hubert_dataset.py:286-296,351-353,430-456)
  *   avh_add_noise
  *       <- AVHubertDataset.add_noise with the noise clip already selected (avhubert/hubert_dataset.py:317-346)
+ *   avh_video_preprocess, and avh_forward* with video_dtype == AVH_U8 (+ avh_set_video_preprocess)
+ *       <- AVHubertDataset.load_video's eval transform: Normalize(0,255) -> CenterCrop(88) -> Normalize(mean,std)
+ *          (avhubert/hubert_dataset.py:222-226,298-302; avhubert/utils.py:56-95), i.e. raw uint8 gray frames go
+ *          host->device (4x fewer bytes than fp32) and are normalised on the device
  *
  * Conventions: every function returns 0 on success and non-zero on failure; avh_last_error() returns the
  * message of the last failure on the calling thread.  No exceptions cross the boundary.  All work is
@@ -44,7 +48,7 @@ extern "C" {
 #endif
 
 /* element types of caller-provided buffers */
-enum { AVH_F32 = 0, AVH_F16 = 1, AVH_BF16 = 2 };
+enum { AVH_F32 = 0, AVH_F16 = 1, AVH_BF16 = 2, AVH_U8 = 3 /* raw video frames only */ };
 /* arithmetic of the dense contractions */
 enum {
   AVH_COMPUTE_BF16 = 0, /* bf16 operands, fp32 accumulation (tcgen05 kind::f16) */
@@ -87,7 +91,8 @@ AVH_API int avh_load_tensor(avh_handle* h, const char* key, const void* data, in
 AVH_API int avh_finalize_weights(avh_handle* h);
 
 /* extract_finetune.  All pointers are DEVICE pointers.
- *   video  [B,1,T,88,88] contiguous, or NULL (zero-filled modality arm, hubert.py:703-704)
+ *   video  [B,1,T,88,88] contiguous (AVH_F32/F16/BF16), or raw [B,1,T,src_h,src_w] uint8 frames (AVH_U8, see
+ *          avh_set_video_preprocess), or NULL (zero-filled modality arm, hubert.py:703-704)
  *   audio  [B,F,T] with element strides audio_strides[3] (the collater hands a transposed view,
  *          hubert_dataset.py:453), or NULL (hubert.py:705-708)
  *   padding_mask [B,T] bytes, non-zero = padded frame, or NULL
@@ -97,6 +102,16 @@ AVH_API int avh_finalize_weights(avh_handle* h);
 AVH_API int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
                 const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
                 void* out, int out_dtype, void* stream);
+
+/* Raw-video geometry for video_dtype == AVH_U8: video is then [B,1,T,src_h,src_w] uint8 gray frames (mouth ROI as
+ * stored by the dataset, e.g. 96 x 96); avh_forward* first applies x/255, the centre crop to 88 x 88 with offsets
+ * (src-88)/2 and (x-mean)/std (defaults 0.421 / 0.165, hubert_pretraining.py:144-149).  Default: 88 x 88 (no crop). */
+AVH_API int avh_set_video_preprocess(avh_handle* h, int src_h, int src_w, double mean, double std);
+
+/* The same transform as a stand-alone device op: frames [n_frames, src_h, src_w] uint8 -> out [n_frames, crop, crop]
+ * (out_dtype AVH_F32 results are bit-identical to the reference's float64 numpy + cast).  crop % 8 == 0. */
+AVH_API int avh_video_preprocess(const uint8_t* frames, int64_t n_frames, int src_h, int src_w, int crop, double mean,
+                         double std, void* out, int out_dtype, void* stream);
 
 /* Same computation with HOST buffers (pinned memory recommended): copies the inputs host->device, runs
  * avh_forward and copies `out` device->host, all on `stream`; returns after the stream has drained.

@@ -11,5 +11,6 @@ from .hubert import AVHubertConfig, AVHubertModel  # noqa: F401
 from .hubert_asr import HubertEncoderWrapper  # noqa: F401
 from . import audio  # noqa: F401
 from . import sharding  # noqa: F401
+from . import video  # noqa: F401
 
-__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoderWrapper", "audio", "sharding"]
+__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoderWrapper", "audio", "sharding", "video"]

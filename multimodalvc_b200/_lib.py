@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libavh_b200.so")
 
-AVH_F32, AVH_F16, AVH_BF16 = 0, 1, 2
+AVH_F32, AVH_F16, AVH_BF16, AVH_U8 = 0, 1, 2, 3
 AVH_COMPUTE_BF16, AVH_COMPUTE_FP32 = 0, 1
 AVH_FUSE_CONCAT, AVH_FUSE_ADD = 0, 1
 
@@ -17,7 +17,7 @@ EXPORTS = [
     "avh_abi_version", "avh_last_error", "avh_create", "avh_destroy", "avh_load_tensor", "avh_finalize_weights",
     "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
-    "avh_gemm_set_trace",
+    "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess",
 ]
 
 
@@ -67,6 +67,8 @@ def load():
     lib.avh_add_noise.argtypes = [vp, vp, i32, vp, i64, ctypes.c_float, vp, vp, vp]
     lib.avh_gemm_bf16.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
     lib.avh_gemm_set_trace.argtypes = [vp]
+    lib.avh_set_video_preprocess.argtypes = [vp, i32, i32, ctypes.c_double, ctypes.c_double]
+    lib.avh_video_preprocess.argtypes = [vp, i64, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, i32, vp]
     lib.avh_set_profiling.argtypes = [vp, i32]
     lib.avh_profile_json.argtypes = [vp, ctypes.c_char_p, i64]
     lib.avh_launch_count.restype = i64

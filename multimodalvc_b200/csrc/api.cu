@@ -191,15 +191,19 @@ struct avh_handle {
   Plan* prof_plan = nullptr;
   struct Staging {                // device staging of avh_forward_host, one set per stream
     void* video = nullptr; void* audio = nullptr; void* mask = nullptr; void* out = nullptr;
-    size_t video_cap = 0, audio_cap = 0, mask_cap = 0, out_cap = 0;
+    void* video_pp = nullptr;     // normalised + cropped frames when the caller hands raw uint8 video
+    size_t video_cap = 0, audio_cap = 0, mask_cap = 0, out_cap = 0, video_pp_cap = 0;
   };
   std::map<void*, Staging> staging;
+  // raw-video geometry and normalisation for video_dtype == AVH_U8 (avh_set_video_preprocess)
+  int vp_src_h = 88, vp_src_w = 88;
+  double vp_mean = 0.421, vp_std = 0.165;
 };
 
 namespace avh {
 namespace {
 
-int dtype_size(int dt) { return dt == AVH_F32 ? 4 : 2; }
+int dtype_size(int dt) { return dt == AVH_F32 ? 4 : (dt == AVH_U8 ? 1 : 2); }
 
 // ============================================================================ weight folding / packing
 struct Packer {
@@ -1069,6 +1073,7 @@ int avh_destroy(avh_handle* h) {
     if (kv.second.audio) cudaFree(kv.second.audio);
     if (kv.second.mask) cudaFree(kv.second.mask);
     if (kv.second.out) cudaFree(kv.second.out);
+    if (kv.second.video_pp) cudaFree(kv.second.video_pp);
   }
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
@@ -1134,6 +1139,20 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
   AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
   AVH_CUDA_OK(cudaSetDevice(h->device));
+  if (video != nullptr && video_dtype == AVH_U8) {
+    // raw gray frames [B,1,T,src_h,src_w]: the dataset's /255 -> centre crop 88 -> (x-mean)/std on the device
+    // (hubert_dataset.py:222-226), into a per-stream buffer in the module's dtype
+    avh_handle::Staging& st = h->staging[stream];
+    const int pdt = h->cfg.compute_mode == AVH_COMPUTE_FP32 ? AVH_F32 : AVH_BF16;
+    if (avh::ensure_cap(&st.video_pp, &st.video_pp_cap, (size_t)B * T * 7744 * avh::dtype_size(pdt))) return 1;
+    if (avh::launch_video_preprocess(reinterpret_cast<const unsigned char*>(video), (long long)B * T, h->vp_src_h,
+                                     h->vp_src_w, 88, h->vp_mean, h->vp_std, st.video_pp, pdt,
+                                     reinterpret_cast<cudaStream_t>(stream)))
+      return 1;
+    video = st.video_pp;
+    video_dtype = pdt;
+  }
+  AVH_CHECK(video == nullptr || video_dtype == AVH_F32 || video_dtype == AVH_F16 || video_dtype == AVH_BF16, "bad video dtype");
   avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer,
                                reinterpret_cast<cudaStream_t>(stream));
   if (p == nullptr) return 1;
@@ -1162,6 +1181,22 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
     ++i;
   }
   return 0;
+}
+
+int avh_set_video_preprocess(avh_handle* h, int src_h, int src_w, double mean, double stdv) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(src_h >= 88 && src_w >= 88 && src_h <= 4096 && src_w <= 4096, "raw frames must be at least 88 x 88");
+  AVH_CHECK(stdv != 0.0, "std must be non-zero");
+  h->vp_src_h = src_h; h->vp_src_w = src_w; h->vp_mean = mean; h->vp_std = stdv;
+  return 0;
+}
+
+int avh_video_preprocess(const uint8_t* frames, int64_t n_frames, int src_h, int src_w, int crop, double mean,
+                         double stdv, void* out, int out_dtype, void* stream) {
+  AVH_CHECK(frames != nullptr && out != nullptr, "null argument");
+  AVH_CHECK(out_dtype == AVH_F32 || out_dtype == AVH_F16 || out_dtype == AVH_BF16, "bad output dtype");
+  return avh::launch_video_preprocess(frames, n_frames, src_h, src_w, crop, mean, stdv, out, out_dtype,
+                                      reinterpret_cast<cudaStream_t>(stream));
 }
 
 int avh_set_profiling(avh_handle* h, int on) {
@@ -1207,7 +1242,8 @@ int avh_forward_host_async(avh_handle* h, const void* video, int video_dtype, co
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   avh_handle::Staging& st = h->staging[stream];
   const int D = h->cfg.encoder_embed_dim, Fa = h->cfg.audio_feat_dim;
-  const size_t vbytes = (size_t)B * T * 88 * 88 * avh::dtype_size(video_dtype);
+  const size_t vbytes = video_dtype == AVH_U8 ? (size_t)B * T * h->vp_src_h * h->vp_src_w
+                                              : (size_t)B * T * 88 * 88 * avh::dtype_size(video_dtype);
   const size_t abytes = (size_t)B * T * Fa * avh::dtype_size(audio_dtype);
   const size_t obytes = (size_t)B * T * D * avh::dtype_size(out_dtype);
   if (video) {

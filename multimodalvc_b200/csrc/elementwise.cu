@@ -317,9 +317,66 @@ __global__ void avgpool_kernel(const void* __restrict__ in, void* __restrict__ o
   store_lp(out, dt, i, s / (float)(H * W));
 }
 
+// Video pre-processing of the dataset's eval transform (avhubert/hubert_dataset.py:222-226,298-302;
+// avhubert/utils.py:56-95): uint8 gray frames [n, src_h, src_w] -> x/255 -> centre crop -> (x - mean)/std.  The
+// reference does this in float64 numpy and casts to float32 (hubert_dataset.py:432): the 256 possible results are
+// computed once per CTA in double and looked up, so fp32 outputs are bit-identical to the reference's.
+__global__ void __launch_bounds__(256)
+video_preprocess_kernel(const unsigned char* __restrict__ in, void* __restrict__ out, int out_dt, long long n_frames,
+                        int src_h, int src_w, int crop, int dh, int dw, double mean, double stdv) {
+  pdl_launch_dependents();
+  __shared__ float lut[256];
+  lut[threadIdx.x] = (float)((((double)threadIdx.x - 0.0) / 255.0 - mean) / stdv);
+  __syncthreads();
+  pdl_wait();
+  const int groups = crop / 8;                              // 8 output pixels per thread
+  const long long total = n_frames * crop * groups;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i % groups);
+  const long long r = i / groups;
+  const int y = (int)(r % crop);
+  const long long f = r / crop;
+  const unsigned char* src = in + (f * src_h + (y + dh)) * (long long)src_w + dw + g * 8;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = lut[src[k]];
+  const long long o = (f * crop + y) * (long long)crop + g * 8;
+  if (out_dt == DT_F32) {
+    float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else if (out_dt == DT_BF16) {
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  } else {
+    __half2 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + o) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
 
 }  // namespace
+
+int launch_video_preprocess(const unsigned char* frames, long long n_frames, int src_h, int src_w, int crop, double mean,
+                            double stdv, void* out, int out_dt, cudaStream_t stream) {
+  if (n_frames <= 0) return 0;
+  AVH_CHECK(crop >= 8 && crop % 8 == 0 && crop <= src_h && crop <= src_w, "crop must be a multiple of 8 and fit the frame");
+  AVH_CHECK(stdv != 0.0, "std must be non-zero");
+  AVH_CHECK((reinterpret_cast<uintptr_t>(out) & 31) == 0, "output must be 32-byte aligned");
+  // CenterCrop of the reference: delta = int(round(w - tw) / 2.)  (utils.py:86-88; truncation toward zero)
+  const int dh = (src_h - crop) / 2, dw = (src_w - crop) / 2;
+  const long long total = n_frames * crop * (crop / 8);
+  AVH_CHECK(total / 256 + 1 < (1ll << 31), "too many frames for one launch");
+  AVH_CUDA_OK(launch_pdl(video_preprocess_kernel, dim3((unsigned)blocks_for(total, 256)), dim3(256), 0, stream, frames, out,
+                         out_dt, n_frames, src_h, src_w, crop, dh, dw, mean, stdv));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
 
 int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* gamma, const float* beta, float eps,
                      float* out_f32, void* out_lp, int lp_dt, const unsigned char* row_zero, long long rows, int C,

@@ -20,6 +20,7 @@ import torch.nn as nn
 from . import _lib
 
 _DTYPES = {torch.float32: _lib.AVH_F32, torch.float16: _lib.AVH_F16, torch.bfloat16: _lib.AVH_BF16}
+_U8 = _lib.AVH_U8        # raw uint8 video frames (normalised + centre-cropped on the device)
 
 
 @dataclass
@@ -193,6 +194,9 @@ class AVHubertModel(nn.Module):
         self._handle = None
         self._handle_key = None
         self._dirty = True
+        self._video_geo = None
+        # normalisation of raw uint8 video (task config image_mean / image_std, hubert_pretraining.py:144-149)
+        self.image_mean, self.image_std = 0.421, 0.165
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
 
     # ------------------------------------------------------------------ reference API surface
@@ -236,6 +240,7 @@ class AVHubertModel(nn.Module):
             _lib.load().avh_destroy(self._handle)
             self._handle = None
             self._handle_key = None
+            self._video_geo = None
 
     def __del__(self):
         try:
@@ -314,13 +319,22 @@ class AVHubertModel(nn.Module):
         if ref.device != dev:
             raise RuntimeError(f"inputs are on {ref.device} but the module is on {dev}")
         B = ref.size(0)
+        video_dt = 0
         if src_video is not None:
-            if src_video.dim() != 5 or src_video.size(1) != 1 or tuple(src_video.shape[3:]) != (88, 88):
+            T = src_video.size(2) if src_video.dim() == 5 else -1
+            if src_video.dtype == torch.uint8:
+                # raw gray frames [B,1,T,H,W]: normalised and centre-cropped on the device (video.py)
+                if src_video.dim() != 5 or src_video.size(1) != 1 or min(src_video.shape[3:]) < 88:
+                    raise ValueError(f"uint8 video must be [B,1,T,H>=88,W>=88], got {tuple(src_video.shape)}")
+                self._set_video_geometry(handle, int(src_video.size(3)), int(src_video.size(4)))
+                video_dt = _U8
+            elif src_video.dim() != 5 or src_video.size(1) != 1 or tuple(src_video.shape[3:]) != (88, 88):
                 raise ValueError(f"video must be [B,1,T,88,88], got {tuple(src_video.shape)}")
-            T = src_video.size(2)
             src_video = src_video.contiguous()
-            if src_video.dtype not in _DTYPES:
-                src_video = src_video.float()
+            if video_dt != _U8:
+                if src_video.dtype not in _DTYPES:
+                    src_video = src_video.float()
+                video_dt = _DTYPES[src_video.dtype]
         if src_audio is not None:
             if src_audio.dim() != 3 or src_audio.size(1) != self.cfg.audio_feat_dim:
                 raise ValueError(f"audio must be [B,{self.cfg.audio_feat_dim},T], got {tuple(src_audio.shape)}")
@@ -347,13 +361,19 @@ class AVHubertModel(nn.Module):
             _lib.check(_lib.load().avh_forward(
                 handle,
                 ctypes.c_void_p(src_video.data_ptr()) if src_video is not None else None,
-                _DTYPES[src_video.dtype] if src_video is not None else 0,
+                video_dt,
                 ctypes.c_void_p(src_audio.data_ptr()) if src_audio is not None else None,
                 _DTYPES[src_audio.dtype] if src_audio is not None else 0,
                 strides,
                 ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None,
                 B, T, ol, ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
         return out, padding_mask
+
+    def _set_video_geometry(self, handle, H, W):
+        geo = (H, W, float(self.image_mean), float(self.image_std))
+        if getattr(self, "_video_geo", None) != geo:
+            _lib.check(_lib.load().avh_set_video_preprocess(handle, H, W, geo[2], geo[3]))
+            self._video_geo = geo
 
     def extract_finetune_host(self, video, audio, padding_mask=None, output_layer=None, out=None, wait=True):
         """End-to-end call with HOST tensors (pinned recommended): H2D copies, forward and the D2H read of the
@@ -375,13 +395,20 @@ class AVHubertModel(nn.Module):
         for t in (video, audio):
             if t is not None and (t.device.type != "cpu" or not t.is_contiguous()):
                 raise ValueError("extract_finetune_host takes contiguous CPU tensors")
+        video_dt = 0
+        if video is not None:
+            if video.dtype == torch.uint8:        # raw frames [B,1,T,H,W]: 1 byte per pixel over PCIe
+                self._set_video_geometry(handle, int(video.size(3)), int(video.size(4)))
+                video_dt = _U8
+            else:
+                video_dt = _DTYPES[video.dtype]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             lib = _lib.load()
             _lib.check((lib.avh_forward_host if wait else lib.avh_forward_host_async)(
                 handle,
                 ctypes.c_void_p(video.data_ptr()) if video is not None else None,
-                _DTYPES[video.dtype] if video is not None else 0,
+                video_dt,
                 ctypes.c_void_p(audio.data_ptr()) if audio is not None else None,
                 _DTYPES[audio.dtype] if audio is not None else 0,
                 ctypes.c_void_p(pm.data_ptr()) if pm is not None else None,

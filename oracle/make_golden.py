@@ -110,12 +110,45 @@ def make_audio_fixtures():
     print("audio fixtures written")
 
 
+def make_video_fixtures():
+    """Outputs of the REAL transform classes (avhubert/utils.py) and of the real collater for raw uint8 frames."""
+    ds = ref_import.install_dataset(fo.logfbank)
+    # the real avhubert/utils.py, loaded by path (ref_import stubs the module name for the model import)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("avhubert_utils_real", os.path.join(ref_import.REF, "avhubert", "utils.py"))
+    cu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cu)
+    from oracle import video_oracle as vo
+    out = {}
+    for name, (T, H, W) in {"roi96": (7, 96, 96), "odd_97x101": (3, 97, 101), "exact88": (2, 88, 88)}.items():
+        frames = vo.synthetic_frames(T, H, W, seed=T + H)
+        tf = cu.Compose([cu.Normalize(0.0, 255.0), cu.CenterCrop((88, 88)), cu.Normalize(0.421, 0.165)])
+        y = tf(frames)                                       # float64 [T,88,88]
+        out["frames_" + name] = frames
+        out["out_" + name] = y
+        assert np.array_equal(y, vo.video_transform(frames)), "video restatement disagrees with the reference"
+    obj = ds.AVHubertDataset.__new__(ds.AVHubertDataset)
+    obj.pad_audio, obj.random_crop, obj.max_sample_size = True, False, 500
+    clips = [vo.synthetic_frames(n, 96, 96, seed=50 + n) for n in (5, 9, 2)]
+    items = [torch.from_numpy(np.expand_dims(tf(c), -1).astype(np.float32)) for c in clips]
+    coll, pmask, _ = obj.collater_audio(items, 9)
+    out["coll_lens"] = np.array([5, 9, 2])
+    out["coll_frames"] = np.concatenate(clips)
+    out["coll_out"] = coll.numpy()
+    out["coll_mask"] = pmask.numpy()
+    np.savez_compressed(os.path.join(OUT, "video_reference.npz"), **out)
+    print("video fixtures written")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if not ref_import.available():
         sys.exit("reference tree not available; fixtures can only be generated where /root/reference exists")
     torch.set_num_threads(8)
     make_audio_fixtures()
+    make_video_fixtures()
+    if "--video-only" in sys.argv:
+        return
     for case in ENCODER_CASES:
         make_encoder_case(*case)
 
