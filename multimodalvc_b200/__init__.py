@@ -8,9 +8,9 @@ CUDA kernels (tcgen05/TMEM/TMA GEMM + implicit-GEMM convolutions, flash-style at
 behind the C ABI declared in ``include/avh_b200.h``.
 """
 from .hubert import AVHubertConfig, AVHubertModel  # noqa: F401
-from .hubert_asr import HubertEncoderWrapper  # noqa: F401
+from .hubert_asr import HubertEncoder, HubertEncoderWrapper  # noqa: F401
 from . import audio  # noqa: F401
 from . import sharding  # noqa: F401
 from . import video  # noqa: F401
 
-__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoderWrapper", "audio", "sharding", "video"]
+__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoder", "HubertEncoderWrapper", "audio", "sharding", "video"]

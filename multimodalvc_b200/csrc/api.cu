@@ -189,6 +189,7 @@ struct avh_handle {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // 2 per step of the last profiled forward
   Plan* prof_plan = nullptr;
+  Plan* last_plan = nullptr;      // plan of the most recent avh_forward (avh_read_stage reads its stages)
   struct Staging {                // device staging of avh_forward_host, one set per stream
     void* video = nullptr; void* audio = nullptr; void* mask = nullptr; void* out = nullptr;
     void* video_pp = nullptr;     // normalised + cropped frames when the caller hands raw uint8 video
@@ -991,7 +992,7 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
-  if (h->plans.size() >= 8) h->plans.clear();      // bound workspace growth for ragged shape streams
+  if (h->plans.size() >= 8) { h->plans.clear(); h->last_plan = nullptr; h->prof_plan = nullptr; }   // bound workspace growth for ragged shape streams
   std::unique_ptr<Plan> p(new Plan());
   p->B = B; p->T = T; p->has_video = has_video; p->has_audio = has_audio; p->has_mask = has_mask;
   p->output_layer = output_layer;
@@ -1113,6 +1114,8 @@ int avh_finalize_weights(avh_handle* h) {
   AVH_CHECK(h != nullptr, "null handle");
   AVH_CUDA_OK(cudaSetDevice(h->device));
   h->plans.clear();
+  h->last_plan = nullptr;
+  h->prof_plan = nullptr;
   h->warena.release();
   h->warena = avh::Arena();
   avh::Packer sizer{h, nullptr, avh::Sizer(), ""};
@@ -1156,6 +1159,7 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer,
                                reinterpret_cast<cudaStream_t>(stream));
   if (p == nullptr) return 1;
+  h->last_plan = p;
   p->args.video = video; p->args.video_dt = video_dtype;
   p->args.audio = audio; p->args.audio_dt = audio_dtype;
   if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
@@ -1281,6 +1285,7 @@ int avh_forward_host(avh_handle* h, const void* video, int video_dtype, const vo
 int avh_read_stage(avh_handle* h, const char* name, float* dst, int64_t capacity_elems, void* stream) {
   AVH_CHECK(h != nullptr && name != nullptr && dst != nullptr, "null argument");
   for (auto& kv : h->plans) {
+    if (h->last_plan != nullptr && kv.second.get() != h->last_plan) continue;     // the most recent forward's plan
     auto it = kv.second->stages.find(name);
     if (it == kv.second->stages.end()) continue;
     const long long n = it->second.second.second;

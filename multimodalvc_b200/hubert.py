@@ -440,6 +440,29 @@ class AVHubertModel(nn.Module):
             lib.avh_set_profiling(handle, 0)
         return json.loads(buf.value.decode())
 
+    @torch.no_grad()
+    def extract_features(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
+        """avhubert/hubert.py:676-692 (forward(features_only=True), :591-653) in eval mode: returns
+        (features [B,T,D], padding_mask).  ``ret_conv=True`` gives the encoder INPUT (post_extract_proj output with
+        padded frames zeroed, as the reference's in-place index_put leaves it) — layer 0 of
+        avhubert/clustering/dump_hubert_feature.py:95-106; otherwise the output of layer ``output_layer`` (1-based,
+        no final LayerNorm) or of the whole encoder.  Both modalities are required, as in the reference."""
+        if mask:
+            raise NotImplementedError("span masking (mask=True) is not implemented on the device path")
+        if source["audio"] is None or source["video"] is None:
+            raise ValueError("extract_features needs both modalities (forward_features fails on None in the "
+                             "reference, hubert.py:609-610); use extract_finetune for single-modality input")
+        if not ret_conv:
+            return self.extract_finetune(source, padding_mask, output_layer=output_layer)
+        if not self.cfg.capture_stages:           # the encoder input is only kept when the handle captures stages
+            self.cfg.capture_stages = True
+            self._destroy_handle()
+            self._dirty = True
+        x, pm = self.extract_finetune(source, padding_mask, output_layer=1)
+        B, T, D = x.shape
+        feats = self.read_stage("enc_in", B * T * D).view(B, T, D).to(x.dtype)
+        return feats, pm
+
     def forward(self, *args, **kwargs):
         raise NotImplementedError("the pretraining forward (masked prediction, avhubert/hubert.py:591-674) is out "
                                   "of scope; use extract_finetune")

@@ -1,6 +1,13 @@
-"""Mirror of the reference's encoder wrapper (avhubert/hubert_asr.py:375-409): the object MMS-LLaMA owns as
-``self.avhubert`` (src/model.py:96-97,220) and calls as ``self.avhubert(source={...}, padding_mask=...)``."""
+"""Mirrors of the reference's encoder wrappers: ``HubertEncoderWrapper`` (avhubert/hubert_asr.py:375-409), the
+object MMS-LLaMA owns as ``self.avhubert`` (src/model.py:96-97,220) and calls as
+``self.avhubert(source={...}, padding_mask=...)``, and ``HubertEncoder`` (avhubert/hubert_asr.py:251-372), the
+encoder of the CTC / seq2seq fine-tuning models."""
+import ctypes
+
+import torch
 import torch.nn as nn
+
+from . import _lib
 
 
 class HubertEncoderWrapper(nn.Module):
@@ -27,3 +34,78 @@ class HubertEncoderWrapper(nn.Module):
         if encoder_out["padding_mask"] is not None:
             encoder_out["padding_mask"] = encoder_out["padding_mask"].index_select(0, new_order)
         return encoder_out
+
+
+class HubertEncoder(nn.Module):
+    """avhubert/hubert_asr.py:251-372 around an already-built ``AVHubertModel`` (the reference builds it from the
+    checkpoint's config through the fairseq task, :299-305; here the caller passes it in).  ``forward`` =
+    extract_finetune (no grad: the device path is inference-only) -> T x B x C -> final_dropout (identity in eval)
+    -> optional ``proj`` (CTC vocabulary head ``Linear(d, len(tgt_dict))`` or ``Linear(d, decoder_embed_dim)``).
+    The projection runs on the library's tcgen05 GEMM (bf16 operands, fp32 accumulation)."""
+
+    def __init__(self, w2v_model, tgt_dict_size=None, decoder_embed_dim=None, final_dropout=0.0, apply_mask=False,
+                 freeze_finetune_updates=0):
+        super().__init__()
+        w2v_model.remove_pretraining_modules()
+        d = w2v_model.encoder.embedding_dim
+        self.w2v_model = w2v_model
+        self.apply_mask = apply_mask
+        self.final_dropout = nn.Dropout(final_dropout)
+        self.freeze_finetune_updates = freeze_finetune_updates
+        self.num_updates = 0
+        if tgt_dict_size is not None:
+            self.proj = _linear(d, tgt_dict_size)
+        elif decoder_embed_dim is not None and decoder_embed_dim != d:
+            self.proj = _linear(d, decoder_embed_dim)
+        else:
+            self.proj = None
+
+    def set_num_updates(self, num_updates):
+        self.num_updates = num_updates
+
+    @torch.no_grad()
+    def forward(self, source, padding_mask, tbc=True, **kwargs):
+        if self.training:
+            raise RuntimeError("HubertEncoder on the device path is inference-only: call .eval()")
+        x, padding_mask = self.w2v_model.extract_finetune(source=source, padding_mask=padding_mask, mask=False)
+        if self.proj is not None:
+            x = _project(x, self.proj)
+        if tbc:
+            x = x.transpose(0, 1)                 # B x T x C -> T x B x C
+        return {
+            "encoder_out": x,
+            "encoder_padding_mask": padding_mask,
+            "padding_mask": padding_mask,
+        }
+
+    reorder_encoder_out = HubertEncoderWrapper.reorder_encoder_out
+
+    def max_positions(self):
+        return None
+
+
+def _linear(in_features, out_features):
+    """fairseq-style Linear (hubert_asr.py:644-649): xavier_uniform weight, zero bias."""
+    m = nn.Linear(in_features, out_features)
+    nn.init.xavier_uniform_(m.weight)
+    nn.init.constant_(m.bias, 0.0)
+    return m
+
+
+def _project(x, lin):
+    """[B,T,D] @ W^T + b through avh_gemm_bf16; output columns padded to a multiple of 32 inside the call."""
+    B, T, D = x.shape
+    N = lin.out_features
+    Np = (N + 31) // 32 * 32
+    a = x.reshape(B * T, D).to(torch.bfloat16).contiguous()
+    w = torch.zeros(Np, D, device=x.device, dtype=torch.bfloat16)
+    w[:N] = lin.weight.detach().to(torch.bfloat16)
+    bias = torch.zeros(Np, device=x.device, dtype=torch.float32)
+    bias[:N] = lin.bias.detach().float()
+    out = torch.empty(B * T, Np, device=x.device, dtype=torch.float32)
+    vp = ctypes.c_void_p
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.load().avh_gemm_bf16(vp(a.data_ptr()), vp(w.data_ptr()), B * T, Np, D, vp(bias.data_ptr()), 0,
+                                             None, 0, vp(out.data_ptr()), 1, 0, 0, 0, vp(stream)))
+    return out[:, :N].to(x.dtype).view(B, T, N)

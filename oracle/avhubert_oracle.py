@@ -273,6 +273,23 @@ class OracleAVHubert(nn.Module):
         return out["x"], pm
 
 
+def _oracle_extract_features(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
+    """avhubert/hubert.py:676-692 -> forward(features_only=True) (:591-653) in eval mode with mask=False: both
+    modalities are required (forward_features on None fails in the reference); `features` is the post_extract_proj
+    output, whose padded frames the encoder zeroes IN PLACE (index_put, wav2vec2.py:869-870), `x` the encoder
+    output (layer k = output_layer, no final LayerNorm then)."""
+    if source["audio"] is None or source["video"] is None:
+        raise ValueError("extract_features needs both modalities (hubert.py:609-610)")
+    out, pm = self.stage_outputs(source, padding_mask, output_layer)
+    feats = out["enc_in"]
+    if pm is not None:
+        feats = feats.masked_fill(pm.unsqueeze(-1), 0.0)
+    return (feats if ret_conv else out["x"]), pm
+
+
+OracleAVHubert.extract_features = torch.no_grad()(_oracle_extract_features)
+
+
 def randomize_norm_stats(model: nn.Module, seed: int = 4321):
     """Make BN folding / PReLU non-trivial for parity tests: running_mean ~ N(0,0.1),
     running_var ~ U(0.5,1.5), BN affine ~ N(1,0.1)/N(0,0.1), PReLU slopes ~ U(0.1,0.4), LN affine perturbed."""

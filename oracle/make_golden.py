@@ -110,6 +110,27 @@ def make_audio_fixtures():
     print("audio fixtures written")
 
 
+def make_extract_features_case():
+    """Outputs of the REAL AVHubertModel.extract_features (hubert.py:676-692) on the tiny ragged case:
+    ret_conv features, layer-1 features, full output."""
+    oracle = ao.build_oracle("tiny", seed=1234)
+    ref, _ = ref_import.build_reference_model("tiny")
+    ref.load_state_dict(oracle.state_dict(), strict=False)
+    ref.eval()
+    src, pm = ao.synthetic_inputs(3, 20, lengths=[20, 13, 7], seed=11)
+    out = {}
+    with torch.no_grad():
+        for key, kw in {"conv": dict(ret_conv=True), "layer1": dict(output_layer=1), "full": dict()}.items():
+            y, pm_out = ref.extract_features({k: v.clone() for k, v in src.items()}, pm.clone(), mask=False, **kw)
+            y_o, _ = oracle.extract_features(src, pm, **kw)
+            err = (y - y_o).abs().max().item()
+            print(f"extract_features[{key}]: ref vs oracle max abs diff {err:.3e}")
+            assert err < 2e-4
+            out[key] = y.numpy().astype(np.float32)
+        out["pm_out"] = pm_out.numpy()
+    np.savez_compressed(os.path.join(OUT, "enc_extract_features.npz"), **out)
+
+
 def make_video_fixtures():
     """Outputs of the REAL transform classes (avhubert/utils.py) and of the real collater for raw uint8 frames."""
     ds = ref_import.install_dataset(fo.logfbank)
@@ -147,6 +168,7 @@ def main():
     torch.set_num_threads(8)
     make_audio_fixtures()
     make_video_fixtures()
+    make_extract_features_case()
     if "--video-only" in sys.argv:
         return
     for case in ENCODER_CASES:

@@ -202,3 +202,48 @@ def test_large_b16_t150_properties():
     pm[:, 150:] = True
     yp, _ = m.extract_finetune({"audio": a, "video": v}, pm)
     assert cosine(yp[:, :150].float().cpu(), y1.float().cpu()) > 0.9995
+
+
+def test_extract_features_matches_reference_golden():
+    """AVHubertModel.extract_features (hubert.py:676-692): conv features (encoder input with padded frames zeroed),
+    layer-k features and the full output against outputs of the REAL reference (enc_extract_features.npz)."""
+    import numpy as np
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "enc_extract_features.npz"))
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.float32)
+    src, pm = to_dev(c["src"], c["pm"])
+    for key, kw in {"conv": dict(ret_conv=True), "layer1": dict(output_layer=1), "full": dict()}.items():
+        y, pm_out = m.extract_features(src, pm, mask=False, **kw)
+        assert rel_err(y.cpu(), torch.from_numpy(z[key])) < FP32_TOL, key
+        assert torch.equal(pm_out.cpu(), torch.from_numpy(z["pm_out"]))
+    y, _ = m.extract_features(src, pm, ret_conv=True)
+    assert not y[c["pm"].cuda()].any()                       # padded frames of the conv features are zero
+    with pytest.raises(ValueError):
+        m.extract_features({"audio": None, "video": src["video"]}, pm)
+    mb = make_device_model(c["oracle"], c["over"], c["size"], torch.bfloat16)
+    srcb, _ = to_dev(c["src"], c["pm"], dtype=torch.bfloat16)
+    yb, _ = mb.extract_features(srcb, pm, ret_conv=True)
+    assert cosine(yb.float().cpu(), torch.from_numpy(z["conv"])) > BF16_COS
+
+
+def test_hubert_encoder_ctc_head():
+    """HubertEncoder (hubert_asr.py:251-354): T x B x C output, three-key dict, optional vocabulary projection."""
+    from multimodalvc_b200 import HubertEncoder
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.bfloat16)
+    src, pm = to_dev(c["src"], c["pm"], dtype=torch.bfloat16)
+    enc = HubertEncoder(m).cuda().eval()
+    out = enc(src, pm)
+    y, _ = m.extract_finetune(src, pm)
+    assert set(out) == {"encoder_out", "encoder_padding_mask", "padding_mask"}
+    assert torch.equal(out["encoder_out"], y.transpose(0, 1)) and torch.equal(out["padding_mask"], pm)
+    assert torch.equal(enc(src, pm, tbc=False)["encoder_out"], y)
+    head = HubertEncoder(m, tgt_dict_size=41).cuda().to(torch.bfloat16).eval()          # CTC vocabulary of 41 units
+    torch.nn.init.normal_(head.proj.bias, std=0.5)
+    o = head(src, pm)["encoder_out"]
+    assert o.shape == (y.size(1), y.size(0), 41)
+    ref = (y.float() @ head.proj.weight.float().t() + head.proj.bias.float()).transpose(0, 1)
+    assert (o.float() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-2   # bf16 output rounding
+    with pytest.raises(RuntimeError):
+        head.train()(src, pm)
