@@ -20,6 +20,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <tuple>
 #include <memory>
 #include <string>
 #include <vector>
@@ -141,6 +142,10 @@ struct CallArgs {          // per-call pointers the steps read through the plan
   const unsigned char* mask = nullptr;
   void* out = nullptr;
   int out_dt = 0;
+  bool operator<(const CallArgs& o) const {
+    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask, out, out_dt) <
+           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask, o.out, o.out_dt);
+  }
 };
 
 struct Plan {
@@ -154,7 +159,19 @@ struct Plan {
   StemFusedPlan stemf;
   std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
   CallArgs args;
+  // CUDA graphs of the launch list, one per distinct set of caller pointers (the kernels' arguments are baked in at
+  // capture).  A forward costs ~200 launches = ~3 ms of host time — as long as the GPU needs for the step; a graph
+  // launch is one driver call.  Framework allocators hand the same addresses back for same-shaped tensors, and the
+  // host-buffer entry point always runs from its own staging buffers, so the cache hits after the first calls.
+  std::map<CallArgs, cudaGraphExec_t> graphs;
+  int direct_runs = 0;              // un-captured forwards so far (the first one also configures the kernels)
+  int graph_kernels = 0;            // kernel launches inside one graph (for avh_launch_count)
+  void drop_graphs() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+  }
   ~Plan() {
+    drop_graphs();
     for (GemmPlan* g : gemms) delete g;
     for (ConvWinPlan* g : convwins) delete g;
     for (ConvFramePlan* g : convframes) delete g;
@@ -1166,6 +1183,49 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   p->args.mask = padding_mask;
   p->args.out = out; p->args.out_dt = out_dtype;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static int graphs_env = -1;
+  if (graphs_env < 0) {
+    const char* ev = std::getenv("AVH_GRAPHS");
+    const char* dbg = std::getenv("AVH_STEM_DBG");
+    graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr) ? 0 : 1;
+  }
+  if (graphs_env == 1 && !h->profiling && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+    auto it = p->graphs.find(p->args);
+    if (it != p->graphs.end()) {
+      AVH_CUDA_OK(cudaGraphLaunch(it->second, s));
+      avh::count_launch(p->graph_kernels);
+      return 0;
+    }
+    if (p->direct_runs >= 1) {
+      // capture this argument set: the steps only enqueue kernels / async copies on `s`
+      if (p->graphs.size() >= 16) p->drop_graphs();
+      const long long before = avh::g_launches.load();
+      cudaGraph_t graph = nullptr;
+      bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        for (auto& st : p->steps)
+          if (st.run(s)) { ok = false; break; }
+        if (cudaStreamEndCapture(s, &graph) != cudaSuccess || graph == nullptr) ok = false;
+      }
+      const int captured = (int)(avh::g_launches.load() - before);
+      avh::count_launch(-captured);            // captured launches have not run yet
+      cudaGraphExec_t exec = nullptr;
+      if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      if (ok) {
+        p->graphs[p->args] = exec;
+        p->graph_kernels = captured;
+        AVH_CUDA_OK(cudaGraphLaunch(exec, s));
+        avh::count_launch(captured);
+        return 0;
+      }
+      // capture is not available for this launch list on this driver: remember, clear the error, run directly
+      cudaGetLastError();
+      avh::g_err.clear();
+      graphs_env = 0;
+    }
+  }
+  ++p->direct_runs;
   if (h->profiling) {
     while (h->prof_events.size() < 2 * p->steps.size()) {
       cudaEvent_t e;
