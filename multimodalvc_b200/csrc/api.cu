@@ -142,9 +142,10 @@ struct CallArgs {          // per-call pointers the steps read through the plan
   const unsigned char* mask = nullptr;
   void* out = nullptr;
   int out_dt = 0;
+  // graph-cache key: the INPUT pointers (the output is written by the last step, which stays outside the graph)
   bool operator<(const CallArgs& o) const {
-    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask, out, out_dt) <
-           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask, o.out, o.out_dt);
+    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask) <
+           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask);
   }
 };
 
@@ -159,13 +160,16 @@ struct Plan {
   StemFusedPlan stemf;
   std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
   CallArgs args;
-  // CUDA graphs of the launch list, one per distinct set of caller pointers (the kernels' arguments are baked in at
-  // capture).  A forward costs ~200 launches = ~3 ms of host time — as long as the GPU needs for the step; a graph
-  // launch is one driver call.  Framework allocators hand the same addresses back for same-shaped tensors, and the
-  // host-buffer entry point always runs from its own staging buffers, so the cache hits after the first calls.
+  // CUDA graphs of the launch list (all steps but the last, which writes the caller's output and is launched
+  // directly), one per distinct set of INPUT pointers (kernel arguments are baked in at capture).  A forward is ~200
+  // launches = ~3 ms of host time — as long as the GPU needs for the step; a graph launch is one driver call.
+  // Framework allocators hand the same addresses back for same-shaped tensors and the host-buffer entry point always
+  // runs from its own staging buffers, so the cache hits after the first calls; a caller that never repeats an
+  // address stops being captured (captures/calls guard) and gets plain launches.
   std::map<CallArgs, cudaGraphExec_t> graphs;
   int direct_runs = 0;              // un-captured forwards so far (the first one also configures the kernels)
   int graph_kernels = 0;            // kernel launches inside one graph (for avh_launch_count)
+  long long calls = 0, captures = 0;
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     graphs.clear();
@@ -1190,21 +1194,23 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
     graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr) ? 0 : 1;
   }
   if (graphs_env == 1 && !h->profiling && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+    ++p->calls;
     auto it = p->graphs.find(p->args);
     if (it != p->graphs.end()) {
       AVH_CUDA_OK(cudaGraphLaunch(it->second, s));
       avh::count_launch(p->graph_kernels);
-      return 0;
+      return p->steps.back().run(s);
     }
-    if (p->direct_runs >= 1) {
+    const bool thrashing = p->captures >= 16 && 2 * p->captures > p->calls;     // inputs never come back: stop capturing
+    if (p->direct_runs >= 1 && !thrashing && p->steps.size() >= 2) {
       // capture this argument set: the steps only enqueue kernels / async copies on `s`
       if (p->graphs.size() >= 16) p->drop_graphs();
       const long long before = avh::g_launches.load();
       cudaGraph_t graph = nullptr;
       bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (ok) {
-        for (auto& st : p->steps)
-          if (st.run(s)) { ok = false; break; }
+        for (size_t i = 0; i + 1 < p->steps.size(); ++i)
+          if (p->steps[i].run(s)) { ok = false; break; }
         if (cudaStreamEndCapture(s, &graph) != cudaSuccess || graph == nullptr) ok = false;
       }
       const int captured = (int)(avh::g_launches.load() - before);
@@ -1215,9 +1221,10 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
       if (ok) {
         p->graphs[p->args] = exec;
         p->graph_kernels = captured;
+        ++p->captures;
         AVH_CUDA_OK(cudaGraphLaunch(exec, s));
         avh::count_launch(captured);
-        return 0;
+        return p->steps.back().run(s);
       }
       // capture is not available for this launch list on this driver: remember, clear the error, run directly
       cudaGetLastError();
