@@ -94,15 +94,17 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                       // from here on: activations of the previous kernel
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {                  // the resident weights are launch constants: request them before the wait
     if (elect_one()) {
       mbar_expect_tx(b_full, B_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem_b + t * B_TAP_BYTES, &tma_b, b_full, t * CH, 0);
     }
     __syncwarp();
+  }
+  pdl_wait();                       // from here on: activations of the previous kernel
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {

@@ -147,8 +147,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above (K table, barrier init, TMEM allocation, descriptor prefetch) touched only launch-constant
-  // data; from here on the kernel reads and writes activations of its predecessors
+  // Weights are launch constants too: the B tiles of the first pipeline stages go in flight BEFORE the dependency
+  // wait (they come from DRAM — 25 MB of weights per layer never stay in L2 — and were the longest part of the
+  // 1.1 us between the wait and the first MMA); the A tiles (activations) follow after the wait.
+  int pre_b = 0;
+  if (PAIR == 1 && warp == 0 && unit < num_tiles) {
+    const int n_blk0 = unit / p.num_m_blk;
+    pre_b = p.num_kb < STAGES ? p.num_kb : STAGES;
+    const uint32_t stage_tx0 = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+    for (int kb = 0; kb < pre_b; ++kb) {
+      int4 e;
+      if (p.ktable != nullptr) e = ktab[kb];
+      else e = make_int4(kb * BK, 0, kb * BK, 0);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[kb], stage_tx0);
+        tma_load_2d(smem_b + kb * b_stage_bytes, &tma_b, &full_bar[kb], e.z, n_blk0 * BN + e.w);
+      }
+      __syncwarp();
+    }
+  }
+  // everything above (K table, barrier init, TMEM allocation, descriptor prefetch, first weight tiles) touched only
+  // launch-constant data; from here on the kernel reads and writes activations of its predecessors
   pdl_wait();
   if (threadIdx.x == 0) AVH_TRACE(1);
 
@@ -172,14 +191,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (p.ktable != nullptr) e = ktab[kb];
         else e = make_int4(kb * BK, 0, kb * BK, 0);
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        const bool b_early = PAIR == 1 && tile == unit && kb < pre_b;      // B tile already requested before the wait
         if (elect_one()) {
-          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+          if (leader && !b_early) mbar_expect_tx(&full_bar[stage], stage_tx);
           if (PAIR == 2) {
             tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
             tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
           } else {
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
-            tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
+            if (!b_early) tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
           }
           if (tile == unit && kb == 0) AVH_TRACE(2);
         }
