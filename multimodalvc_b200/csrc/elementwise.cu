@@ -59,7 +59,8 @@ __global__ void layernorm_kernel(const void* __restrict__ in, int in_dt, long lo
 }
 
 // fp32 rows with C % 128 == 0: float4 loads, row cached in registers (C <= 2048)
-template <int VEC>
+// IN_BF16: the row is bf16 (the fused audio|video features in bf16 mode) instead of fp32.
+template <int VEC, bool IN_BF16 = false>
 __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long ld_in,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float eps, float* __restrict__ out_f32, void* __restrict__ out_lp,
@@ -86,11 +87,22 @@ __global__ void layernorm_f32_vec_kernel(const float* __restrict__ in, long long
   pdl_wait();
   if (row >= rows) return;
   const bool zero = row_zero != nullptr && row_zero[row] != 0;
-  const float4* x = reinterpret_cast<const float4*>(in + row * ld_in);
   float4 v[VEC];
   float s = 0.f;
+  if (IN_BF16) {
+    const uint2* x = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(in) + row * ld_in);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) v[i] = x[lane + 32 * i];
+    for (int i = 0; i < VEC; ++i) {
+      const uint2 u = x[lane + 32 * i];
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v[i] = make_float4(a.x, a.y, b2.x, b2.y);
+    }
+  } else {
+    const float4* x = reinterpret_cast<const float4*>(in + row * ld_in);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = x[lane + 32 * i];
+  }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) * (1.f / C);
@@ -395,7 +407,16 @@ int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* ga
   else if (vec_ok && C == 2048) AVH_LN_VEC(16);
   else if (vec_ok && C == 256) AVH_LN_VEC(2);
   else if (vec_ok && C == 128) AVH_LN_VEC(1);
-  else
+  else if (in_dt == DT_BF16 && ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0 && (C == 2048 || C == 1536 || C == 1024 || C == 768)) {
+#define AVH_LN_VECB(V)                                                                                           \
+  AVH_CUDA_OK(launch_pdl(layernorm_f32_vec_kernel<V, true>, dim3(grid), dim3(wpb * 32), 0, stream,                \
+                         reinterpret_cast<const float*>(in), ld_in, gamma, beta, eps, out_f32, out_lp, lp_dt, row_zero, rows))
+    if (C == 2048) AVH_LN_VECB(16);
+    else if (C == 1536) AVH_LN_VECB(12);
+    else if (C == 1024) AVH_LN_VECB(8);
+    else AVH_LN_VECB(6);
+#undef AVH_LN_VECB
+  } else
     AVH_CUDA_OK(launch_pdl(layernorm_kernel, dim3(grid), dim3(wpb * 32), 0, stream, in, in_dt, ld_in, gamma, beta, eps,
                            out_f32, out_lp, lp_dt, row_zero, rows, C));
 #undef AVH_LN_VEC
