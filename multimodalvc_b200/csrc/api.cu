@@ -529,6 +529,20 @@ struct Builder {
     pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
     pr.a_col_nblk = a_col_nblk;
     pr.block_n = block_n;
+    {   // tuning knob: AVH_GEMM_BN="fc1:256,qkv_proj:192" forces the tile width of a kernel class
+      static const char* ov = std::getenv("AVH_GEMM_BN");
+      if (ov != nullptr && block_n == 0) {
+        const std::string key = tag + ":";
+        const std::string all(ov);
+        size_t pos = 0;
+        while (pos < all.size()) {
+          const size_t end = all.find(',', pos) == std::string::npos ? all.size() : all.find(',', pos);
+          const std::string item = all.substr(pos, end - pos);
+          if (item.compare(0, key.size(), key) == 0) pr.block_n = std::atoi(item.c_str() + key.size());
+          pos = end + 1;
+        }
+      }
+    }
     pr.ep = ep;
     if (sizing) return true;
     GemmPlan* gp = new GemmPlan();
