@@ -281,11 +281,45 @@ def main():
     barrier()
     ms_e2e_u8 = u0.elapsed_time(u1)
 
+    # ---- the WHOLE path of SURVEY 8(a) from raw host inputs: uint8 frames + int16 waveforms (pinned) -> H2D ->
+    #      log-fbank/stack/LN/collate kernel (A1-A6) -> frame transform + encoder (A7-A17) -> D2H of the features
+    n_samp = T_FRAMES * 640
+    host_wav = [torch.cat([torch.from_numpy(fo.synthetic_wave(n_samp, 5000 * rank + 16 * r + i)) for i in range(B_PER_GPU)])
+                .pin_memory() for r in range(N_ROTATE)]
+    wav_off = (torch.arange(B_PER_GPU + 1, dtype=torch.int64) * n_samp).to(dev)
+    vlen = torch.full((B_PER_GPU,), T_FRAMES, dtype=torch.int32, device=dev)
+    dev_wav = [torch.empty_like(host_wav[0], device=dev) for _ in range(S)]
+    dev_u8 = [torch.empty_like(host_u8[0], device=dev) for _ in range(S)]
+
+    def step_raw_av(i):
+        st = streams[i % S]
+        st.synchronize()
+        with torch.cuda.stream(st):
+            dev_wav[i % S].copy_(host_wav[i % N_ROTATE], non_blocking=True)
+            dev_u8[i % S].copy_(host_u8[i % N_ROTATE], non_blocking=True)
+            a, _ = audio.logfbank_stack_collate_packed(dev_wav[i % S], wav_off, T_FRAMES, vlen)
+            yy = model.extract_finetune({"audio": a, "video": dev_u8[i % S]}, None)[0]
+            host_out[i % S].copy_(yy, non_blocking=True)
+
+    for i in range(2 * S):
+        step_raw_av(i)
+    join()
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    fork(r0)
+    for i in range(args.steps):
+        step_raw_av(i)
+    join()
+    r1.record()
+    barrier()
+    ms_e2e_raw = r0.elapsed_time(r1)
+
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_e2e_u8], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_u8 = t.tolist()
+        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw = t.tolist()
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -350,6 +384,13 @@ def main():
                               "d2h_bytes_per_step": int(host_out[0].numel() * 2), "ms_per_step": ms_e2e_u8 / args.steps,
                               "input": "uint8 gray frames [16,1,150,96,96] from pinned host memory; normalise + centre "
                                        "crop on the device (avh_forward_host with AVH_U8 video)"},
+            "e2e_raw_audio_video": {
+                "value": clips / (ms_e2e_raw * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(host_u8[0].numel() + host_wav[0].numel() * 2),
+                "d2h_bytes_per_step": int(host_out[0].numel() * 2), "ms_per_step": ms_e2e_raw / args.steps,
+                "input": "uint8 gray frames [16,1,150,96,96] + int16 16 kHz waveforms [16 x 96000] from pinned host memory; "
+                         "log-fbank/stack/LayerNorm/collate (avh_fbank), frame normalise + crop and the encoder on the "
+                         "device: rows A1-A17 of SURVEY 8(a) in one timed region"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor",

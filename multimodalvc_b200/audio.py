@@ -68,6 +68,28 @@ def logfbank_stack_collate(wavs: Sequence[torch.Tensor], video_lens: Optional[Se
     return out.transpose(1, 2), pm.view(torch.bool)
 
 
+def logfbank_stack_collate_packed(flat: torch.Tensor, offsets: torch.Tensor, T: int,
+                                  video_lens: Optional[torch.Tensor] = None, normalize: bool = True):
+    """Same computation for clips that are already packed on the device (no host work, nothing allocated but the
+    outputs): ``flat`` int16 CUDA tensor holding the clips back to back, ``offsets`` int64 CUDA tensor [B+1],
+    ``video_lens`` optional int32 CUDA tensor [B].  Returns (audio [B,104,T] float32 view, padding_mask [B,T])."""
+    if flat.dtype != torch.int16 or not flat.is_cuda or offsets.dtype != torch.int64 or not offsets.is_cuda:
+        raise ValueError("flat must be an int16 CUDA tensor and offsets an int64 CUDA tensor")
+    B = int(offsets.numel()) - 1
+    device = flat.device
+    out = torch.empty(B, T, STACK * NFILT, device=device, dtype=torch.float32)
+    pm = torch.empty(B, T, device=device, dtype=torch.uint8)
+    if B <= 0 or T <= 0:
+        return out.transpose(1, 2), pm.bool()
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(_lib.load().avh_fbank(
+            ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(offsets.data_ptr()),
+            ctypes.c_void_p(video_lens.data_ptr()) if video_lens is not None else None, B, int(T), int(bool(normalize)),
+            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(pm.data_ptr()), ctypes.c_void_p(stream)))
+    return out.transpose(1, 2), pm.view(torch.bool)
+
+
 def add_noise(wavs: Sequence[torch.Tensor], noise: torch.Tensor, snr_db: float, device=None) -> List[torch.Tensor]:
     """avhubert/hubert_dataset.py:317-346 for a batch of clips sharing one noise clip and SNR.
     wavs: int16 1-D tensors; noise: float32 1-D tensor (tiled when shorter, cropped from 0 when longer).

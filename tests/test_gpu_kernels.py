@@ -182,3 +182,15 @@ def test_add_noise_matches_reference_within_one_lsb():
     loud = torch.from_numpy(z["loud"])
     out = audio.add_noise([loud], noise, -5)[0].cpu().numpy().astype(np.int32)
     assert np.abs(out - z["mix_loud"].astype(np.int32)).max() <= 1
+
+
+def test_logfbank_packed_entry_point_matches_list_entry_point():
+    wavs = [fo.synthetic_wave(96000, 11), fo.synthetic_wave(96000, 12), fo.synthetic_wave(96000, 13)]
+    a_ref, pm_ref = audio.logfbank_stack_collate([torch.from_numpy(w) for w in wavs], video_lens=[150] * 3)
+    flat = torch.from_numpy(np.concatenate(wavs)).cuda()
+    off = (torch.arange(4, dtype=torch.int64) * 96000).cuda()
+    vl = torch.full((3,), 150, dtype=torch.int32, device="cuda")
+    a, pm = audio.logfbank_stack_collate_packed(flat, off, 150, vl)
+    assert a.shape == (3, 104, 150) and torch.equal(a, a_ref) and torch.equal(pm, pm_ref)
+    with pytest.raises(ValueError):
+        audio.logfbank_stack_collate_packed(flat.cpu(), off, 150, vl)
