@@ -74,6 +74,14 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(v for k, v in names.items() if self.mask & k), "samples": len(sm)}
 
 
+def synthetic_wave(n_samples, seed):
+    """Synthetic 16 kHz int16 audio of SURVEY 8(d): clip(round(3000 * randn)).  (Defined here so that the product arm
+    of the bench imports nothing from oracle/.)"""
+    import numpy as np
+    r = np.random.RandomState(seed)
+    return np.clip(np.round(3000.0 * r.randn(n_samples)), -32768, 32767).astype(np.int16)
+
+
 def build_oracle_large(threads):
     import torch
     from oracle import avhubert_oracle as ao
@@ -180,12 +188,11 @@ def main():
     model = model.to(dev, torch.bfloat16).eval()
 
     # ---- synthetic inputs: N_ROTATE distinct batches so no step finds its inputs in L2 from the previous one
-    from oracle import fbank_oracle as fo        # waveform generator only (numpy RNG); features come from OUR kernel
     g = torch.Generator().manual_seed(100 + rank)
     host_v, host_a, dev_v, dev_a = [], [], [], []
     for r in range(N_ROTATE):
         v = torch.randn(B_PER_GPU, 1, T_FRAMES, 88, 88, generator=g).to(torch.bfloat16)
-        wavs = [torch.from_numpy(fo.synthetic_wave(T_FRAMES * 640, 1000 * rank + 16 * r + i)) for i in range(B_PER_GPU)]
+        wavs = [torch.from_numpy(synthetic_wave(T_FRAMES * 640, 1000 * rank + 16 * r + i)) for i in range(B_PER_GPU)]
         a, _ = audio.logfbank_stack_collate(wavs, video_lens=[T_FRAMES] * B_PER_GPU, device=dev)
         a = a.to(torch.bfloat16)
         host_v.append(v.pin_memory())
@@ -284,7 +291,7 @@ def main():
     # ---- the WHOLE path of SURVEY 8(a) from raw host inputs: uint8 frames + int16 waveforms (pinned) -> H2D ->
     #      log-fbank/stack/LN/collate kernel (A1-A6) -> frame transform + encoder (A7-A17) -> D2H of the features
     n_samp = T_FRAMES * 640
-    host_wav = [torch.cat([torch.from_numpy(fo.synthetic_wave(n_samp, 5000 * rank + 16 * r + i)) for i in range(B_PER_GPU)])
+    host_wav = [torch.cat([torch.from_numpy(synthetic_wave(n_samp, 5000 * rank + 16 * r + i)) for i in range(B_PER_GPU)])
                 .pin_memory() for r in range(N_ROTATE)]
     wav_off = (torch.arange(B_PER_GPU + 1, dtype=torch.int64) * n_samp).to(dev)
     vlen = torch.full((B_PER_GPU,), T_FRAMES, dtype=torch.int32, device=dev)
