@@ -225,7 +225,11 @@ def main():
 
     # ---- device-resident timing
     torch.cuda.synchronize(dev)
-    for i in range(max(args.warmup, S)):
+    # warm-up: at least W steps, and enough for every (stream, input batch) pair to have been seen twice — the library
+    # runs the first call of a shape directly and captures a CUDA graph per distinct set of input pointers on the
+    # next ones; with fewer warm-up steps those one-off captures (ms of host time each) fall into the timed region
+    n_warm = max(args.warmup, S * N_ROTATE + S)
+    for i in range(n_warm):
         step(i)
     join()
     barrier()
@@ -382,6 +386,7 @@ def main():
             "config": {"workload": "BASELINE config 2: AV-HuBERT Large (24L, d=1024) extract_finetune, audio+video, "
                                    "batch 16 x 6 s clips (150 frames) per GPU, random-init weights",
                        "per_gpu_batch": B_PER_GPU, "frames": T_FRAMES, "parallelism": f"batch-sharded x{world}, no collective", "streams_per_gpu": S,
+                       "untimed_warmup_steps": n_warm,
                        "l2": f"{N_ROTATE} rotating input batches + 0.65 GB weights + ~1 GB activations per step >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(host_v[0].numel() * 2 + host_a[0].numel() * 2),
