@@ -117,6 +117,11 @@ struct BlockW {
   ConvUnit c1, c2, ds;
   bool has_ds = false;
   float* slope2 = nullptr;
+  // bf16 frame-row path: conv2 and the 1x1 shortcut conv in ONE GEMM — weights [cout, 9*cout + cin] with both
+  // BatchNorm scales folded in, bias = b2 + b_ds, scale = 1
+  PackedW c2ds;
+  float* c2ds_bias = nullptr;
+  float* ones = nullptr;
 };
 struct LinearW {
   PackedW w;
@@ -379,6 +384,40 @@ bool pack_all(Packer& pk) {
       ok &= pack_conv(pk, pre + "conv2.weight", pre + "bn2", "", 3, 1, &bw.c2);
       bw.has_ds = (L > 0 && bi == 0);
       if (bw.has_ds) ok &= pack_conv(pk, pre + "downsample.0.weight", pre + "downsample.1", "", 1, stride, &bw.ds);
+      if (bw.has_ds) {
+        const HostTensor* w2 = pk.get(pre + "conv2.weight");
+        const HostTensor* wd = pk.get(pre + "downsample.0.weight");
+        auto bn_fold = [&](const std::string& bn, std::vector<float>* sc, std::vector<float>* bi) {
+          const HostTensor* g = pk.get(bn + ".weight");
+          const HostTensor* b = pk.get(bn + ".bias");
+          const HostTensor* m = pk.get(bn + ".running_mean");
+          const HostTensor* v = pk.get(bn + ".running_var");
+          if (!g || !b || !m || !v) return false;
+          sc->resize(g->v.size()); bi->resize(g->v.size());
+          for (size_t o = 0; o < g->v.size(); ++o) {
+            const float inv = 1.0f / std::sqrt(v->v[o] + 1e-5f);
+            (*sc)[o] = g->v[o] * inv;
+            (*bi)[o] = b->v[o] - m->v[o] * (*sc)[o];
+          }
+          return true;
+        };
+        std::vector<float> s2v, b2v, sdv, bdv;
+        if (w2 && wd && bn_fold(pre + "bn2", &s2v, &b2v) && bn_fold(pre + "downsample.1", &sdv, &bdv)) {
+          const int cout = (int)w2->shape[0], cmid = (int)w2->shape[1], cin = (int)wd->shape[1];
+          const int K = 9 * cmid + cin;
+          std::vector<float> packed((size_t)cout * K), bias(cout), ones(cout, 1.0f);
+          for (int o = 0; o < cout; ++o) {
+            for (int c = 0; c < cmid; ++c)
+              for (int t = 0; t < 9; ++t)
+                packed[(size_t)o * K + (size_t)t * cmid + c] = s2v[o] * w2->v[((size_t)o * cmid + c) * 9 + t];
+            for (int c = 0; c < cin; ++c) packed[(size_t)o * K + 9 * cmid + c] = sdv[o] * wd->v[(size_t)o * cin + c];
+            bias[o] = b2v[o] + bdv[o];
+          }
+          bw.c2ds = pk.pack(packed, cout, K, K);
+          bw.c2ds_bias = pk.upload_f(bias);
+          bw.ones = pk.upload_f(ones);
+        } else ok = false;
+      }
       const HostTensor* s2 = pk.get(pre + "relu2.weight");
       if (s2) {
         const int cout = 64 << L;
@@ -688,13 +727,20 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     static int frame_env = -1;
     if (frame_env < 0) { const char* ev = std::getenv("AVH_CONV_FRAME"); frame_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
     const bool frame_mode = !f32 && frame_env != 0;
+    struct Shortcut { const void* A2 = nullptr; int Cin = 0, Sin = 0, stride = 1; const PackedW* w = nullptr;
+                      const float* bias = nullptr; const float* ones = nullptr; };
     auto conv_frame = [&](const void* in, int Hin, int Sin, int Cin, const ConvUnit& cu, void* out, int Hout, int nimg,
-                          const float* slope1, const void* res, const float* slope2, const std::string& tg) -> bool {
+                          const float* slope1, const void* res, const float* slope2, const std::string& tg,
+                          const Shortcut* sc = nullptr) -> bool {
       ConvFrameProblem fp;
       fp.A = in; fp.frames = nimg; fp.Hin = Hin; fp.Sin = Sin; fp.Pin = Sin * Sin; fp.Cin = Cin;
       fp.B = cu.w.w; fp.Cout = cu.cout; fp.ks = cu.ks; fp.stride = cu.stride;
       fp.Hout = Hout; fp.Sout = Hout; fp.Pout = Hout * Hout;
       fp.scale = cu.scale; fp.bias = cu.bias; fp.slope1 = slope1; fp.R = res; fp.slope2 = slope2; fp.C = out;
+      if (sc != nullptr) {        // conv2 + shortcut conv in one GEMM: folded weights, scale 1, summed bias, then PReLU
+        fp.B = sc->w->w; fp.scale = sc->ones; fp.bias = sc->bias;
+        fp.A2 = sc->A2; fp.ds_Cin = sc->Cin; fp.ds_Sin = sc->Sin; fp.ds_Pin = sc->Sin * sc->Sin; fp.ds_stride = sc->stride;
+      }
       b.tag = tg;
       void* table = b.alloc(conv_frame_table_bytes(fp));
       if (sizing) return true;
@@ -707,7 +753,8 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
           const int iy = oy * cu.stride + k - (cu.ks == 3 ? 1 : 0);
           taps += (iy >= 0 && iy < Hin) ? 1 : 0;
         }
-      const double fl = 2.0 * (double)nimg * taps * taps * (double)Cin * (double)cu.cout;
+      const double fl = 2.0 * (double)nimg * taps * taps * (double)Cin * (double)cu.cout +
+                        (sc != nullptr ? 2.0 * (double)nimg * Hout * Hout * (double)sc->Cin * (double)cu.cout : 0.0);
       plan->steps.push_back(Step{[cp](cudaStream_t s) { return conv_frame_launch(*cp, s); }, b.tag, fl});
       return true;
     };
@@ -765,8 +812,11 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
           Act dsout;
           if (frame_mode && L > 0) {
             const int Hp = bi == 0 ? HS[L - 1] : Hn, Sp = (bi == 0 && L == 1) ? Hp + 1 : Hp, Cin = bi == 0 ? Cc / 2 : Cc;
+            static int dsf_env = -1;
+            if (dsf_env < 0) { const char* ev = std::getenv("AVH_DS_FUSED"); dsf_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
             const void* resp = cur.data;
-            if (bw.has_ds) {
+            const bool fuse_ds = bw.has_ds && dsf_env != 0;
+            if (bw.has_ds && !fuse_ds) {
               if (!conv_frame(cur.op, Hp, Sp, Cin, bw.ds, fb.ds[L].data, Hn, nf, nullptr, nullptr, nullptr, "downsample"))
                 return false;
               resp = fb.ds[L].data;
@@ -774,8 +824,16 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             if (!conv_frame(cur.op, Hp, Sp, Cin, bw.c1, mid.data, Hn, nf, bw.c1.slope, nullptr, nullptr,
                             (bi == 0 ? "conv_s2_c" : "conv3x3_c") + std::to_string(Cin)))
               return false;
-            if (!conv_frame(mid.data, Hn, Hn, Cc, bw.c2, out.data, Hn, nf, nullptr, resp, bw.slope2,
-                            "conv3x3_c" + std::to_string(Cc)))
+            if (fuse_ds) {
+              // block 0 of layers 2-4: out = PReLU(BN2(conv2(mid)) + BN_ds(conv1x1_s2(x))) as ONE GEMM (the shortcut's
+              // K steps read the block input x directly): no shortcut launch, no shortcut map written and re-read
+              Shortcut sc;
+              sc.A2 = cur.op; sc.Cin = Cin; sc.Sin = Sp; sc.stride = 2; sc.w = &bw.c2ds; sc.bias = bw.c2ds_bias; sc.ones = bw.ones;
+              if (!conv_frame(mid.data, Hn, Hn, Cc, bw.c2, out.data, Hn, nf, bw.slope2, nullptr, nullptr,
+                              "conv3x3_c" + std::to_string(Cc), &sc))
+                return false;
+            } else if (!conv_frame(mid.data, Hn, Hn, Cc, bw.c2, out.data, Hn, nf, nullptr, resp, bw.slope2,
+                                   "conv3x3_c" + std::to_string(Cc)))
               return false;
             cur = out;
             continue;

@@ -54,6 +54,9 @@ struct FrameParams {
   int ks, stride, pad;
   int block_n, stages;
   int chunks;                   // Cin / 64
+  // fused 1x1 stride-s shortcut (downsample_basic_block): extra K steps over a SECOND input tensor, the pixel
+  // (oy*ds_stride, ox*ds_stride) of it, against weight columns [ds_bcol, ds_bcol + ds_chunks*64)
+  int ds_chunks, ds_stride, ds_Sin, ds_Cin, ds_bcol;
   long long ldr;                // residual row stride (elements) = output row stride
   const int* tiles;             // [grid + 1] offsets followed by the tile lists
   const float* scale;
@@ -75,7 +78,8 @@ __device__ __forceinline__ void decode_tile(int code, int& m_blk, int& oy, int& 
 template <int OCC, int MODE>
 __global__ void __launch_bounds__(FOcc<OCC>::NUM_THREADS, OCC)
 conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                  const __grid_constant__ CUtensorMap tma_c, const FrameParams p) {
+                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
+                  const FrameParams p) {
   constexpr int EPI_WARPS = FOcc<OCC>::EPI_WARPS;
   constexpr int NUM_THREADS = FOcc<OCC>::NUM_THREADS;
   constexpr int TMEM_COLS = FOcc<OCC>::TMEM_COLS;
@@ -114,6 +118,7 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_c);
+    if (p.ds_chunks > 0) tma_prefetch_desc(&tma_a2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -162,6 +167,17 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           }
         }
       }
+      for (int kc = 0; kc < p.ds_chunks; ++kc) {          // fused shortcut: centre pixel of the block's input
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a2, &full_bar[stage],
+                      ((oy * p.ds_stride) * p.ds_Sin + ox * p.ds_stride) * p.ds_Cin + kc * BK, m0);
+          tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], p.ds_bcol + kc * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -178,7 +194,7 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         ny += (iy >= 0 && iy < p.Hin) ? 1 : 0;
         nx += (ix >= 0 && ix < p.Hin) ? 1 : 0;
       }
-      const int num_kb = ny * nx * p.chunks;
+      const int num_kb = ny * nx * p.chunks + p.ds_chunks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -320,7 +336,7 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-typedef void (*FrameKernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, FrameParams);
+typedef void (*FrameKernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FrameParams);
 
 FrameKernelFn pick_kernel(int occ, int mode) {
   if (occ == 2) return mode == 0 ? conv_frame_kernel<2, 0> : mode == 1 ? conv_frame_kernel<2, 1> : conv_frame_kernel<2, 2>;
@@ -364,7 +380,15 @@ int conv_frame_plan(const ConvFrameProblem& pr, ConvFramePlan* plan) {
   const long long a_cols = (long long)pr.Pin * pr.Cin, c_cols = (long long)pr.Pout * pr.Cout;
   AVH_CHECK(a_cols < (1ll << 31) && c_cols < (1ll << 31), "frame rows too wide");
   if (encode_2d(&plan->tma_a, pr.A, pr.frames, (int)a_cols, a_cols, BM)) return 1;
-  if (encode_2d(&plan->tma_b, pr.B, pr.Cout, pr.ks * pr.ks * pr.Cin, (long long)pr.ks * pr.ks * pr.Cin, bn)) return 1;
+  const int b_cols = pr.ks * pr.ks * pr.Cin + (pr.A2 != nullptr ? pr.ds_Cin : 0);
+  if (encode_2d(&plan->tma_b, pr.B, pr.Cout, b_cols, b_cols, bn)) return 1;
+  plan->tma_a2 = plan->tma_a;
+  if (pr.A2 != nullptr) {
+    AVH_CHECK(pr.ds_Cin % 64 == 0 && pr.ds_stride >= 1 && pr.ds_Sin >= 1, "bad shortcut geometry");
+    const long long a2_cols = (long long)pr.ds_Pin * pr.ds_Cin;
+    AVH_CHECK(a2_cols < (1ll << 31), "frame rows too wide");
+    if (encode_2d(&plan->tma_a2, pr.A2, pr.frames, (int)a2_cols, a2_cols, BM)) return 1;
+  }
   if (encode_c(&plan->tma_c, pr.C, pr.frames, (int)c_cols, c_cols, 0)) return 1;
 
   // ---- tile lists: longest-processing-time greedy over groups of frame blocks
@@ -385,7 +409,8 @@ int conv_frame_plan(const ConvFrameProblem& pr, ConvFramePlan* plan) {
     for (int m = g0; m < std::min(num_m, g0 + group); ++m)
       for (int oy = 0; oy < pr.Hout; ++oy)
         for (int ox = 0; ox < pr.Hout; ++ox) {
-          const int nk = valid_taps(oy, pr.stride, pad, pr.ks, pr.Hin) * valid_taps(ox, pr.stride, pad, pr.ks, pr.Hin) * chunks;
+          const int nk = valid_taps(oy, pr.stride, pad, pr.ks, pr.Hin) * valid_taps(ox, pr.stride, pad, pr.ks, pr.Hin) * chunks +
+                         (pr.A2 != nullptr ? pr.ds_Cin / 64 : 0);
           for (int s = 0; s < nsub; ++s)
             ts.push_back(T{m | (oy << 16) | (ox << 21) | (s << 26), nk * kblock + 500.0});
         }
@@ -433,6 +458,9 @@ int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream) {
   p.ks = pr.ks; p.stride = pr.stride; p.pad = pr.ks == 3 ? 1 : 0;
   p.block_n = pr.block_n; p.stages = plan.stages;
   p.chunks = pr.Cin / 64;
+  p.ds_chunks = pr.A2 != nullptr ? pr.ds_Cin / 64 : 0;
+  p.ds_stride = pr.ds_stride; p.ds_Sin = pr.ds_Sin; p.ds_Cin = pr.ds_Cin;
+  p.ds_bcol = pr.ks * pr.ks * pr.Cin;
   p.ldr = (long long)pr.Pout * pr.Cout;
   p.tiles = plan.tiles_dev;
   p.scale = pr.scale; p.bias = pr.bias; p.slope1 = pr.slope1; p.slope2 = pr.slope2;
@@ -451,7 +479,7 @@ int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream) {
     }
   }
   const int threads = occ == 2 ? FOcc<2>::NUM_THREADS : FOcc<1>::NUM_THREADS;
-  AVH_CUDA_OK(launch_pdl(fn, dim3(plan.grid), dim3(threads), plan.smem, stream, plan.tma_a, plan.tma_b, plan.tma_c, p));
+  AVH_CUDA_OK(launch_pdl(fn, dim3(plan.grid), dim3(threads), plan.smem, stream, plan.tma_a, plan.tma_b, plan.tma_c, plan.tma_a2, p));
   count_launch(1);
   return 0;
 }

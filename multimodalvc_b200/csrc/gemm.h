@@ -111,10 +111,15 @@ struct ConvFrameProblem {
   const void* R = nullptr;        // bf16 residual in the output layout (conv2 form) or null
   const float* slope2 = nullptr;  // PReLU after the residual add
   void* C = nullptr;              // bf16 [frames, Pout*Cout]
+  // optional fused 1x1 stride-s shortcut conv (downsample_basic_block, resnet.py:20-24) accumulated into the same
+  // tile: second input A2 [frames, ds_Pin*ds_Cin] (pixel pitch ds_Sin), sampled at (oy*ds_stride, ox*ds_stride);
+  // its weights are the columns [ks*ks*Cin, +ds_Cin) of B.  Both BatchNorm scales must be folded into B then.
+  const void* A2 = nullptr;
+  int ds_Cin = 0, ds_Sin = 0, ds_Pin = 0, ds_stride = 1;
   int block_n = 0, occ = 0;       // 0 = chosen by conv_frame_plan
 };
 struct ConvFramePlan {
-  CUtensorMap tma_a, tma_b, tma_c;
+  CUtensorMap tma_a, tma_b, tma_c, tma_a2;
   ConvFrameProblem prob;
   int grid = 0, stages = 0;
   size_t smem = 0;
