@@ -1265,7 +1265,11 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
     const char* dbg = std::getenv("AVH_STEM_DBG");
     graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr) ? 0 : 1;
   }
-  if (graphs_env == 1 && !h->profiling && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+  // a caller that is itself capturing this stream (e.g. torch.cuda.graph) gets plain launches recorded into ITS graph
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) cudaStreamIsCapturing(s, &cap_status);
+  if (graphs_env == 1 && !h->profiling && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+      cap_status == cudaStreamCaptureStatusNone) {
     ++p->calls;
     auto it = p->graphs.find(p->args);
     if (it != p->graphs.end()) {

@@ -273,3 +273,31 @@ def test_cuda_graph_replay_matches_direct_launches():
         ys = [m.extract_finetune(src, pm)[0] for _ in range(3)]
     st.synchronize()
     assert all(torch.equal(y0, y) for y in ys)
+
+
+def test_forward_inside_a_user_cuda_graph():
+    """A caller may capture extract_finetune into its own CUDA graph (static input/output tensors): the library then
+    records plain launches into that capture instead of starting a nested one."""
+    c = load_encoder_case("tiny_av_ragged")
+    m = make_device_model(c["oracle"], c["over"], c["size"], torch.bfloat16)
+    src, pm = to_dev(c["src"], c["pm"], dtype=torch.bfloat16)
+    y_ref = m.extract_finetune(src, pm)[0].clone()
+    static_src = {k: v.clone() for k, v in src.items()}
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):                       # plan for this stream + kernel configuration before capture
+        m.extract_finetune(static_src, pm)
+    torch.cuda.current_stream().wait_stream(st)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        y_static = m.extract_finetune(static_src, pm)[0]
+    static_src["video"].copy_(src["video"] * 0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    y_half = m.extract_finetune({"audio": src["audio"], "video": src["video"] * 0.5}, pm)[0]
+    assert torch.equal(y_static, y_half)
+    static_src["video"].copy_(src["video"])
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_static, y_ref)
