@@ -17,6 +17,10 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#include <cstdlib>
+#include <mutex>
+#include <set>
+
 namespace avh {
 namespace {
 
@@ -43,7 +47,13 @@ struct WinParams {
   const __nv_bfloat16* R;
 };
 
-template <bool RES>
+// PAIR = 2: a cluster of two CTAs on the SMs of one TPC runs ONE tcgen05.mma.cta_group::2 of 256 rows per tap and
+// K step — each CTA stages the window of its own 128-row tile and holds HALF of every weight tap (32 of the 64 output
+// channels).  A 128 x 64 x 16 MMA needs 32 clk of tensor pipe but ~53 clk of its issuing thread, so the single-CTA
+// form looked issue-bound (36 MMAs = 1900 clk per tile).  Measured: bit-identical results, 0.487 vs 0.468 ms per step —
+// the kernel is bound by HBM traffic (278 / 444 MB per launch), not by MMA issue, so PAIR = 1 stays the default
+// (AVH_WINDOW_PAIR=2 selects this form).
+template <bool RES, int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_c, const WinParams p) {
@@ -51,7 +61,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + B_BYTES;
+  uint8_t* smem_a = smem + B_BYTES / PAIR;
   uint8_t* epi_stage = smem_a + p.stages * p.win_bytes;
   float* colvec = reinterpret_cast<float*>(epi_stage + EPI_BYTES);     // scale | bias | slope1 | slope2, 64 each
   uint64_t* b_full = reinterpret_cast<uint64_t*>(colvec + 4 * CH);
@@ -63,6 +73,11 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = PAIR == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / PAIR, num_units = gridDim.x / PAIR;
+  const int num_work = (p.num_tiles + PAIR - 1) / PAIR;          // tiles (PAIR 1) or tile pairs
+  constexpr int B_TAP = B_TAP_BYTES / PAIR;                        // bytes of one tap held by this CTA
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
@@ -78,11 +93,14 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 4 * PAIR);
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 128);
+  if (warp == 2) {
+    if (PAIR == 2) tmem_alloc_pair(tmem_slot, 128);
+    else tmem_alloc(tmem_slot, 128);
+  }
   if (threadIdx.x < CH) {           // launch-constant per-channel vectors
     const int c = threadIdx.x;
     colvec[c] = __ldg(p.scale + c);
@@ -91,61 +109,77 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     colvec[3 * CH + c] = p.slope2 != nullptr ? __ldg(p.slope2 + c) : 1.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) {                  // the resident weights are launch constants: request them before the wait
     if (elect_one()) {
-      mbar_expect_tx(b_full, B_BYTES);
-      for (int t = 0; t < 9; ++t) tma_load_2d(smem_b + t * B_TAP_BYTES, &tma_b, b_full, t * CH, 0);
+      if (leader) mbar_expect_tx(b_full, B_BYTES);                 // both halves report to the leader's barrier
+      for (int t = 0; t < 9; ++t) {
+        if (PAIR == 2) tma_load_2d_pair(smem_b + t * B_TAP, &tma_b, b_full, t * CH, cta_rank * (CH / 2));
+        else tma_load_2d(smem_b + t * B_TAP, &tma_b, b_full, t * CH, 0);
+      }
     }
     __syncwarp();
   }
   pdl_wait();                       // from here on: activations of the previous kernel
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int w = unit; w < num_work; w += num_units) {
+      const int tile = w * PAIR + cta_rank;       // a tile past the end loads zeros (TMA out-of-bounds fill)
       mbar_wait(&a_empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&a_full[stage], (uint32_t)p.win_rows * 128u);
-        tma_load_2d(smem_a + stage * p.win_bytes, &tma_a, &a_full[stage], 0, tile * BM - p.S - 1);
+        if (leader) mbar_expect_tx(&a_full[stage], (uint32_t)PAIR * (uint32_t)p.win_rows * 128u);
+        if (PAIR == 2) tma_load_2d_pair(smem_a + stage * p.win_bytes, &tma_a, &a_full[stage], 0, tile * BM - p.S - 1);
+        else tma_load_2d(smem_a + stage * p.win_bytes, &tma_a, &a_full[stage], 0, tile * BM - p.S - 1);
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, CH);
-    mbar_wait(b_full, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      mbar_wait(&a_full[stage], phase);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * CH;
-      const uint32_t a_base = smem_u32(smem_a + stage * p.win_bytes);
-      const uint32_t b_base = smem_u32(smem_b);
-      if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * PAIR, CH);
+      mbar_wait(b_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = unit; w < num_work; w += num_units, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * CH;
+        const uint32_t a_base = smem_u32(smem_a + stage * p.win_bytes);
+        const uint32_t b_base = smem_u32(smem_b);
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          // tap (kh, kw): rows of the window starting at kh*S + kw
-          const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)((t / 3) * p.S + (t % 3)) * 128u);
-          const uint64_t bdesc = umma_desc_sw128(b_base + t * B_TAP_BYTES);
+          for (int t = 0; t < 9; ++t) {
+            // tap (kh, kw): rows of the window starting at kh*S + kw
+            const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)((t / 3) * p.S + (t % 3)) * 128u);
+            const uint64_t bdesc = umma_desc_sw128(b_base + t * B_TAP);
 #pragma unroll
-          for (int k = 0; k < CH / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+            for (int k = 0; k < CH / 16; ++k) {
+              if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+              else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (t | k) != 0);
+            }
+          }
+          if (PAIR == 2) {
+            umma_commit_pair(&a_empty[stage]);      // windows of BOTH CTAs reusable once these MMAs have read them
+            umma_commit_pair(&tmem_full[acc]);
+          } else {
+            umma_commit(&a_empty[stage]);
+            umma_commit(&tmem_full[acc]);
+          }
         }
-        umma_commit(&a_empty[stage]);      // window reusable once these MMAs have read it
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: thread = row
@@ -155,8 +189,9 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     uint8_t* stg = epi_stage + (warp - 4) * 4096;
     const int S = p.S, H = p.S - 1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int w = unit; w < num_work; w += num_units, ++it) {
       if ((it & 1) != eset) continue;
+      const int tile = w * PAIR + cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = tile * BM + q * 32;
@@ -183,7 +218,10 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         if (sub == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         float v[32];
 #pragma unroll
@@ -244,9 +282,13 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, 128);
+  if (warp == 2) {
+    if (PAIR == 2) tmem_dealloc_pair(tmem_base, 128);
+    else tmem_dealloc(tmem_base, 128);
+  }
 }
 
 }  // namespace
@@ -259,18 +301,23 @@ int conv_window_plan(const ConvWinProblem& pr, ConvWinPlan* plan) {
   plan->win_rows = BM + 2 * (pr.S + 1);
   AVH_CHECK(plan->win_rows <= 256, "window exceeds the TMA box limit");
   const int win_bytes = ((plan->win_rows * 128 + 1023) / 1024) * 1024;
-  const int fixed = 1024 + B_BYTES + EPI_BYTES + 4 * CH * 4 + (1 + 2 * MAX_STAGES + 4) * 8 + 16;
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* ev = std::getenv("AVH_WINDOW_PAIR"); pair_env = (ev != nullptr && ev[0] == '2') ? 2 : 1; }
+  const int sms0 = device_sm_count();
+  plan->pair = (pair_env == 2 && sms0 >= 2) ? 2 : 1;
+  const int fixed = 1024 + B_BYTES / plan->pair + EPI_BYTES + 4 * CH * 4 + (1 + 2 * MAX_STAGES + 4) * 8 + 16;
   int stages = (SMEM_LIMIT - fixed) / win_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   AVH_CHECK(stages >= 2, "window too large for shared memory");
   plan->stages = stages;
   plan->smem = (size_t)fixed + (size_t)stages * win_bytes;
   if (encode_2d(&plan->tma_a, pr.A, pr.rows, CH, CH, plan->win_rows)) return 1;
-  if (encode_2d(&plan->tma_b, pr.B, CH, 9 * CH, 9 * CH, CH)) return 1;
+  if (encode_2d(&plan->tma_b, pr.B, CH, 9 * CH, 9 * CH, CH / plan->pair)) return 1;
   if (encode_c(&plan->tma_c, pr.C, pr.rows, CH, CH, 0)) return 1;
   const long long tiles = (pr.rows + BM - 1) / BM;
-  const int sms = device_sm_count();
-  plan->grid = (int)(tiles < sms ? tiles : sms);
+  const long long work = (tiles + plan->pair - 1) / plan->pair;
+  const long long units = sms0 / plan->pair;
+  plan->grid = (int)(work < units ? work : units) * plan->pair;
   return 0;
 }
 
@@ -288,18 +335,33 @@ int conv_window_launch(const ConvWinPlan& plan, cudaStream_t stream) {
   p.slope1 = pr.slope1;
   p.slope2 = pr.slope2;
   p.R = reinterpret_cast<const __nv_bfloat16*>(pr.R);
-  static bool configured = false;
-  if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(conv_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    AVH_CUDA_OK(cudaFuncSetAttribute(conv_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    configured = true;
+  typedef void (*WinFn)(CUtensorMap, CUtensorMap, CUtensorMap, WinParams);
+  WinFn fn = plan.pair == 2 ? (pr.R != nullptr ? conv_window_kernel<true, 2> : conv_window_kernel<false, 2>)
+                            : (pr.R != nullptr ? conv_window_kernel<true, 1> : conv_window_kernel<false, 1>);
+  static std::mutex mu;
+  static std::set<const void*> configured;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (configured.find(reinterpret_cast<const void*>(fn)) == configured.end()) {
+      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured.insert(reinterpret_cast<const void*>(fn));
+    }
   }
-  if (pr.R != nullptr)
-    AVH_CUDA_OK(launch_pdl(conv_window_kernel<true>, dim3(plan.grid), dim3(NUM_THREADS), plan.smem, stream, plan.tma_a,
-                           plan.tma_b, plan.tma_c, p));
-  else
-    AVH_CUDA_OK(launch_pdl(conv_window_kernel<false>, dim3(plan.grid), dim3(NUM_THREADS), plan.smem, stream, plan.tma_a,
-                           plan.tma_b, plan.tma_c, p));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)plan.pair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  AVH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, plan.tma_a, plan.tma_b, plan.tma_c, p));
   count_launch(1);
   return 0;
 }

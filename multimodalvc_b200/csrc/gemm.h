@@ -92,6 +92,7 @@ struct ConvWinPlan {
   CUtensorMap tma_a, tma_b, tma_c;
   ConvWinProblem prob;
   int grid = 0, stages = 0, win_rows = 0;
+  int pair = 1;                   // 1 = single CTAs (default); 2 = CTA pairs (tcgen05 cta_group::2, AVH_WINDOW_PAIR=2)
   size_t smem = 0;
 };
 int conv_window_plan(const ConvWinProblem& prob, ConvWinPlan* plan);
