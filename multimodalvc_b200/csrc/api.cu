@@ -1263,7 +1263,8 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   if (graphs_env < 0) {
     const char* ev = std::getenv("AVH_GRAPHS");
     const char* dbg = std::getenv("AVH_STEM_DBG");
-    graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr) ? 0 : 1;
+    const char* dbg2 = std::getenv("AVH_WIN_DBG");
+    graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr || dbg2 != nullptr) ? 0 : 1;
   }
   // a caller that is itself capturing this stream (e.g. torch.cuda.graph) gets plain launches recorded into ITS graph
   cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;

@@ -17,9 +17,11 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <set>
+#include <vector>
 
 namespace avh {
 namespace {
@@ -45,14 +47,24 @@ struct WinParams {
   const float* slope1;
   const float* slope2;
   const __nv_bfloat16* R;
+  unsigned long long* dbg;     // debug (AVH_WIN_DBG=1): per CTA 8 stall counters in SM clocks, else null
 };
+
+__device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, unsigned long long* dbg, long long& acc) {
+  if (dbg == nullptr) { mbar_wait(bar, parity); return; }
+  const long long c0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - c0;
+}
 
 // PAIR = 2: a cluster of two CTAs on the SMs of one TPC runs ONE tcgen05.mma.cta_group::2 of 256 rows per tap and
 // K step — each CTA stages the window of its own 128-row tile and holds HALF of every weight tap (32 of the 64 output
 // channels).  A 128 x 64 x 16 MMA needs 32 clk of tensor pipe but ~53 clk of its issuing thread, so the single-CTA
-// form looked issue-bound (36 MMAs = 1900 clk per tile).  Measured: bit-identical results, 0.487 vs 0.468 ms per step —
-// the kernel is bound by HBM traffic (278 / 444 MB per launch), not by MMA issue, so PAIR = 1 stays the default
-// (AVH_WINDOW_PAIR=2 selects this form).
+// form looked issue-bound (36 MMAs = 1900 clk per tile).  Measured: bit-identical results, 0.487 vs 0.468 ms per step.
+// The stall counters (AVH_WIN_DBG=1) show the producer waiting for free stages 78 % of the time and the MMA warp busy
+// 93 %: ~64 clk per 128 x 64 x 16 MMA in either form, i.e. the tensor core is fed at half rate — an SS-form MMA with
+// N = 64 re-reads its 4 KB A slice from shared memory for only 64 output columns (the same bound the first fused stem
+// hit).  PAIR = 1 stays the default (AVH_WINDOW_PAIR=2 selects this form).
 template <bool RES, int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -79,6 +91,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   const int num_work = (p.num_tiles + PAIR - 1) / PAIR;          // tiles (PAIR 1) or tile pairs
   constexpr int B_TAP = B_TAP_BYTES / PAIR;                        // bytes of one tap held by this CTA
   pdl_launch_dependents();
+  const long long k_start = clock64();
+  long long st0 = 0, st1 = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -131,7 +145,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     uint32_t phase = 0;
     for (int w = unit; w < num_work; w += num_units) {
       const int tile = w * PAIR + cta_rank;       // a tile past the end loads zeros (TMA out-of-bounds fill)
-      mbar_wait(&a_empty[stage], phase ^ 1);
+      wait_dbg(&a_empty[stage], phase ^ 1, p.dbg, st0);
       if (elect_one()) {
         if (leader) mbar_expect_tx(&a_full[stage], (uint32_t)PAIR * (uint32_t)p.win_rows * 128u);
         if (PAIR == 2) tma_load_2d_pair(smem_a + stage * p.win_bytes, &tma_a, &a_full[stage], 0, tile * BM - p.S - 1);
@@ -140,6 +154,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    if (p.dbg != nullptr && lane == 0) p.dbg[blockIdx.x * 8 + 1] = st0;
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
@@ -151,8 +166,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       for (int w = unit; w < num_work; w += num_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        mbar_wait(&a_full[stage], phase);
+        wait_dbg(&tmem_empty[acc], acc_phase ^ 1, p.dbg, st0);
+        wait_dbg(&a_full[stage], phase, p.dbg, st1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * CH;
         const uint32_t a_base = smem_u32(smem_a + stage * p.win_bytes);
@@ -180,6 +195,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (p.dbg != nullptr && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = st0; p.dbg[blockIdx.x * 8 + 3] = st1; p.dbg[blockIdx.x * 8 + 6] = it; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: thread = row
@@ -206,7 +222,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) rres[j] = __ldg(rp + j);
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      wait_dbg(&tmem_full[acc], acc_phase, p.dbg, st0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CH;
       uint32_t packed[32];
@@ -279,6 +295,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       }
     }
     if (lane == 0) tma_wait_group0();
+    if (p.dbg != nullptr && lane == 0 && (warp == 4 || warp == 8)) p.dbg[blockIdx.x * 8 + 4 + ((warp - 4) >> 2)] = st0;
   }
 
   tc_fence_before();
@@ -289,6 +306,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     if (PAIR == 2) tmem_dealloc_pair(tmem_base, 128);
     else tmem_dealloc(tmem_base, 128);
   }
+  if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 8] = clock64() - k_start;
 }
 
 }  // namespace
@@ -361,6 +379,31 @@ int conv_window_launch(const ConvWinPlan& plan, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  p.dbg = nullptr;
+  static int dbg_env = -1;
+  if (dbg_env < 0) { const char* ev = std::getenv("AVH_WIN_DBG"); dbg_env = ev != nullptr ? std::atoi(ev) : 0; }
+  if (dbg_env > 0) {
+    // debug only: stall accounting of one launch (synchronises the stream), printed to stderr
+    --dbg_env;
+    unsigned long long* d = nullptr;
+    AVH_CUDA_OK(cudaMalloc(&d, (size_t)plan.grid * 64));
+    AVH_CUDA_OK(cudaMemset(d, 0, (size_t)plan.grid * 64));
+    p.dbg = d;
+    AVH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, plan.tma_a, plan.tma_b, plan.tma_c, p));
+    AVH_CUDA_OK(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> hst((size_t)plan.grid * 8);
+    AVH_CUDA_OK(cudaMemcpy(hst.data(), d, (size_t)plan.grid * 64, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    static const char* names[8] = {"total", "prod_wait_empty", "mma_wait_tmem_empty", "mma_wait_a_full", "epi0_wait_full",
+                                   "epi1_wait_full", "tiles", "-"};
+    for (int c : {0, plan.grid / 2, plan.grid - 1}) {
+      std::fprintf(stderr, "[conv_window dbg] res=%d cta %d:", pr.R != nullptr, c);
+      for (int i = 0; i < 7; ++i) std::fprintf(stderr, " %s=%llu", names[i], hst[(size_t)c * 8 + i]);
+      std::fprintf(stderr, "\n");
+    }
+    count_launch(1);
+    return 0;
+  }
   AVH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, plan.tma_a, plan.tma_b, plan.tma_c, p));
   count_launch(1);
   return 0;
