@@ -301,3 +301,22 @@ def test_forward_inside_a_user_cuda_graph():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(y_static, y_ref)
+
+
+def test_many_shapes_plan_eviction_and_graph_reuse():
+    """More distinct (B, T) shapes than the plan cache holds (8): plans and their CUDA graphs are evicted and rebuilt
+    while earlier work may still be queued; every shape must reproduce its first result bit for bit afterwards."""
+    from oracle import avhubert_oracle as ao
+    oracle = ao.build_oracle("tiny", seed=1234)
+    m = make_device_model(oracle, {}, "tiny", torch.bfloat16)
+    shapes = [(1, 3), (2, 5), (1, 8), (3, 4), (2, 9), (1, 12), (2, 2), (3, 7), (1, 17), (2, 11), (4, 3)]
+    inputs, first = [], []
+    for i, (B, T) in enumerate(shapes):
+        src, _ = ao.synthetic_inputs(B, T, seed=100 + i)
+        src = {k: v.cuda().to(torch.bfloat16) for k, v in src.items()}
+        inputs.append(src)
+        first.append(m.extract_finetune(src, None)[0].clone())
+    for rnd in range(3):
+        for src, y0 in zip(inputs, first):
+            assert torch.equal(m.extract_finetune(src, None)[0], y0)
+    torch.cuda.synchronize()
