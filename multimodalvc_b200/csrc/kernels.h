@@ -47,6 +47,8 @@ int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cuda
 // mean over the H*W valid pixels of the padded layout [n,H+1,W+1,C] -> [n, C] (bf16 or fp32 in and out)
 int launch_video_preprocess(const unsigned char* frames, long long n_frames, int src_h, int src_w, int crop, double mean,
                             double stdv, void* out, int out_dt, cudaStream_t stream);
+int launch_ln_center_stats(const float* in, void* xc, float* mu, void* part, int np, long long rows, int C,
+                           cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int pitch, int fp32, cudaStream_t stream);
 
 // ---- audio frontend ---------------------------------------------------------------------------------

@@ -320,3 +320,29 @@ def test_many_shapes_plan_eviction_and_graph_reuse():
         for src, y0 in zip(inputs, first):
             assert torch.equal(m.extract_finetune(src, None)[0], y0)
     torch.cuda.synchronize()
+
+
+def test_layernorm_folding_variant_in_a_subprocess():
+    """AVH_LN_FUSED=1 (LayerNorm folded into out_proj/fc2 -> qkv/fc1; off by default because it is slower) must stay
+    within the bf16 gate against the reference golden and close to the default path.  The switch is read once per
+    process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, 'tests'); "
+        "from helpers import load_encoder_case, make_device_model, to_dev, cosine; "
+        "c = load_encoder_case('large_b2_t40'); "
+        "m = make_device_model(c['oracle'], c['over'], c['size'], torch.bfloat16); "
+        "src, pm = to_dev(c['src'], c['pm'], dtype=torch.bfloat16); "
+        "y = m.extract_finetune(src, pm)[0]; y2 = m.extract_finetune(src, pm)[0]; "
+        "assert torch.equal(y, y2); "
+        "print('COS', cosine(y.float().cpu(), c['y_ref']))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, AVH_LN_FUSED=flag)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[flag] = float(r.stdout.strip().split("COS")[-1])
+    assert outs["1"] > BF16_COS and abs(outs["1"] - outs["0"]) < 1e-4, outs
