@@ -1050,7 +1050,10 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   // mean / rstd / gamma / beta in their epilogue: no LayerNorm launches inside the layer stack (48 for Large, 194 ->
   // 147 launches per step).  Measured: results within 5e-6 of the unfused path, but 3916 vs 4127 clips/s — out_proj and
   // fc2 are one-wave kernels whose epilogue is fully exposed, and trading the TMA reduce-add (x is never read) for a
-  // read-modify-write of x plus a second store costs +4-6 us per launch, more than the 3.9 us LayerNorm it removes.
+  // read-modify-write of x plus a second store costs +6.7 us per launch in the pipeline, more than the 3.9 us
+  // LayerNorm it removes.  AVH_LN_DBG elimination runs: ~4 us of it is the thread-per-row read of x (32 different
+  // cache lines per load instruction, even when requested a box ahead), the second store and the sums are free, the
+  // other ~2.5 us come with the smaller smem ring (4 stages) and the store-form epilogue.
   static int lnf_env = -1;
   if (lnf_env < 0) { const char* ev = std::getenv("AVH_LN_FUSED"); lnf_env = (ev != nullptr && ev[0] == '1') ? 1 : 0; }
   const bool ln_fused = !f32 && c.layer_norm_first && lnf_env != 0 && (D == 768 || D == 1024) && n_layers > 0 &&

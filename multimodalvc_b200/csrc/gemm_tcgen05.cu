@@ -72,6 +72,8 @@ struct KernelParams {
   const int4* ktable;
   int c_mode;                   // 0 = per-thread global stores, 1 = TMA store of C, 2 = TMA reduce-add into C (= R)
   unsigned long long* trace;    // debug: [grid][16] SM clock stamps (null in production)
+  int lnf_dbg;                  // debug (AVH_LN_DBG bits, timing experiments only — results become wrong): 1 skip the
+                                // centred bf16 store, 2 skip the statistics, 4 skip the residual loads
   Epilogue ep;
 };
 
@@ -317,6 +319,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
 
+      // LNF 1: the residual (x) of this warp's first 32-column box is requested while the main loop still runs, and
+      // inside the box loop the next box's residual is requested before the current one is consumed
+      uint4 rpre[8];
+      if (LNF == 1) {
+        const int pc0 = n_blk * BN + half * 32;
+        if (store && !zero && half * 32 < BN && pc0 < p.N && !(p.lnf_dbg & 4)) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.R) + orow * ep.ldr + pc0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp + j);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (warp == 4 && lane == 0) {
@@ -347,7 +360,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             // residual row segment (32 columns) straight from global while the TMEM load is in flight
             uint4 rres[8];
             if (has_res && live && col0 < p.N) {
-              if (out_f32) {
+              if (LNF == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rres[j] = rpre[j];
+                const int nc0 = col0 + HSTRIDE * 32;            // this warp's next box
+                if (c0 + HSTRIDE * 32 < BN && nc0 < p.N && !(p.lnf_dbg & 4)) {
+                  const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.R) + orow * ep.ldr + nc0);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp + j);
+                }
+              } else if (out_f32) {
                 const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.R) + orow * ep.ldr + col0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rres[j] = __ldg(rp + j);
@@ -430,7 +452,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             if (LNF == 1) {
               // centred bf16 copy of the new residual-stream values + this warp's share of the row sums
-              if (col0 < p.N && live) {
+              if (col0 < p.N && live && !(p.lnf_dbg & 2)) {
                 float d1 = 0.f, d2 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -480,7 +502,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (lane == 0 && row0 < p.M) {
             if (p.c_mode == 2) tma_reduce_add_2d(&tma_c, stg, n_blk * BN + cbase, row0);
             else tma_store_2d(&tma_c, stg, n_blk * BN + cbase, row0);
-            if (LNF == 1 && n_blk * BN + cbase < p.N) tma_store_2d(&tma_c2, epi_stage2 + (warp - 4) * 2048, n_blk * BN + cbase, row0);
+            if (LNF == 1 && n_blk * BN + cbase < p.N && !(p.lnf_dbg & 1)) tma_store_2d(&tma_c2, epi_stage2 + (warp - 4) * 2048, n_blk * BN + cbase, row0);
             tma_commit_group();
           }
         }
@@ -831,6 +853,9 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   kp.c_mode = plan.c_mode;
 
   kp.trace = g_trace;
+  static int lnf_dbg_env = -1;
+  if (lnf_dbg_env < 0) { const char* ev = std::getenv("AVH_LN_DBG"); lnf_dbg_env = ev ? std::atoi(ev) : 0; }
+  kp.lnf_dbg = lnf_dbg_env;
   kp.ep = pr.ep;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);
