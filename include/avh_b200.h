@@ -89,6 +89,12 @@ AVH_API int avh_load_tensor(avh_handle* h, const char* key, const void* data, in
 /* Fold eval-mode BatchNorm into conv epilogues, fold weight-norm of pos_conv, fold the q scaling, repack
  * every weight into the kernels' K-major bf16 layouts and upload.  Fails listing the first missing key. */
 AVH_API int avh_finalize_weights(avh_handle* h);
+/* Frees the fp32 host copies avh_load_tensor keeps for re-finalisation (~1.3 GB for Large).  After this call a
+ * weight update must re-load EVERY tensor before the next avh_finalize_weights (nn.Module.load_state_dict does). */
+AVH_API int avh_drop_host_weights(avh_handle* h);
+/* Drains `stream`, then frees the execution plans, workspaces and host-path staging buffers bound to it (a caller
+ * retiring a CUDA stream; torch.cuda.Stream objects going out of scope). */
+AVH_API int avh_release_stream(avh_handle* h, void* stream);
 
 /* extract_finetune.  All pointers are DEVICE pointers.
  *   video  [B,1,T,88,88] contiguous (AVH_F32/F16/BF16), or raw [B,1,T,src_h,src_w] uint8 frames (AVH_U8, see
@@ -105,7 +111,9 @@ AVH_API int avh_forward(avh_handle* h, const void* video, int video_dtype, const
 
 /* Raw-video geometry for video_dtype == AVH_U8: video is then [B,1,T,src_h,src_w] uint8 gray frames (mouth ROI as
  * stored by the dataset, e.g. 96 x 96); avh_forward* first applies x/255, the centre crop to 88 x 88 with offsets
- * (src-88)/2 and (x-mean)/std (defaults 0.421 / 0.165, hubert_pretraining.py:144-149).  Default: 88 x 88 (no crop). */
+ * (src-88)/2 and (x-mean)/std (defaults 0.421 / 0.165, hubert_pretraining.py:144-149).  Default: 88 x 88 (no crop).
+ * Frames flagged in padding_mask become 0.0 (the collater zero-pads AFTER the per-sample Normalize,
+ * hubert_dataset.py:430-456), whatever bytes the caller left in them. */
 AVH_API int avh_set_video_preprocess(avh_handle* h, int src_h, int src_w, double mean, double std);
 
 /* The same transform as a stand-alone device op: frames [n_frames, src_h, src_w] uint8 -> out [n_frames, crop, crop]

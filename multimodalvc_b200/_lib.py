@@ -17,7 +17,8 @@ EXPORTS = [
     "avh_abi_version", "avh_last_error", "avh_create", "avh_destroy", "avh_load_tensor", "avh_finalize_weights",
     "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
-    "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess",
+    "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess", "avh_drop_host_weights",
+    "avh_release_stream",
 ]
 
 
@@ -59,6 +60,8 @@ def load():
     lib.avh_destroy.argtypes = [vp]
     lib.avh_load_tensor.argtypes = [vp, ctypes.c_char_p, vp, i32, ctypes.POINTER(i64), i32]
     lib.avh_finalize_weights.argtypes = [vp]
+    lib.avh_drop_host_weights.argtypes = [vp]
+    lib.avh_release_stream.argtypes = [vp, vp]
     lib.avh_forward.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host_async.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]

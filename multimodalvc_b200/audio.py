@@ -90,6 +90,27 @@ def logfbank_stack_collate_packed(flat: torch.Tensor, offsets: torch.Tensor, T: 
     return out.transpose(1, 2), pm.view(torch.bool)
 
 
+def add_noise_packed(flat: torch.Tensor, offsets: torch.Tensor, noise: torch.Tensor, snr_db: float) -> torch.Tensor:
+    """add_noise for clips already packed on the device: ``flat`` int16 CUDA tensor (clips back to back), ``offsets``
+    int64 CUDA tensor [B+1], ``noise`` float32 CUDA tensor.  Returns the mixed int16 clips in the same packing."""
+    if flat.dtype != torch.int16 or not flat.is_cuda or offsets.dtype != torch.int64 or not offsets.is_cuda:
+        raise ValueError("flat must be an int16 CUDA tensor and offsets an int64 CUDA tensor")
+    device = flat.device
+    B = int(offsets.numel()) - 1
+    out = torch.empty_like(flat)
+    if B <= 0:
+        return out
+    nz = noise.to(device=device, dtype=torch.float32).contiguous()
+    scratch = torch.empty(4 * B, device=device, dtype=torch.float64)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(_lib.load().avh_add_noise(
+            ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(offsets.data_ptr()), B,
+            ctypes.c_void_p(nz.data_ptr()), int(nz.numel()), float(snr_db), ctypes.c_void_p(out.data_ptr()),
+            ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(stream)))
+    return out
+
+
 def add_noise(wavs: Sequence[torch.Tensor], noise: torch.Tensor, snr_db: float, device=None) -> List[torch.Tensor]:
     """avhubert/hubert_dataset.py:317-346 for a batch of clips sharing one noise clip and SNR.
     wavs: int16 1-D tensors; noise: float32 1-D tensor (tiled when shorter, cropped from 0 when longer).
@@ -98,15 +119,7 @@ def add_noise(wavs: Sequence[torch.Tensor], noise: torch.Tensor, snr_db: float, 
     if len(wavs) == 0:
         return []
     flat, offsets, lens = _pack(wavs, device)
-    nz = noise.to(device=device, dtype=torch.float32).contiguous()
-    out = torch.empty_like(flat)
-    scratch = torch.empty(4 * len(wavs), device=device, dtype=torch.float64)
-    with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(_lib.load().avh_add_noise(
-            ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(offsets.data_ptr()), len(wavs),
-            ctypes.c_void_p(nz.data_ptr()), int(nz.numel()), float(snr_db), ctypes.c_void_p(out.data_ptr()),
-            ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(stream)))
+    out = add_noise_packed(flat, offsets, noise.to(device), snr_db)
     res, o = [], 0
     for n in lens:
         res.append(out[o:o + n])

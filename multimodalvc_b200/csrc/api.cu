@@ -22,6 +22,7 @@
 #include <map>
 #include <tuple>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,19 @@ int device_sm_count() {
     cached_dev = dev;
   }
   return cached_n;
+}
+
+int ensure_dyn_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> done;      // (device, function) -> bytes granted
+  int dev = 0;
+  AVH_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find({dev, fn});
+  if (it != done.end() && it->second >= bytes) return 0;
+  AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[{dev, fn}] = bytes;
+  return 0;
 }
 
 namespace {
@@ -179,6 +193,8 @@ struct Plan {
   int direct_runs = 0;              // un-captured forwards so far (the first one also configures the kernels)
   int graph_kernels = 0;            // kernel launches inside one graph (for avh_launch_count)
   long long calls = 0, captures = 0;
+  long long last_use = 0;           // LRU clock value of the most recent forward through this plan
+  cudaStream_t stream = nullptr;
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     graphs.clear();
@@ -216,6 +232,7 @@ struct avh_handle {
   int* pos_acol = nullptr;        // device [D/64] window start per N tile
   std::vector<LayerW> layers;
   std::map<std::string, std::unique_ptr<Plan>> plans;
+  long long plan_clock = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // 2 per step of the last profiled forward
   Plan* prof_plan = nullptr;
@@ -572,8 +589,8 @@ struct Builder {
     return plan->arena.take(bytes);
   }
   std::string tag = "misc";     // name given to the steps pushed next
-  void push(std::function<int(cudaStream_t)> f) {
-    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, 0.0});
+  void push(std::function<int(cudaStream_t)> f, double flops = 0.0) {
+    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, flops});
   }
 
   // K-step table for one GEMM: every tap x every 64-wide K chunk (x 3 split-precision products in fp32 mode)
@@ -1091,7 +1108,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       b.tag = "attention";
       b.push([=](cudaStream_t s) {
         return launch_attention(q, hm ? pl->args.mask : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
-      });
+      }, 4.0 * (double)B * Hh * (double)T * (double)T * 64.0);      // QK^T + PV, dense (padding not excluded)
       sync_op(ctx);
     }
     {   // out_proj + residual
@@ -1156,9 +1173,24 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
   auto it = h->plans.find(key);
-  if (it != h->plans.end()) return it->second.get();
-  if (h->plans.size() >= 8) { h->plans.clear(); h->last_plan = nullptr; h->prof_plan = nullptr; }   // bound workspace growth for ragged shape streams
+  if (it != h->plans.end()) {
+    it->second->last_use = ++h->plan_clock;
+    return it->second.get();
+  }
+  // bound workspace growth for ragged shape streams: evict the least recently used plan (one cudaFree, not all)
+  static int cap_env = -1;
+  if (cap_env < 0) { const char* ev = std::getenv("AVH_PLAN_CACHE"); cap_env = (ev != nullptr && std::atoi(ev) > 0) ? std::atoi(ev) : 24; }
+  while ((int)h->plans.size() >= cap_env) {
+    auto victim = h->plans.begin();
+    for (auto jt = h->plans.begin(); jt != h->plans.end(); ++jt)
+      if (jt->second->last_use < victim->second->last_use) victim = jt;
+    if (h->last_plan == victim->second.get()) h->last_plan = nullptr;
+    if (h->prof_plan == victim->second.get()) h->prof_plan = nullptr;
+    h->plans.erase(victim);
+  }
   std::unique_ptr<Plan> p(new Plan());
+  p->last_use = ++h->plan_clock;
+  p->stream = stream;
   p->B = B; p->T = T; p->has_video = has_video; p->has_audio = has_audio; p->has_mask = has_mask;
   p->output_layer = output_layer;
   size_t bytes = 0;
@@ -1295,6 +1327,33 @@ int avh_finalize_weights(avh_handle* h) {
   return 0;
 }
 
+int avh_drop_host_weights(avh_handle* h) {
+  AVH_CHECK(h != nullptr, "null handle");
+  h->raw.clear();
+  return 0;
+}
+
+int avh_release_stream(avh_handle* h, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  AVH_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  for (auto it = h->plans.begin(); it != h->plans.end();) {
+    if (it->second->stream == reinterpret_cast<cudaStream_t>(stream)) {
+      if (h->last_plan == it->second.get()) h->last_plan = nullptr;
+      if (h->prof_plan == it->second.get()) h->prof_plan = nullptr;
+      it = h->plans.erase(it);
+    } else ++it;
+  }
+  auto st = h->staging.find(stream);
+  if (st != h->staging.end()) {
+    void* ptrs[5] = {st->second.video, st->second.audio, st->second.mask, st->second.out, st->second.video_pp};
+    for (void* q : ptrs)
+      if (q) cudaFree(q);
+    h->staging.erase(st);
+  }
+  return 0;
+}
+
 int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
                 const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
                 void* out, int out_dtype, void* stream) {
@@ -1314,7 +1373,7 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
     const int pdt = h->cfg.compute_mode == AVH_COMPUTE_FP32 ? AVH_F32 : AVH_BF16;
     if (avh::ensure_cap(&st.video_pp, &st.video_pp_cap, (size_t)B * T * 7744 * avh::dtype_size(pdt))) return 1;
     if (avh::launch_video_preprocess(reinterpret_cast<const unsigned char*>(video), (long long)B * T, h->vp_src_h,
-                                     h->vp_src_w, 88, h->vp_mean, h->vp_std, st.video_pp, pdt,
+                                     h->vp_src_w, 88, h->vp_mean, h->vp_std, st.video_pp, pdt, padding_mask,
                                      reinterpret_cast<cudaStream_t>(stream)))
       return 1;
     video = st.video_pp;
@@ -1415,7 +1474,7 @@ int avh_video_preprocess(const uint8_t* frames, int64_t n_frames, int src_h, int
                          double stdv, void* out, int out_dtype, void* stream) {
   AVH_CHECK(frames != nullptr && out != nullptr, "null argument");
   AVH_CHECK(out_dtype == AVH_F32 || out_dtype == AVH_F16 || out_dtype == AVH_BF16, "bad output dtype");
-  return avh::launch_video_preprocess(frames, n_frames, src_h, src_w, crop, mean, stdv, out, out_dtype,
+  return avh::launch_video_preprocess(frames, n_frames, src_h, src_w, crop, mean, stdv, out, out_dtype, nullptr,
                                       reinterpret_cast<cudaStream_t>(stream));
 }
 

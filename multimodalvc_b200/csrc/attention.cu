@@ -211,11 +211,7 @@ template <int NW, int BKV, int MINB, int NRES>
 int launch_att_t(const void* qkv, const unsigned char* kpm, void* out, int B, int T, int D, int H, cudaStream_t stream) {
   constexpr int BQ = NW * 16;
   const size_t smem = (size_t)(BQ + 2 * NRES * BKV) * PITCH * 2 + BKV * 4;
-  static bool configured = false;
-  if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(attention_kernel<NW, BKV, MINB, NRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(attention_kernel<NW, BKV, MINB, NRES>), (int)smem)) return 1;
   dim3 grid((T + BQ - 1) / BQ, H, B);
   AVH_CUDA_OK(launch_pdl(attention_kernel<NW, BKV, MINB, NRES>, grid, dim3(NW * 32), smem, stream,
                          reinterpret_cast<const __nv_bfloat16*>(qkv), kpm, reinterpret_cast<__nv_bfloat16*>(out), T, D));

@@ -14,6 +14,9 @@ namespace avh {
 void set_last_error(const std::string& msg);   // defined in api.cu
 int device_sm_count();                         // SMs of the current device (cached per device)
 void count_launch(int n);                      // kernel-launch counter reported by avh_launch_count()
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  The attribute belongs to the function in
+// one device's context, so the "already done" state is keyed by (device, function); returns 0 on success.
+int ensure_dyn_smem(const void* fn, int bytes);
 #define AVH_CUDA_OK(expr)                                                                       \
   do {                                                                                          \
     cudaError_t _e = (expr);                                                                    \

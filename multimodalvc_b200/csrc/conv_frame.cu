@@ -468,16 +468,7 @@ int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream) {
   const int occ = pr.occ == 2 ? 2 : 1;
   const int mode = pr.R != nullptr ? 2 : (pr.slope1 != nullptr ? 1 : 0);
   FrameKernelFn fn = pick_kernel(occ, mode);
-  static std::mutex mu;
-  static std::set<const void*> configured;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (configured.find(reinterpret_cast<const void*>(fn)) == configured.end()) {
-      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       occ == 2 ? FOcc<2>::SMEM_LIMIT : FOcc<1>::SMEM_LIMIT));
-      configured.insert(reinterpret_cast<const void*>(fn));
-    }
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(fn), occ == 2 ? FOcc<2>::SMEM_LIMIT : FOcc<1>::SMEM_LIMIT)) return 1;
   const int threads = occ == 2 ? FOcc<2>::NUM_THREADS : FOcc<1>::NUM_THREADS;
   AVH_CUDA_OK(launch_pdl(fn, dim3(plan.grid), dim3(threads), plan.smem, stream, plan.tma_a, plan.tma_b, plan.tma_c, plan.tma_a2, p));
   count_launch(1);

@@ -356,15 +356,7 @@ int conv_window_launch(const ConvWinPlan& plan, cudaStream_t stream) {
   typedef void (*WinFn)(CUtensorMap, CUtensorMap, CUtensorMap, WinParams);
   WinFn fn = plan.pair == 2 ? (pr.R != nullptr ? conv_window_kernel<true, 2> : conv_window_kernel<false, 2>)
                             : (pr.R != nullptr ? conv_window_kernel<true, 1> : conv_window_kernel<false, 1>);
-  static std::mutex mu;
-  static std::set<const void*> configured;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (configured.find(reinterpret_cast<const void*>(fn)) == configured.end()) {
-      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      configured.insert(reinterpret_cast<const void*>(fn));
-    }
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(fn), SMEM_LIMIT)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);
   cfg.blockDim = dim3(NUM_THREADS);

@@ -368,7 +368,8 @@ __global__ void ln_center_stats_kernel(const float* __restrict__ in, __nv_bfloat
 // computed once per CTA in double and looked up, so fp32 outputs are bit-identical to the reference's.
 __global__ void __launch_bounds__(256)
 video_preprocess_kernel(const unsigned char* __restrict__ in, void* __restrict__ out, int out_dt, long long n_frames,
-                        int src_h, int src_w, int crop, int dh, int dw, double mean, double stdv) {
+                        int src_h, int src_w, int crop, int dh, int dw, double mean, double stdv,
+                        const unsigned char* __restrict__ frame_zero) {
   pdl_launch_dependents();
   __shared__ float lut[256];
   lut[threadIdx.x] = (float)((((double)threadIdx.x - 0.0) / 255.0 - mean) / stdv);
@@ -386,6 +387,12 @@ video_preprocess_kernel(const unsigned char* __restrict__ in, void* __restrict__
   float v[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] = lut[src[k]];
+  // the collater zero-pads AFTER the per-sample Normalize (hubert_dataset.py:430-456): pad frames are 0.0 in
+  // normalised space, not (0/255 - mean)/std
+  if (frame_zero != nullptr && frame_zero[f]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  }
   const long long o = (f * crop + y) * (long long)crop + g * 8;
   if (out_dt == DT_F32) {
     float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
@@ -407,7 +414,7 @@ inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per);
 }  // namespace
 
 int launch_video_preprocess(const unsigned char* frames, long long n_frames, int src_h, int src_w, int crop, double mean,
-                            double stdv, void* out, int out_dt, cudaStream_t stream) {
+                            double stdv, void* out, int out_dt, const unsigned char* frame_zero, cudaStream_t stream) {
   if (n_frames <= 0) return 0;
   AVH_CHECK(crop >= 8 && crop % 8 == 0 && crop <= src_h && crop <= src_w, "crop must be a multiple of 8 and fit the frame");
   AVH_CHECK(stdv != 0.0, "std must be non-zero");
@@ -417,7 +424,7 @@ int launch_video_preprocess(const unsigned char* frames, long long n_frames, int
   const long long total = n_frames * crop * (crop / 8);
   AVH_CHECK(total / 256 + 1 < (1ll << 31), "too many frames for one launch");
   AVH_CUDA_OK(launch_pdl(video_preprocess_kernel, dim3((unsigned)blocks_for(total, 256)), dim3(256), 0, stream, frames, out,
-                         out_dt, n_frames, src_h, src_w, crop, dh, dw, mean, stdv));
+                         out_dt, n_frames, src_h, src_w, crop, dh, dw, mean, stdv, frame_zero));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

@@ -380,11 +380,7 @@ int launch_fbank(const FbankArgs& a, cudaStream_t stream) {
   if (rows == 0) return 0;
   AVH_CHECK(a.wav != nullptr && a.offsets != nullptr && a.out != nullptr, "null pointer");
   if (upload_tables()) return 1;
-  static bool configured = false;
-  if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    configured = true;
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(fbank_kernel), (int)sizeof(Smem))) return 1;
   const int sms = device_sm_count();
   const long long want = rows < (long long)sms * 5 ? rows : (long long)sms * 5;
   fbank_kernel<<<(int)want, WARPS * 32, sizeof(Smem), stream>>>(a);

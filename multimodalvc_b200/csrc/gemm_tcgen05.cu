@@ -908,16 +908,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     else if (occ == 2) fn = gemm_kernel<1, 2, -1, -1, -1, -1, -1>;
     else fn = gemm_kernel<1, 1, -1, -1, -1, -1, -1>;
   }
-  static std::mutex mu;
-  static std::set<const void*> configured;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (configured.find(reinterpret_cast<const void*>(fn)) == configured.end()) {
-      AVH_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       occ == 2 ? Occ<2>::SMEM_LIMIT : Occ<1>::SMEM_LIMIT));
-      configured.insert(reinterpret_cast<const void*>(fn));
-    }
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(fn), occ == 2 ? Occ<2>::SMEM_LIMIT : Occ<1>::SMEM_LIMIT)) return 1;
   AVH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, plan.tma_a, plan.tma_b, plan.tma_c, plan.tma_c2, kp));
   count_launch(1);
   return 0;

@@ -45,8 +45,10 @@ int launch_maxpool_stem(const void* in, void* out, int nf, int T, int fp32, cuda
 // [n*Ho*Wo, 9*C] (K index = (kh*3+kw)*C + c)
 int launch_im2col_s2(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream);
 // mean over the H*W valid pixels of the padded layout [n,H+1,W+1,C] -> [n, C] (bf16 or fp32 in and out)
+// raw uint8 gray frames [n, src_h, src_w] -> /255, centre crop, (x - mean) / std (avhubert/utils.py:56-95); frames
+// flagged in frame_zero ([n], may be null: the key-padding mask) are written as 0.0, as the collater's zero padding is
 int launch_video_preprocess(const unsigned char* frames, long long n_frames, int src_h, int src_w, int crop, double mean,
-                            double stdv, void* out, int out_dt, cudaStream_t stream);
+                            double stdv, void* out, int out_dt, const unsigned char* frame_zero, cudaStream_t stream);
 int launch_ln_center_stats(const float* in, void* xc, float* mu, void* part, int np, long long rows, int C,
                            cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int pitch, int fp32, cudaStream_t stream);

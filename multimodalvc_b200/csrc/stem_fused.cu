@@ -417,11 +417,7 @@ int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, i
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.w = reinterpret_cast<const __nv_bfloat16*>(plan.w);
   p.scale = scale; p.bias = bias; p.slope = slope;
-  static bool configured = false;
-  if (!configured) {
-    AVH_CUDA_OK(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured = true;
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(stem_fused_kernel), (int)SMEM_BYTES)) return 1;
   const int grid = p.num_items < sms ? p.num_items : sms;
   p.dbg = nullptr;
   static int dbg_env = -1;

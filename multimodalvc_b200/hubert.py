@@ -195,6 +195,7 @@ class AVHubertModel(nn.Module):
         self._handle_key = None
         self._dirty = True
         self._video_geo = None
+        self._host_keepalive = {}
         # normalisation of raw uint8 video (task config image_mean / image_std, hubert_pretraining.py:144-149)
         self.image_mean, self.image_std = 0.421, 0.165
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
@@ -296,39 +297,43 @@ class AVHubertModel(nn.Module):
                                                _DTYPES[t.dtype], shape, t.dim()))
             torch.cuda.synchronize(p.device)
         _lib.check(lib.avh_finalize_weights(self._handle))
+        # every refresh re-loads the whole state dict, so the library's fp32 host copies (1.3 GB for Large) can go
+        _lib.check(lib.avh_drop_host_weights(self._handle))
         self._dirty = False
         return self._handle
 
     # ------------------------------------------------------------------ the hot path
-    @torch.no_grad()
-    def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
-        """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
-        padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask)."""
+    def _check_mode(self, mask):
         if mask:
             raise NotImplementedError("apply_input_mask (mask=True) is off in every shipped fine-tune/inference "
                                       "config and is not implemented on the device path")
         if self.training:
             raise RuntimeError("training-mode forward (batch-statistics BatchNorm, dropout, LayerDrop) is not "
                                "implemented; call .eval() — the encoder is frozen on every inference path")
-        src_audio, src_video = source["audio"], source["video"]
+
+    def _check_inputs(self, handle, src_video, src_audio, padding_mask, device):
+        """Validation shared by the device and the host entry points.  Returns (video, video_dt, audio, pm_u8, pm, B, T)
+        with video/audio contiguous-or-strided tensors on `device` ('cpu' for the host path) in a dtype the library
+        reads, and pm the [B,T] bool mask (forward_padding_mask applied) or None."""
         if src_audio is None and src_video is None:
             raise ValueError("both modalities are None")
-        handle = self._ensure_handle()
-        dev = self.encoder.layer_norm.weight.device
+        for t in (src_video, src_audio):
+            if t is not None and t.device != device:
+                raise RuntimeError(f"inputs are on {t.device} but this call expects {device}")
         ref = src_video if src_video is not None else src_audio
-        if ref.device != dev:
-            raise RuntimeError(f"inputs are on {ref.device} but the module is on {dev}")
-        B = ref.size(0)
+        B, T = ref.size(0), -1
         video_dt = 0
         if src_video is not None:
-            T = src_video.size(2) if src_video.dim() == 5 else -1
+            if src_video.dim() != 5 or src_video.size(1) != 1:
+                raise ValueError(f"video must be [B,1,T,88,88] (or raw uint8 [B,1,T,H,W]), got {tuple(src_video.shape)}")
+            T = src_video.size(2)
             if src_video.dtype == torch.uint8:
                 # raw gray frames [B,1,T,H,W]: normalised and centre-cropped on the device (video.py)
-                if src_video.dim() != 5 or src_video.size(1) != 1 or min(src_video.shape[3:]) < 88:
+                if min(src_video.shape[3:]) < 88:
                     raise ValueError(f"uint8 video must be [B,1,T,H>=88,W>=88], got {tuple(src_video.shape)}")
                 self._set_video_geometry(handle, int(src_video.size(3)), int(src_video.size(4)))
                 video_dt = _U8
-            elif src_video.dim() != 5 or src_video.size(1) != 1 or tuple(src_video.shape[3:]) != (88, 88):
+            elif tuple(src_video.shape[3:]) != (88, 88):
                 raise ValueError(f"video must be [B,1,T,88,88], got {tuple(src_video.shape)}")
             src_video = src_video.contiguous()
             if video_dt != _U8:
@@ -343,11 +348,26 @@ class AVHubertModel(nn.Module):
             T = src_audio.size(2)
             if src_audio.dtype not in _DTYPES:
                 src_audio = src_audio.float()
+        if B < 1 or T < 1:
+            raise ValueError("empty batch")
         pm_u8 = None
         if padding_mask is not None:
+            if padding_mask.dim() != 2 or padding_mask.size(0) != B:
+                raise ValueError(f"padding_mask must be [B,T'], got {tuple(padding_mask.shape)}")
             if padding_mask.size(1) != T:
                 padding_mask = self.forward_padding_mask(T, padding_mask)
-            pm_u8 = padding_mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
+            pm_u8 = padding_mask.to(device=device, dtype=torch.bool).contiguous().view(torch.uint8)
+        return src_video, video_dt, src_audio, pm_u8, padding_mask, B, T
+
+    @torch.no_grad()
+    def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
+        """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
+        padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask)."""
+        self._check_mode(mask)
+        handle = self._ensure_handle()
+        dev = self.encoder.layer_norm.weight.device
+        src_video, video_dt, src_audio, pm_u8, padding_mask, B, T = self._check_inputs(
+            handle, source["video"], source["audio"], padding_mask, dev)
         out_dtype = self.encoder.layer_norm.weight.dtype
         if out_dtype not in _DTYPES:
             out_dtype = torch.float32
@@ -375,33 +395,28 @@ class AVHubertModel(nn.Module):
             _lib.check(_lib.load().avh_set_video_preprocess(handle, H, W, geo[2], geo[3]))
             self._video_geo = geo
 
+    @torch.no_grad()
     def extract_finetune_host(self, video, audio, padding_mask=None, output_layer=None, out=None, wait=True):
         """End-to-end call with HOST tensors (pinned recommended): H2D copies, forward and the D2H read of the
-        features all happen inside ``avh_forward_host``.  video [B,1,T,88,88] / audio [B,F,T] contiguous CPU
-        tensors (either may be None); returns a CPU tensor [B,T,D].  ``wait=False`` only enqueues on the current
-        stream (the caller synchronises it before reading ``out``), which lets several batches be in flight on
-        different streams."""
+        features all happen inside ``avh_forward_host``.  video [B,1,T,88,88] (or raw uint8 [B,1,T,H,W]) / audio
+        [B,F,T] CPU tensors (either may be None; made contiguous if they are not); returns a CPU tensor [B,T,D].
+        ``wait=False`` only enqueues on the current stream (the caller synchronises it before reading ``out``),
+        which lets several batches be in flight on different streams.  Same checks as ``extract_finetune``; the
+        byte counts the library copies are those of the validated shapes."""
+        self._check_mode(False)
         handle = self._ensure_handle()
         dev = self.encoder.layer_norm.weight.device
-        ref = video if video is not None else audio
-        B = ref.size(0)
-        T = video.size(2) if video is not None else audio.size(2)
+        video, video_dt, audio, pm, _, B, T = self._check_inputs(handle, video, audio, padding_mask, torch.device("cpu"))
+        if audio is not None:
+            audio = audio.contiguous()            # the host entry point reads a dense [B,F,T] block
         out_dtype = self.encoder.layer_norm.weight.dtype
+        if out_dtype not in _DTYPES:
+            out_dtype = torch.float32
         if out is None:
             out = torch.empty(B, T, self.encoder_embed_dim, dtype=out_dtype).pin_memory()
-        pm = None
-        if padding_mask is not None:
-            pm = padding_mask.contiguous().view(torch.uint8)
-        for t in (video, audio):
-            if t is not None and (t.device.type != "cpu" or not t.is_contiguous()):
-                raise ValueError("extract_finetune_host takes contiguous CPU tensors")
-        video_dt = 0
-        if video is not None:
-            if video.dtype == torch.uint8:        # raw frames [B,1,T,H,W]: 1 byte per pixel over PCIe
-                self._set_video_geometry(handle, int(video.size(3)), int(video.size(4)))
-                video_dt = _U8
-            else:
-                video_dt = _DTYPES[video.dtype]
+        elif (out.device.type != "cpu" or not out.is_contiguous() or out.dtype not in _DTYPES
+              or tuple(out.shape) != (B, T, self.encoder_embed_dim)):
+            raise ValueError(f"out must be a contiguous CPU tensor [{B},{T},{self.encoder_embed_dim}]")
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             lib = _lib.load()
@@ -414,6 +429,10 @@ class AVHubertModel(nn.Module):
                 ctypes.c_void_p(pm.data_ptr()) if pm is not None else None,
                 B, T, 0 if output_layer is None else int(output_layer),
                 ctypes.c_void_p(out.data_ptr()), _DTYPES[out.dtype], ctypes.c_void_p(stream)))
+            if not wait:
+                # the async copy reads these host buffers after this call returns: keep them alive until the caller
+                # has synchronised the stream (replaced by the next call on the same stream)
+                self._host_keepalive[stream] = (video, audio, pm, out)
         return out
 
     def read_stage(self, name, numel):

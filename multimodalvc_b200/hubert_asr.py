@@ -26,7 +26,7 @@ class HubertEncoderWrapper(nn.Module):
         }
 
     def reorder_encoder_out(self, encoder_out, new_order):
-        """avhubert/hubert_asr.py:396-409"""
+        """avhubert/hubert_asr.py:396-409 (the wrapper reorders all three entries)"""
         if encoder_out["encoder_out"] is not None:
             encoder_out["encoder_out"] = encoder_out["encoder_out"].index_select(1, new_order)
         if encoder_out["encoder_padding_mask"] is not None:
@@ -78,7 +78,13 @@ class HubertEncoder(nn.Module):
             "padding_mask": padding_mask,
         }
 
-    reorder_encoder_out = HubertEncoderWrapper.reorder_encoder_out
+    def reorder_encoder_out(self, encoder_out, new_order):
+        """avhubert/hubert_asr.py:356-365: unlike the wrapper's, "padding_mask" is left as it is"""
+        if encoder_out["encoder_out"] is not None:
+            encoder_out["encoder_out"] = encoder_out["encoder_out"].index_select(1, new_order)
+        if encoder_out["encoder_padding_mask"] is not None:
+            encoder_out["encoder_padding_mask"] = encoder_out["encoder_padding_mask"].index_select(0, new_order)
+        return encoder_out
 
     def max_positions(self):
         return None
@@ -92,16 +98,30 @@ def _linear(in_features, out_features):
     return m
 
 
+def _packed_head(lin, device):
+    """bf16 weight [Np, D] / fp32 bias [Np] of a projection head, columns padded to a multiple of 32, cached on the
+    module until its parameters change (version counters) or move."""
+    key = (lin.weight._version, lin.bias._version, lin.weight.data_ptr(), str(device))
+    cache = getattr(lin, "_avh_packed", None)
+    if cache is None or cache[0] != key:
+        N, D = lin.out_features, lin.in_features
+        Np = (N + 31) // 32 * 32
+        w = torch.zeros(Np, D, device=device, dtype=torch.bfloat16)
+        w[:N] = lin.weight.detach().to(device=device, dtype=torch.bfloat16)
+        bias = torch.zeros(Np, device=device, dtype=torch.float32)
+        bias[:N] = lin.bias.detach().to(device=device, dtype=torch.float32)
+        cache = (key, w, bias)
+        lin._avh_packed = cache
+    return cache[1], cache[2]
+
+
 def _project(x, lin):
-    """[B,T,D] @ W^T + b through avh_gemm_bf16; output columns padded to a multiple of 32 inside the call."""
+    """[B,T,D] @ W^T + b through avh_gemm_bf16 (output columns padded to a multiple of 32 in the cached copy)."""
     B, T, D = x.shape
     N = lin.out_features
-    Np = (N + 31) // 32 * 32
+    w, bias = _packed_head(lin, x.device)
+    Np = w.size(0)
     a = x.reshape(B * T, D).to(torch.bfloat16).contiguous()
-    w = torch.zeros(Np, D, device=x.device, dtype=torch.bfloat16)
-    w[:N] = lin.weight.detach().to(torch.bfloat16)
-    bias = torch.zeros(Np, device=x.device, dtype=torch.float32)
-    bias[:N] = lin.bias.detach().float()
     out = torch.empty(B * T, Np, device=x.device, dtype=torch.float32)
     vp = ctypes.c_void_p
     with torch.cuda.device(x.device):

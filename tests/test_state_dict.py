@@ -61,3 +61,18 @@ def test_wrapper_contract():
     assert out["encoder_out"].shape == (5, 2, 8)
     out = w.reorder_encoder_out(out, torch.tensor([1, 0]))
     assert out["encoder_out"].shape == (5, 2, 8)
+
+
+def test_reorder_encoder_out_variants_follow_the_reference():
+    """avhubert/hubert_asr.py:396-409 (wrapper: all three entries reordered) vs :356-365 (HubertEncoder:
+    'padding_mask' left alone)."""
+    from multimodalvc_b200 import HubertEncoder
+    pm = torch.tensor([[True, False], [False, False]])
+    x = torch.arange(2 * 2 * 3, dtype=torch.float32).view(2, 2, 3)           # T x B x C
+    order = torch.tensor([1, 0])
+    d = {"encoder_out": x, "encoder_padding_mask": pm, "padding_mask": pm}
+    out = HubertEncoderWrapper.reorder_encoder_out(None, dict(d), order)
+    assert torch.equal(out["encoder_out"], x[:, [1, 0]])
+    assert torch.equal(out["encoder_padding_mask"], pm[[1, 0]]) and torch.equal(out["padding_mask"], pm[[1, 0]])
+    out = HubertEncoder.reorder_encoder_out(None, dict(d), order)
+    assert torch.equal(out["encoder_padding_mask"], pm[[1, 0]]) and torch.equal(out["padding_mask"], pm)
