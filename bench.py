@@ -39,12 +39,13 @@ def clip_flops(T=T_FRAMES, audio=True):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region (NVML, ~5 ms period; same fields as the
-    nvidia-smi clocks line of B200_PROFILING.md)."""
+    """SM clock and throttle reasons (NVML, ~2 ms period; same fields as the nvidia-smi clocks line of
+    B200_PROFILING.md).  Runs from before the warm-up; `summary(t0, t1)` reports the samples taken inside a timed
+    region (host perf_counter window around the synchronised region)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.sm, self.max_sm, self.mask, self.stop_flag = index, [], None, 0, False
+        self.index, self.samples, self.max_sm, self.stop_flag, self.ready = index, [], None, False, threading.Event()
 
     def run(self):
         try:
@@ -59,19 +60,32 @@ class ClockSampler(threading.Thread):
                     pass
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ready.set()
             while not self.stop_flag:
-                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                time.sleep(0.005)
+                self.samples.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                     int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                time.sleep(0.002)
         except Exception as e:      # clocks are evidence, not part of the measurement: never fail the run
             self.err = str(e)
+            self.ready.set()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-        sm = sorted(self.sm)
-        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_min_mhz": float(sm[0]) if sm else None,
-                "sm_max_mhz": float(self.max_sm) if self.max_sm else None,
-                "reasons": sorted(v for k, v in names.items() if self.mask & k), "samples": len(sm)}
+        sel = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1)]
+        note = None
+        if not sel and self.samples and t0 is not None:      # region shorter than the sampling period: nearest sample
+            sel = [min(self.samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))]
+            note = "region shorter than the sampling period: nearest sample"
+        sm = sorted(x[1] for x in sel)
+        mask = 0
+        for x in sel:
+            mask |= x[2]
+        out = {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_min_mhz": float(sm[0]) if sm else None,
+               "sm_max_mhz": float(self.max_sm) if self.max_sm else None,
+               "reasons": sorted(v for k, v in names.items() if mask & k), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def synthetic_wave(n_samples, seed):
@@ -283,6 +297,9 @@ def main():
             main_stream.wait_stream(st)
 
     # ---- device-resident timing
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.ready.wait(timeout=10)
     torch.cuda.synchronize(dev)
     # warm-up: at least W steps, and enough for every (stream, input batch) pair to have been seen twice — the library
     # runs the first call of a shape directly and captures a CUDA graph per distinct set of input pointers on the
@@ -292,11 +309,10 @@ def main():
         step(i)
     join()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     e0.record()
     fork(e0)
     for i in range(args.steps):
@@ -304,10 +320,10 @@ def main():
     join()
     e1.record()
     barrier()
+    t_region1 = time.perf_counter()
     launches = _lib.launch_count()
     ms = e0.elapsed_time(e1)
-    sampler.stop_flag = True
-    sampler.join(timeout=3)
+    clocks_timed = sampler.summary(t_region0, t_region1)
     checksum = float(y.float().abs().mean().item())
 
     # ---- sustained leg: >= SUSTAIN_S seconds of back-to-back steps (the driver-sized region above is ~0.1 s, i.e.
@@ -315,10 +331,9 @@ def main():
     sustained = None
     if args.sustain_s > 0:
         n_sus = max(args.steps, int(args.sustain_s / max(ms / args.steps * 1e-3, 1e-4)) + 1)
-        sus_sampler = ClockSampler(local_rank)
-        sus_sampler.start()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_sus0 = time.perf_counter()
         s0.record()
         fork(s0)
         for i in range(n_sus):
@@ -327,9 +342,9 @@ def main():
         s1.record()
         barrier()
         ms_sus = s0.elapsed_time(s1)
-        sus_sampler.stop_flag = True
-        sus_sampler.join(timeout=3)
-        sustained = (n_sus, ms_sus, sus_sampler.summary())
+        sustained = (n_sus, ms_sus, sampler.summary(t_sus0, time.perf_counter()))
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
 
     # ---- end to end through the host-buffer entry point
     for i in range(2 * S):
@@ -504,7 +519,7 @@ def main():
                                      "normalised bf16 frames [16,1,150,88,88] + bf16 audio features from pinned host memory "
                                      "(cast outside the timed region; kept for continuity with round 1's `e2e`)"),
             "gpu_launches": launches,
-            "clocks": sampler.summary(),
+            "clocks": clocks_timed,
             "roofline": {"bound": "tensor",
                          "kernel": "gemm_kernel (tcgen05/TMEM/TMA): encoder Linear layers + positional conv + projections",
                          "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,

@@ -152,6 +152,14 @@ AVH_API int avh_fbank(const int16_t* wav, const int64_t* offsets, const int32_t*
 AVH_API int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clips, const float* noise, int64_t noise_len,
                   float snr_db, int16_t* out, double* scratch, void* stream);
 
+/* Kernel-level entry point of the attention core (tests, tools): qkv bf16 [rows, 3*D] = fused projection with q
+ * pre-scaled by head_dim^-0.5, out bf16 [rows, D].  Dense batches: rows = B*T, clip b at row b*T, padding_mask
+ * [B,T] or NULL.  Packed ragged batches (impl 1 only): cu_rows int32 [B+1] first row of every clip, T = longest clip.
+ * impl 0 = mma.sync kernel, 1 = tcgen05 / TMEM kernel.  Replaces the attention inside
+ * F.multi_head_attention_forward (fairseq/fairseq/modules/multihead_attention.py:170-192). */
+AVH_API int avh_attention_bf16(const void* qkv, const uint8_t* padding_mask, const int32_t* cu_rows, int64_t rows, int B,
+                               int T, int D, int H, int impl, void* out, void* stream);
+
 /* Bare tcgen05 GEMM for kernel-level tests and profiling: C[M,N] = A[M,K] * B[N,K]^T (+bias)(gelu)(+R).
  * A,B bf16 row-major (K contiguous, K % 8 == 0), bias fp32 [N] or NULL, R/C bf16 or fp32 [M,N].
  * block_n: 0 = auto, else a multiple of 32 <= 256; pair: 0 = default, 1 = single-CTA tiles, 2 = CTA-pair tiles;

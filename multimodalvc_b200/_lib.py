@@ -18,7 +18,7 @@ EXPORTS = [
     "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
     "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess", "avh_drop_host_weights",
-    "avh_release_stream",
+    "avh_release_stream", "avh_attention_bf16",
 ]
 
 
@@ -69,6 +69,7 @@ def load():
     lib.avh_fbank.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.avh_add_noise.argtypes = [vp, vp, i32, vp, i64, ctypes.c_float, vp, vp, vp]
     lib.avh_gemm_bf16.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.avh_attention_bf16.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]
     lib.avh_gemm_set_trace.argtypes = [vp]
     lib.avh_set_video_preprocess.argtypes = [vp, i32, i32, ctypes.c_double, ctypes.c_double]
     lib.avh_video_preprocess.argtypes = [vp, i64, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, i32, vp]

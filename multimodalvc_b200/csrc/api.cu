@@ -181,6 +181,7 @@ struct Plan {
   std::vector<ConvWinPlan*> convwins;
   std::vector<ConvFramePlan*> convframes;
   StemFusedPlan stemf;
+  AttnTcPlan att;
   std::map<std::string, std::pair<const void*, std::pair<int, long long>>> stages;   // name -> (ptr, (dtype, numel))
   CallArgs args;
   // CUDA graphs of the launch list (all steps but the last, which writes the caller's output and is launched
@@ -1093,6 +1094,9 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     ep.ln_mode = 1; ep.ln_mu = ln_mu; ep.ln_part = ln_part; ep.ln_np = ln_np_prod; ep.ln_xc = hbuf.data; ep.ln_ldxc = D;
     ln_np_cur = ln_np_prod;
   };
+  static int att_tc_env = -1;
+  if (att_tc_env < 0) { const char* ev = std::getenv("AVH_ATT_TC"); att_tc_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
+  const bool att_tc = !f32 && att_tc_env != 0 && (size_t)((T + 127) / 128 * 128) * 4 <= 48 * 1024;
   for (int l = 0; l < n_layers; ++l) {
     const LayerW& lw = h->layers[l];
     if (c.layer_norm_first && !ln_fused) ln_to_h(x, lw.ln1_g, lw.ln1_b, nullptr);
@@ -1106,9 +1110,18 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     {
       const void* q = qkv.data; void* o = ctx.data;
       b.tag = "attention";
-      b.push([=](cudaStream_t s) {
-        return launch_attention(q, hm ? pl->args.mask : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
-      }, 4.0 * (double)B * Hh * (double)T * (double)T * 64.0);      // QK^T + PV, dense (padding not excluded)
+      const double att_flops = 4.0 * (double)B * Hh * (double)T * (double)T * 64.0;   // QK^T + PV, dense (padding not excluded)
+      if (att_tc) {
+        // bf16 mode: tcgen05 / TMEM kernel (attention_tc.cu); AVH_ATT_TC=0 selects the mma.sync kernel
+        if (!sizing && l == 0 && attention_tc_plan(q, N, B, T, D, Hh, &plan->att)) return false;
+        b.push([=](cudaStream_t s) {
+          return attention_tc_launch(pl->att, hm ? pl->args.mask : nullptr, nullptr, o, s);
+        }, att_flops);
+      } else {
+        b.push([=](cudaStream_t s) {
+          return launch_attention(q, hm ? pl->args.mask : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
+        }, att_flops);
+      }
       sync_op(ctx);
     }
     {   // out_proj + residual
@@ -1590,6 +1603,20 @@ int avh_add_noise(const int16_t* wav, const int64_t* offsets, int n_clips, const
                   float snr_db, int16_t* out, double* scratch, void* stream) {
   return avh::launch_add_noise(wav, reinterpret_cast<const long long*>(offsets), n_clips, noise, noise_len, snr_db,
                                out, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_attention_bf16(const void* qkv, const uint8_t* padding_mask, const int32_t* cu_rows, int64_t rows, int B, int T,
+                       int D, int H, int impl, void* out, void* stream) {
+  AVH_CHECK(qkv != nullptr && out != nullptr, "null pointer");
+  AVH_CHECK(impl == 0 || impl == 1, "impl must be 0 (mma.sync) or 1 (tcgen05)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == 0) {
+    AVH_CHECK(cu_rows == nullptr, "the mma.sync kernel takes dense [B, T] batches only");
+    return avh::launch_attention(qkv, padding_mask, out, B, T, D, H, 0, s);
+  }
+  avh::AttnTcPlan plan;
+  if (avh::attention_tc_plan(qkv, rows, B, T, D, H, &plan)) return 1;
+  return avh::attention_tc_launch(plan, padding_mask, cu_rows, out, s);
 }
 
 int avh_gemm_set_trace(void* dev_buf) {

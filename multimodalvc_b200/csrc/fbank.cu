@@ -240,18 +240,53 @@ fbank_kernel(FbankArgs a) {
 }
 
 // ------------------------------------------------------------------------------------ noise mixer
+// Every pass walks a clip in chunks of 8 consecutive samples per thread (one 16-byte load when the clip starts on an
+// 8-sample boundary, as packed clips of whole video frames do) and tracks the position inside the tiled noise clip
+// incrementally: ONE 64-bit modulo per chunk instead of one per sample (the per-sample form was ALU-bound at
+// 0.5 TB/s: profiles/r2_ncu_hbm_kernels.txt).
+template <typename F>
+__device__ __forceinline__ void for_each_chunk8(const int16_t* __restrict__ clean, long long s0, long long len,
+                                                const float* __restrict__ noise, long long noise_len, F&& body) {
+  const bool aligned = ((s0 & 7) == 0) && ((reinterpret_cast<uintptr_t>(clean) & 15) == 0);
+  const long long nchunk = (len + 7) >> 3;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (long long)gridDim.x * blockDim.x) {
+    const long long i0 = c << 3;
+    const int n = (int)(len - i0 < 8 ? len - i0 : 8);
+    int16_t v[8];
+    if (aligned && n == 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(clean + s0 + i0));
+      *reinterpret_cast<uint4*>(v) = raw;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = k < n ? clean[s0 + i0 + k] : (int16_t)0;
+    }
+    float nz[8];
+    long long j = i0 % noise_len;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      nz[k] = noise[j];
+      if (++j == noise_len) j = 0;
+    }
+    body(i0, n, v, nz, aligned);
+  }
+}
+
 // pass 1: per clip sum(clean^2), sum(noise^2) in float64.  scratch[4*clip + {0,1}]
-__global__ void noise_stats_kernel(const int16_t* __restrict__ clean, const long long* __restrict__ offsets,
-                                   const float* __restrict__ noise, long long noise_len, double* scratch) {
+__global__ void __launch_bounds__(256)
+noise_stats_kernel(const int16_t* __restrict__ clean, const long long* __restrict__ offsets,
+                   const float* __restrict__ noise, long long noise_len, double* scratch) {
   const int clip = blockIdx.y;
   const long long s0 = offsets[clip], len = offsets[clip + 1] - s0;
   double sc = 0.0, sn = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
-    const float c = (float)clean[s0 + i];
-    const float n = noise[i % noise_len];
-    sc += (double)(c * c);       // np.square on float32, then accumulated
-    sn += (double)(n * n);
-  }
+  for_each_chunk8(clean, s0, len, noise, noise_len, [&](long long, int n, const int16_t* v, const float* nz, bool) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n) {
+        const float c = (float)v[k];
+        sc += (double)(c * c);       // np.square on float32, then accumulated
+        sn += (double)(nz[k] * nz[k]);
+      }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sc += __shfl_xor_sync(0xffffffffu, sc, o);
@@ -279,18 +314,23 @@ __device__ __forceinline__ double ord2f(unsigned long long u) {
   return __longlong_as_double((long long)u);
 }
 // pass 2: per clip max / min of mixed = clean + noise * scale (float32).  scratch[4*clip + {2,3}] as ordered u64
-__global__ void noise_minmax_kernel(const int16_t* __restrict__ clean, const long long* __restrict__ offsets,
+__global__ void __launch_bounds__(256)
+noise_minmax_kernel(const int16_t* __restrict__ clean, const long long* __restrict__ offsets,
                                     const float* __restrict__ noise, long long noise_len, float snr_db,
                                     double* scratch) {
   const int clip = blockIdx.y;
   const long long s0 = offsets[clip], len = offsets[clip + 1] - s0;
   const float scale = noise_scale(scratch, clip, len, snr_db);
   float mx = -INFINITY, mn = INFINITY;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
-    const float m = __fadd_rn((float)clean[s0 + i], __fmul_rn(noise[i % noise_len], scale));
-    mx = fmaxf(mx, m);
-    mn = fminf(mn, m);
-  }
+  for_each_chunk8(clean, s0, len, noise, noise_len, [&](long long, int n, const int16_t* v, const float* nz, bool) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n) {
+        const float m = __fadd_rn((float)v[k], __fmul_rn(nz[k], scale));
+        mx = fmaxf(mx, m);
+        mn = fminf(mn, m);
+      }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -303,7 +343,8 @@ __global__ void noise_minmax_kernel(const int16_t* __restrict__ clean, const lon
   }
 }
 // pass 3: rescale if clipping, truncate toward zero to int16 (numpy astype)
-__global__ void noise_mix_kernel(const int16_t* __restrict__ clean, const long long* __restrict__ offsets,
+__global__ void __launch_bounds__(256)
+noise_mix_kernel(const int16_t* __restrict__ clean, const long long* __restrict__ offsets,
                                  const float* __restrict__ noise, long long noise_len, float snr_db,
                                  const double* __restrict__ scratch, int16_t* __restrict__ out) {
   const int clip = blockIdx.y;
@@ -317,12 +358,23 @@ __global__ void noise_mix_kernel(const int16_t* __restrict__ clean, const long l
     rescale = true;
     rate = (mx >= fabsf(mn)) ? (32767.f / mx) : (-32768.f / mn);
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
-    float m = __fadd_rn((float)clean[s0 + i], __fmul_rn(noise[i % noise_len], scale));
-    if (rescale) m = __fmul_rn(m, rate);
-    m = fminf(fmaxf(m, -32768.f), 32767.f);      // guard; the rescale already bounds |m|
-    out[s0 + i] = (int16_t)(int)m;               // C cast truncates toward zero like numpy astype(int16)
-  }
+  for_each_chunk8(clean, s0, len, noise, noise_len, [&](long long i0, int n, const int16_t* v, const float* nz, bool aligned) {
+    int16_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float m = __fadd_rn((float)v[k], __fmul_rn(nz[k], scale));
+      if (rescale) m = __fmul_rn(m, rate);
+      m = fminf(fmaxf(m, -32768.f), 32767.f);      // guard; the rescale already bounds |m|
+      o[k] = (int16_t)(int)m;                      // C cast truncates toward zero like numpy astype(int16)
+    }
+    if (aligned && n == 8 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      *reinterpret_cast<uint4*>(out + s0 + i0) = *reinterpret_cast<const uint4*>(o);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < n) out[s0 + i0 + k] = o[k];
+    }
+  });
 }
 __global__ void noise_init_kernel(double* scratch, int n_clips) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -153,6 +153,16 @@ struct StemFusedPlan {
 int stem_fused_plan(const void* w_packed, StemFusedPlan* plan);
 int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, int T, int b0, int nb, const float* scale,
                       const float* bias, const float* slope, void* pooled_out, cudaStream_t stream);
+// ---- self-attention on tcgen05 / TMEM (attention_tc.cu): S = Q K^T and O = P V as UMMAs, P read from tensor memory
+struct AttnTcPlan {
+  CUtensorMap tma_q, tma_kv;      // boxes of 128 / kv_rows rows x 64 columns over the QKV matrix [rows, 3*D]
+  int B = 0, T = 0, D = 0, H = 0;
+  int kv_rows = 0, stages = 0, stage_bytes = 0, mask_floats = 0;
+  size_t smem = 0;
+};
+int attention_tc_plan(const void* qkv, long long rows, int B, int T, int D, int H, AttnTcPlan* plan);
+// kpm: [B, T] key-padding mask or null; cu: [B + 1] first row of every clip for packed ragged batches, or null
+int attention_tc_launch(const AttnTcPlan& plan, const unsigned char* kpm, const int* cu, void* out, cudaStream_t stream);
 // tensor-map helpers shared by the GEMM kernels (gemm_tcgen05.cu)
 int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows);
 int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32);

@@ -77,6 +77,17 @@ struct KernelParams {
   Epilogue ep;
 };
 
+// debug stall accounting (only when a trace buffer is attached): cycles a role spent blocked on an mbarrier
+#define AVH_WAIT_ACC(bar, parity, acc)                    \
+  do {                                                    \
+    if (p.trace == nullptr) mbar_wait((bar), (parity));   \
+    else {                                                \
+      const long long _c0 = clock64();                    \
+      mbar_wait((bar), (parity));                         \
+      (acc) += clock64() - _c0;                           \
+    }                                                     \
+  } while (0)
+
 #define AVH_TRACE(slot)                                                                            \
   do {                                                                                             \
     if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
@@ -184,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
+    long long prod_wait = 0;
     const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
     for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile % p.num_m_blk;
@@ -195,7 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int4 e;
         if (p.ktable != nullptr) e = ktab[kb];
         else e = make_int4(kb * BK, 0, kb * BK, 0);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        AVH_WAIT_ACC(&empty_bar[stage], phase ^ 1, prod_wait);
         const bool b_early = PAIR == 1 && tile == unit && kb < pre_b;      // B tile already requested before the wait
         if (elect_one()) {
           if (leader && !b_early) mbar_expect_tx(&full_bar[stage], stage_tx);
@@ -212,6 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (p.trace != nullptr && lane == 0) p.trace[(size_t)blockIdx.x * 16 + 14] = (unsigned long long)prod_wait;
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
@@ -219,14 +232,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long wait_full = 0, wait_tmem = 0;
       for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        AVH_WAIT_ACC(&tmem_empty[acc], acc_phase ^ 1, wait_tmem);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          AVH_WAIT_ACC(&full_bar[stage], phase, wait_full);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
@@ -251,6 +265,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           AVH_TRACE(5);
         }
         __syncwarp();
+      }
+      if (p.trace != nullptr && lane == 0) {
+        p.trace[(size_t)blockIdx.x * 16 + 12] = (unsigned long long)wait_full;
+        p.trace[(size_t)blockIdx.x * 16 + 13] = (unsigned long long)wait_tmem;
       }
     }
   } else if (warp >= 4) {

@@ -194,3 +194,79 @@ def test_logfbank_packed_entry_point_matches_list_entry_point():
     assert a.shape == (3, 104, 150) and torch.equal(a, a_ref) and torch.equal(pm, pm_ref)
     with pytest.raises(ValueError):
         audio.logfbank_stack_collate_packed(flat.cpu(), off, 150, vl)
+
+
+def _attention_ref(qkv, lens, T, D, H):
+    """fp32 softmax(q k^T) v per clip and head on the bf16-rounded inputs (q is pre-scaled)."""
+    B = len(lens)
+    x = qkv.float().view(B, T, 3, H, 64)
+    out = torch.zeros(B, T, H, 64)
+    for b, n in enumerate(lens):
+        q, k, v = x[b, :, 0].transpose(0, 1), x[b, :n, 1].transpose(0, 1), x[b, :n, 2].transpose(0, 1)   # [H,T,64]
+        out[b] = (torch.softmax(q @ k.transpose(1, 2), dim=-1) @ v).transpose(0, 1)
+    return out.view(B * T, D)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("T,lens", [(1, [1, 1]), (20, [20, 7]), (75, [75, 1]), (150, [150, 97, 150]), (160, [160, 33]),
+                                    (161, [161, 130]), (300, [300, 129, 128]), (600, [600, 417]), (1000, [1000, 513])])
+def test_attention_kernels_vs_fp32_reference(impl, T, lens):
+    """Both attention kernels (mma.sync, tcgen05 / TMEM) on dense padded batches with key-padding masks: single key
+    block (T <= 160), streamed 128-key blocks with the two-pass maxima (T > 160), ragged tails, 1-frame clips."""
+    import ctypes
+    from multimodalvc_b200 import _lib
+    H, D, B = 4, 256, len(lens)
+    g = torch.Generator().manual_seed(T)
+    qkv = (torch.randn(B * T, 3 * D, generator=g) * 1.5).bfloat16()
+    kpm = torch.zeros(B, T, dtype=torch.uint8)
+    for b, n in enumerate(lens):
+        kpm[b, n:] = 1
+    ref = _attention_ref(qkv, lens, T, D, H)
+    d_qkv, d_kpm = qkv.cuda(), kpm.cuda()
+    out = torch.full((B * T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    vp = ctypes.c_void_p
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.load().avh_attention_bf16(vp(d_qkv.data_ptr()), vp(d_kpm.data_ptr()), None, B * T, B, T, D, H, impl,
+                                              vp(out.data_ptr()), vp(st)))
+    torch.cuda.synchronize()
+    o = out.float().cpu()
+    assert torch.isfinite(o).all()
+    assert (o - ref).abs().max() < 0.03 * ref.abs().max() + 1e-3        # bf16 P and bf16 output
+    assert torch.nn.functional.cosine_similarity(o.flatten(), ref.flatten(), dim=0) > 0.9999
+
+
+def test_attention_tc_packed_ragged_batch_equals_dense():
+    """cu_rows form (clips packed back to back, no pad rows) gives the same bits as the dense padded form."""
+    import ctypes
+    from multimodalvc_b200 import _lib
+    H, D = 4, 256
+    lens = [300, 17, 150, 129, 1]
+    T = max(lens)
+    B = len(lens)
+    g = torch.Generator().manual_seed(5)
+    dense = torch.zeros(B, T, 3 * D, dtype=torch.bfloat16)
+    packed = []
+    for b, n in enumerate(lens):
+        x = (torch.randn(n, 3 * D, generator=g) * 1.5).bfloat16()
+        dense[b, :n] = x
+        packed.append(x)
+    packed = torch.cat(packed).cuda()
+    kpm = torch.zeros(B, T, dtype=torch.uint8)
+    for b, n in enumerate(lens):
+        kpm[b, n:] = 1
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    vp = ctypes.c_void_p
+    st = torch.cuda.current_stream().cuda_stream
+    lib = _lib.load()
+    o_d = torch.zeros(B * T, D, device="cuda", dtype=torch.bfloat16)
+    o_p = torch.zeros(sum(lens), D, device="cuda", dtype=torch.bfloat16)
+    d = dense.view(B * T, 3 * D).cuda()
+    k = kpm.cuda()
+    _lib.check(lib.avh_attention_bf16(vp(d.data_ptr()), vp(k.data_ptr()), None, B * T, B, T, D, H, 1, vp(o_d.data_ptr()), vp(st)))
+    _lib.check(lib.avh_attention_bf16(vp(packed.data_ptr()), None, vp(cu.data_ptr()), sum(lens), B, T, D, H, 1,
+                                      vp(o_p.data_ptr()), vp(st)))
+    torch.cuda.synchronize()
+    r = 0
+    for b, n in enumerate(lens):
+        assert torch.equal(o_p[r:r + n], o_d.view(B, T, D)[b, :n]), b
+        r += n

@@ -63,6 +63,7 @@ def test_extract_finetune_accepts_raw_uint8_video(dtype):
     frames = vo.synthetic_frames(B * T, 96, 96, seed=11).reshape(B, 1, T, 96, 96)
     raw = torch.from_numpy(frames).cuda()
     norm = torch.from_numpy(vo.video_transform(frames.reshape(B * T, 96, 96)).astype(np.float32)).view(B, 1, T, 88, 88)
+    norm = norm.masked_fill(c["pm"].view(B, 1, T, 1, 1), 0.0)      # the collater zero-pads AFTER Normalize
     audio = c["src"]["audio"].cuda().to(dtype)
     pm = c["pm"].cuda()
     y_raw, _ = m.extract_finetune({"audio": audio, "video": raw}, pm)
