@@ -109,6 +109,17 @@ AVH_API int avh_forward(avh_handle* h, const void* video, int video_dtype, const
                 const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
                 void* out, int out_dtype, void* stream);
 
+/* extract_finetune for RAGGED batches without computing on pad frames (BASELINE config 3): same
+ * padded tensors as avh_forward (video [B,1,T,88,88] or raw uint8, audio [B,F,T] + strides, out [B,T,D]) plus the HOST
+ * array lengths[B] (valid frames per clip, 1..T; padding must be a suffix, as the collater writes it,
+ * hubert_dataset.py:433-447).  Inside, frames and tokens are packed back to back (sum(lengths) rows rounded up to
+ * 128), attention runs per clip, and the output rows of pad positions are written as ZEROS — the one deviation from
+ * the dense path, where the reference leaves non-zero values nobody reads behind the padding mask.  Valid positions
+ * carry the same values as avh_forward with the equivalent padding mask (bf16 mode only). */
+AVH_API int avh_forward_ragged(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                               const int64_t* audio_strides, const int32_t* lengths, int B, int T, int output_layer,
+                               void* out, int out_dtype, void* stream);
+
 /* Raw-video geometry for video_dtype == AVH_U8: video is then [B,1,T,src_h,src_w] uint8 gray frames (mouth ROI as
  * stored by the dataset, e.g. 96 x 96); avh_forward* first applies x/255, the centre crop to 88 x 88 with offsets
  * (src-88)/2 and (x-mean)/std (defaults 0.421 / 0.165, hubert_pretraining.py:144-149).  Default: 88 x 88 (no crop).

@@ -165,16 +165,31 @@ struct CallArgs {          // per-call pointers the steps read through the plan
   const unsigned char* mask = nullptr;
   void* out = nullptr;
   int out_dt = 0;
+  int pitch = 0;             // ragged plans: time pitch of the caller's padded tensors (baked into captured launches)
   // graph-cache key: the INPUT pointers (the output is written by the last step, which stays outside the graph)
   bool operator<(const CallArgs& o) const {
-    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask) <
-           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask);
+    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask, pitch) <
+           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask, o.pitch);
   }
 };
 
 struct Plan {
   int B = 0, T = 0, output_layer = 0;
   bool has_video = false, has_audio = false, has_mask = false;
+  // packed ragged batches (avh_forward_ragged): every buffer holds Nb = round_up(sum of clip lengths, 128) token /
+  // frame rows with the clips back to back; T is then the longest clip the plan serves (attention tiling).  The
+  // per-call geometry lives in a small device descriptor `rag` (int32): [0] stem work items, [1] rows in use,
+  // [16..16+B] first row of every clip (cu), then the stem's (clip, band, t0, t1) item list.
+  bool ragged = false;
+  long long Nb = 0;
+  int* rag = nullptr;
+  int rag_ints = 0, rag_items_off = 0, rag_max_items = 0;
+  static constexpr int RAG_SLOTS = 4;
+  int* rag_host[RAG_SLOTS] = {nullptr, nullptr, nullptr, nullptr};      // pinned mirrors, used round robin
+  cudaEvent_t rag_done[RAG_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  int rag_next = 0;
+  int* pos_row_map = nullptr;
+
   Arena arena;
   std::vector<Step> steps;
   std::vector<GemmPlan*> gemms;
@@ -205,6 +220,10 @@ struct Plan {
     for (GemmPlan* g : gemms) delete g;
     for (ConvWinPlan* g : convwins) delete g;
     for (ConvFramePlan* g : convframes) delete g;
+    for (int i = 0; i < RAG_SLOTS; ++i) {
+      if (rag_host[i]) cudaFreeHost(rag_host[i]);
+      if (rag_done[i]) cudaEventDestroy(rag_done[i]);
+    }
     arena.release();
   }
 };
@@ -678,7 +697,8 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   const bool f32 = b.f32;
   const int B = plan->B, T = plan->T, D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim;
   const int Hh = c.encoder_attention_heads;
-  const long long N = (long long)B * T;
+  const bool rg = plan->ragged;
+  const long long N = rg ? plan->Nb : (long long)B * T;
   const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
   const size_t es = f32 ? 4 : 2;            // bytes per activation value
   const int act_dt = f32 ? DT_F32 : DT_BF16;
@@ -711,6 +731,13 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 
   // fused token features [N, E]: audio arm in columns [0,D), video arm in [D,2D) (concat) or summed (add)
   Act fused = new_act(N, E);
+  if (rg) {
+    plan->rag_items_off = 16 + ((B + 1 + 3) / 4) * 4;
+    plan->rag_max_items = 11 * (int)(N / 2 + B);
+    plan->rag_ints = plan->rag_items_off + 4 * plan->rag_max_items;
+    int* r = reinterpret_cast<int*>(b.alloc((size_t)plan->rag_ints * 4));
+    if (!sizing) plan->rag = r;
+  }
   const int v_off = c.modality_fuse == AVH_FUSE_CONCAT ? D : 0;
   const int a_off = 0;
 
@@ -720,10 +747,15 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     const int target = c.frontend_chunk_frames > 0 ? c.frontend_chunk_frames : 2400;
     int CB = std::max(1, target / T);
     CB = (B + ((B + CB - 1) / CB) - 1) / ((B + CB - 1) / CB);       // even split over ceil(B/CB) chunks
-    const int CF = CB * T;
+    if (rg) CB = B;                                                  // ragged: one chunk of Nb packed frames
+    const int CF = rg ? (int)N : CB * T;
     FrontendBufs fb;
-    fb.im2col = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * 2 * P);
-    fb.stem_out = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * es);      // same clip-padded row space as the patches
+    static int stemf_env0 = -1;
+    if (stemf_env0 < 0) { const char* ev = std::getenv("AVH_STEM_FUSED"); stemf_env0 = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
+    if (f32 || !stemf_env0) {     // patch matrix + un-pooled stem maps: only the unfused stem (fp32 mode) needs them
+      fb.im2col = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * 2 * P);
+      fb.stem_out = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * es);      // same clip-padded row space as the patches
+    }
     static const int HS[4] = {22, 11, 6, 3};
     fb.pooled = new_act((long long)CF * 23 * 23, 64);
     for (int L = 0; L < 4; ++L) {
@@ -814,8 +846,8 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 
     for (int b0 = 0; b0 < B; b0 += CB) {
       const int nb = std::min(CB, B - b0);
-      const int nf = nb * T;
-      const long long f0 = (long long)b0 * T;
+      const int nf = rg ? (int)N : nb * T;
+      const long long f0 = rg ? 0 : (long long)b0 * T;
       // ---- stem: one fused kernel in bf16 mode (stem_fused.cu) ...
       static int stemf_env = -1;
       if (stemf_env < 0) { const char* ev = std::getenv("AVH_STEM_FUSED"); stemf_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
@@ -824,7 +856,13 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         void* po = fb.pooled.data;
         b.tag = "stem_fused";
         const double fl = 2.0 * (double)nf * 1936.0 * 64.0 * 245.0;
-        if (!sizing)
+        if (!sizing && rg)
+          plan->steps.push_back(Step{[=](cudaStream_t s) {
+            return stem_fused_launch_ragged(pl->stemf, pl->args.video, pl->args.video_dt, pl->args.pitch,
+                                            reinterpret_cast<const int4*>(pl->rag + pl->rag_items_off), pl->rag, pl->rag + 16,
+                                            h->stem.scale, h->stem.bias, h->stem.slope, po, s);
+          }, b.tag, fl});
+        else if (!sizing)
           plan->steps.push_back(Step{[=](cudaStream_t s) {
             return stem_fused_launch(pl->stemf, pl->args.video, pl->args.video_dt, T, b0, nb, h->stem.scale, h->stem.bias,
                                      h->stem.slope, po, s);
@@ -950,10 +988,16 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     {
       void* dst = arows.data;
       b.tag = "audio_rows";
-      b.push([=](cudaStream_t s) {
-        return launch_bct_to_rows(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
-                                  B, Fa, T, dst, act_dt, Fp, s);
-      });
+      if (rg)
+        b.push([=](cudaStream_t s) {
+          return launch_bct_to_rows_ragged(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
+                                           B, Fa, pl->rag + 16, dst, act_dt, Fp, N, s);
+        });
+      else
+        b.push([=](cudaStream_t s) {
+          return launch_bct_to_rows(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
+                                    B, Fa, T, dst, act_dt, Fp, s);
+        });
       sync_op(arows);
     }
     Epilogue ep = ep_base(reinterpret_cast<char*>(fused.data) + (size_t)a_off * es, E);
@@ -1009,9 +1053,18 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   // ========================================================================== positional conv + GELU + residual
   {
     const int G = 64, Tp = T + G;
-    void* xpad = b.alloc((size_t)B * Tp * P * D * 2);      // bf16 [B*(T+64), P*D], gap rows stay zero
+    const long long pad_rows = rg ? N + (long long)G * B : (long long)B * Tp;
+    void* xpad = b.alloc((size_t)pad_rows * P * D * 2);      // bf16 [B*(T+64), P*D], gap rows stay zero
     const int planes = P;
     b.tag = "pos_pad";
+    int* row_map = nullptr;
+    if (rg) {
+      // packed clips: clip b at padded rows [cu[b] + 64 b, +T_b); the kernel also zeroes the gap rows (they move from
+      // call to call) and writes the padded-row -> packed-row map the convolution's epilogue stores through
+      row_map = reinterpret_cast<int*>(b.alloc((size_t)pad_rows * 4));
+      if (!sizing) plan->pos_row_map = row_map;
+      b.push([=](cudaStream_t s) { return launch_pos_pad_ragged(x, D, xpad, row_map, pl->rag + 16, B, D, G, pad_rows, s); });
+    } else
     b.push([=](cudaStream_t s) { return launch_split_rows(x, D, xpad, planes, N, D, T, Tp, s); });
     b.tag = "pos_conv";
     const int KT = c.conv_pos, win = h->pos_window;
@@ -1021,8 +1074,9 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     ep.C = x; ep.ldc = D; ep.c_fp32 = 1;
     ep.col_bias = h->pos_bias; ep.act = ACT_GELU;
     ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
-    ep.map_mode = MAP_2LEVEL; ep.S2 = Tp; ep.S1 = Tp; ep.H = 1; ep.W = T; ep.O2 = T; ep.O1 = 0; ep.O0 = 0;
-    if (!b.gemm(xpad, (long long)B * Tp, P * D, h->pos_w, (long long)B * Tp, taps, win / 64, D, ep, 64, h->pos_acol))
+    if (rg) ep.row_map = row_map;
+    else { ep.map_mode = MAP_2LEVEL; ep.S2 = Tp; ep.S1 = Tp; ep.H = 1; ep.W = T; ep.O2 = T; ep.O1 = 0; ep.O0 = 0; }
+    if (!b.gemm(xpad, pad_rows, P * D, h->pos_w, pad_rows, taps, win / 64, D, ep, 64, h->pos_acol))
       return false;
   }
 
@@ -1096,7 +1150,9 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   };
   static int att_tc_env = -1;
   if (att_tc_env < 0) { const char* ev = std::getenv("AVH_ATT_TC"); att_tc_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
-  const bool att_tc = !f32 && att_tc_env != 0 && (size_t)((T + 127) / 128 * 128) * 4 <= 48 * 1024;
+  // measured (tools/att_bench.py, Large head count): tcgen05 11.4 vs 12.8 us at 16 x 150, 21.6 vs 29.0 at 8 x 300,
+  // 31.9 vs 44.3 at 4 x 600; short clips (64 x 38 frames: 12.6 vs 9.3 us) stay on the mma.sync kernel
+  const bool att_tc = !f32 && (rg || (att_tc_env != 0 && T > 96)) && (size_t)((T + 127) / 128 * 128) * 4 <= 48 * 1024;
   for (int l = 0; l < n_layers; ++l) {
     const LayerW& lw = h->layers[l];
     if (c.layer_norm_first && !ln_fused) ln_to_h(x, lw.ln1_g, lw.ln1_b, nullptr);
@@ -1115,7 +1171,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         // bf16 mode: tcgen05 / TMEM kernel (attention_tc.cu); AVH_ATT_TC=0 selects the mma.sync kernel
         if (!sizing && l == 0 && attention_tc_plan(q, N, B, T, D, Hh, &plan->att)) return false;
         b.push([=](cudaStream_t s) {
-          return attention_tc_launch(pl->att, hm ? pl->args.mask : nullptr, nullptr, o, s);
+          return attention_tc_launch(pl->att, hm ? pl->args.mask : nullptr, pl->ragged ? pl->rag + 16 : nullptr, o, s);
         }, att_flops);
       } else {
         b.push([=](cudaStream_t s) {
@@ -1166,6 +1222,19 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   }
   // ========================================================================== output
   b.tag = "final_ln";
+  if (rg) {
+    // packed rows -> the caller's [B, pitch_T, D] tensor, zeros at the pad positions
+    float* y = x;
+    if (c.layer_norm_first && plan->output_layer == 0) {
+      y = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));
+      float* g = h->enc_ln_g; float* be = h->enc_ln_b;
+      b.push([=](cudaStream_t s) { return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, y, nullptr, DT_BF16, nullptr, N, D, s); });
+    }
+    b.tag = "unpack";
+    b.push([=](cudaStream_t s) {
+      return launch_unpack_rows(y, pl->rag + 16, pl->args.out, pl->args.out_dt, B, pl->args.pitch, D, s);
+    });
+  } else
   if (c.layer_norm_first && plan->output_layer == 0) {
     float* g = h->enc_ln_g; float* be = h->enc_ln_b;
     b.push([=](cudaStream_t s) {
@@ -1181,8 +1250,9 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 // One plan (= workspace + launch list) per shape AND per CUDA stream: forwards enqueued on different streams
 // never share scratch memory, so a caller can keep several batches in flight on one device.
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
-               cudaStream_t stream) {
-  const std::string key = std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
+               cudaStream_t stream, long long ragged_rows = 0) {
+  const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) +
+                          std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
   auto it = h->plans.find(key);
@@ -1206,10 +1276,21 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
   p->stream = stream;
   p->B = B; p->T = T; p->has_video = has_video; p->has_audio = has_audio; p->has_mask = has_mask;
   p->output_layer = output_layer;
+  p->ragged = ragged_rows > 0;
+  p->Nb = ragged_rows;
   size_t bytes = 0;
   if (!build_plan(h, p.get(), true, &bytes)) return nullptr;
   if (p->arena.init(bytes + (1 << 20))) return nullptr;
   if (!build_plan(h, p.get(), false, nullptr)) return nullptr;
+  if (p->ragged) {
+    for (int i = 0; i < Plan::RAG_SLOTS; ++i) {
+      if (cudaMallocHost(reinterpret_cast<void**>(&p->rag_host[i]), (size_t)p->rag_ints * 4) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->rag_done[i], cudaEventDisableTiming) != cudaSuccess) {
+        set_last_error("pinned descriptor allocation failed");
+        return nullptr;
+      }
+    }
+  }
   Plan* raw = p.get();
   h->plans[key] = std::move(p);
   return raw;
@@ -1340,69 +1421,7 @@ int avh_finalize_weights(avh_handle* h) {
   return 0;
 }
 
-int avh_drop_host_weights(avh_handle* h) {
-  AVH_CHECK(h != nullptr, "null handle");
-  h->raw.clear();
-  return 0;
-}
-
-int avh_release_stream(avh_handle* h, void* stream) {
-  AVH_CHECK(h != nullptr, "null handle");
-  AVH_CUDA_OK(cudaSetDevice(h->device));
-  AVH_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
-  for (auto it = h->plans.begin(); it != h->plans.end();) {
-    if (it->second->stream == reinterpret_cast<cudaStream_t>(stream)) {
-      if (h->last_plan == it->second.get()) h->last_plan = nullptr;
-      if (h->prof_plan == it->second.get()) h->prof_plan = nullptr;
-      it = h->plans.erase(it);
-    } else ++it;
-  }
-  auto st = h->staging.find(stream);
-  if (st != h->staging.end()) {
-    void* ptrs[5] = {st->second.video, st->second.audio, st->second.mask, st->second.out, st->second.video_pp};
-    for (void* q : ptrs)
-      if (q) cudaFree(q);
-    h->staging.erase(st);
-  }
-  return 0;
-}
-
-int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
-                const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
-                void* out, int out_dtype, void* stream) {
-  AVH_CHECK(h != nullptr, "null handle");
-  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
-  AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
-  AVH_CHECK(B >= 1 && T >= 1, "empty batch");
-  AVH_CHECK((long long)B * T < (1ll << 24), "batch too large");
-  AVH_CHECK(out != nullptr, "null output");
-  AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
-  AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
-  AVH_CUDA_OK(cudaSetDevice(h->device));
-  if (video != nullptr && video_dtype == AVH_U8) {
-    // raw gray frames [B,1,T,src_h,src_w]: the dataset's /255 -> centre crop 88 -> (x-mean)/std on the device
-    // (hubert_dataset.py:222-226; SURVEY 8(f)-1), into a per-stream buffer in the module's dtype
-    avh_handle::Staging& st = h->staging[stream];
-    const int pdt = h->cfg.compute_mode == AVH_COMPUTE_FP32 ? AVH_F32 : AVH_BF16;
-    if (avh::ensure_cap(&st.video_pp, &st.video_pp_cap, (size_t)B * T * 7744 * avh::dtype_size(pdt))) return 1;
-    if (avh::launch_video_preprocess(reinterpret_cast<const unsigned char*>(video), (long long)B * T, h->vp_src_h,
-                                     h->vp_src_w, 88, h->vp_mean, h->vp_std, st.video_pp, pdt, padding_mask,
-                                     reinterpret_cast<cudaStream_t>(stream)))
-      return 1;
-    video = st.video_pp;
-    video_dtype = pdt;
-  }
-  AVH_CHECK(video == nullptr || video_dtype == AVH_F32 || video_dtype == AVH_F16 || video_dtype == AVH_BF16, "bad video dtype");
-  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer,
-                               reinterpret_cast<cudaStream_t>(stream));
-  if (p == nullptr) return 1;
-  h->last_plan = p;
-  p->args.video = video; p->args.video_dt = video_dtype;
-  p->args.audio = audio; p->args.audio_dt = audio_dtype;
-  if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
-  p->args.mask = padding_mask;
-  p->args.out = out; p->args.out_dt = out_dtype;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
   static int graphs_env = -1;
   if (graphs_env < 0) {
     const char* ev = std::getenv("AVH_GRAPHS");
@@ -1473,6 +1492,136 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
     ++i;
   }
   return 0;
+}
+
+int avh_drop_host_weights(avh_handle* h) {
+  AVH_CHECK(h != nullptr, "null handle");
+  h->raw.clear();
+  return 0;
+}
+
+int avh_release_stream(avh_handle* h, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  AVH_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  for (auto it = h->plans.begin(); it != h->plans.end();) {
+    if (it->second->stream == reinterpret_cast<cudaStream_t>(stream)) {
+      if (h->last_plan == it->second.get()) h->last_plan = nullptr;
+      if (h->prof_plan == it->second.get()) h->prof_plan = nullptr;
+      it = h->plans.erase(it);
+    } else ++it;
+  }
+  auto st = h->staging.find(stream);
+  if (st != h->staging.end()) {
+    void* ptrs[5] = {st->second.video, st->second.audio, st->second.mask, st->second.out, st->second.video_pp};
+    for (void* q : ptrs)
+      if (q) cudaFree(q);
+    h->staging.erase(st);
+  }
+  return 0;
+}
+
+int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
+                void* out, int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
+  AVH_CHECK(B >= 1 && T >= 1, "empty batch");
+  AVH_CHECK((long long)B * T < (1ll << 24), "batch too large");
+  AVH_CHECK(out != nullptr, "null output");
+  AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
+  AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  if (video != nullptr && video_dtype == AVH_U8) {
+    // raw gray frames [B,1,T,src_h,src_w]: the dataset's /255 -> centre crop 88 -> (x-mean)/std on the device
+    // (hubert_dataset.py:222-226; SURVEY 8(f)-1), into a per-stream buffer in the module's dtype
+    avh_handle::Staging& st = h->staging[stream];
+    const int pdt = h->cfg.compute_mode == AVH_COMPUTE_FP32 ? AVH_F32 : AVH_BF16;
+    if (avh::ensure_cap(&st.video_pp, &st.video_pp_cap, (size_t)B * T * 7744 * avh::dtype_size(pdt))) return 1;
+    if (avh::launch_video_preprocess(reinterpret_cast<const unsigned char*>(video), (long long)B * T, h->vp_src_h,
+                                     h->vp_src_w, 88, h->vp_mean, h->vp_std, st.video_pp, pdt, padding_mask,
+                                     reinterpret_cast<cudaStream_t>(stream)))
+      return 1;
+    video = st.video_pp;
+    video_dtype = pdt;
+  }
+  AVH_CHECK(video == nullptr || video_dtype == AVH_F32 || video_dtype == AVH_F16 || video_dtype == AVH_BF16, "bad video dtype");
+  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer,
+                               reinterpret_cast<cudaStream_t>(stream));
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  p->args.video = video; p->args.video_dt = video_dtype;
+  p->args.audio = audio; p->args.audio_dt = audio_dtype;
+  if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
+  p->args.mask = padding_mask;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  return run_plan(h, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_forward_ragged(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                       const int64_t* audio_strides, const int32_t* lengths, int B, int T, int output_layer, void* out,
+                       int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(h->cfg.compute_mode == AVH_COMPUTE_BF16, "packed ragged batches run in bf16 mode only (use avh_forward)");
+  AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
+  AVH_CHECK(lengths != nullptr && out != nullptr, "null argument");
+  AVH_CHECK(B >= 1 && T >= 1 && B <= 4096, "bad batch");
+  AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
+  AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
+  long long N = 0;
+  int tmax = 0;
+  for (int b = 0; b < B; ++b) {
+    AVH_CHECK(lengths[b] >= 1 && lengths[b] <= T, "clip lengths must be in [1, T]");
+    N += lengths[b];
+    tmax = lengths[b] > tmax ? lengths[b] : tmax;
+  }
+  AVH_CHECK(N < (1ll << 24), "batch too large");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (video != nullptr && video_dtype == AVH_U8) {
+    avh_handle::Staging& st = h->staging[stream];
+    if (avh::ensure_cap(&st.video_pp, &st.video_pp_cap, (size_t)B * T * 7744 * 2)) return 1;
+    if (avh::launch_video_preprocess(reinterpret_cast<const unsigned char*>(video), (long long)B * T, h->vp_src_h,
+                                     h->vp_src_w, 88, h->vp_mean, h->vp_std, st.video_pp, AVH_BF16, nullptr, s))
+      return 1;
+    video = st.video_pp;
+    video_dtype = AVH_BF16;
+  }
+  AVH_CHECK(video == nullptr || video_dtype == AVH_F32 || video_dtype == AVH_F16 || video_dtype == AVH_BF16, "bad video dtype");
+  // one plan per (clips, 128-row bucket of the packed rows, attention tiling class of the longest clip)
+  const long long Nb = (N + 127) / 128 * 128;
+  const int Tcap = tmax <= 160 ? 160 : (tmax + 127) / 128 * 128;
+  avh::Plan* p = avh::get_plan(h, B, Tcap, video != nullptr, audio != nullptr, false, output_layer, s, Nb);
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  // per-call geometry -> pinned mirror -> device descriptor (ordered on the stream before the launches that read it)
+  const int slot = p->rag_next;
+  p->rag_next = (slot + 1) % avh::Plan::RAG_SLOTS;
+  AVH_CUDA_OK(cudaEventSynchronize(p->rag_done[slot]));       // the copy that last used this mirror has run
+  int* rh = p->rag_host[slot];
+  rh[1] = (int)N;
+  int acc = 0;
+  for (int b = 0; b < B; ++b) { rh[16 + b] = acc; acc += lengths[b]; }
+  rh[16 + B] = acc;
+  int used_ints = 16 + B + 1;
+  if (video != nullptr) {
+    const int n_items = avh::stem_fused_ragged_items(lengths, B, avh::device_sm_count(),
+                                                     reinterpret_cast<int4*>(rh + p->rag_items_off), p->rag_max_items);
+    AVH_CHECK(n_items >= 0, "stem work list overflow");
+    rh[0] = n_items;
+    used_ints = p->rag_items_off + 4 * n_items;
+  } else rh[0] = 0;
+  AVH_CUDA_OK(cudaMemcpyAsync(p->rag, rh, (size_t)used_ints * 4, cudaMemcpyHostToDevice, s));
+  AVH_CUDA_OK(cudaEventRecord(p->rag_done[slot], s));
+  p->args.video = video; p->args.video_dt = video_dtype;
+  p->args.audio = audio; p->args.audio_dt = audio_dtype;
+  if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
+  p->args.mask = nullptr;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  p->args.pitch = T;
+  return run_plan(h, p, s);
 }
 
 int avh_set_video_preprocess(avh_handle* h, int src_h, int src_w, double mean, double stdv) {

@@ -409,9 +409,121 @@ video_preprocess_kernel(const unsigned char* __restrict__ in, void* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------- packed ragged batches
+// Clips sit back to back: cu[b] = first row of clip b, cu[B] = total rows.  (no work on pad frames.)
+__device__ __forceinline__ int find_clip(const int* __restrict__ cu, int B, int r) {     // largest b with cu[b] <= r
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(cu + mid) <= r) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// strided [B, C, Tpitch] -> packed rows [rows_cap, ldo]; rows >= cu[B] are written as zeros
+__global__ void bct_to_rows_ragged_kernel(const void* __restrict__ in, int in_dt, long long sb, long long sc, long long st,
+                                          int B, int C, const int* __restrict__ cu, void* __restrict__ out, int out_dt,
+                                          long long ldo, long long rows_cap) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_cap * C) return;
+  const int c = (int)(i % C);
+  const int r = (int)(i / C);
+  float v = 0.f;
+  if (r < __ldg(cu + B)) {
+    const int b = find_clip(cu, B, r);
+    v = load_any(in, in_dt, b * sb + c * sc + (long long)(r - __ldg(cu + b)) * st);
+  }
+  store_lp(out, out_dt, (long long)r * ldo + c, v);
+}
+// residual stream [rows, cols] fp32 -> zero-gapped bf16 layout of the positional conv: clip b occupies padded rows
+// [cu[b] + gap*b, +T_b), followed by `gap` zero rows; row_map[padded row] = packed row, or -1 for gap / tail rows
+__global__ void pos_pad_ragged_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
+                                      int* __restrict__ row_map, const int* __restrict__ cu, int B, int cols, int gap,
+                                      long long rows_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = cols >> 2;
+  if (i >= rows_pad * c4n) return;
+  const int rp = (int)(i / c4n);
+  const int c = (int)(i - (long long)rp * c4n) * 4;
+  int lo = 0, hi = B - 1;                       // largest b with cu[b] + gap*b <= rp
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(cu + mid) + gap * mid <= rp) lo = mid; else hi = mid - 1;
+  }
+  const int t = rp - (__ldg(cu + lo) + gap * lo);
+  const int src = (t < __ldg(cu + lo + 1) - __ldg(cu + lo)) ? __ldg(cu + lo) + t : -1;
+  uint2 u = make_uint2(0u, 0u);
+  if (src >= 0) {
+    const float4 x = *reinterpret_cast<const float4*>(in + (long long)src * ld + c);
+    u = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+  }
+  *reinterpret_cast<uint2*>(out + (long long)rp * cols + c) = u;
+  if (c == 0) row_map[rp] = src;
+}
+// packed fp32 rows -> dense [B, T, cols] in out_dt, zeros at the pad positions
+__global__ void unpack_rows_kernel(const float* __restrict__ in, const int* __restrict__ cu, void* __restrict__ out, int out_dt,
+                                   int B, int T, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = cols >> 2;
+  if (i >= (long long)B * T * c4n) return;
+  const long long bt = i / c4n;
+  const int c = (int)(i - bt * c4n) * 4;
+  const int b = (int)(bt / T), t = (int)(bt - (long long)b * T);
+  const int r0 = __ldg(cu + b);
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < __ldg(cu + b + 1) - r0) x = *reinterpret_cast<const float4*>(in + (long long)(r0 + t) * cols + c);
+  const long long o = bt * cols + c;
+  if (out_dt == DT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = x;
+  else if (out_dt == DT_BF16)
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+  else {
+    const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  }
+}
+
 inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
 
 }  // namespace
+
+int launch_bct_to_rows_ragged(const void* in, int in_dt, long long sb, long long sc, long long st, int B, int C,
+                              const int* cu, void* out, int out_dt, long long ldo, long long rows_cap, cudaStream_t stream) {
+  const long long n = rows_cap * C;
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(bct_to_rows_ragged_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, in_dt, sb, sc, st, B,
+                         C, cu, out, out_dt, ldo, rows_cap));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_pos_pad_ragged(const float* in, long long ld, void* out, int* row_map, const int* cu, int B, int cols, int gap,
+                          long long rows_pad, cudaStream_t stream) {
+  AVH_CHECK(cols % 4 == 0 && ld % 4 == 0, "pos_pad needs 4-column granularity");
+  const long long n = rows_pad * (cols / 4);
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(pos_pad_ragged_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, ld,
+                         reinterpret_cast<__nv_bfloat16*>(out), row_map, cu, B, cols, gap, rows_pad));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_unpack_rows(const float* in, const int* cu, void* out, int out_dt, int B, int T, int cols, cudaStream_t stream) {
+  AVH_CHECK(cols % 4 == 0, "unpack_rows needs 4-column granularity");
+  const long long n = (long long)B * T * (cols / 4);
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(unpack_rows_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, cu, out, out_dt, B, T, cols));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
 
 int launch_video_preprocess(const unsigned char* frames, long long n_frames, int src_h, int src_w, int crop, double mean,
                             double stdv, void* out, int out_dt, const unsigned char* frame_zero, cudaStream_t stream) {

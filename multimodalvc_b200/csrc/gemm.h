@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <vector_types.h>
 #include <stdint.h>
 
 #include <vector>
@@ -33,6 +34,7 @@ struct Epilogue {
   int S1 = 1, S2 = 1, H = 1, W = 1;
   long long O0 = 0, O1 = 0, O2 = 0;
   int invalid_zero = 0;                 // invalid rows: 1 -> store zeros, 0 -> skip
+  const int* row_map = nullptr;         // device [M]: tile row -> output row, -1 = skip (overrides map_mode; ragged pos-conv)
   // ---- LayerNorm of the residual stream folded into the GEMMs around it (bf16 mode, pre-LN layers) ----
   // ln_mode 1, PRODUCER (x = x + A B^T + bias, fp32): also writes xc = bf16(x - mu[row]) (the next GEMM's operand,
   //   centred on the row mean of the PREVIOUS x) and, per row and per (N tile, epilogue warp set), the partial sums
@@ -163,6 +165,11 @@ struct AttnTcPlan {
 int attention_tc_plan(const void* qkv, long long rows, int B, int T, int D, int H, AttnTcPlan* plan);
 // kpm: [B, T] key-padding mask or null; cu: [B + 1] first row of every clip for packed ragged batches, or null
 int attention_tc_launch(const AttnTcPlan& plan, const unsigned char* kpm, const int* cu, void* out, cudaStream_t stream);
+// ragged batches (clips of different lengths packed back to back in the output): host-built work list + launch
+int stem_fused_ragged_items(const int* lengths, int n_clips, int sms, int4* items, int max_items);   // returns count or -1
+int stem_fused_launch_ragged(const StemFusedPlan& plan, const void* video, int in_dt, int Tpitch, const int4* items,
+                             const int* n_items, const int* cu, const float* scale, const float* bias, const float* slope,
+                             void* out, cudaStream_t stream);
 // tensor-map helpers shared by the GEMM kernels (gemm_tcgen05.cu)
 int encode_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows);
 int encode_c(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int fp32);

@@ -54,7 +54,8 @@ struct Occ {
   static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;    // producer, mma, alloc, spare + epilogue warps
   static constexpr int TMEM_COLS = 512 / OCC;
   static constexpr int ACC_STRIDE = 256 / OCC;                // TMEM columns per accumulator stage
-  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;    // per-warp 32 rows x 128 B staging boxes
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 8192;    // per warp TWO 32 rows x 128 B staging boxes (the TMA store
+                                                              // of box i drains while box i+1 is computed)
   static constexpr int SMEM_LIMIT = OCC == 2 ? 113 * 1024 : 227 * 1024;
   static constexpr int HSTRIDE = EPI_WARPS / 4;               // column-box interleave between epilogue warp sets
 };
@@ -282,6 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const bool out_f32 = OUTF32 >= 0 ? OUTF32 != 0 : ep.c_fp32 != 0;
     const bool res_any = RES >= 0 ? RES != 0 : ep.R != nullptr;
     int it = 0;
+    int box_count = 0;                    // boxes this warp has stored so far (staging buffer = parity)
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m_blk = tile % p.num_m_blk;
       const int n_blk = tile / p.num_m_blk;
@@ -301,6 +303,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (!(h < ep.H && w < ep.W)) {
           if (ep.invalid_zero) zero = true; else store = false;
         }
+      }
+      if (ep.row_map != nullptr) {
+        const int mr = r < p.M ? __ldg(ep.row_map + r) : -1;
+        orow = mr;
+        store = mr >= 0;
       }
       if (store && ep.row_zero != nullptr && ep.row_zero[orow]) zero = true;
       // LayerNorm folding: per-row quantities of this thread's row
@@ -355,7 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         AVH_TRACE(8);
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
-      uint8_t* stg = epi_stage + (warp - 4) * 4096;
+      uint8_t* stg = epi_stage + (warp - 4) * 8192;
 
       if (p.c_mode != 0) {
         // ---- thread = row: TMEM -> registers -> fused math -> 128-byte-swizzled smem box -> TMA store / reduce-add
@@ -501,12 +508,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               else mbar_arrive(&tmem_empty[acc]);
             }
           }
-          // the previous box of this warp must have been read out of smem before it is overwritten
-          if (lane == 0) tma_wait_group_read0();
+          // the box stored two boxes ago must have been read out of this staging buffer before it is overwritten
+          uint8_t* sbox = stg + (box_count & 1) * 4096;
+          ++box_count;
+          if (lane == 0) {
+            if (LNF == 1) tma_wait_group_read0();
+            else tma_wait_group_read1();
+          }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(sbox + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           if (LNF == 1) {
             uint8_t* stg2 = epi_stage2 + (warp - 4) * 2048;      // row-major 32 x 32 bf16 box (64-byte rows)
@@ -517,11 +529,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M) {
-            if (p.c_mode == 2) tma_reduce_add_2d(&tma_c, stg, n_blk * BN + cbase, row0);
-            else tma_store_2d(&tma_c, stg, n_blk * BN + cbase, row0);
-            if (LNF == 1 && n_blk * BN + cbase < p.N && !(p.lnf_dbg & 1)) tma_store_2d(&tma_c2, epi_stage2 + (warp - 4) * 2048, n_blk * BN + cbase, row0);
-            tma_commit_group();
+          if (lane == 0) {
+            if (row0 < p.M) {
+              if (p.c_mode == 2) tma_reduce_add_2d(&tma_c, sbox, n_blk * BN + cbase, row0);
+              else tma_store_2d(&tma_c, sbox, n_blk * BN + cbase, row0);
+              if (LNF == 1 && n_blk * BN + cbase < p.N && !(p.lnf_dbg & 1)) tma_store_2d(&tma_c2, epi_stage2 + (warp - 4) * 2048, n_blk * BN + cbase, row0);
+            }
+            tma_commit_group();       // one group per box, stored or not: "all but the newest group" = the box before
           }
         }
         if (LNF == 1 && store)
@@ -811,7 +825,8 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
   // box stores, or reduce-add when the residual is the output itself (x += ...) and nothing follows the add
   {
     const Epilogue& e = pr.ep;
-    const bool identity = e.map_mode != MAP_2LEVEL || (e.O2 == e.S2 && e.O1 == e.S1 && e.O0 == 0 && e.invalid_zero);
+    const bool identity = e.row_map == nullptr &&
+                          (e.map_mode != MAP_2LEVEL || (e.O2 == e.S2 && e.O1 == e.S1 && e.O0 == 0 && e.invalid_zero));
     int mode = 0;
     if (identity && (bn % (e.c_fp32 ? 32 : 64) == 0 || pr.N <= bn)) {
       mode = 1;

@@ -23,6 +23,13 @@ int launch_layernorm(const void* in, int in_dt, long long ld_in, const float* ga
 int launch_bct_to_rows(const void* in, int in_dt, long long sb, long long sc, long long st, int B, int C, int T,
                        void* out, int out_dt, long long ldo, cudaStream_t stream);
 
+// ---- packed ragged batches: clips back to back, cu[b] = first row of clip b (device int32 [B+1])
+int launch_bct_to_rows_ragged(const void* in, int in_dt, long long sb, long long sc, long long st, int B, int C,
+                              const int* cu, void* out, int out_dt, long long ldo, long long rows_cap, cudaStream_t stream);
+int launch_pos_pad_ragged(const float* in, long long ld, void* out, int* row_map, const int* cu, int B, int cols, int gap,
+                          long long rows_pad, cudaStream_t stream);
+int launch_unpack_rows(const float* in, const int* cu, void* out, int out_dt, int B, int T, int cols, cudaStream_t stream);
+
 // flat element-wise dtype conversion
 int launch_convert(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t stream);
 

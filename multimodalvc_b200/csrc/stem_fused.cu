@@ -54,6 +54,9 @@ struct StemParams {
   int in_dt;
   int T, b0, nb;
   int nseg, seglen, num_items;
+  const int4* items;           // ragged batches: device item list {clip, band, t0, t1} (num_items read from n_items), else null
+  const int* cu;               // ragged batches: [clips + 1] first output frame of every clip; T is then the input clip pitch
+  const int* n_items;          // ragged batches: device int holding the number of items of this call
   __nv_bfloat16* out;          // [nb*T, 529, 64]
   const __nv_bfloat16* w;      // [64, 5*64], K = dt*64 + kh*8 + kw
   const float* scale;
@@ -71,18 +74,35 @@ __device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t parity, unsigne
 }
 
 struct Item {
-  int bl, j, t0, t1, f_first, f_last;
+  int j, t0, t1, f_first, f_last;
+  int T;             // frames of the item's clip
+  long long in0;     // index of the clip's first frame in the input video
+  long long out0;    // ... and in the output maps
 };
 __device__ __forceinline__ Item decode_item(const StemParams& p, int item) {
   Item it;
-  const int sg = item % p.nseg;
-  const int rest = item / p.nseg;
-  it.j = rest % 11;
-  it.bl = rest / 11;
-  it.t0 = sg * p.seglen;
-  it.t1 = min(p.T, it.t0 + p.seglen);
+  if (p.items != nullptr) {
+    // ragged batch: (clip, band, segment) list written by the host for this call; clips sit Tstride frames apart in
+    // the (padded) input and back to back in the output
+    const int4 e = __ldg(p.items + item);           // {clip, band, t0, t1}
+    const int c0 = __ldg(p.cu + e.x);
+    it.j = e.y; it.t0 = e.z; it.t1 = e.w;
+    it.T = __ldg(p.cu + e.x + 1) - c0;
+    it.in0 = (long long)e.x * p.T;
+    it.out0 = c0;
+  } else {
+    const int sg = item % p.nseg;
+    const int rest = item / p.nseg;
+    it.j = rest % 11;
+    const int bl = rest / 11;
+    it.t0 = sg * p.seglen;
+    it.T = p.T;
+    it.t1 = min(p.T, it.t0 + p.seglen);
+    it.in0 = (long long)(p.b0 + bl) * p.T;
+    it.out0 = (long long)bl * p.T;
+  }
   it.f_first = max(0, it.t0 - 2);
-  it.f_last = min(p.T - 1, it.t1 + 1);
+  it.f_last = min(it.T - 1, it.t1 + 1);
   return it;
 }
 
@@ -122,7 +142,9 @@ __device__ __forceinline__ void epilogue_half(uint32_t taddr, int prow, bool ski
 }
 
 __global__ void __launch_bounds__(NT, 1)
-stem_fused_kernel(const StemParams p) {
+stem_fused_kernel(const StemParams p_in) {
+  StemParams p = p_in;
+  if (p.n_items != nullptr) p.num_items = __ldg(p.n_items);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -178,7 +200,7 @@ stem_fused_kernel(const StemParams p) {
       int next_free = im.f_first;
       for (int t = im.t0; t < im.t1; t += 2, ++pc) {
         const bool two = t + 1 < im.t1;
-        const int lo = max(t - 2, 0), hi = min(t + (two ? 3 : 2), p.T - 1);
+        const int lo = max(t - 2, 0), hi = min(t + (two ? 3 : 2), im.T - 1);
         {
           wait_acc(&d_empty[h], (pc & 1) ^ 1, p.dbg, st1);
           tc_fence_after();
@@ -250,7 +272,7 @@ stem_fused_kernel(const StemParams p) {
       const bool skip_top = im.j == 0 && prow == 0;
       for (int t = im.t0; t < im.t1; t += 2, ++pc) {
         const bool do_store = t + fp < im.t1;
-        __nv_bfloat16* orow = p.out + (((long long)(im.bl * p.T + t + fp) * 23 + (2 * im.j + prow)) * 23) * 64 + ch;
+        __nv_bfloat16* orow = p.out + (((im.out0 + t + fp) * 23 + (2 * im.j + prow)) * 23) * 64 + ch;
         wait_acc(&d_full[0], pc & 1, p.dbg, st0);
         tc_fence_after();
         epilogue_half<0>(lane_base + TM_D0, prow, skip_top, sc, bi, sl, orow, do_store, &d_empty[0], lane);
@@ -272,7 +294,7 @@ stem_fused_kernel(const StemParams p) {
     uint4 rv[2];                                           // bf16 fast path: 16-byte pieces bt and bt + 128 of the 165
     float rf[11];                                          // other dtypes: elements bt + 128 k of the 1320
     auto prefetch = [&](const Item& m, int ff) {
-      const long long src = ((long long)(p.b0 + m.bl) * p.T + ff) * 7744;
+      const long long src = (m.in0 + ff) * 7744;
       const int h0 = 8 * m.j - 5;
       if (fast) {
 #pragma unroll
@@ -410,6 +432,7 @@ int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, i
   }
   StemParams p;
   p.video = video; p.in_dt = in_dt; p.T = T; p.b0 = b0; p.nb = nb;
+  p.items = nullptr; p.cu = nullptr; p.n_items = nullptr;
   p.nseg = best_seg;
   p.seglen = (T + best_seg - 1) / best_seg;
   p.seglen += p.seglen & 1;
@@ -445,6 +468,55 @@ int stem_fused_launch(const StemFusedPlan& plan, const void* video, int in_dt, i
     return 0;
   }
   AVH_CUDA_OK(launch_pdl(stem_fused_kernel, dim3(grid), dim3(NT), SMEM_BYTES, stream, p));
+  count_launch(1);
+  return 0;
+}
+
+// ---- ragged batches: the (clip, band, time segment) work list of one call, built on the host from the clip lengths.
+// Segments are even-length (frames are processed in pairs); every segment re-builds 2 + 2 boundary frames, so the
+// segment length trades boundary work against whole waves over the SMs.
+int stem_fused_ragged_items(const int* lengths, int n_clips, int sms, int4* items, int max_items) {
+  long long total = 0;
+  int tmax = 0;
+  for (int b = 0; b < n_clips; ++b) { total += lengths[b]; tmax = lengths[b] > tmax ? lengths[b] : tmax; }
+  int best_len = 2;
+  double best = 1e30;
+  for (int len = 2; len <= ((tmax + 1) & ~1) || len == 2; len += 2) {
+    long long segs = 0;
+    for (int b = 0; b < n_clips; ++b) segs += (lengths[b] + len - 1) / len;
+    const long long n = segs * 11;
+    if (n > max_items) continue;
+    const long long rounds = (n + sms - 1) / sms;
+    const double cost = (double)rounds * (len + 3.0);
+    if (cost < best) { best = cost; best_len = len; }
+  }
+  int n = 0;
+  for (int b = 0; b < n_clips; ++b)
+    for (int j = 0; j < 11; ++j)
+      for (int t0 = 0; t0 < lengths[b]; t0 += best_len) {
+        if (n >= max_items) return -1;
+        const int t1 = t0 + best_len < lengths[b] ? t0 + best_len : lengths[b];
+        items[n++] = make_int4(b, j, t0, t1);
+      }
+  return n;
+}
+
+int stem_fused_launch_ragged(const StemFusedPlan& plan, const void* video, int in_dt, int Tpitch, const int4* items,
+                             const int* n_items, const int* cu, const float* scale, const float* bias, const float* slope,
+                             void* out, cudaStream_t stream) {
+  AVH_CHECK(in_dt == DT_BF16 || in_dt == DT_F16 || in_dt == DT_F32, "unsupported video dtype");
+  AVH_CHECK(in_dt != DT_BF16 || (reinterpret_cast<uintptr_t>(video) & 15) == 0, "video must be 16-byte aligned");
+  StemParams p;
+  p.video = video; p.in_dt = in_dt; p.T = Tpitch; p.b0 = 0; p.nb = 0;
+  p.nseg = 1; p.seglen = 2; p.num_items = 0;
+  p.items = items; p.cu = cu; p.n_items = n_items;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(plan.w);
+  p.scale = scale; p.bias = bias; p.slope = slope;
+  p.dbg = nullptr;
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(stem_fused_kernel), (int)SMEM_BYTES)) return 1;
+  AVH_CUDA_OK(launch_pdl(stem_fused_kernel, dim3(device_sm_count()), dim3(NT), SMEM_BYTES, stream, p));
+  AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
 }

@@ -57,6 +57,9 @@ class AVHubertConfig:
     compute_dtype: str = "auto"        # "auto": fp32 module -> fp32-faithful mode, half/bf16 module -> bf16 mode
     frontend_chunk_frames: int = 0     # 0 = library default
     capture_stages: bool = False       # keep intermediate stages readable (tests)
+    ragged: str = "dense"              # "dense": compute on the padded [B,T] batch, every output position as the
+                                       # reference's; "packed": bf16 mode, frames/tokens of ragged batches packed back to
+                                       # back (no work on pad frames), output rows at pad positions are zeros
 
     @staticmethod
     def named(size, **kw):
@@ -359,10 +362,22 @@ class AVHubertModel(nn.Module):
             pm_u8 = padding_mask.to(device=device, dtype=torch.bool).contiguous().view(torch.uint8)
         return src_video, video_dt, src_audio, pm_u8, padding_mask, B, T
 
+    @staticmethod
+    def lengths_from_padding_mask(padding_mask):
+        """Valid frames per clip of a collater-style mask (True = padded, padding is a suffix: hubert_dataset.py:433-447)
+        as a python list, or None when the mask is not of that form (padding inside a clip, an empty clip).  A CUDA mask
+        costs one device->host copy; pass `lengths=` to extract_finetune to avoid it."""
+        pm = padding_mask.detach().to("cpu", torch.bool)
+        if pm.size(1) > 1 and not bool((pm[:, 1:] >= pm[:, :-1]).all()):
+            return None
+        lengths = (~pm).sum(1).tolist()
+        return lengths if min(lengths) >= 1 else None
+
     @torch.no_grad()
-    def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
+    def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None, lengths=None):
         """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
-        padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask)."""
+        padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask).  With cfg.ragged == "packed" (bf16
+        mode) ragged batches run packed; `lengths` (valid frames per clip) may be given to skip reading the mask back."""
         self._check_mode(mask)
         handle = self._ensure_handle()
         dev = self.encoder.layer_norm.weight.device
@@ -376,6 +391,25 @@ class AVHubertModel(nn.Module):
         if src_audio is not None:
             strides = (ctypes.c_int64 * 3)(*src_audio.stride())
         ol = 0 if output_layer is None else int(output_layer)
+        if self.cfg.ragged not in ("dense", "packed"):
+            raise ValueError(f"cfg.ragged must be 'dense' or 'packed', got {self.cfg.ragged}")
+        if (self.cfg.ragged == "packed" and padding_mask is not None and self._handle_key[1] == _lib.AVH_COMPUTE_BF16):
+            if lengths is None:
+                lengths = self.lengths_from_padding_mask(padding_mask)
+            elif len(lengths) != B or min(lengths) < 1 or max(lengths) > T:
+                raise ValueError("lengths must hold one value in [1, T] per clip")
+            if lengths is not None:
+                with torch.cuda.device(dev):
+                    stream = torch.cuda.current_stream(dev).cuda_stream
+                    _lib.check(_lib.load().avh_forward_ragged(
+                        handle,
+                        ctypes.c_void_p(src_video.data_ptr()) if src_video is not None else None,
+                        video_dt,
+                        ctypes.c_void_p(src_audio.data_ptr()) if src_audio is not None else None,
+                        _DTYPES[src_audio.dtype] if src_audio is not None else 0,
+                        strides, (ctypes.c_int32 * B)(*[int(n) for n in lengths]),
+                        B, T, ol, ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
+                return out, padding_mask
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.load().avh_forward(

@@ -195,3 +195,60 @@ def test_two_devices_in_one_process():
             d_src, d_pm = to_dev(src, pm, device=dev, dtype=dtype)
             y, _ = m.extract_finetune(d_src, d_pm)
             assert cosine(y.float().cpu(), y_ref) > BF16_COS
+
+
+def test_packed_ragged_mode_equals_dense_mode_on_valid_frames_tiny():
+    """cfg.ragged='packed' (no work on pad frames): valid positions carry the dense path's values (same kernels, same
+    per-row arithmetic; GEMM rows are independent), pad positions are zeros; also vs the oracle."""
+    oracle = ao.build_oracle("tiny", seed=1234)
+    lengths = [40, 17, 1, 33, 40, 8]
+    src, pm = ao.synthetic_inputs(6, 40, lengths=lengths, seed=31)
+    with torch.no_grad():
+        y_ref, _ = oracle.extract_finetune(src, pm)
+    dense = make_device_model(oracle, {}, "tiny", torch.bfloat16)
+    packed = make_device_model(oracle, {}, "tiny", torch.bfloat16, ragged="packed")
+    d_src, d_pm = to_dev(src, pm, dtype=torch.bfloat16)
+    y_d, _ = dense.extract_finetune(d_src, d_pm)
+    for trial in range(3):                                  # 2nd call captures the CUDA graph, 3rd replays it
+        y_p, pm_out = packed.extract_finetune(d_src, d_pm)
+        assert torch.equal(pm_out, d_pm)
+        for i, n in enumerate(lengths):
+            assert cosine(y_p[i, :n].float().cpu(), y_d[i, :n].float().cpu()) > 0.9999, (trial, i)
+            assert cosine(y_p[i, :n].float().cpu(), y_ref[i, :n]) > BF16_COS, (trial, i)
+            assert not y_p[i, n:].any()
+    # explicit lengths (no mask read-back), video only / audio only, early exit
+    y_l, _ = packed.extract_finetune(d_src, d_pm, lengths=lengths)
+    assert torch.equal(y_l, y_p)
+    for drop in ("audio", "video"):
+        one = dict(d_src)
+        one[drop] = None
+        y1, _ = packed.extract_finetune(one, d_pm, output_layer=1)
+        y2, _ = dense.extract_finetune(one, d_pm, output_layer=1)
+        for i, n in enumerate(lengths):
+            assert cosine(y1[i, :n].float().cpu(), y2[i, :n].float().cpu()) > 0.9999, (drop, i)
+
+
+def test_packed_ragged_mode_large_long_clips_vs_oracle(large):
+    """Large, ragged 25..600-frame clips in packed mode (streamed attention per clip through cu_rows, ragged stem work
+    list, positional conv through the row map) against the oracle on each clip alone."""
+    oracle, _ = large
+    m = make_device_model(oracle, {}, "large", torch.bfloat16, ragged="packed")
+    lengths = [600, 25, 161, 310, 97]
+    T = max(lengths)
+    v = torch.zeros(len(lengths), 1, T, 88, 88)
+    a = torch.zeros(len(lengths), 104, T)
+    pm = torch.ones(len(lengths), T, dtype=torch.bool)
+    for j, n in enumerate(lengths):
+        cv, ca = _clip(100 + j, n)
+        v[j, :, :n] = cv
+        a[j, :, :n] = ca
+        pm[j, :n] = False
+    y, _ = m.extract_finetune({"audio": a.cuda().bfloat16(), "video": v.cuda().bfloat16()}, pm.cuda())
+    y2, _ = m.extract_finetune({"audio": a.cuda().bfloat16(), "video": v.cuda().bfloat16()}, pm.cuda())
+    assert torch.equal(y, y2)
+    for j, n in enumerate(lengths):
+        cv, ca = _clip(100 + j, n)
+        with torch.no_grad():
+            y_ref, _ = oracle.extract_finetune({"audio": ca[None], "video": cv[None]}, None)
+        assert cosine(y[j, :n].float().cpu(), y_ref[0]) > BF16_COS, (j, n)
+        assert not y[j, n:].any()

@@ -61,6 +61,12 @@ def main():
         tiles = mt * nt
         units = 148 // pair
         rounds = (tiles + units - 1) // units
+        drain = (t[lead, 8] - t[lead, 5])        # last MMA issued -> last epilogue starts (MMA drain)
+        epi = (t[lead, 9] - t[lead, 8])          # last epilogue
+        fin = (t[lead, 10] - t[lead, 9])         # store drain + final sync
+        print(f"   tail split: mma drain {drain.mean():6.0f}  last epilogue {epi.mean():6.0f}  store drain + sync {fin.mean():6.0f}"
+              f" | fill split: prologue+wait {(t[lead, 1] - t[lead, 0]).mean():6.0f} first TMA->first full "
+              f"{(t[lead, 3] - t[lead, 1]).mean():6.0f}")
         print(f"{name:9s} pair={pair} BN={bn}: leaders={n} tiles={tiles} rounds={rounds} clk={c} MHz | total {total.mean():7.0f} "
               f"fill {fill.mean():6.0f} main {main_loop.mean():7.0f} (max {main_loop.max():7.0f}) tail {tail.mean():6.0f} | "
               f"mma wait operands {t[lead, 12].mean():7.0f} wait tmem {t[lead, 13].mean():6.0f} | producer wait "
