@@ -256,6 +256,8 @@ def main():
                     help="CUDA streams per GPU; consecutive steps alternate between them (each has its own workspace)")
     ap.add_argument("--sustain-s", type=float, default=3.0,
                     help="seconds of back-to-back steps for the `sustained` leg after the timed region (0 = skip)")
+    ap.add_argument("--config3-passes", type=int, default=5, help="timed passes over the 64 ragged clips of config 3 (0 = skip)")
+    ap.add_argument("--config3-tokens", type=int, default=4800, help="packed frames per ragged sub-batch")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-class breakdown here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -464,12 +466,64 @@ def main():
     barrier()
     ms_e2e_raw = r0.elapsed_time(r1)
 
+    # ---- BASELINE config 3: 64 ragged clips (U{25..600} frames, seed 7) with key-padding masks, sharded over the ranks
+    #      (balanced_shards), each rank running its clips as packed sub-batches (cfg.ragged='packed': no work on pad
+    #      frames).  Device-resident inputs; one "pass" = all 64 clips once.
+    cfg3 = None
+    if args.config3_passes > 0:
+        from multimodalvc_b200 import sharding
+        g3 = torch.Generator().manual_seed(7)
+        lengths3 = torch.randint(25, 601, (64,), generator=g3).tolist()
+        mine = sharding.balanced_shards(lengths3, world)[rank]
+        subs = sharding.token_buckets(mine, lengths3, max_tokens=args.config3_tokens, max_clips=32)
+        gin = torch.Generator().manual_seed(300 + rank)
+        batches = []
+        for sb in subs:
+            tb = max(lengths3[i] for i in sb)
+            v3 = torch.zeros(len(sb), 1, tb, 88, 88, dtype=torch.bfloat16)
+            a3 = torch.zeros(len(sb), 104, tb, dtype=torch.bfloat16)
+            pm3 = torch.ones(len(sb), tb, dtype=torch.bool)
+            for j, i in enumerate(sb):
+                n = lengths3[i]
+                v3[j, :, :n] = torch.randn(1, n, 88, 88, generator=gin).to(torch.bfloat16)
+                a3[j, :, :n] = torch.randn(104, n, generator=gin).to(torch.bfloat16)
+                pm3[j, :n] = False
+            batches.append((v3.to(dev), a3.to(dev), pm3.to(dev), [lengths3[i] for i in sb]))
+        model.cfg.ragged = "packed"
+
+        def pass3(k):
+            for j, (v3, a3, pm3, ln3) in enumerate(batches):
+                with torch.cuda.stream(streams[(k * len(batches) + j) % S]):
+                    model.extract_finetune({"audio": a3, "video": v3}, pm3, lengths=ln3)
+
+        for k in range(3):
+            pass3(k)
+        join()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        fork(c0)
+        for k in range(args.config3_passes):
+            pass3(k)
+        join()
+        c1.record()
+        barrier()
+        model.cfg.ragged = "dense"
+        frames_mine = sum(lengths3[i] for i in mine)
+        padded_dense = sum(len(sb) * max(lengths3[i] for i in sb) for sb in subs)
+        cfg3 = {"ms": c0.elapsed_time(c1), "frames_all": sum(lengths3), "frames_rank0": frames_mine,
+                "sub_batches_rank0": [[len(sb), sum(lengths3[i] for i in sb)] for sb in subs],
+                "pad_fraction_if_dense_rank0": 1.0 - frames_mine / float(padded_dense)}
+
     # ---- max over ranks
     ms_sus = sustained[1] if sustained else 0.0
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, cfg3["ms"] if cfg3 else 0.0], device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus = t.tolist()
+        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3 = t.tolist()
+        if cfg3:
+            cfg3["ms"] = ms_c3
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -588,6 +642,18 @@ def main():
             line["sustained"] = {"value": v_sus, "unit": UNIT, "steps": n_sus, "seconds": ms_sus * 1e-3,
                                  "ms_per_step": ms_sus / n_sus, "clocks": sus_clk, "tflops_per_gpu": w_sus,
                                  "frac_of_sustained_peak": w_sus / peak_sus, "frac_of_burst_peak": w_sus / peak_burst}
+        if cfg3:
+            sec = cfg3["ms"] * 1e-3 / args.config3_passes
+            fps3 = cfg3["frames_all"] / sec
+            fps2 = value * T_FRAMES
+            line["config3"] = {
+                "workload": "BASELINE config 3: Large, 64 ragged clips of 25..600 frames (U, seed 7) + key-padding masks, "
+                            f"clips dealt to {world} rank(s) by balanced_shards, packed sub-batches of <= "
+                            f"{args.config3_tokens} frames (cfg.ragged='packed'), device-resident inputs",
+                "clips_per_s": 64.0 / sec, "frames_per_s": fps3, "ms_per_pass": sec * 1e3, "passes": args.config3_passes,
+                "frames": cfg3["frames_all"], "config2_frames_per_s": fps2, "frac_of_config2_frame_rate": fps3 / fps2,
+                "sub_batches_rank0_clips_frames": cfg3["sub_batches_rank0"],
+                "pad_fraction_if_dense_rank0": cfg3["pad_fraction_if_dense_rank0"]}
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"classes": prof, "total_ms": total_prof_ms}, f, indent=1, sort_keys=True)

@@ -10,7 +10,8 @@ behind the C ABI declared in ``include/avh_b200.h``.
 from .hubert import AVHubertConfig, AVHubertModel  # noqa: F401
 from .hubert_asr import HubertEncoder, HubertEncoderWrapper  # noqa: F401
 from . import audio  # noqa: F401
+from . import distributed  # noqa: F401
 from . import sharding  # noqa: F401
 from . import video  # noqa: F401
 
-__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoder", "HubertEncoderWrapper", "audio", "sharding", "video"]
+__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoder", "HubertEncoderWrapper", "audio", "distributed", "sharding", "video"]

@@ -54,3 +54,22 @@ def length_buckets(indices: Sequence[int], lengths: Sequence[int], max_pad_frac:
     if cur:
         out.append(cur)
     return out
+
+
+def token_buckets(indices: Sequence[int], lengths: Sequence[int], max_tokens: int = 4800, max_clips: int = 64) -> List[List[int]]:
+    """Sub-batches for the PACKED ragged path (cfg.ragged='packed': no work on pad frames, so padding waste is not a
+    constraint): clips in decreasing-length order, a new sub-batch whenever the packed frame count would pass
+    `max_tokens` (one forward ~ one or two config-2-sized steps keeps the GEMMs at their efficient M)."""
+    idx = sorted(indices, key=lambda i: (-lengths[i], i))
+    out: List[List[int]] = []
+    cur: List[int] = []
+    tot = 0
+    for i in idx:
+        if cur and (tot + lengths[i] > max_tokens or len(cur) >= max_clips):
+            out.append(cur)
+            cur, tot = [], 0
+        cur.append(i)
+        tot += lengths[i]
+    if cur:
+        out.append(cur)
+    return out

@@ -99,3 +99,18 @@ def test_two_rank_sharded_run_under_gloo():
     assert units == len(lengths)
     assert part == [n * 31 + 7 for n in lengths]          # every clip processed exactly once
     assert tmax == 2.0
+
+
+def test_token_buckets_partition_and_respect_the_budget():
+    g = torch.Generator().manual_seed(7)
+    lengths = torch.randint(25, 601, (64,), generator=g).tolist()          # BASELINE config 3
+    for world in (1, 2, 8):
+        for shard in sharding.balanced_shards(lengths, world):
+            buckets = sharding.token_buckets(shard, lengths, max_tokens=4800, max_clips=32)
+            assert sorted(i for b in buckets for i in b) == sorted(shard)
+            for b in buckets:
+                assert len(b) <= 32
+                assert sum(lengths[i] for i in b) <= 4800 or len(b) == 1
+                assert [lengths[i] for i in b] == sorted((lengths[i] for i in b), reverse=True)
+    assert sharding.token_buckets([], lengths) == []
+    assert sharding.token_buckets([3], [10, 10, 10, 9000]) == [[3]]          # a clip longer than the budget runs alone
