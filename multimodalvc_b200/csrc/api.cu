@@ -600,6 +600,9 @@ struct Builder {
   Sizer sizer;
   int P;
   bool f32;      // fp32-faithful mode
+  float* sk_ws = nullptr;        // stream-K workspace of the plan's GEMMs (launches of a plan are serialised on its stream)
+  size_t sk_bytes = 0;
+  int* sk_flags = nullptr;
 
   void* alloc(size_t bytes) {
     if (sizing) {
@@ -640,6 +643,7 @@ struct Builder {
     pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
     pr.a_col_nblk = a_col_nblk;
     pr.block_n = block_n;
+    pr.sk_ws = sk_ws; pr.sk_ws_bytes = sk_bytes; pr.sk_flags = sk_flags;
     {   // tuning knob: AVH_GEMM_BN="fc1:256,qkv_proj:192" forces the tile width of a kernel class
       static const char* ov = std::getenv("AVH_GEMM_BN");
       if (ov != nullptr && block_n == 0) {
@@ -729,6 +733,11 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     return ep;
   };
 
+  // stream-K workspace: one fp32 partial tile (128 x 256) per SM + flags (zero from the arena's initial fill; the
+  // kernels hand the flags back as zeros)
+  b.sk_bytes = (size_t)device_sm_count() * 128 * 256 * 4;
+  b.sk_ws = reinterpret_cast<float*>(b.alloc(b.sk_bytes));
+  b.sk_flags = reinterpret_cast<int*>(b.alloc(4096));
   // fused token features [N, E]: audio arm in columns [0,D), video arm in [D,2D) (concat) or summed (add)
   Act fused = new_act(N, E);
   if (rg) {
@@ -1797,6 +1806,20 @@ int avh_gemm_bf16(const void* A, const void* B, int64_t M, int N, int K, const f
   pr.block_n = block_n;
   pr.pair = pair;
   pr.occ = occ;
+  {   // stream-K workspace for the stand-alone entry point (tests, tools): one per device, allocated on first use
+    static std::map<int, std::pair<float*, int*>> ws;
+    int dev = 0;
+    AVH_CUDA_OK(cudaGetDevice(&dev));
+    const size_t bytes = (size_t)avh::device_sm_count() * 128 * 256 * 4;
+    if (ws.find(dev) == ws.end()) {
+      float* w = nullptr; int* f = nullptr;
+      AVH_CUDA_OK(cudaMalloc(&w, bytes));
+      AVH_CUDA_OK(cudaMalloc(&f, 4096));
+      AVH_CUDA_OK(cudaMemset(f, 0, 4096));
+      ws[dev] = {w, f};
+    }
+    pr.sk_ws = ws[dev].first; pr.sk_ws_bytes = bytes; pr.sk_flags = ws[dev].second;
+  }
   pr.ep.C = C; pr.ep.ldc = N; pr.ep.c_fp32 = c_fp32;
   pr.ep.col_bias = bias;
   pr.ep.act = gelu ? avh::ACT_GELU : avh::ACT_NONE;

@@ -75,12 +75,20 @@ struct GemmProblem {
   int block_n = 0;          // output-tile width: multiple of 32, <= 256; 0 = chosen by gemm_plan (wave fitting)
   int occ = 0;              // CTAs per SM: 0 = chosen by gemm_plan, 1, or 2 (block_n <= 128 only)
   int pair = 0;             // 0 = default (CTA pairs, tcgen05 cta_group::2), 1 = single-CTA form, 2 = pairs
+  // stream-K workspace (optional): fp32 partial accumulators [units][pair * 128][block_n] + one flag per CTA, zeroed
+  // once by the owner of the buffers.  With it, gemm_plan may cut the tile x k-block space into equal ranges per unit
+  // instead of whole tiles (deterministic: fixed partition, partials added in unit order).
+  float* sk_ws = nullptr;
+  size_t sk_ws_bytes = 0;
+  int* sk_flags = nullptr;  // >= 2 * SMs ints
+  int streamk = 0;          // 0 = gemm_plan decides (needs the workspace), 1 = force on, -1 = off
   Epilogue ep;
 };
 
 struct GemmPlan {
   CUtensorMap tma_a, tma_b, tma_c, tma_c2;      // tma_c2: bf16 centred copy of an ln_mode-1 producer (32-column boxes)
   int c_mode = 0;
+  int sk = 0;                     // stream-K partition in use
   GemmProblem prob;
   int grid = 0;
   int stages = 0;

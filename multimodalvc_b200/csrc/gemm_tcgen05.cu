@@ -74,6 +74,13 @@ struct KernelParams {
   const int4* ktable;
   int c_mode;                   // 0 = per-thread global stores, 1 = TMA store of C, 2 = TMA reduce-add into C (= R)
   unsigned long long* trace;    // debug: [grid][16] SM clock stamps (null in production)
+  // stream-K (sk != 0): the tile x k-block space is cut into one contiguous range per work unit; a unit whose range
+  // starts inside a tile writes that partial accumulator (fp32) to sk_ws[unit] and raises sk_flags[unit]; the unit that
+  // holds the tile's first k-block owns the tile: it adds the partials of the following units in unit order (fixed
+  // partition + fixed order = bit-identical reruns) and runs the epilogue.  Flags are reset by their consumer.
+  int sk;
+  float* sk_ws;                 // [units][PAIR * 128][block_n] fp32
+  int* sk_flags;                // [units], zero between launches
   int lnf_dbg;                  // debug (AVH_LN_DBG bits, timing experiments only — results become wrong): 1 skip the
                                 // centred bf16 store, 2 skip the statistics, 4 skip the residual loads
   Epilogue ep;
@@ -94,6 +101,36 @@ struct KernelParams {
   do {                                                                                             \
     if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
   } while (0)
+
+// Work of one unit (CTA or CTA pair): classic persistent tiles (tile = unit, unit + units, ...; whole K each) or, in
+// stream-K mode, the k-blocks [unit * U / units, (unit + 1) * U / units) of the tile-major k-block sequence.
+struct SegIter {
+  int sk, num_kb, num_units;
+  int tile, tiles_end;          // persistent mode
+  long long pos, end;           // stream-K mode
+  __device__ __forceinline__ SegIter(int sk_, int unit, int num_units_, int num_tiles, int num_kb_)
+      : sk(sk_), num_kb(num_kb_), num_units(num_units_), tile(unit), tiles_end(num_tiles) {
+    const long long U = (long long)num_tiles * num_kb_;
+    pos = (long long)unit * U / num_units_;
+    end = (long long)(unit + 1) * U / num_units_;
+  }
+  // next segment: tile index and k-block range [kb0, kb1); false when the unit's work is done
+  __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
+    if (!sk) {
+      if (tile >= tiles_end) return false;
+      t = tile; kb0 = 0; kb1 = num_kb;
+      tile += num_units;
+      return true;
+    }
+    if (pos >= end) return false;
+    t = (int)(pos / num_kb);
+    kb0 = (int)(pos - (long long)t * num_kb);
+    const long long left = end - pos;
+    kb1 = left < (long long)(num_kb - kb0) ? kb0 + (int)left : num_kb;
+    pos += kb1 - kb0;
+    return true;
+  }
+};
 
 // ACT (ACT_*), RES (residual add), S2 (second PReLU), SCALE (per-column scale) and OUTF32 (fp32 output and
 // residual, else bf16) are compile-time when >= 0 and read from the Epilogue struct when -1.
@@ -169,19 +206,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // wait (they come from DRAM — 25 MB of weights per layer never stay in L2 — and were the longest part of the
   // 1.1 us between the wait and the first MMA); the A tiles (activations) follow after the wait.
   int pre_b = 0;
-  if (PAIR == 1 && warp == 0 && unit < num_tiles) {
-    const int n_blk0 = unit / p.num_m_blk;
-    pre_b = p.num_kb < STAGES ? p.num_kb : STAGES;
+  if (PAIR == 1 && warp == 0) {
+    SegIter first(p.sk, unit, num_units, num_tiles, p.num_kb);
+    int t0, f_kb0 = 0, f_kb1 = 0;
+    if (first.next(t0, f_kb0, f_kb1)) {
+    const int n_blk0 = t0 / p.num_m_blk;
+    pre_b = f_kb1 - f_kb0 < STAGES ? f_kb1 - f_kb0 : STAGES;
     const uint32_t stage_tx0 = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
     for (int kb = 0; kb < pre_b; ++kb) {
       int4 e;
-      if (p.ktable != nullptr) e = ktab[kb];
-      else e = make_int4(kb * BK, 0, kb * BK, 0);
+      if (p.ktable != nullptr) e = ktab[f_kb0 + kb];
+      else e = make_int4((f_kb0 + kb) * BK, 0, (f_kb0 + kb) * BK, 0);
       if (elect_one()) {
         mbar_expect_tx(&full_bar[kb], stage_tx0);
         tma_load_2d(smem_b + kb * b_stage_bytes, &tma_b, &full_bar[kb], e.z, n_blk0 * BN + e.w);
       }
       __syncwarp();
+    }
     }
   }
   // everything above (K table, barrier init, TMEM allocation, descriptor prefetch, first weight tiles) touched only
@@ -199,18 +240,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint32_t phase = 0;
     long long prod_wait = 0;
     const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
+    SegIter segs(p.sk, unit, num_units, num_tiles, p.num_kb);
+    int tile, kb0, kb1;
+    bool first_seg = true;
+    for (; segs.next(tile, kb0, kb1); first_seg = false) {
       const int m_blk = tile % p.num_m_blk;
       const int n_blk = tile / p.num_m_blk;
       const int m0 = (m_blk * PAIR + cta_rank) * BM;
       const int n0 = n_blk * BN + cta_rank * (BN / PAIR);
       const int a_col_base = p.a_col_nblk != nullptr ? __ldg(p.a_col_nblk + n_blk) : n_blk * p.a_col_per_nblk;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         int4 e;
         if (p.ktable != nullptr) e = ktab[kb];
         else e = make_int4(kb * BK, 0, kb * BK, 0);
         AVH_WAIT_ACC(&empty_bar[stage], phase ^ 1, prod_wait);
-        const bool b_early = PAIR == 1 && tile == unit && kb < pre_b;      // B tile already requested before the wait
+        const bool b_early = PAIR == 1 && first_seg && kb - kb0 < pre_b;   // B tile already requested before the wait
         if (elect_one()) {
           if (leader && !b_early) mbar_expect_tx(&full_bar[stage], stage_tx);
           if (PAIR == 2) {
@@ -220,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], e.x + a_col_base, m0 + e.y);
             if (!b_early) tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], e.z, n0 + e.w);
           }
-          if (tile == unit && kb == 0) AVH_TRACE(2);
+          if (first_seg && kb == kb0) AVH_TRACE(2);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -235,24 +279,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int it = 0;
       long long wait_full = 0, wait_tmem = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      SegIter segs(p.sk, unit, num_units, num_tiles, p.num_kb);
+      int tile, kb0, kb1;
+      for (; segs.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         AVH_WAIT_ACC(&tmem_empty[acc], acc_phase ^ 1, wait_tmem);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           AVH_WAIT_ACC(&full_bar[stage], phase, wait_full);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
           if (elect_one()) {
-            if (it == 0 && kb == 0) AVH_TRACE(3);
+            if (it == 0 && kb == kb0) AVH_TRACE(3);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-              if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-              else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
+              else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
             }
             if (PAIR == 2) umma_commit_pair(&empty_bar[stage]);   // smem slot reusable in BOTH CTAs
             else umma_commit(&empty_bar[stage]);
@@ -284,12 +330,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const bool out_f32 = OUTF32 >= 0 ? OUTF32 != 0 : ep.c_fp32 != 0;
     const bool res_any = RES >= 0 ? RES != 0 : ep.R != nullptr;
     int it = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+    SegIter segs(p.sk, unit, num_units, num_tiles, p.num_kb);
+    int tile, kb0, kb1;
+    for (; segs.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile % p.num_m_blk;
       const int n_blk = tile / p.num_m_blk;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = (m_blk * PAIR + cta_rank) * BM + q * 32;     // first row of this warp's quarter
+      if (p.sk && kb0 > 0) {
+        // ---- stream-K, tail part of a tile owned by an earlier unit: raw fp32 accumulator -> workspace slot of this
+        //      unit (thread = row, 128 contiguous bytes per 32-column chunk), then raise the flag
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        // slot layout: float4 index ((chunk * 8 + j) * 128 + row): the 32 lanes of a warp write (and the owner reads)
+        // 512 contiguous bytes per instruction — the row-major form (32 cache lines per instruction) cost 11 us per GEMM
+        uint4* wslot = reinterpret_cast<uint4*>(p.sk_ws + ((size_t)unit * PAIR + cta_rank) * (size_t)BM * BN) + q * 32 + lane;
+        const uint32_t taddr_p = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+        for (int ch = half; ch < BN / 32; ch += HSTRIDE) {
+          uint32_t rawv[32];
+          tmem_ld_32x32(taddr_p + ch * 32, rawv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            wslot[(size_t)(ch * 8 + j) * BM] = make_uint4(rawv[4 * j], rawv[4 * j + 1], rawv[4 * j + 2], rawv[4 * j + 3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        // one flag per CTA of the unit: the consumer CTA of the same rank reads exactly the rows this CTA wrote
+        if (threadIdx.x == 128) atomicExch(p.sk_flags + unit * PAIR + cta_rank, 1);
+        continue;
+      }
+      // stream-K owner of a tile whose K range continues in the following units: their partials are added (in unit
+      // order) to the accumulator values before the epilogue math
+      int sk_first = 0, sk_last = -1;
+      if (p.sk && kb1 < p.num_kb) {
+        const long long U = (long long)num_tiles * p.num_kb;
+        const long long tile_end = (long long)(tile + 1) * p.num_kb;
+        sk_first = unit + 1;
+        sk_last = unit + 1;
+        while ((long long)(sk_last + 1) * U / num_units < tile_end) ++sk_last;     // unit whose range reaches the tile end
+        if (lane == 0) {
+          for (int v = sk_first; v <= sk_last; ++v) {
+            const uint64_t t0w = global_timer_ns();
+            while (*reinterpret_cast<volatile int*>(p.sk_flags + v * PAIR + cta_rank) == 0) {
+              if (global_timer_ns() - t0w > 4000000000ull) { printf("avh: stream-K flag watchdog unit=%d waits %d\n", unit, v); __trap(); }
+            }
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
       const long long r = (long long)row0 + lane;
       bool store = r < p.M;
       bool zero = false;
@@ -404,10 +501,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
               }
             }
+            // stream-K owner: the first partial of this chunk is requested while the TMEM load is in flight (the
+            // residual registers are free: stream-K is planned only for GEMMs without a separate residual operand)
+            const bool sk_add = c0 < BN && sk_last >= sk_first;
+            if (sk_add) {
+              const uint4* pp = reinterpret_cast<const uint4*>(p.sk_ws + ((size_t)sk_first * PAIR + cta_rank) * (size_t)BM * BN) +
+                                (size_t)((c0 >> 5) * 8) * BM + q * 32 + lane;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rres[j] = __ldcg(pp + (size_t)j * BM);
+            }
             tmem_ld_wait();
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (c0 < BN) ? __uint_as_float(rawv[j]) : 0.f;
+            if (sk_add) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += __uint_as_float(rres[j].x); v[4 * j + 1] += __uint_as_float(rres[j].y);
+                v[4 * j + 2] += __uint_as_float(rres[j].z); v[4 * j + 3] += __uint_as_float(rres[j].w);
+              }
+              for (int pv = sk_first + 1; pv <= sk_last; ++pv) {       // further partials (K split over > 2 units), in order
+                const float4* pp = reinterpret_cast<const float4*>(p.sk_ws + ((size_t)pv * PAIR + cta_rank) * (size_t)BM * BN) +
+                                   (size_t)((c0 >> 5) * 8) * BM + q * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t4 = __ldcg(pp + (size_t)j * BM);
+                  v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+                }
+              }
+            }
             if (col0 < p.N) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -644,6 +766,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (it == 0) AVH_TRACE(7);
         AVH_TRACE(9);
       }
+      if (sk_last >= sk_first) {
+        // every epilogue warp of this CTA has read its partial rows: hand the flags back (zero between launches)
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        if (threadIdx.x == 128)
+          for (int v = sk_first; v <= sk_last; ++v) p.sk_flags[v * PAIR + cta_rank] = 0;
+      }
     }
     if (lane == 0 && p.c_mode != 0) tma_wait_group0();     // bulk stores of this thread are complete
   }
@@ -742,23 +870,33 @@ int default_pair() {
   return v;
 }
 
-// modelled cycles of one launch (measured on B200, tools/micro/mma_bench.cu + tools/gemm_sweep.py): a k-block
-// (4 tcgen05.mma of 128 x BN x 16 + barrier handling) costs max(415, 2*BN) clk — 98 % of the tensor pipe at
-// BN >= 224; `occ` CTAs on an SM issue independently but share the tensor pipe and the L2->SM operand stream
-// (~80 B/clk/SM).  Tiles run in whole waves.
-double model_cycles(long long M, int N, int num_kb, int bn, int pair, int occ, int sms) {
+// Modelled SM clocks of one launch (tools/gemm_stall.py, B200): a k-block of a 128 x bn tile needs 2 bn clk of tensor
+// pipe, >= ~415 clk of issue + barrier handling, and (16 KB of A + 128 bn B of B) through the SM's L2 ingress at
+// ~66 B/clk — the ingress bounds every single-CTA tile (bn 256: 785 clk measured, 192: 600-630, 160: 512-531); a CTA pair
+// loads half of B per SM (bn 256: 537-544 clk, tensor-bound).  Around the main loop: ~3.2 kclk from entry to the first
+// MMA (4.2 for pairs) and the exposed last epilogue (more for fp32 / reduce-add outputs, ~1.9x for pairs).  Persistent
+// tiles run in whole rounds; stream-K (sk) gives every unit the same number of k-blocks + ~1.5 kclk of partial traffic.
+double model_cycles(long long M, int N, int num_kb, int bn, int pair, int occ, int sms, int sk, int out_f32) {
   const long long mt = (M + (long long)BM * pair - 1) / ((long long)BM * pair);
   const long long nt = (N + bn - 1) / bn;
   const long long units = (long long)sms * occ / pair;
-  const long long rounds = (mt * nt + units - 1) / units;
-  double kblock = 415.0;                                   // issue + barrier handling floor of one k-block
-  if (2.0 * bn > kblock) kblock = 2.0 * bn;                // tensor pipe: 4 MMAs of BN/2 clk
-  const double pipe = occ * 4.0 * (bn / 2.0);
-  const double l2 = occ * (double)(A_STAGE_BYTES + (bn / pair) * BK * 2) / 80.0;
+  const long long tiles = mt * nt;
+  double kblock = 415.0;
+  if (2.0 * bn > kblock) kblock = 2.0 * bn;
+  const double ingress = occ * (double)(A_STAGE_BYTES + (bn / pair) * BK * 2) / 66.0;
+  const double pipe = occ * 2.0 * bn;
   if (pipe > kblock) kblock = pipe;
-  if (l2 > kblock) kblock = l2;
-  const double per_tile = num_kb * kblock + 400.0;
-  return rounds * per_tile + 8.0 * bn + 2500.0;          // + exposed last epilogue + launch
+  if (ingress > kblock) kblock = ingress;
+  const double fill = pair == 2 ? 4200.0 : 3200.0;
+  const double tail = (1500.0 + bn * (out_f32 ? 20.0 : 11.0)) * (pair == 2 ? 1.9 : 1.0);
+  double main_loop;
+  if (sk) {
+    const long long U = tiles * num_kb;
+    main_loop = (double)((U + units - 1) / units) * kblock + 1500.0;
+  } else {
+    main_loop = (double)((tiles + units - 1) / units) * (num_kb * kblock + 300.0);
+  }
+  return fill + main_loop + tail;
 }
 
 }  // namespace
@@ -794,9 +932,23 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
               "ln consumer must be a bf16-output GEMM with the column sums in col_scale");
     occ = 1;
   }
+  // Stream-K is OFF unless AVH_GEMM_SK=1 (forced where applicable) or AVH_GEMM_SK=2 (cost model decides).  Measured at
+  // M = 2400 (profiles/r2_gemm_streamk.txt): correct and bit-reproducible, but slower than whole tiles in rounds — qkv
+  // 22.6 vs 18.1 us, fc1 22.0 vs 20.6, fc2 24.8 vs 23.0 (BN 160) — although it removes the idle part of the last round:
+  // units at different k offsets no longer request the same A / B k-blocks at the same time, and the k-block time rises
+  // by more than the balance gains.  Kept for shapes with very few tiles per SM (fc2 at BN 256: 29.7 vs 32.0 us).
+  static int sk_env = -2;
+  if (sk_env == -2) { const char* ev = std::getenv("AVH_GEMM_SK"); sk_env = ev ? std::atoi(ev) : 0; }
+  if (sk_env == 2) sk_env = -1;      // -1 = model decides
+  // stream-K needs the TMA epilogue (tile rows = output rows), no LayerNorm folding and a workspace
+  const Epilogue& e0 = pr.ep;
+  const bool sk_possible = pr.sk_ws != nullptr && pr.sk_flags != nullptr && pr.streamk >= 0 && sk_env != 0 &&
+                           e0.ln_mode == 0 && e0.row_map == nullptr && e0.map_mode != MAP_2LEVEL && e0.row_zero == nullptr &&
+                           (e0.R == nullptr || (e0.R == e0.C && e0.slope2 == nullptr && e0.c_fp32));
+  int sk = 0;
   {
     double best = 1e30;
-    int best_bn = bn, best_occ = occ ? occ : 1;
+    int best_bn = bn, best_occ = occ ? occ : 1, best_sk = 0;
     const int step = pr.ep.c_fp32 ? 32 : 64;      // the TMA epilogue stores 128-byte boxes
     for (int oc = 1; oc <= 2; ++oc) {
       if (occ != 0 && oc != occ) continue;
@@ -804,17 +956,37 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
       for (int c = step; c <= 256 / oc; c += step) {
         if (bn != 0 && c != bn) continue;
         if (bn == 0 && c > ((pr.N + step - 1) / step) * step) break;
-        const double t = model_cycles(pr.M, pr.N, pr.num_kb, c, pair, oc, sms);
-        if (t < best) { best = t; best_bn = c; best_occ = oc; }
+        for (int k = 0; k <= 1; ++k) {
+          if (k == 1) {
+            if (!sk_possible || oc == 2 || (c % step) != 0 || pr.N % c != 0) continue;
+            const long long units = (long long)sms / pair;
+            const long long mt0 = (pr.M + (long long)BM * pair - 1) / ((long long)BM * pair);
+            const long long tiles0 = mt0 * (pr.N / c);
+            if (tiles0 % units == 0 || tiles0 * pr.num_kb < units) continue;          // nothing to balance
+            if ((size_t)units * pair * BM * c * 4 > pr.sk_ws_bytes) continue;
+          }
+          if (k == 0 && (pr.streamk == 1 || sk_env == 1) && sk_possible) {
+            // forced on: skip the persistent form when stream-K is applicable for this width
+            const long long units = (long long)sms / pair;
+            const long long mt0 = (pr.M + (long long)BM * pair - 1) / ((long long)BM * pair);
+            if (oc == 1 && pr.N % c == 0 && (mt0 * (pr.N / c)) % units != 0 && mt0 * (pr.N / c) * pr.num_kb >= units &&
+                (size_t)units * pair * BM * c * 4 <= pr.sk_ws_bytes)
+              continue;
+          }
+          const double t = model_cycles(pr.M, pr.N, pr.num_kb, c, pair, oc, sms, k, pr.ep.c_fp32);
+          if (t < best) { best = t; best_bn = c; best_occ = oc; best_sk = k; }
+        }
       }
     }
     if (bn == 0) bn = best_bn;
     occ = (bn <= 128) ? best_occ : 1;
-    if (bn == 0) { bn = 64; occ = 1; }
+    sk = best_sk;
+    if (bn == 0) { bn = 64; occ = 1; sk = 0; }
   }
   plan->prob.block_n = bn;
   plan->prob.pair = pair;
   plan->prob.occ = occ;
+  plan->sk = sk;
   if (encode_2d(&plan->tma_a, pr.A, pr.a_rows, pr.a_cols, pr.lda, BM)) return 1;
   if (encode_2d(&plan->tma_b, pr.B, pr.b_rows, pr.b_cols, pr.ldb, bn / pair)) return 1;
   // TMA epilogue whenever tile rows map 1:1 onto output rows (Linear layers, implicit 3x3 convs, stem): plain
@@ -836,6 +1008,7 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
     if (force < 0) { const char* ev = std::getenv("AVH_GEMM_CMODE"); force = ev ? std::atoi(ev) : 9; }
     if (force == 0 && e.ln_mode == 0) mode = 0;
     AVH_CHECK(e.ln_mode == 0 || mode == 1, "LayerNorm folding needs the TMA-store epilogue");
+    if (mode == 0) plan->sk = 0;
     plan->c_mode = mode;
     if (mode != 0) {
       if (encode_c(&plan->tma_c, e.C, pr.M, pr.N, e.ldc, e.c_fp32)) return 1;
@@ -849,7 +1022,7 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
   const long long nt = (pr.N + bn - 1) / bn;
   const long long tiles = mt * nt;
   const long long units = (long long)sms * occ / pair;
-  plan->grid = (int)(tiles < units ? tiles : units) * pair;
+  plan->grid = (int)((tiles < units && !plan->sk) ? tiles : units) * pair;
   const int stage_bytes = A_STAGE_BYTES + (bn / pair) * BK * 2;
   const int ktab_bytes = pr.ktable != nullptr ? ((pr.num_kb * 16 + 1023) / 1024) * 1024 : 0;
   const int smem_limit = occ == 2 ? Occ<2>::SMEM_LIMIT : Occ<1>::SMEM_LIMIT;
@@ -880,6 +1053,9 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   kp.a_col_nblk = pr.a_col_nblk;
   kp.ktable = reinterpret_cast<const int4*>(pr.ktable);
   kp.c_mode = plan.c_mode;
+  kp.sk = plan.sk;
+  kp.sk_ws = pr.sk_ws;
+  kp.sk_flags = pr.sk_flags;
 
   kp.trace = g_trace;
   static int lnf_dbg_env = -1;

@@ -270,3 +270,18 @@ def test_attention_tc_packed_ragged_batch_equals_dense():
     for b, n in enumerate(lens):
         assert torch.equal(o_p[r:r + n], o_d.view(B, T, D)[b, :n]), b
         r += n
+
+
+def test_gemm_stream_k_matches_reference_and_is_deterministic():
+    """Stream-K partition (equal k-block ranges per SM, partials added by the tile's owner in unit order) forced on for
+    the encoder shapes, single CTAs and CTA pairs: same tolerance as the persistent form, bit-identical reruns."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for sk in ("1", "0"):
+        env = dict(os.environ, AVH_GEMM_SK=sk)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm_sk_check.py")], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, (sk, r.stdout[-3000:], r.stderr[-2000:])
+        assert "FAIL" not in r.stdout

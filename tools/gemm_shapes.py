@@ -32,7 +32,7 @@ def main():
         ref = (A.float() @ Ws[0].float().t())
         for pair in (1, 2):
             for occ in (1, 2):
-                for bn in (96, 128, 160, 192, 208, 224, 256):
+                for bn in (128, 160, 192, 224, 256):
                     if (occ == 2 and (bn > 128 or pair == 2)) or (f32 and bn % 32) or (not f32 and bn % 64 and N > bn):
                         continue
 
@@ -62,7 +62,7 @@ def main():
                     nt = (N + bn - 1) // bn
                     ctas = mt * nt * pair
                     byt = ctas * (K // 64) * (16384 + (bn // pair) * 128)
-                    print(f"{name:9s} pair={pair} occ={occ} BN={bn:3d}: {us:6.2f} us  {2.0 * M * N * K / us / 1e6:6.0f} TFLOP/s  "
+                    print(f"{name:9s} sk={os.environ.get('AVH_GEMM_SK', '-')} pair={pair} occ={occ} BN={bn:3d}: {us:6.2f} us  {2.0 * M * N * K / us / 1e6:6.0f} TFLOP/s  "
                           f"ctas={ctas:3d} L2->SM {byt / 1e6:6.1f} MB = {byt / (us * 1e-6) / 1e12:5.2f} TB/s  err={err:.1e}",
                           flush=True)
 
