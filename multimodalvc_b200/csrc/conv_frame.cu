@@ -21,6 +21,7 @@
 #include "gemm.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <set>
 #include <vector>
@@ -75,7 +76,11 @@ __device__ __forceinline__ void decode_tile(int code, int& m_blk, int& oy, int& 
 }
 
 // MODE 0: BN only (downsample), 1: BN + PReLU (conv1), 2: BN + residual + PReLU (conv2)
-template <int OCC, int MODE>
+// PAIR 2: a cluster of two CTAs (the two SMs of a TPC) owns a 256-frame x BN tile and drives ONE
+// tcgen05.mma.cta_group::2 per K step: each CTA stages its own 128 frames of A and HALF of the weight tile, so an SM
+// pulls 16 KB + 64 BN B per k-block through its ~64 B/clk L2 ingress instead of 16 KB + 128 BN — the single-CTA tiles
+// of these layers are bound by that ingress (785 clk per k-block at BN 256 against 512 clk of tensor work).
+template <int OCC, int MODE, int PAIR>
 __global__ void __launch_bounds__(FOcc<OCC>::NUM_THREADS, OCC)
 conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
@@ -90,7 +95,7 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const int BN = p.block_n;
   const int STAGES = p.stages;
-  const int b_stage_bytes = BN * BK * 2;
+  const int b_stage_bytes = (BN / PAIR) * BK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* epi_stage = smem_b + STAGES * b_stage_bytes;
@@ -103,17 +108,20 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = PAIR == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / PAIR;
   pdl_launch_dependents();
 
-  // launch-constant data: per-channel vectors, this CTA's tile list bounds
+  // launch-constant data: per-channel vectors, this unit's tile list bounds
   for (int c = threadIdx.x; c < p.Cout; c += NUM_THREADS) {
     colvec[c] = __ldg(p.scale + c);
     colvec[MAX_COUT + c] = __ldg(p.bias + c);
     colvec[2 * MAX_COUT + c] = p.slope1 != nullptr ? __ldg(p.slope1 + c) : 1.f;
     colvec[3 * MAX_COUT + c] = p.slope2 != nullptr ? __ldg(p.slope2 + c) : 1.f;
   }
-  const int t_begin = __ldg(p.tiles + blockIdx.x);
-  const int t_end = __ldg(p.tiles + blockIdx.x + 1);
+  const int t_begin = __ldg(p.tiles + unit);
+  const int t_end = __ldg(p.tiles + unit + 1);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -127,13 +135,17 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], EPI_WARPS);
+      mbar_init(&tmem_empty[s], PAIR * EPI_WARPS);
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
@@ -142,11 +154,11 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+    const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
     for (int ti = t_begin; ti < t_end; ++ti) {
       int m_blk, oy, ox, nsub;
       decode_tile(__ldg(p.tiles + ti), m_blk, oy, ox, nsub);
-      const int m0 = m_blk * BM, n0 = nsub * BN;
+      const int m0 = (m_blk * PAIR + cta_rank) * BM, n0 = nsub * BN + cta_rank * (BN / PAIR);
       for (int kh = 0; kh < p.ks; ++kh) {
         const int iy = oy * p.stride + kh - p.pad;
         if (iy < 0 || iy >= p.Hin) continue;
@@ -158,9 +170,14 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           for (int kc = 0; kc < p.chunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[stage], stage_tx);
-              tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], a_col + kc * BK, m0);
-              tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], b_col + kc * BK, n0);
+              if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+              if (PAIR == 2) {
+                tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], a_col + kc * BK, m0);
+                tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], b_col + kc * BK, n0);
+              } else {
+                tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], a_col + kc * BK, m0);
+                tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], b_col + kc * BK, n0);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -170,18 +187,23 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       for (int kc = 0; kc < p.ds_chunks; ++kc) {          // fused shortcut: centre pixel of the block's input
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], stage_tx);
-          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a2, &full_bar[stage],
-                      ((oy * p.ds_stride) * p.ds_Sin + ox * p.ds_stride) * p.ds_Cin + kc * BK, m0);
-          tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], p.ds_bcol + kc * BK, n0);
+          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+          const int a2_col = ((oy * p.ds_stride) * p.ds_Sin + ox * p.ds_stride) * p.ds_Cin + kc * BK;
+          if (PAIR == 2) {
+            tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a2, &full_bar[stage], a2_col, m0);
+            tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], p.ds_bcol + kc * BK, n0);
+          } else {
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a2, &full_bar[stage], a2_col, m0);
+            tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], p.ds_bcol + kc * BK, n0);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(BM, BN);
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+    const uint32_t idesc = umma_idesc_bf16(BM * PAIR, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -207,13 +229,20 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < BK / 16; ++k) {
+            if (PAIR == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if (PAIR == 2) umma_commit_pair(&empty_bar[stage]);      // smem slot reusable in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (elect_one()) {
+        if (PAIR == 2) umma_commit_pair(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
+      }
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -228,7 +257,7 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       decode_tile(__ldg(p.tiles + ti), m_blk, oy, ox, nsub);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row0 = m_blk * BM + q * 32;
+      const int row0 = (m_blk * PAIR + cta_rank) * BM + q * 32;
       const long long r = (long long)row0 + lane;
       const bool live = r < p.frames;
       const int ch0 = nsub * BN;                                   // first output channel of the tile
@@ -302,7 +331,10 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           // last TMEM read of this accumulator stage by this warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         } else if (MODE == 2 && live) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.R + r * p.ldr + ccol0 + (bx + HSTRIDE) * 64);
 #pragma unroll
@@ -324,23 +356,31 @@ conv_frame_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (half >= nboxes) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (PAIR == 2) mbar_arrive_leader(&tmem_empty[acc]);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       }
     }
     if (lane == 0) tma_wait_group0();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 typedef void (*FrameKernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FrameParams);
 
-FrameKernelFn pick_kernel(int occ, int mode) {
-  if (occ == 2) return mode == 0 ? conv_frame_kernel<2, 0> : mode == 1 ? conv_frame_kernel<2, 1> : conv_frame_kernel<2, 2>;
-  return mode == 0 ? conv_frame_kernel<1, 0> : mode == 1 ? conv_frame_kernel<1, 1> : conv_frame_kernel<1, 2>;
+FrameKernelFn pick_kernel(int occ, int mode, int pair) {
+  if (pair == 2) return mode == 0 ? conv_frame_kernel<1, 0, 2> : mode == 1 ? conv_frame_kernel<1, 1, 2> : conv_frame_kernel<1, 2, 2>;
+  if (occ == 2) return mode == 0 ? conv_frame_kernel<2, 0, 1> : mode == 1 ? conv_frame_kernel<2, 1, 1> : conv_frame_kernel<2, 2, 1>;
+  return mode == 0 ? conv_frame_kernel<1, 0, 1> : mode == 1 ? conv_frame_kernel<1, 1, 1> : conv_frame_kernel<1, 2, 1>;
 }
 
 int valid_taps(int o, int stride, int pad, int ks, int Hin) {
@@ -365,11 +405,20 @@ int conv_frame_plan(const ConvFrameProblem& pr, ConvFramePlan* plan) {
   const int pad = pr.ks == 3 ? 1 : 0;
   int bn = pr.block_n, occ = pr.occ;
   if (bn == 0) bn = pr.Cout >= 256 ? 256 : pr.Cout;
+  // CTA pairs (cta_group::2) for the 256-wide tiles of layers 3-4; AVH_FRAME_PAIR=1 selects single-CTA tiles everywhere,
+  // =2 pairs wherever the tile allows.  Measured per step (2400 frames): 256-channel 3x3 convs 0.204 vs 0.232 ms,
+  // 512-channel 0.175 vs 0.179, but the 128-channel layer (BN 128) 0.300 vs 0.284 ms against two single CTAs per SM.
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* ev = std::getenv("AVH_FRAME_PAIR"); pair_env = ev != nullptr ? std::atoi(ev) : 0; }
+  int pair = pr.pair != 0 ? pr.pair : (pair_env == 1 ? 1 : (pair_env == 2 ? 2 : (bn == 256 ? 2 : 1)));
+  if (device_sm_count() < 2 || bn % 128 != 0) pair = 1;        // each CTA of a pair stages bn / 2 weight rows (64-row boxes)
+  if (pair == 2) occ = 1;
   if (occ == 0) occ = bn <= 128 ? 2 : 1;
   AVH_CHECK(bn % 64 == 0 && bn <= 256 && pr.Cout % bn == 0 && (occ == 1 || (occ == 2 && bn <= 128)), "bad tile shape");
   plan->prob.block_n = bn;
   plan->prob.occ = occ;
-  const int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  plan->pair = pair;
+  const int stage_bytes = A_STAGE_BYTES + (bn / pair) * BK * 2;
   const int smem_limit = occ == 2 ? FOcc<2>::SMEM_LIMIT : FOcc<1>::SMEM_LIMIT;
   const int epi_bytes = occ == 2 ? FOcc<2>::EPI_STAGE_BYTES : FOcc<1>::EPI_STAGE_BYTES;
   int stages = (smem_limit - 1024 - epi_bytes - COLVEC_BYTES - BAR_BYTES) / stage_bytes;
@@ -381,7 +430,7 @@ int conv_frame_plan(const ConvFrameProblem& pr, ConvFramePlan* plan) {
   AVH_CHECK(a_cols < (1ll << 31) && c_cols < (1ll << 31), "frame rows too wide");
   if (encode_2d(&plan->tma_a, pr.A, pr.frames, (int)a_cols, a_cols, BM)) return 1;
   const int b_cols = pr.ks * pr.ks * pr.Cin + (pr.A2 != nullptr ? pr.ds_Cin : 0);
-  if (encode_2d(&plan->tma_b, pr.B, pr.Cout, b_cols, b_cols, bn)) return 1;
+  if (encode_2d(&plan->tma_b, pr.B, pr.Cout, b_cols, b_cols, bn / pair)) return 1;
   plan->tma_a2 = plan->tma_a;
   if (pr.A2 != nullptr) {
     AVH_CHECK(pr.ds_Cin % 64 == 0 && pr.ds_stride >= 1 && pr.ds_Sin >= 1, "bad shortcut geometry");
@@ -393,14 +442,14 @@ int conv_frame_plan(const ConvFrameProblem& pr, ConvFramePlan* plan) {
 
   // ---- tile lists: longest-processing-time greedy over groups of frame blocks
   const int sms = device_sm_count();
-  const int num_m = (int)((pr.frames + BM - 1) / BM);
+  const int num_m = (int)((pr.frames + (long long)BM * pair - 1) / ((long long)BM * pair));   // frame blocks of a unit
   const int nsub = pr.Cout / bn;
   const int chunks = pr.Cin / 64;
   const long long tiles_total = (long long)num_m * pr.Hout * pr.Hout * nsub;
-  const int grid = (int)std::min<long long>(tiles_total, (long long)sms * occ);
+  const int grid = (int)std::min<long long>(tiles_total, (long long)sms * occ / pair);        // work units (CTAs or pairs)
   const double kblock = std::max(415.0, 2.0 * bn * occ);      // clk per k-block (gemm_tcgen05.cu model_cycles)
   const size_t in_frame_bytes = (size_t)a_cols * 2;
-  int group = (int)std::max<size_t>(1, (size_t)(24u << 20) / (in_frame_bytes * BM));
+  int group = (int)std::max<size_t>(1, (size_t)(24u << 20) / (in_frame_bytes * BM * pair));
   struct T { int code; double cost; };
   std::vector<std::vector<int>> lists(grid);
   std::vector<double> load(grid, 0.0);
@@ -431,7 +480,7 @@ int conv_frame_plan(const ConvFrameProblem& pr, ConvFramePlan* plan) {
   }
   table[grid] = off;
   for (int c = 0; c < grid; ++c) table.insert(table.end(), lists[c].begin(), lists[c].end());
-  plan->grid = grid;
+  plan->grid = grid * pair;
   plan->tiles_host = table;
   return 0;
 }
@@ -467,10 +516,24 @@ int conv_frame_launch(const ConvFramePlan& plan, cudaStream_t stream) {
   p.R = reinterpret_cast<const __nv_bfloat16*>(pr.R);
   const int occ = pr.occ == 2 ? 2 : 1;
   const int mode = pr.R != nullptr ? 2 : (pr.slope1 != nullptr ? 1 : 0);
-  FrameKernelFn fn = pick_kernel(occ, mode);
+  FrameKernelFn fn = pick_kernel(occ, mode, plan.pair);
   if (ensure_dyn_smem(reinterpret_cast<const void*>(fn), occ == 2 ? FOcc<2>::SMEM_LIMIT : FOcc<1>::SMEM_LIMIT)) return 1;
   const int threads = occ == 2 ? FOcc<2>::NUM_THREADS : FOcc<1>::NUM_THREADS;
-  AVH_CUDA_OK(launch_pdl(fn, dim3(plan.grid), dim3(threads), plan.smem, stream, plan.tma_a, plan.tma_b, plan.tma_c, plan.tma_a2, p));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)plan.pair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  AVH_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, plan.tma_a, plan.tma_b, plan.tma_c, plan.tma_a2, p));
   count_launch(1);
   return 0;
 }

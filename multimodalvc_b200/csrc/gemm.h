@@ -143,11 +143,12 @@ struct ConvFrameProblem {
   const void* A2 = nullptr;
   int ds_Cin = 0, ds_Sin = 0, ds_Pin = 0, ds_stride = 1;
   int block_n = 0, occ = 0;       // 0 = chosen by conv_frame_plan
+  int pair = 0;                   // 0 = default (CTA pairs where the tile allows), 1 = single CTAs, 2 = pairs
 };
 struct ConvFramePlan {
   CUtensorMap tma_a, tma_b, tma_c, tma_a2;
   ConvFrameProblem prob;
-  int grid = 0, stages = 0;
+  int grid = 0, stages = 0, pair = 1;
   size_t smem = 0;
   std::vector<int> tiles_host;    // [grid+1] offsets + per-CTA tile lists
   const int* tiles_dev = nullptr;
