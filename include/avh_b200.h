@@ -70,7 +70,8 @@ typedef struct avh_config {
   int32_t compute_mode;            /* AVH_COMPUTE_* */
   int32_t frontend_chunk_frames;   /* video frames per lip-frontend pass; 0 = default */
   int32_t capture_stages;          /* non-zero: keep copies of intermediate stages for avh_read_stage (tests) */
-  int32_t reserved[4];
+  int32_t reserved[4];             /* reserved[0] != 0: the handle holds a bare fairseq TransformerEncoder (state-dict keys
+                                      "encoder.*" only; avh_encoder_forward is its one forward entry point) */
 } avh_config;
 
 typedef struct avh_handle avh_handle;
@@ -108,6 +109,14 @@ AVH_API int avh_release_stream(avh_handle* h, void* stream);
 AVH_API int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
                 const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
                 void* out, int out_dtype, void* stream);
+
+/* fairseq TransformerEncoder.forward(x, padding_mask, layer) (fairseq/fairseq/models/wav2vec/wav2vec2.py:859-902) on
+ * caller-provided features x [B,T,D] (device, AVH_F32/F16/BF16): padded frames zeroed, positional conv + GELU, the
+ * layers, final LayerNorm when pre-LN and output_layer == 0; out [B,T,D].  Works on any finalised handle (it uses the
+ * "encoder.*" weights); a handle created with reserved[0] != 0 needs no other weights — the encoder of
+ * src/sub_model/modules.py:108-142 (Speech_Rate_Predictor, d = 256) is served this way. */
+AVH_API int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T,
+                                int output_layer, void* out, int out_dtype, void* stream);
 
 /* extract_finetune for RAGGED batches without computing on pad frames (BASELINE config 3): same
  * padded tensors as avh_forward (video [B,1,T,88,88] or raw uint8, audio [B,F,T] + strides, out [B,T,D]) plus the HOST

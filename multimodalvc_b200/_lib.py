@@ -18,7 +18,7 @@ EXPORTS = [
     "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
     "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess", "avh_drop_host_weights",
-    "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged",
+    "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward",
 ]
 
 
@@ -65,6 +65,7 @@ def load():
     lib.avh_forward.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_ragged.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32), i32, i32, i32, vp,
                                        i32, vp]
+    lib.avh_encoder_forward.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host_async.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_read_stage.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]

@@ -165,11 +165,13 @@ struct CallArgs {          // per-call pointers the steps read through the plan
   const unsigned char* mask = nullptr;
   void* out = nullptr;
   int out_dt = 0;
+  const void* xin = nullptr; // encoder-only plans: features [B,T,D]
+  int xin_dt = 0;
   int pitch = 0;             // ragged plans: time pitch of the caller's padded tensors (baked into captured launches)
   // graph-cache key: the INPUT pointers (the output is written by the last step, which stays outside the graph)
   bool operator<(const CallArgs& o) const {
-    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask, pitch) <
-           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask, o.pitch);
+    return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask, pitch, xin, xin_dt) <
+           std::tie(o.video, o.video_dt, o.audio, o.audio_dt, o.as[0], o.as[1], o.as[2], o.mask, o.pitch, o.xin, o.xin_dt);
   }
 };
 
@@ -180,6 +182,7 @@ struct Plan {
   // frame rows with the clips back to back; T is then the longest clip the plan serves (attention tiling).  The
   // per-call geometry lives in a small device descriptor `rag` (int32): [0] stem work items, [1] rows in use,
   // [16..16+B] first row of every clip (cu), then the stem's (clip, band, t0, t1) item list.
+  bool enc_only = false;           // avh_encoder_forward: TransformerEncoder on caller-provided features [B,T,D]
   bool ragged = false;
   long long Nb = 0;
   int* rag = nullptr;
@@ -401,8 +404,9 @@ bool pack_all(Packer& pk) {
   const int D = c.encoder_embed_dim;
   const std::string R = "feature_extractor_video.resnet.";
   bool ok = true;
+  const bool enc_only = c.reserved[0] != 0;      // handle of a bare TransformerEncoder (avh_encoder_forward only)
   // ---- stem: Conv3d weight [64,1,5,7,7] -> [64, 5*64]
-  {
+  if (!enc_only) {
     const HostTensor* w = pk.get(R + "frontend3D.0.weight");
     const HostTensor* g = pk.get(R + "frontend3D.1.weight");
     const HostTensor* b = pk.get(R + "frontend3D.1.bias");
@@ -436,7 +440,7 @@ bool pack_all(Packer& pk) {
     } else ok = false;
   }
   // ---- ResNet-18 trunk (avhubert/resnet.py:77-129)
-  for (int L = 0; L < 4; ++L)
+  for (int L = 0; L < (enc_only ? 0 : 4); ++L)
     for (int bi = 0; bi < 2; ++bi) {
       BlockW& bw = h->blocks[L][bi];
       const std::string pre = R + "trunk.layer" + std::to_string(L + 1) + "." + std::to_string(bi) + ".";
@@ -488,14 +492,14 @@ bool pack_all(Packer& pk) {
       } else ok = false;
     }
   // ---- modality projections, fusion LN, post_extract_proj
-  ok &= pack_linear(pk, "feature_extractor_video.proj", &h->proj_v);
-  ok &= pack_linear(pk, "feature_extractor_audio.proj", &h->proj_a);
-  {
+  if (!enc_only) {
+    ok &= pack_linear(pk, "feature_extractor_video.proj", &h->proj_v);
+    ok &= pack_linear(pk, "feature_extractor_audio.proj", &h->proj_a);
     const HostTensor* g = pk.get("layer_norm.weight");
     const HostTensor* b = pk.get("layer_norm.bias");
     if (g && b) { h->fuse_ln_g = pk.upload_f(g->v); h->fuse_ln_b = pk.upload_f(b->v); } else ok = false;
   }
-  h->has_post_proj = (c.modality_fuse == AVH_FUSE_CONCAT);
+  h->has_post_proj = !enc_only && (c.modality_fuse == AVH_FUSE_CONCAT);
   if (h->has_post_proj) ok &= pack_linear(pk, "post_extract_proj", &h->post_proj);
   // ---- positional conv: weight-norm(dim=2) fold, grouped -> per-N-tile windowed dense K-major
   {
@@ -1022,8 +1026,16 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 
   // ========================================================================== fusion LN + post_extract_proj
   float* x = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));      // residual stream, fp32
-  Act lnE = new_act(N, E);
-  {
+  if (plan->enc_only) {
+    // TransformerEncoder.forward on the caller's features: x = features with padded frames zeroed (wav2vec2.py:869-870)
+    const bool hm0 = plan->has_mask;
+    b.tag = "load_features";
+    b.push([=](cudaStream_t s) {
+      return launch_load_rows(pl->args.xin, pl->args.xin_dt, x, hm0 ? pl->args.mask : nullptr, N, D, s);
+    });
+  }
+  Act lnE = plan->enc_only ? Act() : new_act(N, E);
+  if (!plan->enc_only) {
     const void* src = fused.data;
     float* of = f32 ? reinterpret_cast<float*>(lnE.data) : nullptr;
     void* ol = f32 ? nullptr : lnE.data;
@@ -1259,8 +1271,8 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 // One plan (= workspace + launch list) per shape AND per CUDA stream: forwards enqueued on different streams
 // never share scratch memory, so a caller can keep several batches in flight on one device.
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
-               cudaStream_t stream, long long ragged_rows = 0) {
-  const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) +
+               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false) {
+  const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) + (enc_only ? "e:" : "") +
                           std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
@@ -1287,6 +1299,7 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
   p->output_layer = output_layer;
   p->ragged = ragged_rows > 0;
   p->Nb = ragged_rows;
+  p->enc_only = enc_only;
   size_t bytes = 0;
   if (!build_plan(h, p.get(), true, &bytes)) return nullptr;
   if (p->arena.init(bytes + (1 << 20))) return nullptr;
@@ -1346,7 +1359,7 @@ int avh_create(const avh_config* cfg, int device, avh_handle** out) {
   AVH_CHECK(cfg->encoder_attention_heads * 64 == cfg->encoder_embed_dim, "head dim must be 64");
   AVH_CHECK(cfg->conv_pos >= 2 && cfg->conv_pos % 2 == 0 && cfg->conv_pos <= 128, "conv_pos must be even and <= 128");
   AVH_CHECK(cfg->conv_pos_groups >= 1 && cfg->encoder_embed_dim % cfg->conv_pos_groups == 0, "bad conv_pos_groups");
-  AVH_CHECK(cfg->audio_feat_dim >= 1 && cfg->audio_feat_dim <= 1024, "bad audio_feat_dim");
+  AVH_CHECK(cfg->reserved[0] != 0 || (cfg->audio_feat_dim >= 1 && cfg->audio_feat_dim <= 1024), "bad audio_feat_dim");
   AVH_CHECK(cfg->modality_fuse == AVH_FUSE_CONCAT || cfg->modality_fuse == AVH_FUSE_ADD, "bad modality_fuse");
   AVH_CHECK(cfg->compute_mode == AVH_COMPUTE_BF16 || cfg->compute_mode == AVH_COMPUTE_FP32, "bad compute_mode");
   int ndev = 0;
@@ -1535,6 +1548,7 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
                 void* out, int out_dtype, void* stream) {
   AVH_CHECK(h != nullptr, "null handle");
   AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(h->cfg.reserved[0] == 0, "this handle holds a bare TransformerEncoder: use avh_encoder_forward");
   AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
   AVH_CHECK(B >= 1 && T >= 1, "empty batch");
   AVH_CHECK((long long)B * T < (1ll << 24), "batch too large");
@@ -1568,12 +1582,33 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   return run_plan(h, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T,
+                        int output_layer, void* out, int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(x != nullptr && out != nullptr, "null argument");
+  AVH_CHECK(x_dtype == AVH_F32 || x_dtype == AVH_F16 || x_dtype == AVH_BF16, "bad feature dtype");
+  AVH_CHECK(B >= 1 && T >= 1 && (long long)B * T < (1ll << 24), "bad batch");
+  AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  avh::Plan* p = avh::get_plan(h, B, T, false, false, padding_mask != nullptr, output_layer, s, 0, true);
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  p->args = avh::CallArgs();
+  p->args.xin = x; p->args.xin_dt = x_dtype;
+  p->args.mask = padding_mask;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  return run_plan(h, p, s);
+}
+
 int avh_forward_ragged(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
                        const int64_t* audio_strides, const int32_t* lengths, int B, int T, int output_layer, void* out,
                        int out_dtype, void* stream) {
   AVH_CHECK(h != nullptr, "null handle");
   AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
   AVH_CHECK(h->cfg.compute_mode == AVH_COMPUTE_BF16, "packed ragged batches run in bf16 mode only (use avh_forward)");
+  AVH_CHECK(h->cfg.reserved[0] == 0, "this handle holds a bare TransformerEncoder: use avh_encoder_forward");
   AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
   AVH_CHECK(lengths != nullptr && out != nullptr, "null argument");
   AVH_CHECK(B >= 1 && T >= 1 && B <= 4096, "bad batch");

@@ -488,9 +488,30 @@ __global__ void unpack_rows_kernel(const float* __restrict__ in, const int* __re
   }
 }
 
+// [rows, cols] of any float dtype -> fp32 residual stream, rows flagged in row_zero written as zeros
+__global__ void load_rows_kernel(const void* __restrict__ in, int in_dt, float* __restrict__ out,
+                                 const unsigned char* __restrict__ row_zero, long long rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  out[i] = (row_zero != nullptr && row_zero[r]) ? 0.f : load_any(in, in_dt, i);
+}
+
 inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
 
 }  // namespace
+
+int launch_load_rows(const void* in, int in_dt, float* out, const unsigned char* row_zero, long long rows, int cols,
+                     cudaStream_t stream) {
+  const long long n = rows * cols;
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(load_rows_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, in, in_dt, out, row_zero, rows, cols));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
 
 int launch_bct_to_rows_ragged(const void* in, int in_dt, long long sb, long long sc, long long st, int B, int C,
                               const int* cu, void* out, int out_dt, long long ldo, long long rows_cap, cudaStream_t stream) {

@@ -30,6 +30,9 @@ int launch_pos_pad_ragged(const float* in, long long ld, void* out, int* row_map
                           long long rows_pad, cudaStream_t stream);
 int launch_unpack_rows(const float* in, const int* cu, void* out, int out_dt, int B, int T, int cols, cudaStream_t stream);
 
+// [rows, cols] (fp32 / fp16 / bf16) -> fp32, rows flagged in row_zero (may be null) zeroed: index_put(x, padding_mask, 0)
+int launch_load_rows(const void* in, int in_dt, float* out, const unsigned char* row_zero, long long rows, int cols,
+                     cudaStream_t stream);
 // flat element-wise dtype conversion
 int launch_convert(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t stream);
 

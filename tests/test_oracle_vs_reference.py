@@ -1,6 +1,8 @@
 """Pins oracle/avhubert_oracle.py: (a) against the golden outputs the REAL reference produced
 (tests/golden/enc_*.npz, made by oracle/make_golden.py) — runs anywhere; (b) live against the real reference
 modules when /root/reference is present (this container only)."""
+import os
+
 import pytest
 import torch
 
@@ -47,3 +49,26 @@ def test_zero_padded_inputs_make_valid_positions_independent_of_padding():
         y_pad, _ = o.extract_finetune(src, pm)
         y_short, _ = o.extract_finetune(short, None)
     assert (y_pad[:, :8] - y_short).abs().max().item() < 1e-4
+
+
+def test_sr_predictor_oracle_matches_golden_of_the_real_class(golden_dir):
+    """oracle/sr_oracle.py vs the output of the REAL Speech_Rate_Predictor (tests/golden/sr_predictor.npz, made by
+    oracle/make_golden_sr.py) — and live against the reference class when /root/reference is present."""
+    import numpy as np
+    import torch
+    from oracle import sr_oracle
+    z = np.load(os.path.join(golden_dir, "sr_predictor.npz"))
+    layers, seed, B, T, xs = [int(v) for v in z["meta"]]
+    oracle = sr_oracle.build(layers, seed=seed)
+    x = sr_oracle.synthetic_features(B, T, seed=xs)
+    with torch.no_grad():
+        y = oracle(x)
+    assert y.shape == (B, 1) and (y > 0).all()
+    assert np.abs(y.numpy() - z["y"]).max() < 1e-5
+    from oracle import ref_import
+    if ref_import.available():
+        from oracle import make_golden_sr
+        ref = make_golden_sr.real_class()(layers).eval()
+        ref.load_state_dict(oracle.state_dict(), strict=True)
+        with torch.no_grad():
+            assert (ref(x) - y).abs().max() < 1e-5
