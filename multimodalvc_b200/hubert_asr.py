@@ -99,33 +99,48 @@ def _linear(in_features, out_features):
 
 
 def _packed_head(lin, device):
-    """bf16 weight [Np, D] / fp32 bias [Np] of a projection head, columns padded to a multiple of 32, cached on the
-    module until its parameters change (version counters) or move."""
+    """bf16 weight planes [Np, D] (hi, mid = bf16 of the rounding residual) / fp32 bias [Np] of a projection head,
+    columns padded to a multiple of 32, cached on the module until its parameters change (version counters) or move."""
     key = (lin.weight._version, lin.bias._version, lin.weight.data_ptr(), str(device))
     cache = getattr(lin, "_avh_packed", None)
     if cache is None or cache[0] != key:
         N, D = lin.out_features, lin.in_features
         Np = (N + 31) // 32 * 32
-        w = torch.zeros(Np, D, device=device, dtype=torch.bfloat16)
-        w[:N] = lin.weight.detach().to(device=device, dtype=torch.bfloat16)
+        wf = torch.zeros(Np, D, device=device, dtype=torch.float32)
+        wf[:N] = lin.weight.detach().to(device=device, dtype=torch.float32)
+        hi = wf.to(torch.bfloat16)
+        mid = (wf - hi.float()).to(torch.bfloat16)
         bias = torch.zeros(Np, device=device, dtype=torch.float32)
         bias[:N] = lin.bias.detach().to(device=device, dtype=torch.float32)
-        cache = (key, w, bias)
+        cache = (key, hi, mid, bias)
         lin._avh_packed = cache
-    return cache[1], cache[2]
+    return cache[1], cache[2], cache[3]
 
 
 def _project(x, lin):
-    """[B,T,D] @ W^T + b through avh_gemm_bf16 (output columns padded to a multiple of 32 in the cached copy)."""
+    """[B,T,D] @ W^T + b on the library's tcgen05 GEMM (avh_gemm_bf16).  Half / bf16 modules: one bf16 product.  fp32
+    modules: the split-precision form of the library's fp32 mode — operands as bf16 hi + mid planes, three products
+    (mid*hi, hi*mid, hi*hi) chained through the fp32 residual input, ~2^-16 relative error per product."""
     B, T, D = x.shape
     N = lin.out_features
-    w, bias = _packed_head(lin, x.device)
-    Np = w.size(0)
-    a = x.reshape(B * T, D).to(torch.bfloat16).contiguous()
+    w_hi, w_mid, bias = _packed_head(lin, x.device)
+    Np = w_hi.size(0)
+    xf = x.reshape(B * T, D)
+    a_hi = xf.to(torch.bfloat16).contiguous()
     out = torch.empty(B * T, Np, device=x.device, dtype=torch.float32)
     vp = ctypes.c_void_p
+    lib = _lib.load()
     with torch.cuda.device(x.device):
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        _lib.check(_lib.load().avh_gemm_bf16(vp(a.data_ptr()), vp(w.data_ptr()), B * T, Np, D, vp(bias.data_ptr()), 0,
-                                             None, 0, vp(out.data_ptr()), 1, 0, 0, 0, vp(stream)))
+        stream = vp(torch.cuda.current_stream(x.device).cuda_stream)
+
+        def gemm(a, w, b, res):
+            _lib.check(lib.avh_gemm_bf16(vp(a.data_ptr()), vp(w.data_ptr()), B * T, Np, D, vp(b.data_ptr()) if b is not None else None,
+                                         0, vp(out.data_ptr()) if res else None, 1, vp(out.data_ptr()), 1, 0, 0, 0, stream))
+        if x.dtype == torch.float32:
+            a_mid = (xf.float() - a_hi.float()).to(torch.bfloat16).contiguous()
+            gemm(a_mid, w_hi, None, False)
+            gemm(a_hi, w_mid, None, True)
+            gemm(a_hi, w_hi, bias, True)
+        else:
+            gemm(a_hi, w_hi, bias, False)
     return out[:, :N].to(x.dtype).view(B, T, N)
