@@ -110,6 +110,32 @@ AVH_API int avh_forward(avh_handle* h, const void* video, int video_dtype, const
                 const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
                 void* out, int out_dtype, void* stream);
 
+/* extract_finetune with the module in TRAINING mode and no gradient — what MMS-LLaMA's frozen encoder executes during
+ * training (src/model.py:96-100,280: requires_grad False + no_grad, but the module follows model.train()):
+ *   BatchNorm2d/3d normalise with BATCH statistics and update running_mean / running_var (avhubert/resnet.py:23,44,56,139);
+ *   nn.Dropout at hubert.py:729 (dropout_input), wav2vec2.py:879 (dropout), :980,:990 (dropout1 / dropout3 = dropout),
+ *   :987 (dropout2 = activation_dropout) — Philox masks of this library's own stream (seed per call);
+ *   LayerDrop (wav2vec2.py:887-888): the caller draws the coins and passes layer_skip (HOST, one byte per layer).
+ * GradMultiply (fairseq/fairseq/modules/grad_multiply.py) is the identity in a forward.  attention_dropout must be 0.
+ * Same tensors as avh_forward (float video only).  The updated running statistics are read with avh_read_bn_stats:
+ * flat fp32, per BatchNorm (running_mean[C], running_var[C]) in the order frontend3D.1, then for layer1..4, block 0..1:
+ * bn1, bn2, downsample.1 (when present).  Eval-mode forwards keep using the statistics folded at the last
+ * avh_finalize_weights until the caller re-loads them. */
+typedef struct avh_train_args {
+  float dropout_input, dropout, activation_dropout, attention_dropout;
+  float bn_momentum;               /* nn.BatchNorm default 0.1 */
+  uint64_t seed;                   /* dropout stream of this call */
+  const uint8_t* layer_skip;       /* HOST [encoder_layers], non-zero = layer dropped; NULL = keep all */
+} avh_train_args;
+AVH_API int avh_forward_train(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                              const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
+                              const avh_train_args* args, void* out, int out_dtype, void* stream);
+/* Kernel-level entry point of the dropout used above (tests): x[i] = keep(i) ? x[i] / (1 - p) : 0 in place, keep(i) a
+ * pure function of (seed, site, i) through Philox4x32-10 — nn.Dropout semantics, this library's own random stream. */
+AVH_API int avh_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
+AVH_API int avh_bn_stats_count(avh_handle* h, int64_t* n_floats);
+AVH_API int avh_read_bn_stats(avh_handle* h, float* dst, int64_t capacity, void* stream);
+
 /* fairseq TransformerEncoder.forward(x, padding_mask, layer) (fairseq/fairseq/models/wav2vec/wav2vec2.py:859-902) on
  * caller-provided features x [B,T,D] (device, AVH_F32/F16/BF16): padded frames zeroed, positional conv + GELU, the
  * layers, final LayerNorm when pre-LN and output_layer == 0; out [B,T,D].  Works on any finalised handle (it uses the

@@ -18,7 +18,7 @@ EXPORTS = [
     "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
     "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess", "avh_drop_host_weights",
-    "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward",
+    "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward", "avh_forward_train", "avh_bn_stats_count", "avh_read_bn_stats", "avh_dropout",
 ]
 
 
@@ -37,6 +37,18 @@ class AvhConfig(ctypes.Structure):
         ("frontend_chunk_frames", ctypes.c_int32),
         ("capture_stages", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
+class AvhTrainArgs(ctypes.Structure):
+    _fields_ = [
+        ("dropout_input", ctypes.c_float),
+        ("dropout", ctypes.c_float),
+        ("activation_dropout", ctypes.c_float),
+        ("attention_dropout", ctypes.c_float),
+        ("bn_momentum", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+        ("layer_skip", ctypes.c_void_p),
     ]
 
 
@@ -65,6 +77,11 @@ def load():
     lib.avh_forward.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_ragged.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32), i32, i32, i32, vp,
                                        i32, vp]
+    lib.avh_forward_train.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, i32, ctypes.POINTER(AvhTrainArgs),
+                                      vp, i32, vp]
+    lib.avh_dropout.argtypes = [vp, i32, i64, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32, vp]
+    lib.avh_bn_stats_count.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.avh_read_bn_stats.argtypes = [vp, vp, i64, vp]
     lib.avh_encoder_forward.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.avh_forward_host_async.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]

@@ -125,6 +125,8 @@ struct ConvUnit {         // conv + folded eval-mode BatchNorm (+ PReLU)
   float* scale = nullptr;
   float* bias = nullptr;
   float* slope = nullptr;
+  // training-mode BatchNorm: affine parameters and the running statistics the batch statistics update (device, fp32)
+  float *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;
   int cin = 0, cout = 0, ks = 3, stride = 1;
 };
 struct BlockW {
@@ -154,6 +156,7 @@ struct Step {
   std::function<int(cudaStream_t)> run;
   std::string name;       // kernel class for avh_profile_json
   double flops = 0;       // executed tensor-core FLOPs (GEMM steps)
+  int layer = -1;         // encoder layer the step belongs to (LayerDrop skips it in training mode), -1 = none
 };
 
 struct CallArgs {          // per-call pointers the steps read through the plan
@@ -182,6 +185,12 @@ struct Plan {
   // frame rows with the clips back to back; T is then the longest clip the plan serves (attention tiling).  The
   // per-call geometry lives in a small device descriptor `rag` (int32): [0] stem work items, [1] rows in use,
   // [16..16+B] first row of every clip (cu), then the stem's (clip, band, t0, t1) item list.
+  // training-mode forward (avh_forward_train): BatchNorm batch statistics through the generic convolution path,
+  // Philox dropout at the reference's dropout sites, LayerDrop by skipping a layer's launches; never graph-captured
+  bool train = false;
+  float p_in = 0.f, p_enc = 0.f, p_act = 0.f, bn_momentum = 0.1f;     // set per call
+  unsigned long long seed = 0;
+  std::vector<unsigned char> layer_skip;
   bool enc_only = false;           // avh_encoder_forward: TransformerEncoder on caller-provided features [B,T,D]
   bool ragged = false;
   long long Nb = 0;
@@ -354,6 +363,8 @@ bool pack_conv(Packer& pk, const std::string& wkey, const std::string& bnkey, co
   }
   cu->scale = pk.upload_f(sc);
   cu->bias = pk.upload_f(bi);
+  cu->gamma = pk.upload_f(g->v); cu->beta = pk.upload_f(b->v);
+  cu->rmean = pk.upload_f(m->v); cu->rvar = pk.upload_f(v->v);
   cu->slope = nullptr;
   if (s) {
     std::vector<float> sl(cout);
@@ -437,6 +448,8 @@ bool pack_all(Packer& pk) {
       h->stem.scale = pk.upload_f(sc);
       h->stem.bias = pk.upload_f(bi);
       h->stem.slope = pk.upload_f(sl);
+      h->stem.gamma = pk.upload_f(g->v); h->stem.beta = pk.upload_f(b->v);
+      h->stem.rmean = pk.upload_f(m->v); h->stem.rvar = pk.upload_f(v->v);
     } else ok = false;
   }
   // ---- ResNet-18 trunk (avhubert/resnet.py:77-129)
@@ -616,8 +629,9 @@ struct Builder {
     return plan->arena.take(bytes);
   }
   std::string tag = "misc";     // name given to the steps pushed next
+  int cur_layer = -1;           // encoder layer of the steps pushed next
   void push(std::function<int(cudaStream_t)> f, double flops = 0.0) {
-    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, flops});
+    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, flops, cur_layer});
   }
 
   // K-step table for one GEMM: every tap x every 64-wide K chunk (x 3 split-precision products in fp32 mode)
@@ -672,7 +686,7 @@ struct Builder {
     plan->steps.push_back(Step{[gp, pl, wants_mask](cudaStream_t s) {
       if (wants_mask) gp->prob.ep.row_zero = pl->args.mask;
       return gemm_launch(*gp, s);
-    }, tag, 2.0 * (double)M * (double)W.n * 64.0 * (double)pr.num_kb});
+    }, tag, 2.0 * (double)M * (double)W.n * 64.0 * (double)pr.num_kb, cur_layer});
     return true;
   }
 };
@@ -765,7 +779,8 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     FrontendBufs fb;
     static int stemf_env0 = -1;
     if (stemf_env0 < 0) { const char* ev = std::getenv("AVH_STEM_FUSED"); stemf_env0 = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
-    if (f32 || !stemf_env0) {     // patch matrix + un-pooled stem maps: only the unfused stem (fp32 mode) needs them
+    const bool train = plan->train;
+    if (f32 || !stemf_env0 || train) {     // patch matrix + un-pooled stem maps: only the unfused stem needs them
       fb.im2col = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * 2 * P);
       fb.stem_out = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * es);      // same clip-padded row space as the patches
     }
@@ -782,13 +797,54 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     Act pooled_feat = new_act(N, 512);     // avgpool output = ResEncoder output [B*T, 512]
     if (!sizing) plan->stages["resnet"] = {pooled_feat.data, {act_dt, N * 512}};
 
+    // ---- training mode: BatchNorm with batch statistics.  The convolution writes its raw output into a scratch map of
+    // the output's own layout, bn_stats / bn_finalize produce scale + bias (and update the running statistics),
+    // bn_apply does what the eval-mode epilogue fuses (train_ops.cu; avhubert/resnet.py:23,44,56,139)
+    void* bn_raw = nullptr;
+    double* bn_sums = nullptr;
+    float *bn_scale = nullptr, *bn_bias = nullptr;
+    if (train) {
+      bn_raw = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * es);          // the stem's map is the largest
+      bn_sums = reinterpret_cast<double*>(b.alloc(2 * 512 * sizeof(double)));
+      bn_scale = reinterpret_cast<float*>(b.alloc(512 * 4));
+      bn_bias = reinterpret_cast<float*>(b.alloc(512 * 4));
+    }
+    // launch(ep) enqueues the convolution with epilogue `ep`; in training mode it is called with a raw epilogue
+    auto conv_bn = [&](Epilogue ep, const ConvUnit& cu, long long out_rows, double count, long long period, long long valid,
+                       int S, int Himg, const std::function<bool(const Epilogue&)>& launch) -> bool {
+      if (!train) return launch(ep);
+      Epilogue raw = ep;
+      raw.C = bn_raw;
+      raw.col_scale = nullptr; raw.col_bias = nullptr; raw.act = ACT_NONE; raw.slope1 = nullptr;
+      raw.R = nullptr; raw.slope2 = nullptr;
+      if (!launch(raw)) return false;
+      const int Cc = cu.cout;
+      void* outp = ep.C;
+      const float* s1 = ep.act == ACT_PRELU ? ep.slope1 : nullptr;
+      const void* res = ep.R;
+      const float* s2 = ep.slope2;
+      const float *gm = cu.gamma, *bt = cu.beta;
+      float *rm = cu.rmean, *rv = cu.rvar;
+      const std::string keep = b.tag;
+      b.tag = "bn_train";
+      b.push([=](cudaStream_t s) { return launch_bn_stats(bn_raw, act_dt, out_rows, Cc, period, valid, S, Himg, bn_sums, s); });
+      b.push([=](cudaStream_t s) {
+        return launch_bn_finalize(bn_sums, count, gm, bt, 1e-5f, pl->bn_momentum, rm, rv, bn_scale, bn_bias, Cc, s);
+      });
+      b.push([=](cudaStream_t s) {
+        return launch_bn_apply(bn_raw, outp, act_dt, out_rows, Cc, bn_scale, bn_bias, s1, res, s2, S, Himg, s);
+      });
+      b.tag = keep;
+      return true;
+    };
+
     // 3x3 stride-1 conv over the padded layout as 9 shifted taps
     auto conv3x3_s1 = [&](const Act& in, const ConvUnit& cu, const Act& out, int Himg, int nimg, const float* slope1,
                           const Act* res, const float* slope2) -> bool {
       const int S = Himg + 1;
       static int win_env = -1;
       if (win_env < 0) { const char* ev = std::getenv("AVH_CONV_WINDOW"); win_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
-      if (!f32 && win_env && cu.cin == 64 && cu.cout == 64) {
+      if (!f32 && !train && win_env && cu.cin == 64 && cu.cout == 64) {
         // layer1: operand window resident in smem, nine taps as descriptor row offsets (conv_window.cu)
         b.tag = "conv3x3_c64";
         if (sizing) return true;
@@ -816,7 +872,12 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       ep.O2 = S * S; ep.O1 = S; ep.O0 = 0; ep.invalid_zero = 1;
       const long long rows = (long long)nimg * S * S;
       b.tag = "conv3x3_c" + std::to_string(cu.cin);
-      if (!b.gemm(in.op, rows, P * cu.cin, cu.w, rows, taps, cu.cin / 64, cu.cin, ep)) return false;
+      const void* a_op = in.op;
+      const int a_cols = P * cu.cin, chunks = cu.cin / 64, aps = cu.cin;
+      if (!conv_bn(ep, cu, rows, (double)nimg * Himg * Himg, 0, 0, S, Himg, [&](const Epilogue& e) {
+            return b.gemm(a_op, rows, a_cols, cu.w, rows, taps, chunks, aps, e);
+          }))
+        return false;
       sync_op(out);
       return true;
     };
@@ -824,7 +885,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     // bf16 mode, layers 2-4: one frame per GEMM row, dense [frames, H*H*C] maps, in-image taps only (conv_frame.cu)
     static int frame_env = -1;
     if (frame_env < 0) { const char* ev = std::getenv("AVH_CONV_FRAME"); frame_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
-    const bool frame_mode = !f32 && frame_env != 0;
+    const bool frame_mode = !f32 && !train && frame_env != 0;
     struct Shortcut { const void* A2 = nullptr; int Cin = 0, Sin = 0, stride = 1; const PackedW* w = nullptr;
                       const float* bias = nullptr; const float* ones = nullptr; };
     auto conv_frame = [&](const void* in, int Hin, int Sin, int Cin, const ConvUnit& cu, void* out, int Hout, int nimg,
@@ -864,7 +925,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       // ---- stem: one fused kernel in bf16 mode (stem_fused.cu) ...
       static int stemf_env = -1;
       if (stemf_env < 0) { const char* ev = std::getenv("AVH_STEM_FUSED"); stemf_env = (ev != nullptr && ev[0] == '0') ? 0 : 1; }
-      if (!f32 && stemf_env) {
+      if (!f32 && !train && stemf_env) {
         if (!sizing && b0 == 0 && stem_fused_plan(h->stem_wf.w, &plan->stemf)) return false;
         void* po = fb.pooled.data;
         b.tag = "stem_fused";
@@ -896,7 +957,10 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         std::vector<Tap> taps;
         for (int dt = 0; dt < 5; ++dt) taps.push_back(Tap{(dt - 2) * 1936, 0, dt * 64});
         b.tag = "stem_gemm";
-        if (!b.gemm(fb.im2col, rows, P * 64, h->stem.w, rows, taps, 1, 64, ep)) return false;
+        // batch statistics over the frames of the chunk (gap frames of the clip-padded row space excluded)
+        if (!conv_bn(ep, h->stem, rows, (double)nf * 1936.0, (long long)(T + 2) * 1936, (long long)T * 1936, 0, 0,
+                     [&](const Epilogue& e) { return b.gemm(fb.im2col, rows, P * 64, h->stem.w, rows, taps, 1, 64, e); }))
+          return false;
         void* so = fb.stem_out;
         void* po = fb.pooled.data;
         b.tag = "maxpool";
@@ -958,7 +1022,11 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             ep.map_mode = MAP_2LEVEL; ep.S2 = Hn * Hn; ep.S1 = Hn; ep.H = Hn; ep.W = Hn;
             ep.O2 = S * S; ep.O1 = S; ep.O0 = 0;
             b.tag = "conv_s2_c" + std::to_string(Cin);
-            if (!b.gemm(col, rows, 9 * CinP, bw.c1.w, rows, taps, Cin / 64, Cin, ep)) return false;
+            const long long out_rows = (long long)nf * S * S;
+            if (!conv_bn(ep, bw.c1, out_rows, (double)nf * Hn * Hn, 0, 0, S, Hn, [&](const Epilogue& e) {
+                  return b.gemm(col, rows, 9 * CinP, bw.c1.w, rows, taps, Cin / 64, Cin, e);
+                }))
+              return false;
             sync_op(mid);
             dsout = fb.ds[L];
             dsout.rows = mid.rows;
@@ -967,7 +1035,10 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             epd.map_mode = MAP_2LEVEL; epd.S2 = Hn * Hn; epd.S1 = Hn; epd.H = Hn; epd.W = Hn;
             epd.O2 = S * S; epd.O1 = S; epd.O0 = 0;
             b.tag = "downsample";
-            if (!b.gemm(col, rows, 9 * CinP, bw.ds.w, rows, {Tap{0, 4 * CinP, 0}}, Cin / 64, Cin, epd)) return false;
+            if (!conv_bn(epd, bw.ds, out_rows, (double)nf * Hn * Hn, 0, 0, S, Hn, [&](const Epilogue& e) {
+                  return b.gemm(col, rows, 9 * CinP, bw.ds.w, rows, {Tap{0, 4 * CinP, 0}}, Cin / 64, Cin, e);
+                }))
+              return false;
             res = &dsout;
           } else {
             if (!conv3x3_s1(cur, bw.c1, mid, Hn, nf, bw.c1.slope, nullptr, nullptr)) return false;
@@ -1062,6 +1133,13 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       if (!sizing) plan->stages["fused_ln"] = {x, {DT_F32, N * E}};
     }
   }
+  const bool train = plan->train;
+  if (train) {      // features = self.dropout_input(features), hubert.py:729
+    b.tag = "dropout";
+    b.push([=](cudaStream_t s) {
+      return pl->p_in > 0.f ? launch_dropout(x, DT_F32, nullptr, N * D, pl->p_in, pl->seed, 1u, s) : 0;
+    });
+  }
   if (c.capture_stages) {      // x is overwritten in place by the encoder: keep a copy for stage-level tests
     b.tag = "stage_copy";
     float* enc_in_copy = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));
@@ -1102,6 +1180,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   }
 
   // ========================================================================== transformer layers
+  float* dtmp = train ? reinterpret_cast<float*>(b.alloc((size_t)N * D * 4)) : nullptr;     // block output before dropout + add
   Act hbuf = new_act(N, D);          // LayerNorm output / post-LN operand copy of x
   Act qkv = new_act(N, 3 * D);
   Act ctx = new_act(N, D);
@@ -1135,7 +1214,14 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     float* g = h->enc_ln_g; float* be = h->enc_ln_b;
     b.tag = "layer_ln";
     b.push([=](cudaStream_t s) { return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, x, nullptr, DT_BF16, nullptr, N, D, s); });
-    x_to_h();
+    if (!train) x_to_h();
+  }
+  if (train) {      // x = F.dropout(x, p=self.dropout, training=self.training), wav2vec2.py:879
+    b.tag = "dropout";
+    b.push([=](cudaStream_t s) {
+      return pl->p_enc > 0.f ? launch_dropout(x, DT_F32, nullptr, N * D, pl->p_enc, pl->seed, 2u, s) : 0;
+    });
+    if (!c.layer_norm_first) x_to_h();
   }
   const int n_layers = plan->output_layer > 0 ? std::min(plan->output_layer, c.encoder_layers) : c.encoder_layers;
   // LayerNorm folding (gemm.h, Epilogue::ln_mode; AVH_LN_FUSED=1, off by default): bf16 mode, pre-LN layers.
@@ -1149,7 +1235,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   // other ~2.5 us come with the smaller smem ring (4 stages) and the store-form epilogue.
   static int lnf_env = -1;
   if (lnf_env < 0) { const char* ev = std::getenv("AVH_LN_FUSED"); lnf_env = (ev != nullptr && ev[0] == '1') ? 1 : 0; }
-  const bool ln_fused = !f32 && c.layer_norm_first && lnf_env != 0 && (D == 768 || D == 1024) && n_layers > 0 &&
+  const bool ln_fused = !f32 && !train && c.layer_norm_first && lnf_env != 0 && (D == 768 || D == 1024) && n_layers > 0 &&
                         h->layers[0].qkv_csum != nullptr;
   const int ln_pbn = 160;                                    // tile width of the producers (fixes the slot count)
   const int ln_np_prod = ((D + ln_pbn - 1) / ln_pbn) * 2;
@@ -1176,6 +1262,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   const bool att_tc = !f32 && (rg || (att_tc_env != 0 && T > 96)) && (size_t)((T + 127) / 128 * 128) * 4 <= 48 * 1024;
   for (int l = 0; l < n_layers; ++l) {
     const LayerW& lw = h->layers[l];
+    b.cur_layer = l;               // LayerDrop (training mode) skips every launch of a dropped layer
     if (c.layer_norm_first && !ln_fused) ln_to_h(x, lw.ln1_g, lw.ln1_b, nullptr);
     {   // fused QKV projection
       Epilogue ep = ep_base(qkv.data, 3 * D);
@@ -1201,13 +1288,26 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       }
       sync_op(ctx);
     }
+    // training mode: block output -> dtmp, then target (+)= dropout(dtmp) (dropout1 / dropout3, wav2vec2.py:980,990);
+    // with p = 0 this is the eval arithmetic (fp32 block output added to the fp32 residual stream)
+    auto dropout_add = [&](unsigned site) {
+      float* target = c.layer_norm_first ? x : tmp;
+      b.tag = "dropout";
+      if (!c.layer_norm_first)
+        b.push([=](cudaStream_t s) {
+          return cudaMemcpyAsync(tmp, x, (size_t)N * D * 4, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
+        });
+      b.push([=](cudaStream_t s) { return launch_dropout(target, DT_F32, dtmp, N * D, pl->p_enc, pl->seed, site, s); });
+    };
     {   // out_proj + residual
       Epilogue ep;
       ep.C = c.layer_norm_first ? x : tmp; ep.ldc = D; ep.c_fp32 = 1;
       ep.col_bias = lw.out.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+      if (train) { ep.C = dtmp; ep.R = nullptr; }
       if (ln_fused) ln_producer(ep);
       b.tag = "out_proj";
       if (!b.gemm(ctx.op, N, P * D, lw.out.w, N, {Tap{0, 0, 0}}, D / 64, D, ep, ln_fused ? ln_pbn : 0)) return false;
+      if (train) dropout_add(16u + 4u * (unsigned)l);
     }
     if (c.layer_norm_first && !ln_fused) ln_to_h(x, lw.ln2_g, lw.ln2_b, nullptr);
     else if (ln_fused) {}
@@ -1223,6 +1323,14 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       if (ln_fused) ln_consumer(ep, lw.fc1_csum);
       b.tag = "fc1";
       if (!b.gemm(hbuf.op, N, P * D, ln_fused ? lw.fc1_ln.w : lw.fc1.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      if (train) {      // dropout2 = activation_dropout after the GELU, wav2vec2.py:987
+        void* fd = ffn.data;
+        const unsigned site = 17u + 4u * (unsigned)l;
+        b.tag = "dropout";
+        b.push([=](cudaStream_t s) {
+          return pl->p_act > 0.f ? launch_dropout(fd, act_dt, nullptr, N * F, pl->p_act, pl->seed, site, s) : 0;
+        });
+      }
       sync_op(ffn);
     }
     {   // fc2 + residual
@@ -1231,8 +1339,10 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       ep.col_bias = lw.fc2.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
       const bool prod = ln_fused && l + 1 < n_layers;        // the last fc2 has no consumer: plain reduce-add
       if (prod) ln_producer(ep);
+      if (train) { ep.C = dtmp; ep.R = nullptr; }
       b.tag = "fc2";
       if (!b.gemm(ffn.op, N, P * F, lw.fc2.w, N, {Tap{0, 0, 0}}, F / 64, F, ep, prod ? ln_pbn : 0)) return false;
+      if (train) dropout_add(18u + 4u * (unsigned)l);
     }
     if (!c.layer_norm_first) {
       float* g = lw.ln2_g; float* be = lw.ln2_b;
@@ -1241,6 +1351,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       if (l + 1 < n_layers) x_to_h();
     }
   }
+  b.cur_layer = -1;
   // ========================================================================== output
   b.tag = "final_ln";
   if (rg) {
@@ -1271,8 +1382,9 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 // One plan (= workspace + launch list) per shape AND per CUDA stream: forwards enqueued on different streams
 // never share scratch memory, so a caller can keep several batches in flight on one device.
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
-               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false) {
+               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false) {
   const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) + (enc_only ? "e:" : "") +
+                          (train ? "t:" : "") +
                           std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
@@ -1300,6 +1412,7 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
   p->ragged = ragged_rows > 0;
   p->Nb = ragged_rows;
   p->enc_only = enc_only;
+  p->train = train;
   size_t bytes = 0;
   if (!build_plan(h, p.get(), true, &bytes)) return nullptr;
   if (p->arena.init(bytes + (1 << 20))) return nullptr;
@@ -1454,7 +1567,7 @@ static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
   // a caller that is itself capturing this stream (e.g. torch.cuda.graph) gets plain launches recorded into ITS graph
   cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
   if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) cudaStreamIsCapturing(s, &cap_status);
-  if (graphs_env == 1 && !h->profiling && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+  if (graphs_env == 1 && !h->profiling && !p->train && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
       cap_status == cudaStreamCaptureStatusNone) {
     ++p->calls;
     auto it = p->graphs.find(p->args);
@@ -1506,7 +1619,8 @@ static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
   size_t i = 0;
   for (auto& st : p->steps) {
     if (h->profiling) cudaEventRecord(h->prof_events[2 * i], s);
-    if (st.run(s)) {
+    const bool dropped = p->train && st.layer >= 0 && st.layer < (int)p->layer_skip.size() && p->layer_skip[st.layer] != 0;
+    if (!dropped && st.run(s)) {
       if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
       return 1;
     }
@@ -1580,6 +1694,85 @@ int avh_forward(avh_handle* h, const void* video, int video_dtype, const void* a
   p->args.mask = padding_mask;
   p->args.out = out; p->args.out_dt = out_dtype;
   return run_plan(h, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_forward_train(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                      const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
+                      const avh_train_args* ta, void* out, int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr && ta != nullptr, "null argument");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(h->cfg.reserved[0] == 0, "this handle holds a bare TransformerEncoder");
+  AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
+  AVH_CHECK(B >= 1 && T >= 1 && (long long)B * T < (1ll << 24), "bad batch");
+  AVH_CHECK(out != nullptr, "null output");
+  AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
+  AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
+  AVH_CHECK(video == nullptr || video_dtype == AVH_F32 || video_dtype == AVH_F16 || video_dtype == AVH_BF16,
+            "training-mode forward takes normalised float video");
+  AVH_CHECK(ta->attention_dropout == 0.f, "attention_dropout > 0 is not implemented (0.0 in every shipped fine-tune config)");
+  for (float pr : {ta->dropout_input, ta->dropout, ta->activation_dropout})
+    AVH_CHECK(pr >= 0.f && pr < 1.f, "dropout probabilities must be in [0, 1)");
+  AVH_CHECK(ta->bn_momentum > 0.f && ta->bn_momentum <= 1.f, "bad BatchNorm momentum");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, output_layer, s, 0,
+                               false, true);
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  p->args = avh::CallArgs();
+  p->args.video = video; p->args.video_dt = video_dtype;
+  p->args.audio = audio; p->args.audio_dt = audio_dtype;
+  if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
+  p->args.mask = padding_mask;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  p->p_in = ta->dropout_input; p->p_enc = ta->dropout; p->p_act = ta->activation_dropout;
+  p->bn_momentum = ta->bn_momentum;
+  p->seed = ta->seed;
+  p->layer_skip.assign(h->cfg.encoder_layers, 0);
+  if (ta->layer_skip != nullptr)
+    for (int l = 0; l < h->cfg.encoder_layers; ++l) p->layer_skip[l] = ta->layer_skip[l];
+  return run_plan(h, p, s);
+}
+
+int avh_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+  AVH_CHECK(x != nullptr, "null pointer");
+  AVH_CHECK(dtype == AVH_F32 || dtype == AVH_F16 || dtype == AVH_BF16, "bad dtype");
+  return avh::launch_dropout(x, dtype, nullptr, n, p, seed, site, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_bn_stats_count(avh_handle* h, int64_t* n_floats) {
+  AVH_CHECK(h != nullptr && n_floats != nullptr, "null argument");
+  AVH_CHECK(h->finalized, "weights not finalized");
+  int64_t n = 2 * 64;
+  for (int L = 0; L < 4; ++L)
+    for (int bi = 0; bi < 2; ++bi) n += 2 * (64 << L) * (h->blocks[L][bi].has_ds ? 3 : 2);
+  *n_floats = n;
+  return 0;
+}
+
+int avh_read_bn_stats(avh_handle* h, float* dst, int64_t capacity, void* stream) {
+  AVH_CHECK(h != nullptr && dst != nullptr, "null argument");
+  AVH_CHECK(h->finalized && h->cfg.reserved[0] == 0, "no lip frontend in this handle");
+  int64_t need = 0;
+  if (avh_bn_stats_count(h, &need)) return 1;
+  AVH_CHECK(capacity >= need, "destination too small");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int64_t off = 0;
+  auto put = [&](const avh::ConvUnit& cu, int C) -> int {
+    AVH_CUDA_OK(cudaMemcpyAsync(dst + off, cu.rmean, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+    AVH_CUDA_OK(cudaMemcpyAsync(dst + off + C, cu.rvar, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+    off += 2 * C;
+    return 0;
+  };
+  if (put(h->stem, 64)) return 1;
+  for (int L = 0; L < 4; ++L)
+    for (int bi = 0; bi < 2; ++bi) {
+      const avh::BlockW& bw = h->blocks[L][bi];
+      if (put(bw.c1, 64 << L) || put(bw.c2, 64 << L)) return 1;
+      if (bw.has_ds && put(bw.ds, 64 << L)) return 1;
+    }
+  return 0;
 }
 
 int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T,

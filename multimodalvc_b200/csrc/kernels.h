@@ -63,6 +63,17 @@ int launch_ln_center_stats(const float* in, void* xc, float* mu, void* part, int
                            cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int pitch, int fp32, cudaStream_t stream);
 
+// ---- training-mode forward (train_ops.cu): BatchNorm with batch statistics, Philox dropout
+int launch_bn_stats(const void* raw, int dt, long long rows, int C, long long period, long long valid, int S, int H,
+                    double* sums, cudaStream_t stream);
+int launch_bn_finalize(double* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                       float* rmean, float* rvar, float* scale, float* bias, int C, cudaStream_t stream);
+int launch_bn_apply(const void* raw, void* out, int dt, long long rows, int C, const float* scale, const float* bias,
+                    const float* slope1, const void* res, const float* slope2, int S, int H, cudaStream_t stream);
+// x = dropout(x) in place (any dtype), or x += dropout(add) (fp32); mask = Philox4x32-10(seed, site, element)
+int launch_dropout(void* x, int dt, const float* add, long long n, float p, unsigned long long seed, unsigned int site,
+                   cudaStream_t stream);
+
 // ---- audio frontend ---------------------------------------------------------------------------------
 struct FbankArgs {
   const int16_t* wav;          // concatenated clips

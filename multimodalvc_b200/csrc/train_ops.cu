@@ -1,0 +1,210 @@
+// Training-mode pieces of the AV-HuBERT forward: what changes when the module is in .train() —
+// as the frozen encoder of MMS-LLaMA is during training (src/model.py:280: no_grad, but never .eval()).
+//
+//  * BatchNorm with BATCH statistics (avhubert/resnet.py:23,44,56,139: nn.BatchNorm2d / 3d in training mode): the
+//    convolution writes its raw output, bn_stats reduces per-channel sum and sum of squares (float64 partials,
+//    one atomicAdd per CTA and channel), bn_finalize turns them into the normalising scale / bias (biased variance,
+//    eps 1e-5) and updates running_mean / running_var (momentum, unbiased variance) exactly as torch does, bn_apply
+//    normalises + PReLU (+ residual + PReLU) in place of the fused eval-mode epilogue.
+//  * nn.Dropout (hubert.py:729 dropout_input; wav2vec2.py:879 after the positional conv; :980/:990 dropout1 / dropout3
+//    on the block outputs before the residual add; :987 dropout2 = activation_dropout after the GELU): a
+//    counter-based Philox4x32-10 stream keyed by (seed of the call, call-site id, element index) — every element's
+//    mask is a pure function of those, so reruns with the same seed are bit-identical and no state is kept.
+//    (The masks are NOT torch's: torch draws them from its own Philox offsets per kernel launch geometry.)
+// LayerDrop (wav2vec2.py:887-888) is a host coin: the plan skips the layer's launches.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cuda_fp16.h>
+
+namespace avh {
+namespace {
+
+__device__ __forceinline__ float ld_any(const void* p, int dt, long long i) {
+  if (dt == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  if (dt == DT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_any(void* out, int dt, long long i, float v) {
+  if (dt == DT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  else if (dt == DT_F16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+  else reinterpret_cast<float*>(out)[i] = v;
+}
+
+// ---- per-channel sums over the rows of [rows, C]; rows with (r % period) >= valid are skipped (the gap frames of the
+// stem's clip-padded row space; period = 0: no such gaps), and with S > 0 only the H x H image of the padded S x S layout
+constexpr int BN_ROWS_PER_CTA = 2048;     // few double atomics per channel: ~rows / 2048 CTAs
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const void* __restrict__ raw, int dt, long long rows, int C, long long period, long long valid, int S,
+                int H, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
+  // thread = (channel c, row phase): 256 threads cover C channels x (256 / C) row phases (C = 64..512, power of two)
+  const int c = threadIdx.x % C;
+  const int phases = 256 / C > 0 ? 256 / C : 1;
+  const int ph = threadIdx.x / C;
+  const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_CTA;
+  const long long r1 = r0 + BN_ROWS_PER_CTA < rows ? r0 + BN_ROWS_PER_CTA : rows;
+  __shared__ double s1[256], s2[256];
+  for (int cc = c; cc < C; cc += 256) {          // C > 256: each thread walks several channels
+    double a = 0.0, b2 = 0.0;
+    if (ph < phases) {
+      for (long long r = r0 + ph; r < r1; r += phases) {
+        if (period > 0 && (r % period) >= valid) continue;
+        if (S > 0) {                                   // padded S x S layout: only the H x H image counts
+          const int rem = (int)(r % ((long long)S * S));
+          if ((rem / S) >= H || (rem % S) >= H) continue;
+        }
+        const float v = ld_any(raw, dt, r * C + cc);
+        a += (double)v;
+        b2 += (double)v * (double)v;
+      }
+    }
+    s1[threadIdx.x] = a;
+    s2[threadIdx.x] = b2;
+    __syncthreads();
+    if (ph == 0) {
+      for (int k = 1; k < phases; ++k) { a += s1[threadIdx.x + k * C]; b2 += s2[threadIdx.x + k * C]; }
+      atomicAdd(&sums[cc], a);
+      atomicAdd(&sums[C + cc], b2);
+    }
+    __syncthreads();
+  }
+}
+
+// mean / biased variance -> scale, bias of the normalisation; running statistics updated like torch.nn.BatchNorm
+__global__ void bn_finalize_kernel(double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, float* __restrict__ scale, float* __restrict__ bias, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+  scale[c] = sc;
+  bias[c] = beta[c] - (float)mean * sc;
+  const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+  rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+  rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+  sums[c] = 0.0;                 // ready for the next BatchNorm that uses this scratch
+  sums[C + c] = 0.0;
+}
+
+// out = act2(act1(raw * scale + bias) + res); rows outside the H x H image of the padded S x S layout are zeros
+__global__ void bn_apply_kernel(const void* __restrict__ raw, void* __restrict__ out, int dt, long long rows, int C,
+                                const float* __restrict__ scale, const float* __restrict__ bias,
+                                const float* __restrict__ slope1, const void* __restrict__ res,
+                                const float* __restrict__ slope2, int S, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  bool ok = true;
+  if (S > 0) {
+    const int rem = (int)(r % ((long long)S * S));
+    ok = (rem / S) < H && (rem % S) < H;
+  }
+  float v = 0.f;
+  if (ok) {
+    v = fmaf(ld_any(raw, dt, i), scale[c], bias[c]);
+    if (slope1 != nullptr) v = v > 0.f ? v : v * slope1[c];
+    if (res != nullptr) v += ld_any(res, dt, i);
+    if (slope2 != nullptr) v = v > 0.f ? v : v * slope2[c];
+  }
+  st_any(out, dt, i, v);
+}
+
+// ---- Philox4x32-10 (Salmon et al.): counter = (element block, site), key = seed
+__device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned long long ctr_lo, unsigned int site) {
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+  unsigned int c0 = (unsigned int)ctr_lo, c1 = (unsigned int)(ctr_lo >> 32), c2 = site, c3 = 0x5eedu;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(unsigned int x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// x = dropout(x) in place, or x += dropout(t) when `add` is given (dropout1 / dropout3 before the residual add)
+__global__ void dropout_kernel(void* __restrict__ x, int dt, const float* __restrict__ add, long long n, float p,
+                               unsigned long long seed, unsigned int site) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long base = i4 * 4;
+  if (base >= n) return;
+  const uint4 rnd = philox4x32(seed, (unsigned long long)i4, site);
+  const unsigned int rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+  const float keep = 1.f / (1.f - p);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k;
+    if (i >= n) break;
+    const float m = u01(rv[k]) >= p ? keep : 0.f;
+    if (add != nullptr) {
+      float* xf = reinterpret_cast<float*>(x);
+      xf[i] += add[i] * m;
+    } else {
+      st_any(x, dt, i, ld_any(x, dt, i) * m);
+    }
+  }
+}
+
+inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace
+
+int launch_bn_stats(const void* raw, int dt, long long rows, int C, long long period, long long valid, int S, int H,
+                    double* sums, cudaStream_t stream) {
+  AVH_CHECK(C >= 1 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "bn_stats: channel count must divide or be a multiple of 256");
+  if (rows <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(bn_stats_kernel, dim3(blocks_for(rows, BN_ROWS_PER_CTA)), dim3(256), 0, stream, raw, dt, rows, C,
+                         period, valid, S, H, sums));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_bn_finalize(double* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                       float* rmean, float* rvar, float* scale, float* bias, int C, cudaStream_t stream) {
+  AVH_CUDA_OK(launch_pdl(bn_finalize_kernel, dim3(blocks_for(C, 128)), dim3(128), 0, stream, sums, count, gamma, beta, eps,
+                         momentum, rmean, rvar, scale, bias, C));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_bn_apply(const void* raw, void* out, int dt, long long rows, int C, const float* scale, const float* bias,
+                    const float* slope1, const void* res, const float* slope2, int S, int H, cudaStream_t stream) {
+  const long long n = rows * C;
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, raw, out, dt, rows, C, scale, bias,
+                         slope1, res, slope2, S, H));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_dropout(void* x, int dt, const float* add, long long n, float p, unsigned long long seed, unsigned int site,
+                   cudaStream_t stream) {
+  AVH_CHECK(p >= 0.f && p < 1.f, "dropout probability must be in [0, 1)");
+  AVH_CHECK(add == nullptr || dt == DT_F32, "dropout_add accumulates into an fp32 tensor");
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(dropout_kernel, dim3(blocks_for((n + 3) / 4, 256)), dim3(256), 0, stream, x, dt, add, n, p, seed, site));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace avh

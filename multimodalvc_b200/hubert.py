@@ -198,6 +198,7 @@ class AVHubertModel(nn.Module):
         self._handle_key = None
         self._dirty = True
         self._video_geo = None
+        self._eval_stale = False
         self._host_keepalive = {}
         # normalisation of raw uint8 video (task config image_mean / image_std, hubert_pretraining.py:144-149)
         self.image_mean, self.image_std = 0.421, 0.165
@@ -306,13 +307,44 @@ class AVHubertModel(nn.Module):
         return self._handle
 
     # ------------------------------------------------------------------ the hot path
-    def _check_mode(self, mask):
+    def _check_mode(self, mask, allow_train=False):
         if mask:
             raise NotImplementedError("apply_input_mask (mask=True) is off in every shipped fine-tune/inference "
                                       "config and is not implemented on the device path")
-        if self.training:
-            raise RuntimeError("training-mode forward (batch-statistics BatchNorm, dropout, LayerDrop) is not "
-                               "implemented; call .eval() — the encoder is frozen on every inference path")
+        if self.training and not allow_train:
+            raise RuntimeError("this entry point runs the eval-mode forward only; call .eval() (extract_finetune on "
+                               "device tensors supports the training-mode forward)")
+
+    def _bn_modules(self):
+        """BatchNorm modules in the order avh_read_bn_stats writes their running statistics."""
+        res = self.feature_extractor_video.resnet
+        out = [res.frontend3D[1]]
+        for i in range(1, 5):
+            for blk in getattr(res.trunk, f"layer{i}"):
+                out += [blk.bn1, blk.bn2]
+                if blk.downsample is not None:
+                    out.append(blk.downsample[1])
+        return out
+
+    def _train_args(self, output_layer):
+        """Per-call arguments of the training-mode forward: dropout probabilities of the config, a seed from torch's
+        CPU generator, and the LayerDrop coins — drawn with np.random.random() in layer order up to the exit layer,
+        exactly as the reference does (wav2vec2.py:886-888), so the same numpy seed drops the same layers."""
+        import numpy as np
+        c = self.cfg
+        if c.attention_dropout > 0:
+            raise NotImplementedError("attention_dropout > 0 in training mode is not implemented (0.0 in every "
+                                      "shipped fine-tune config, avhubert/conf/finetune/*.yaml)")
+        n = c.encoder_layers if output_layer is None else min(int(output_layer), c.encoder_layers)
+        skip = [0] * c.encoder_layers
+        for i in range(n):
+            skip[i] = 0 if np.random.random() > c.encoder_layerdrop else 1
+        skip_arr = (ctypes.c_uint8 * c.encoder_layers)(*skip)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        ta = _lib.AvhTrainArgs(dropout_input=float(c.dropout_input), dropout=float(c.dropout),
+                               activation_dropout=float(c.activation_dropout), attention_dropout=0.0, bn_momentum=0.1,
+                               seed=seed, layer_skip=ctypes.cast(skip_arr, ctypes.c_void_p))
+        return ta, skip_arr, skip
 
     def _check_inputs(self, handle, src_video, src_audio, padding_mask, device):
         """Validation shared by the device and the host entry points.  Returns (video, video_dt, audio, pm_u8, pm, B, T)
@@ -378,7 +410,10 @@ class AVHubertModel(nn.Module):
         """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
         padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask).  With cfg.ragged == "packed" (bf16
         mode) ragged batches run packed; `lengths` (valid frames per clip) may be given to skip reading the mask back."""
-        self._check_mode(mask)
+        self._check_mode(mask, allow_train=True)
+        if not self.training and getattr(self, "_eval_stale", False):
+            # training-mode forwards moved the BatchNorm running statistics: fold the current ones for eval
+            self._dirty, self._eval_stale = True, False
         handle = self._ensure_handle()
         dev = self.encoder.layer_norm.weight.device
         src_video, video_dt, src_audio, pm_u8, padding_mask, B, T = self._check_inputs(
@@ -391,6 +426,35 @@ class AVHubertModel(nn.Module):
         if src_audio is not None:
             strides = (ctypes.c_int64 * 3)(*src_audio.stride())
         ol = 0 if output_layer is None else int(output_layer)
+        if self.training:
+            # frozen-encoder-in-train-mode forward (src/model.py:96-100,280): batch-statistics BatchNorm, dropout, LayerDrop
+            if video_dt == _U8:
+                raise NotImplementedError("the training-mode forward takes normalised float video")
+            ta, skip_arr, _ = self._train_args(output_layer)
+            lib = _lib.load()
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                _lib.check(lib.avh_forward_train(
+                    handle,
+                    ctypes.c_void_p(src_video.data_ptr()) if src_video is not None else None, video_dt,
+                    ctypes.c_void_p(src_audio.data_ptr()) if src_audio is not None else None,
+                    _DTYPES[src_audio.dtype] if src_audio is not None else 0, strides,
+                    ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None,
+                    B, T, ol, ctypes.byref(ta), ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
+                if src_video is not None:
+                    n = ctypes.c_int64()
+                    _lib.check(lib.avh_bn_stats_count(handle, ctypes.byref(n)))
+                    flat = torch.empty(n.value, device=dev, dtype=torch.float32)
+                    _lib.check(lib.avh_read_bn_stats(handle, ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+                    off = 0
+                    for bn in self._bn_modules():
+                        C = bn.num_features
+                        bn.running_mean.copy_(flat[off:off + C])
+                        bn.running_var.copy_(flat[off + C:off + 2 * C])
+                        bn.num_batches_tracked += 1
+                        off += 2 * C
+                    self._eval_stale = True
+            return out, padding_mask
         if self.cfg.ragged not in ("dense", "packed"):
             raise ValueError(f"cfg.ragged must be 'dense' or 'packed', got {self.cfg.ragged}")
         if (self.cfg.ragged == "packed" and padding_mask is not None and self._handle_key[1] == _lib.AVH_COMPUTE_BF16):

@@ -47,7 +47,10 @@ class OracleConfig:
     @staticmethod
     def named(size, **kw):
         shape = dict(base=(12, 768, 3072, 12), large=(24, 1024, 4096, 16), tiny=(2, 128, 256, 2))[size]
-        return OracleConfig(*shape, **kw)
+        cfg = OracleConfig(*shape)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        return cfg
 
 
 class _Block(nn.Module):
@@ -211,8 +214,10 @@ class _Encoder(nn.Module):
         if not self.layer_norm_first:
             x = self.layer_norm(x)
         x = x.transpose(0, 1)
+        skip = getattr(self, "layer_skip", None)       # LayerDrop decisions of a training-mode forward (wav2vec2.py:886-888)
         for i, lyr in enumerate(self.layers):
-            x = lyr(x, padding_mask)
+            if not (skip and skip[i]):
+                x = lyr(x, padding_mask)
             if i == layer:
                 break
         x = x.transpose(0, 1)
