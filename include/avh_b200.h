@@ -130,6 +130,13 @@ typedef struct avh_train_args {
 AVH_API int avh_forward_train(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
                               const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, int output_layer,
                               const avh_train_args* args, void* out, int out_dtype, void* stream);
+/* First consumer of the encoder output in MMS-LLaMA (src/model.py:596-609): the per-sample loop
+ * F.interpolate(av_feat[b][:len_in[b]].T[None], size=len_out[b], mode='linear').T into a zero-padded batch + mask, as
+ * one launch.  x [B,T,C], len_in / len_out int32 [B] (DEVICE), out [B,Tout,C] (same dtype, rows >= len_out[b] zero),
+ * mask int64 [B,Tout] (1 = valid) or NULL.  Index arithmetic of ATen's upsample_linear1d (align_corners=False). */
+AVH_API int avh_interp_linear(const void* x, int dtype, int B, int T, int C, const int32_t* len_in, const int32_t* len_out,
+                              int Tout, void* out, int64_t* mask, void* stream);
+
 /* Kernel-level entry point of the dropout used above (tests): x[i] = keep(i) ? x[i] / (1 - p) : 0 in place, keep(i) a
  * pure function of (seed, site, i) through Philox4x32-10 — nn.Dropout semantics, this library's own random stream. */
 AVH_API int avh_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);

@@ -11,7 +11,9 @@ from .hubert import AVHubertConfig, AVHubertModel  # noqa: F401
 from .hubert_asr import HubertEncoder, HubertEncoderWrapper  # noqa: F401
 from . import audio  # noqa: F401
 from . import distributed  # noqa: F401
+from . import fusion  # noqa: F401
+from . import sr_predictor  # noqa: F401
 from . import sharding  # noqa: F401
 from . import video  # noqa: F401
 
-__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoder", "HubertEncoderWrapper", "audio", "distributed", "sharding", "video"]
+__all__ = ["AVHubertConfig", "AVHubertModel", "HubertEncoder", "HubertEncoderWrapper", "audio", "distributed", "fusion", "sharding", "sr_predictor", "video"]

@@ -1734,6 +1734,15 @@ int avh_forward_train(avh_handle* h, const void* video, int video_dtype, const v
   return run_plan(h, p, s);
 }
 
+int avh_interp_linear(const void* x, int dtype, int B, int T, int C, const int32_t* len_in, const int32_t* len_out,
+                      int Tout, void* out, int64_t* mask, void* stream) {
+  AVH_CHECK(x != nullptr && out != nullptr && len_in != nullptr && len_out != nullptr, "null pointer");
+  AVH_CHECK(dtype == AVH_F32 || dtype == AVH_F16 || dtype == AVH_BF16, "bad dtype");
+  AVH_CHECK(B >= 1 && T >= 1 && C >= 1 && Tout >= 1, "bad shape");
+  return avh::launch_interp_linear(x, dtype, B, T, C, len_in, len_out, Tout, out, reinterpret_cast<long long*>(mask),
+                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
 int avh_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
   AVH_CHECK(x != nullptr, "null pointer");
   AVH_CHECK(dtype == AVH_F32 || dtype == AVH_F16 || dtype == AVH_BF16, "bad dtype");

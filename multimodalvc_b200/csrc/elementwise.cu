@@ -488,6 +488,36 @@ __global__ void unpack_rows_kernel(const float* __restrict__ in, const int* __re
   }
 }
 
+// Per-sample linear resize along time (F.interpolate(mode='linear', align_corners=False) on [1, C, len_in[b]] ->
+// len_out[b], src/model.py:601-606) for a whole batch: x [B, T, C] -> out [B, Tout, C], rows >= len_out[b] zero,
+// mask[b, t] = t < len_out[b].  Index arithmetic as ATen's upsample_linear1d: scale = in / out (fp32),
+// src = max(scale * (t + 0.5) - 0.5, 0), i0 = floor(src), i1 = i0 + (i0 < in - 1), w1 = src - i0.
+__global__ void interp_linear_kernel(const void* __restrict__ x, int dt, int B, int T, int C,
+                                     const int* __restrict__ len_in, const int* __restrict__ len_out, int Tout,
+                                     void* __restrict__ out, long long* __restrict__ mask) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Tout * C) return;
+  const int c = (int)(i % C);
+  const long long bt = i / C;
+  const int t = (int)(bt % Tout), b = (int)(bt / Tout);
+  const int n_in = len_in[b], n_out = len_out[b];
+  float v = 0.f;
+  if (t < n_out && n_in > 0) {
+    const float scale = (float)n_in / (float)n_out;
+    float src = scale * ((float)t + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    const int i0 = (int)src;
+    const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    const float w1 = src - (float)i0, w0 = 1.f - w1;
+    const long long base = (long long)b * T * C + c;
+    v = w0 * load_any(x, dt, base + (long long)i0 * C) + w1 * load_any(x, dt, base + (long long)i1 * C);
+  }
+  store_lp(out, dt, i, v);
+  if (c == 0 && mask != nullptr) mask[bt] = t < n_out ? 1 : 0;
+}
+
 // [rows, cols] of any float dtype -> fp32 residual stream, rows flagged in row_zero written as zeros
 __global__ void load_rows_kernel(const void* __restrict__ in, int in_dt, float* __restrict__ out,
                                  const unsigned char* __restrict__ row_zero, long long rows, int cols) {
@@ -502,6 +532,17 @@ __global__ void load_rows_kernel(const void* __restrict__ in, int in_dt, float* 
 inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
 
 }  // namespace
+
+int launch_interp_linear(const void* x, int dt, int B, int T, int C, const int* len_in, const int* len_out, int Tout,
+                         void* out, long long* mask, cudaStream_t stream) {
+  const long long n = (long long)B * Tout * C;
+  if (n <= 0) return 0;
+  AVH_CUDA_OK(launch_pdl(interp_linear_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, x, dt, B, T, C, len_in, len_out,
+                         Tout, out, mask));
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
 
 int launch_load_rows(const void* in, int in_dt, float* out, const unsigned char* row_zero, long long rows, int cols,
                      cudaStream_t stream) {

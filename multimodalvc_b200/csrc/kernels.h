@@ -33,6 +33,9 @@ int launch_unpack_rows(const float* in, const int* cu, void* out, int out_dt, in
 // [rows, cols] (fp32 / fp16 / bf16) -> fp32, rows flagged in row_zero (may be null) zeroed: index_put(x, padding_mask, 0)
 int launch_load_rows(const void* in, int in_dt, float* out, const unsigned char* row_zero, long long rows, int cols,
                      cudaStream_t stream);
+// per-sample linear resize along time of x [B,T,C] to len_out[b] rows (ATen upsample_linear1d arithmetic), zero tail, mask
+int launch_interp_linear(const void* x, int dt, int B, int T, int C, const int* len_in, const int* len_out, int Tout,
+                         void* out, long long* mask, cudaStream_t stream);
 // flat element-wise dtype conversion
 int launch_convert(const void* in, int in_dt, void* out, int out_dt, long long n, cudaStream_t stream);
 
