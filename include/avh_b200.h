@@ -137,6 +137,27 @@ AVH_API int avh_forward_train(avh_handle* h, const void* video, int video_dtype,
 AVH_API int avh_interp_linear(const void* x, int dtype, int B, int T, int C, const int32_t* len_in, const int32_t* len_out,
                               int Tout, void* out, int64_t* mask, void* stream);
 
+/* Pretraining-mode extras.
+ * avh_mask_substitute = the tensor side of AVHubertModel.apply_input_mask (avhubert/hubert.py:442-494) and
+ * apply_feature_mask (:496-536): the host draws the spans (compute_mask_indices, avhubert/utils.py:142-270) and gives ONE
+ * int32 code per (clip, frame) [B*T] (device): >= 0 take frame b'*T+t' of x, -1 keep, -2 zeros, -3 the mask embedding
+ * `emb` [U] (device).  Out of place; every source is read from the un-substituted x, as the reference's right-hand
+ * side is.  layout 0: contiguous units x = [B,T,U] (video [B,1,T,88*88], token rows [B,T,C]); channel_zero [B,U] bytes
+ * (may be NULL) zeroes channels of every frame of a clip (mask_channel_prob).  layout 1: x = [B,U,T] with element
+ * `strides` (the collater's transposed audio view), out contiguous [B,U,T]. */
+AVH_API int avh_mask_substitute(const void* x, int dtype, int layout, const int64_t* strides, int B, int T, int U,
+                                const int32_t* code, const void* emb, int emb_dtype, const uint8_t* channel_zero,
+                                void* out, int out_dtype, void* stream);
+/* AVHubertModel.compute_logits (avhubert/hubert.py:576-589): out[m,v] = (<feats_m, emb_v> + bias[v]) / logit_temp for
+ * sim_type 0 ('dot'), divided by max(|feats_m| |emb_v|, 1e-6) first for sim_type 1 ('cosine'); fp32 arithmetic.
+ * feats [M,K] (row stride ldf), emb [V,K] (row stride lde), bias fp32 [V] or NULL, out fp32 [M,V] (row stride ldo).
+ * With sim_type 0, logit_temp 1 and a bias this is final_proj (nn.Linear, hubert.py:654). */
+AVH_API int avh_compute_logits(const void* feats, int f_dtype, int64_t ldf, const void* emb, int e_dtype, int64_t lde,
+                               const float* bias, int64_t M, int V, int K, int sim_type, float logit_temp, float* out,
+                               int64_t ldo, void* stream);
+/* *acc (device double) = sum of x[i]^2 — features_pen = features.float().pow(2).mean() (hubert.py:629) times numel. */
+AVH_API int avh_sum_squares(const void* x, int dtype, int64_t n, double* acc, void* stream);
+
 /* Kernel-level entry point of the dropout used above (tests): x[i] = keep(i) ? x[i] / (1 - p) : 0 in place, keep(i) a
  * pure function of (seed, site, i) through Philox4x32-10 — nn.Dropout semantics, this library's own random stream. */
 AVH_API int avh_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
@@ -188,7 +209,7 @@ AVH_API int avh_forward_host_async(avh_handle* h, const void* video, int video_d
                            const uint8_t* padding_mask, int B, int T, int output_layer, void* out, int out_dtype,
                            void* stream);
 
-/* Intermediate taps for stage-level parity tests; names: "resnet" [B*T,512], "fused_ln" [B*T,E],
+/* Intermediate taps for stage-level parity tests; names: "resnet" [B*T,512], "fused" [B*T,E] (before the LayerNorm), "fused_ln" [B*T,E],
  * "enc_in" [B*T,D].  Copies the fp32 value of the last avh_forward into `dst` (device, fp32). */
 AVH_API int avh_read_stage(avh_handle* h, const char* name, float* dst, int64_t capacity_elems, void* stream);
 
@@ -233,6 +254,8 @@ AVH_API int avh_profile_json(avh_handle* h, char* buf, int64_t cap);
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 AVH_API int64_t avh_launch_count(void);
 AVH_API void avh_reset_launch_count(void);
+/* CUDA-graph launches issued by the library since the process started (a forward replays 2-3 graph segments). */
+AVH_API int64_t avh_graph_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,8 @@ EXPORTS = [
     "avh_forward", "avh_forward_host", "avh_forward_host_async", "avh_read_stage", "avh_fbank", "avh_add_noise", "avh_gemm_bf16",
     "avh_launch_count", "avh_reset_launch_count", "avh_set_profiling", "avh_profile_json",
     "avh_gemm_set_trace", "avh_set_video_preprocess", "avh_video_preprocess", "avh_drop_host_weights",
-    "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward", "avh_forward_train", "avh_bn_stats_count", "avh_read_bn_stats", "avh_dropout", "avh_interp_linear",
+    "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward", "avh_forward_train", "avh_bn_stats_count", "avh_read_bn_stats", "avh_dropout", "avh_interp_linear", "avh_graph_launch_count",
+    "avh_mask_substitute", "avh_compute_logits", "avh_sum_squares",
 ]
 
 
@@ -80,6 +81,9 @@ def load():
     lib.avh_forward_train.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, i32, ctypes.POINTER(AvhTrainArgs),
                                       vp, i32, vp]
     lib.avh_interp_linear.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp]
+    lib.avh_mask_substitute.argtypes = [vp, i32, i32, ctypes.POINTER(i64), i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
+    lib.avh_compute_logits.argtypes = [vp, i32, i64, vp, i32, i64, vp, i64, i32, i32, i32, ctypes.c_float, vp, i64, vp]
+    lib.avh_sum_squares.argtypes = [vp, i32, i64, vp, vp]
     lib.avh_dropout.argtypes = [vp, i32, i64, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32, vp]
     lib.avh_bn_stats_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.avh_read_bn_stats.argtypes = [vp, vp, i64, vp]
@@ -98,6 +102,7 @@ def load():
     lib.avh_profile_json.argtypes = [vp, ctypes.c_char_p, i64]
     lib.avh_launch_count.restype = i64
     lib.avh_reset_launch_count.restype = None
+    lib.avh_graph_launch_count.restype = i64
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ("avh_abi_version",):

@@ -33,6 +33,7 @@ namespace avh {
 static thread_local std::string g_err;
 void set_last_error(const std::string& msg) { g_err = msg; }
 static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_graph_launches{0};      // cudaGraphLaunch calls (avh_graph_launch_count)
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool pdl_enabled() {
@@ -157,6 +158,7 @@ struct Step {
   std::string name;       // kernel class for avh_profile_json
   double flops = 0;       // executed tensor-core FLOPs (GEMM steps)
   int layer = -1;         // encoder layer the step belongs to (LayerDrop skips it in training mode), -1 = none
+  bool direct = false;    // reads or writes a CALLER pointer (video, audio, features, output): never part of a CUDA graph
 };
 
 struct CallArgs {          // per-call pointers the steps read through the plan
@@ -217,15 +219,23 @@ struct Plan {
   // Framework allocators hand the same addresses back for same-shaped tensors and the host-buffer entry point always
   // runs from its own staging buffers, so the cache hits after the first calls; a caller that never repeats an
   // address stops being captured (captures/calls guard) and gets plain launches.
-  std::map<CallArgs, cudaGraphExec_t> graphs;
+  // Segmented graphs: every maximal run of steps that touch only plan-owned memory is one CUDA graph, captured on the
+  // second forward and replayed ever after whatever tensors the caller passes — the few steps that read the caller's
+  // video / audio / feature pointers or write its output are launched directly in between, and the padding mask is
+  // copied into a plan-owned buffer first (B*T bytes).  (Round 1 keyed whole-forward graphs on the input pointers: a
+  // caller with fresh tensors per batch never hit the cache and paid ~3 ms of host enqueue per 3.9 ms step.)
+  struct Segment { size_t begin, end; cudaGraphExec_t exec; int kernels; };
+  std::vector<Segment> segments;
+  bool segments_ready = false;
+  unsigned char* mask_dev = nullptr;   // staged copy of the caller's padding mask [B*T]
   int direct_runs = 0;              // un-captured forwards so far (the first one also configures the kernels)
-  int graph_kernels = 0;            // kernel launches inside one graph (for avh_launch_count)
-  long long calls = 0, captures = 0;
   long long last_use = 0;           // LRU clock value of the most recent forward through this plan
   cudaStream_t stream = nullptr;
   void drop_graphs() {
-    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-    graphs.clear();
+    for (auto& sg : segments)
+      if (sg.exec) cudaGraphExecDestroy(sg.exec);
+    segments.clear();
+    segments_ready = false;
   }
   ~Plan() {
     drop_graphs();
@@ -630,8 +640,9 @@ struct Builder {
   }
   std::string tag = "misc";     // name given to the steps pushed next
   int cur_layer = -1;           // encoder layer of the steps pushed next
+  bool cur_direct = false;      // the steps pushed next touch caller pointers (kept out of the CUDA graphs)
   void push(std::function<int(cudaStream_t)> f, double flops = 0.0) {
-    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, flops, cur_layer});
+    if (!sizing) plan->steps.push_back(Step{std::move(f), tag, flops, cur_layer, cur_direct});
   }
 
   // K-step table for one GEMM: every tap x every 64-wide K chunk (x 3 split-precision products in fp32 mode)
@@ -684,7 +695,7 @@ struct Builder {
     const bool wants_mask = ep.row_zero != nullptr;     // sentinel: bind the caller's mask at launch
     Plan* pl = plan;
     plan->steps.push_back(Step{[gp, pl, wants_mask](cudaStream_t s) {
-      if (wants_mask) gp->prob.ep.row_zero = pl->args.mask;
+      if (wants_mask) gp->prob.ep.row_zero = pl->mask_dev;
       return gemm_launch(*gp, s);
     }, tag, 2.0 * (double)M * (double)W.n * 64.0 * (double)pr.num_kb, cur_layer});
     return true;
@@ -756,6 +767,10 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
   b.sk_bytes = (size_t)device_sm_count() * 128 * 256 * 4;
   b.sk_ws = reinterpret_cast<float*>(b.alloc(b.sk_bytes));
   b.sk_flags = reinterpret_cast<int*>(b.alloc(4096));
+  {
+    unsigned char* md = reinterpret_cast<unsigned char*>(b.alloc((size_t)B * T + 16));
+    if (!sizing) plan->mask_dev = md;
+  }
   // fused token features [N, E]: audio arm in columns [0,D), video arm in [D,2D) (concat) or summed (add)
   Act fused = new_act(N, E);
   if (rg) {
@@ -935,21 +950,23 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
             return stem_fused_launch_ragged(pl->stemf, pl->args.video, pl->args.video_dt, pl->args.pitch,
                                             reinterpret_cast<const int4*>(pl->rag + pl->rag_items_off), pl->rag, pl->rag + 16,
                                             h->stem.scale, h->stem.bias, h->stem.slope, po, s);
-          }, b.tag, fl});
+          }, b.tag, fl, -1, true});
         else if (!sizing)
           plan->steps.push_back(Step{[=](cudaStream_t s) {
             return stem_fused_launch(pl->stemf, pl->args.video, pl->args.video_dt, T, b0, nb, h->stem.scale, h->stem.bias,
                                      h->stem.slope, po, s);
-          }, b.tag, fl});
+          }, b.tag, fl, -1, true});
       } else
       // ---- ... else (kh,kw) patches -> GEMM over 5 temporal row-shift taps (+BN+PReLU) -> maxpool
       {
         void* col = fb.im2col;
         const int planes = P;
         b.tag = "stem_patches";
+        b.cur_direct = true;
         b.push([=](cudaStream_t s) {
           return launch_stem_patches(pl->args.video, pl->args.video_dt, T, b0, nb, col, planes, s);
         });
+        b.cur_direct = false;
         Epilogue ep = ep_base(fb.stem_out, 64);
         ep.col_scale = h->stem.scale; ep.col_bias = h->stem.bias; ep.act = ACT_PRELU; ep.slope1 = h->stem.slope;
         const long long rows = (long long)nb * (T + 2) * 1936;       // tile rows include the gap frames
@@ -1072,6 +1089,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     {
       void* dst = arows.data;
       b.tag = "audio_rows";
+      b.cur_direct = true;
       if (rg)
         b.push([=](cudaStream_t s) {
           return launch_bct_to_rows_ragged(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
@@ -1082,6 +1100,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
           return launch_bct_to_rows(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2],
                                     B, Fa, T, dst, act_dt, Fp, s);
         });
+      b.cur_direct = false;
       sync_op(arows);
     }
     Epilogue ep = ep_base(reinterpret_cast<char*>(fused.data) + (size_t)a_off * es, E);
@@ -1101,13 +1120,16 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     // TransformerEncoder.forward on the caller's features: x = features with padded frames zeroed (wav2vec2.py:869-870)
     const bool hm0 = plan->has_mask;
     b.tag = "load_features";
+    b.cur_direct = true;
     b.push([=](cudaStream_t s) {
-      return launch_load_rows(pl->args.xin, pl->args.xin_dt, x, hm0 ? pl->args.mask : nullptr, N, D, s);
+      return launch_load_rows(pl->args.xin, pl->args.xin_dt, x, hm0 ? pl->mask_dev : nullptr, N, D, s);
     });
+    b.cur_direct = false;
   }
   Act lnE = plan->enc_only ? Act() : new_act(N, E);
   if (!plan->enc_only) {
     const void* src = fused.data;
+    if (!sizing) plan->stages["fused"] = {fused.data, {act_dt, N * E}};     // pre-LayerNorm features (features_pen)
     float* of = f32 ? reinterpret_cast<float*>(lnE.data) : nullptr;
     void* ol = f32 ? nullptr : lnE.data;
     float* g = h->fuse_ln_g; float* be = h->fuse_ln_b;
@@ -1128,7 +1150,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       // no post_extract_proj (embed == D): the LN output is the encoder input; zero padded rows here
       const bool hm = plan->has_mask;
       b.push([=](cudaStream_t s) {
-        return launch_layernorm(src, act_dt, E, g, be, 1e-5f, x, nullptr, DT_BF16, hm ? pl->args.mask : nullptr, N, E, s);
+        return launch_layernorm(src, act_dt, E, g, be, 1e-5f, x, nullptr, DT_BF16, hm ? pl->mask_dev : nullptr, N, E, s);
       });
       if (!sizing) plan->stages["fused_ln"] = {x, {DT_F32, N * E}};
     }
@@ -1279,11 +1301,11 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
         // bf16 mode: tcgen05 / TMEM kernel (attention_tc.cu); AVH_ATT_TC=0 selects the mma.sync kernel
         if (!sizing && l == 0 && attention_tc_plan(q, N, B, T, D, Hh, &plan->att)) return false;
         b.push([=](cudaStream_t s) {
-          return attention_tc_launch(pl->att, hm ? pl->args.mask : nullptr, pl->ragged ? pl->rag + 16 : nullptr, o, s);
+          return attention_tc_launch(pl->att, hm ? pl->mask_dev : nullptr, pl->ragged ? pl->rag + 16 : nullptr, o, s);
         }, att_flops);
       } else {
         b.push([=](cudaStream_t s) {
-          return launch_attention(q, hm ? pl->args.mask : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
+          return launch_attention(q, hm ? pl->mask_dev : nullptr, o, B, T, D, Hh, f32 ? 1 : 0, s);
         }, att_flops);
       }
       sync_op(ctx);
@@ -1363,18 +1385,22 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
       b.push([=](cudaStream_t s) { return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, y, nullptr, DT_BF16, nullptr, N, D, s); });
     }
     b.tag = "unpack";
+    b.cur_direct = true;
     b.push([=](cudaStream_t s) {
       return launch_unpack_rows(y, pl->rag + 16, pl->args.out, pl->args.out_dt, B, pl->args.pitch, D, s);
     });
   } else
   if (c.layer_norm_first && plan->output_layer == 0) {
+    b.cur_direct = true;
     float* g = h->enc_ln_g; float* be = h->enc_ln_b;
     b.push([=](cudaStream_t s) {
       return launch_layernorm(x, DT_F32, D, g, be, 1e-5f, nullptr, pl->args.out, pl->args.out_dt, nullptr, N, D, s);
     });
   } else {
+    b.cur_direct = true;
     b.push([=](cudaStream_t s) { return launch_convert(x, DT_F32, pl->args.out, pl->args.out_dt, N * D, s); });
   }
+  b.cur_direct = false;
   if (bytes_out) *bytes_out = b.sizer.used;
   return true;
 }
@@ -1464,6 +1490,7 @@ int avh_abi_version(void) { return AVH_ABI_VERSION; }
 const char* avh_last_error(void) { return avh::g_err.c_str(); }
 int64_t avh_launch_count(void) { return avh::g_launches.load(); }
 void avh_reset_launch_count(void) { avh::g_launches.store(0); }
+int64_t avh_graph_launch_count(void) { return avh::g_graph_launches.load(); }
 
 int avh_create(const avh_config* cfg, int device, avh_handle** out) {
   AVH_CHECK(cfg != nullptr && out != nullptr, "null argument");
@@ -1564,48 +1591,65 @@ static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
     const char* dbg2 = std::getenv("AVH_WIN_DBG");
     graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr || dbg2 != nullptr) ? 0 : 1;
   }
+  // the caller's padding mask -> plan-owned copy (every later read is pointer-independent)
+  if (p->has_mask && p->args.mask != nullptr)
+    AVH_CUDA_OK(cudaMemcpyAsync(p->mask_dev, p->args.mask, (size_t)p->B * p->T, cudaMemcpyDeviceToDevice, s));
   // a caller that is itself capturing this stream (e.g. torch.cuda.graph) gets plain launches recorded into ITS graph
   cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
   if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) cudaStreamIsCapturing(s, &cap_status);
-  if (graphs_env == 1 && !h->profiling && !p->train && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
-      cap_status == cudaStreamCaptureStatusNone) {
-    ++p->calls;
-    auto it = p->graphs.find(p->args);
-    if (it != p->graphs.end()) {
-      AVH_CUDA_OK(cudaGraphLaunch(it->second, s));
-      avh::count_launch(p->graph_kernels);
-      return p->steps.back().run(s);
-    }
-    const bool thrashing = p->captures >= 16 && 2 * p->captures > p->calls;     // inputs never come back: stop capturing
-    if (p->direct_runs >= 1 && !thrashing && p->steps.size() >= 2) {
-      // capture this argument set: the steps only enqueue kernels / async copies on `s`
-      if (p->graphs.size() >= 16) p->drop_graphs();
+  const bool graphs_ok = graphs_env == 1 && !h->profiling && !p->train && s != nullptr && s != cudaStreamLegacy &&
+                         s != cudaStreamPerThread && cap_status == cudaStreamCaptureStatusNone;
+  if (graphs_ok && !p->segments_ready && p->direct_runs >= 1) {
+    // second forward of this plan: capture every run of plan-internal steps (they only enqueue kernels / async copies)
+    bool ok = true;
+    size_t i = 0;
+    while (ok && i < p->steps.size()) {
+      if (p->steps[i].direct) { ++i; continue; }
+      size_t j = i;
+      while (j < p->steps.size() && !p->steps[j].direct) ++j;
       const long long before = avh::g_launches.load();
       cudaGraph_t graph = nullptr;
-      bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (ok) {
-        for (size_t i = 0; i + 1 < p->steps.size(); ++i)
-          if (p->steps[i].run(s)) { ok = false; break; }
+        for (size_t k = i; k < j; ++k)
+          if (p->steps[k].run(s)) { ok = false; break; }
         if (cudaStreamEndCapture(s, &graph) != cudaSuccess || graph == nullptr) ok = false;
       }
       const int captured = (int)(avh::g_launches.load() - before);
-      avh::count_launch(-captured);            // captured launches have not run yet
+      avh::count_launch(-captured);            // captured launches have not run
       cudaGraphExec_t exec = nullptr;
       if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
       if (graph != nullptr) cudaGraphDestroy(graph);
-      if (ok) {
-        p->graphs[p->args] = exec;
-        p->graph_kernels = captured;
-        ++p->captures;
-        AVH_CUDA_OK(cudaGraphLaunch(exec, s));
-        avh::count_launch(captured);
-        return p->steps.back().run(s);
-      }
+      if (ok) p->segments.push_back(avh::Plan::Segment{i, j, exec, captured});
+      i = j;
+    }
+    if (ok) p->segments_ready = true;
+    else {
       // capture is not available for this launch list on this driver: remember, clear the error, run directly
+      p->drop_graphs();
       cudaGetLastError();
       avh::g_err.clear();
       graphs_env = 0;
     }
+  }
+  if (graphs_ok && graphs_env == 1 && p->segments_ready) {
+    size_t i = 0, sg = 0;
+    while (i < p->steps.size()) {
+      if (sg < p->segments.size() && p->segments[sg].begin == i) {
+        AVH_CUDA_OK(cudaGraphLaunch(p->segments[sg].exec, s));
+        avh::count_launch(p->segments[sg].kernels);
+        avh::g_graph_launches.fetch_add(1, std::memory_order_relaxed);
+        i = p->segments[sg].end;
+        ++sg;
+      } else {
+        if (p->steps[i].run(s)) {
+          if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
+          return 1;
+        }
+        ++i;
+      }
+    }
+    return 0;
   }
   ++p->direct_runs;
   if (h->profiling) {
@@ -1747,6 +1791,41 @@ int avh_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint32_t 
   AVH_CHECK(x != nullptr, "null pointer");
   AVH_CHECK(dtype == AVH_F32 || dtype == AVH_F16 || dtype == AVH_BF16, "bad dtype");
   return avh::launch_dropout(x, dtype, nullptr, n, p, seed, site, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_mask_substitute(const void* x, int dtype, int layout, const int64_t* strides, int B, int T, int U,
+                        const int32_t* code, const void* emb, int emb_dtype, const uint8_t* channel_zero, void* out,
+                        int out_dtype, void* stream) {
+  AVH_CHECK(x != nullptr && code != nullptr && out != nullptr, "null pointer");
+  AVH_CHECK(x != out, "mask substitution is out of place (sources are read from the un-substituted tensor)");
+  AVH_CHECK(dtype == AVH_F32 || dtype == AVH_F16 || dtype == AVH_BF16, "bad dtype");
+  AVH_CHECK(B >= 0 && T >= 0 && U > 0, "bad shape");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (layout == 0) {
+    AVH_CHECK(out_dtype == dtype, "unit layout keeps the dtype");
+    return avh::launch_mask_units(x, out, dtype, code, emb, emb_dtype, (long long)B * T, U, channel_zero, T, s);
+  }
+  AVH_CHECK(layout == 1, "layout must be 0 (contiguous units) or 1 (strided [B,C,T])");
+  AVH_CHECK(strides != nullptr, "layout 1 needs the three element strides");
+  AVH_CHECK(channel_zero == nullptr, "channel masks apply to the unit layout only");
+  AVH_CHECK(out_dtype == AVH_F32 || out_dtype == AVH_F16 || out_dtype == AVH_BF16, "bad dtype");
+  return avh::launch_mask_bct(x, dtype, strides[0], strides[1], strides[2], out, out_dtype, code, emb, emb_dtype, B, U, T, s);
+}
+
+int avh_compute_logits(const void* feats, int f_dtype, int64_t ldf, const void* emb, int e_dtype, int64_t lde,
+                       const float* bias, int64_t M, int V, int K, int sim_type, float logit_temp, float* out, int64_t ldo,
+                       void* stream) {
+  AVH_CHECK(feats != nullptr && emb != nullptr && out != nullptr, "null pointer");
+  AVH_CHECK(sim_type == 0 || sim_type == 1, "sim_type must be 0 (dot) or 1 (cosine)");
+  AVH_CHECK(logit_temp != 0.f, "logit_temp must be non-zero");
+  AVH_CHECK(K > 0 && ldf >= K && lde >= K && ldo >= V, "bad leading dimension");
+  return avh::launch_logits(feats, f_dtype, ldf, emb, e_dtype, lde, bias, out, ldo, M, V, K, sim_type, 1.0f / logit_temp,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avh_sum_squares(const void* x, int dtype, int64_t n, double* acc, void* stream) {
+  AVH_CHECK(x != nullptr && acc != nullptr, "null pointer");
+  return avh::launch_sumsq(x, dtype, n, acc, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int avh_bn_stats_count(avh_handle* h, int64_t* n_floats) {

@@ -77,6 +77,19 @@ int launch_bn_apply(const void* raw, void* out, int dt, long long rows, int C, c
 int launch_dropout(void* x, int dt, const float* add, long long n, float p, unsigned long long seed, unsigned int site,
                    cudaStream_t stream);
 
+// ---- pretraining-mode extras (pretrain_ops.cu): span-mask substitution, masked-prediction logits, features_pen
+// out unit u ([units, U] contiguous) = in unit code[u] (>= 0) | own (-1) | zeros (-2) | emb (-3); chan_zero [units / T, U]
+int launch_mask_units(const void* in, void* out, int dt, const int* code, const void* emb, int emb_dt, long long units,
+                      int U, const unsigned char* chan_zero, int T, cudaStream_t stream);
+// the same on a strided [B,C,T] tensor (code per (b, t)), contiguous [B,C,T] out
+int launch_mask_bct(const void* in, int dt, long long sb, long long sc, long long st, void* out, int out_dt,
+                    const int* code, const void* emb, int emb_dt, int B, int C, int T, cudaStream_t stream);
+// out[m,v] = (<F_m, E_v> + bias[v]) * inv_temp (mode 0) or / max(|F_m| |E_v|, 1e-6) * inv_temp (mode 1), fp32
+int launch_logits(const void* F, int f_dt, long long ldf, const void* E, int e_dt, long long lde, const float* bias,
+                  float* out, long long ldo, long long M, int V, int K, int mode, float inv_temp, cudaStream_t stream);
+// *acc = sum of squares of x (float64; acc is zeroed first)
+int launch_sumsq(const void* x, int dt, long long n, double* acc, cudaStream_t stream);
+
 // ---- audio frontend ---------------------------------------------------------------------------------
 struct FbankArgs {
   const int16_t* wav;          // concatenated clips

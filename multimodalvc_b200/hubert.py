@@ -14,10 +14,11 @@ import math
 from dataclasses import dataclass, field
 from typing import Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, masking
 
 _DTYPES = {torch.float32: _lib.AVH_F32, torch.float16: _lib.AVH_F16, torch.bfloat16: _lib.AVH_BF16}
 _U8 = _lib.AVH_U8        # raw uint8 video frames (normalised + centre-cropped on the device)
@@ -53,6 +54,27 @@ class AVHubertConfig:
     audio_dropout: float = 0.0
     modality_fuse: str = "concat"
     masking_type: str = "input"
+    # span masking / masked-prediction head (pretraining-mode forward; avhubert/hubert.py:146-258 defaults)
+    logit_temp: float = 0.1
+    target_glu: bool = False
+    mask_length_audio: int = 10
+    mask_prob_audio: float = 0.65
+    mask_length_image: int = 10
+    mask_prob_image: float = 0.65
+    mask_selection: str = "static"
+    mask_other: float = 0
+    no_mask_overlap: bool = False
+    mask_min_space: int = 1
+    mask_channel_length: int = 10
+    mask_channel_prob: float = 0.0
+    mask_channel_selection: str = "static"
+    mask_channel_other: float = 0
+    no_mask_channel_overlap: bool = False
+    mask_channel_min_space: int = 1
+    skip_masked: bool = False
+    skip_nomask: bool = False
+    sim_type: str = "cosine"
+    selection_type: str = "same_other_seq"
     # --- B200 build options (not in the reference) ---
     compute_dtype: str = "auto"        # "auto": fp32 module -> fp32-faithful mode, half/bf16 module -> bf16 mode
     frontend_chunk_frames: int = 0     # 0 = library default
@@ -193,7 +215,18 @@ class AVHubertModel(nn.Module):
         self.encoder = _EncoderParams(cfg)
         self.layer_norm = nn.LayerNorm(self.embed)
         final_dim = cfg.final_dim if cfg.final_dim > 0 else D
-        self.final_proj = nn.Linear(D, final_dim)      # pretraining head; dropped by remove_pretraining_modules
+        if cfg.target_glu:
+            raise NotImplementedError("target_glu is false in every shipped config (and unused by the reference forward)")
+        dictionaries = list(dictionaries) if dictionaries is not None else [None]
+        # pretraining head (hubert.py:409-426); dropped by remove_pretraining_modules
+        self.untie_final_proj = bool(cfg.untie_final_proj)
+        self.final_proj = nn.Linear(D, final_dim * (len(dictionaries) if self.untie_final_proj else 1))
+        self.num_classes = None
+        if not any(d is None for d in dictionaries):
+            self.num_classes = [len(d) for d in dictionaries]
+            self.label_embs_concat = nn.Parameter(torch.FloatTensor(sum(self.num_classes), final_dim).uniform_())
+        sample_rate = getattr(task_cfg, "sample_rate", cfg.label_rate) if task_cfg is not None else cfg.label_rate
+        self.feat2tar_ratio = cfg.label_rate / sample_rate          # hubert.py:346-347 (feature_ds_rate = 1)
         self._handle = None
         self._handle_key = None
         self._dirty = True
@@ -289,7 +322,8 @@ class AVHubertModel(nn.Module):
             self._handle, self._handle_key = hp, key
         with torch.no_grad():
             for name, t in self.state_dict().items():
-                if name == "mask_emb" or name.startswith("final_proj.") or name.endswith("num_batches_tracked"):
+                if (name in ("mask_emb", "label_embs_concat") or name.startswith("final_proj.")
+                        or name.endswith("num_batches_tracked")):
                     continue
                 if not t.is_floating_point():
                     continue
@@ -309,8 +343,8 @@ class AVHubertModel(nn.Module):
     # ------------------------------------------------------------------ the hot path
     def _check_mode(self, mask, allow_train=False):
         if mask:
-            raise NotImplementedError("apply_input_mask (mask=True) is off in every shipped fine-tune/inference "
-                                      "config and is not implemented on the device path")
+            raise NotImplementedError("span masking is applied by extract_finetune / extract_features / forward on "
+                                      "device tensors only")
         if self.training and not allow_train:
             raise RuntimeError("this entry point runs the eval-mode forward only; call .eval() (extract_finetune on "
                                "device tensors supports the training-mode forward)")
@@ -410,7 +444,12 @@ class AVHubertModel(nn.Module):
         """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
         padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask).  With cfg.ragged == "packed" (bf16
         mode) ragged batches run packed; `lengths` (valid frames per clip) may be given to skip reading the mask back."""
-        self._check_mode(mask, allow_train=True)
+        if mask and self.cfg.masking_type == "input":
+            # hubert.py:696-699: video first, then audio (the order fixes the RNG stream); the union is not used here
+            src_video, _ = self.apply_input_mask(source["video"], padding_mask, None)
+            src_audio, _ = self.apply_input_mask(source["audio"], padding_mask, None)
+            source = {"audio": src_audio, "video": src_video}
+        self._check_mode(False, allow_train=True)
         if not self.training and getattr(self, "_eval_stale", False):
             # training-mode forwards moved the BatchNorm running statistics: fold the current ones for eval
             self._dirty, self._eval_stale = True, False
@@ -557,6 +596,142 @@ class AVHubertModel(nn.Module):
             lib.avh_set_profiling(handle, 0)
         return json.loads(buf.value.decode())
 
+    # ------------------------------------------------------------------ pretraining-mode extras
+    def _substitute(self, x, layout, B, T, U, codes, emb, channel_zero=None):
+        """avh_mask_substitute on a device tensor: layout 0 = contiguous [B,T,U] units, 1 = strided [B,U,T]."""
+        dev = x.device
+        if dev.type != "cuda":
+            raise RuntimeError("span masking runs on the device: move the inputs to the module's CUDA device")
+        if x.dtype not in _DTYPES:
+            raise ValueError(f"unsupported dtype {x.dtype}")
+        code_dev = torch.from_numpy(np.ascontiguousarray(codes, dtype=np.int32)).to(dev)
+        out = torch.empty(x.shape, device=dev, dtype=x.dtype)
+        strides = (ctypes.c_int64 * 3)(*x.stride()) if layout == 1 else None
+        if layout == 0:
+            x = x.contiguous()
+        emb_t = emb.detach().to(dev).contiguous() if emb is not None else None
+        cz = channel_zero.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8) if channel_zero is not None else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_mask_substitute(
+                ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype], layout, strides, B, T, U,
+                ctypes.c_void_p(code_dev.data_ptr()),
+                ctypes.c_void_p(emb_t.data_ptr()) if emb_t is not None else None,
+                _DTYPES[emb_t.dtype] if emb_t is not None else 0,
+                ctypes.c_void_p(cz.data_ptr()) if cz is not None else None,
+                ctypes.c_void_p(out.data_ptr()), _DTYPES[out.dtype], ctypes.c_void_p(stream)))
+        return out
+
+    @torch.no_grad()
+    def apply_input_mask(self, x, padding_mask, target_list=None):
+        """avhubert/hubert.py:442-494.  x = audio [B,F,T] or video [B,1,T,H,W] on the device.  The spans come from
+        masking.compute_mask_indices (numpy's global generator, the reference's draw order); masked audio frames
+        become ``mask_emb``, masked video frames the same frames of another clip ('same_other_seq': the shift drawn
+        with torch.randint as the reference does) or another run of the same clip ('same_seq'); zeros when B == 1.
+        Returns (a new contiguous tensor, mask_indices bool [B,T] on the device) — (x, None) when the probability is 0."""
+        if x is None:
+            raise ValueError("apply_input_mask needs both modalities (the reference fails on None, hubert.py:443)")
+        c = self.cfg
+        B, C, T = x.shape[:3]
+        is_audio = x.dim() == 3
+        prob, length = (c.mask_prob_audio, c.mask_length_audio) if is_audio else (c.mask_prob_image, c.mask_length_image)
+        if not prob > 0:
+            return x, None
+        if not is_audio and (x.dim() != 5 or C != 1):
+            raise ValueError(f"video must be [B,1,T,H,W], got {tuple(x.shape)}")
+        m, starts, ends, owners = masking.compute_mask_indices(
+            (B, T), padding_mask, prob, length, c.mask_selection, c.mask_other, min_masks=2,
+            no_overlap=c.no_mask_overlap, min_space=c.mask_min_space)
+        if B == 1:
+            codes = masking.span_codes_constant(m, masking.ZERO)
+        elif is_audio:
+            codes = masking.span_codes_constant(m, masking.EMB)
+        elif c.selection_type == "same_other_seq":
+            perm = (torch.arange(B) + torch.randint(low=1, high=B, size=(1,))) % B
+            codes = masking.span_codes_other_clip(m, perm.numpy())
+        elif c.selection_type == "same_seq":
+            codes = masking.span_codes_same_clip(m, starts, ends, owners)
+        else:
+            raise ValueError(f"unknown selection_type {c.selection_type}")
+        if is_audio:
+            out = self._substitute(x, 1, B, T, C, codes, self.mask_emb)
+        else:
+            out = self._substitute(x, 0, B, T, x.size(3) * x.size(4), codes, None)
+        return out, torch.from_numpy(m).to(x.device)
+
+    @torch.no_grad()
+    def apply_feature_mask(self, x, padding_mask, target_list=None):
+        """avhubert/hubert.py:496-536 on token rows x [B,T,D]: masked rows become ``mask_emb``; with mask_channel_prob
+        > 0 whole channels of a clip are zeroed.  Returns (new tensor, mask_indices or None)."""
+        c = self.cfg
+        B, T, C = x.shape
+        if c.mask_prob_audio != c.mask_prob_image or c.mask_length_audio != c.mask_length_image:
+            raise AssertionError("masking prob/length for image/audio be same for feature masking")
+        m = None
+        codes = np.full((B, T), masking.KEEP, dtype=np.int32)
+        if c.mask_prob_audio > 0:
+            m, _, _, _ = masking.compute_mask_indices(
+                (B, T), padding_mask, c.mask_prob_audio, c.mask_length_image, c.mask_selection, c.mask_other,
+                min_masks=2, no_overlap=c.no_mask_overlap, min_space=c.mask_min_space)
+            codes = masking.span_codes_constant(m, masking.EMB)
+        cz = None
+        if c.mask_channel_prob > 0:
+            mc, _, _, _ = masking.compute_mask_indices(
+                (B, C), None, c.mask_channel_prob, c.mask_channel_length, c.mask_channel_selection,
+                c.mask_channel_other, no_overlap=c.no_mask_channel_overlap, min_space=c.mask_channel_min_space)
+            cz = torch.from_numpy(mc)
+        out = self._substitute(x, 0, B, T, C, codes, self.mask_emb, cz)
+        return out, (torch.from_numpy(m).to(x.device) if m is not None else None)
+
+    @torch.no_grad()
+    def compute_logits(self, feats, emb_mat, bias=None, sim_type=None, logit_temp=None):
+        """avhubert/hubert.py:576-589: feats [B,T,F] (or [M,F]), emb_mat [V,F] -> fp32 logits [B,T,V]; cosine or dot
+        similarity over the last dim divided by ``logit_temp``.  (``bias`` turns the 'dot' form into nn.Linear.)"""
+        sim_type = self.cfg.sim_type if sim_type is None else sim_type
+        if sim_type not in ("dot", "cosine"):
+            raise NotImplementedError
+        temp = float(self.cfg.logit_temp if logit_temp is None else logit_temp)
+        dev = feats.device
+        if dev.type != "cuda":
+            raise RuntimeError("compute_logits runs on the device (there is no CPU path)")
+        lead, K = feats.shape[:-1], feats.size(-1)
+        f2 = feats.reshape(-1, K)
+        if f2.dtype not in _DTYPES or f2.stride(-1) != 1:
+            f2 = f2.float().contiguous()
+        e2 = emb_mat.detach()
+        if e2.dtype not in _DTYPES or e2.stride(-1) != 1 or e2.device != dev:
+            e2 = e2.to(dev).float().contiguous()
+        if e2.dim() != 2 or e2.size(1) != K:
+            raise ValueError(f"emb_mat must be [V,{K}], got {tuple(emb_mat.shape)}")
+        b = bias.detach().to(dev).float().contiguous() if bias is not None else None
+        M, V = f2.size(0), e2.size(0)
+        out = torch.empty(M, V, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_compute_logits(
+                ctypes.c_void_p(f2.data_ptr()), _DTYPES[f2.dtype], f2.stride(0) if M > 1 else K,
+                ctypes.c_void_p(e2.data_ptr()), _DTYPES[e2.dtype], e2.stride(0) if V > 1 else K,
+                ctypes.c_void_p(b.data_ptr()) if b is not None else None, M, V, K,
+                1 if sim_type == "cosine" else 0, temp, ctypes.c_void_p(out.data_ptr()), V, ctypes.c_void_p(stream)))
+        return out.view(*lead, V)
+
+    def _features_pen(self, numel):
+        """features.float().pow(2).mean() over the fused (pre-LayerNorm) features of the last forward (hubert.py:629)."""
+        dev = self.encoder.layer_norm.weight.device
+        stage = self.read_stage("fused", numel)
+        acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_sum_squares(ctypes.c_void_p(stage.data_ptr()), _lib.AVH_F32, numel,
+                                                  ctypes.c_void_p(acc.data_ptr()), ctypes.c_void_p(stream)))
+        return (acc / numel).float().squeeze(0)
+
+    def _need_stages(self):
+        if not self.cfg.capture_stages:           # the encoder input is only kept when the handle captures stages
+            self.cfg.capture_stages = True
+            self._destroy_handle()
+            self._dirty = True
+
     @torch.no_grad()
     def extract_features(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
         """avhubert/hubert.py:676-692 (forward(features_only=True), :591-653) in eval mode: returns
@@ -564,22 +739,99 @@ class AVHubertModel(nn.Module):
         padded frames zeroed, as the reference's in-place index_put leaves it) — layer 0 of
         avhubert/clustering/dump_hubert_feature.py:95-106; otherwise the output of layer ``output_layer`` (1-based,
         no final LayerNorm) or of the whole encoder.  Both modalities are required, as in the reference."""
-        if mask:
-            raise NotImplementedError("span masking (mask=True) is not implemented on the device path")
-        if source["audio"] is None or source["video"] is None:
-            raise ValueError("extract_features needs both modalities (forward_features fails on None in the "
-                             "reference, hubert.py:609-610); use extract_finetune for single-modality input")
-        if not ret_conv:
-            return self.extract_finetune(source, padding_mask, output_layer=output_layer)
-        if not self.cfg.capture_stages:           # the encoder input is only kept when the handle captures stages
-            self.cfg.capture_stages = True
-            self._destroy_handle()
-            self._dirty = True
-        x, pm = self.extract_finetune(source, padding_mask, output_layer=1)
-        B, T, D = x.shape
-        feats = self.read_stage("enc_in", B * T * D).view(B, T, D).to(x.dtype)
-        return feats, pm
+        res = self.forward(source, padding_mask=padding_mask, mask=mask, features_only=True, output_layer=output_layer,
+                           _want_features=ret_conv)
+        return (res["features"] if ret_conv else res["x"]), res["padding_mask"]
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("the pretraining forward (masked prediction, avhubert/hubert.py:591-674) is out "
-                                  "of scope; use extract_finetune")
+    @torch.no_grad()
+    def forward(self, source, target_list=None, padding_mask=None, mask=True, features_only=False, output_layer=None,
+                _want_features=True):
+        """The masked-prediction forward, avhubert/hubert.py:591-674, in EVAL mode (what fairseq's validation step and
+        ``extract_features`` run; the training-mode pass needs the backward of SURVEY row A18).  Input span masking
+        (``masking_type='input'``: frames substituted before the frontends) or feature masking (``'feature'``: token
+        rows replaced by ``mask_emb`` after post_extract_proj), the encoder, then — unless ``features_only`` —
+        final_proj, cosine / dot logits against the label embeddings and the masked / unmasked selections.  Returns
+        the reference's dict.  numpy / torch CPU generators are consumed in the reference's order."""
+        if self.training:
+            raise NotImplementedError("the pretraining forward runs in eval mode here (modality dropout and the "
+                                      "losses' backward belong to the training configuration, SURVEY row A18)")
+        src_audio, src_video = source["audio"], source["video"]
+        if src_audio is None or src_video is None:
+            raise ValueError("forward / extract_features need both modalities (forward_features fails on None in the "
+                             "reference, hubert.py:609-610); use extract_finetune for single-modality input")
+        c = self.cfg
+        mask_indices = None
+        if mask and c.masking_type == "input":
+            src_video, mi_v = self.apply_input_mask(src_video, padding_mask, target_list)
+            src_audio, mi_a = self.apply_input_mask(src_audio, padding_mask, target_list)
+            mask_indices = torch.logical_or(mi_a, mi_v)      # None here fails as in the reference (prob 0 + mask=True)
+        np.random.random(), np.random.random()               # modality-dropout coins: drawn in eval mode too (:611)
+        if target_list is not None:
+            T = src_video.size(2)
+            if self.feat2tar_ratio * T > min(t.size(1) for t in target_list):
+                raise NotImplementedError("labels shorter than the features (forward_targets would trim the features "
+                                          "mid-forward, hubert.py:553-558): trim the inputs to the labelled frames")
+            idx = (torch.arange(T).float() * self.feat2tar_ratio).long()
+            target_list = [t[:, idx.to(t.device)] for t in target_list]
+        feature_mask = bool(mask) and c.masking_type == "feature"
+        want_pen = not features_only
+        if _want_features or feature_mask or want_pen:
+            self._need_stages()
+        src = {"audio": src_audio, "video": src_video}
+        if not feature_mask:
+            x, pm = self.extract_finetune(src, padding_mask, output_layer=output_layer)
+            B, T, D = x.shape
+            features = None
+            if _want_features:
+                features = self.read_stage("enc_in", B * T * D).view(B, T, D).to(x.dtype)
+        else:
+            # features after post_extract_proj (one encoder layer is computed and discarded), mask rows, run the encoder
+            y1, pm = self.extract_finetune(src, padding_mask, output_layer=1)
+            B, T, D = y1.shape
+            feats = self.read_stage("enc_in", B * T * D).view(B, T, D).to(y1.dtype)
+            pen = self._features_pen(B * T * self.embed) if want_pen else None
+            features, mask_indices = self.apply_feature_mask(feats, pm, target_list)
+            x = self._encoder_forward(features, pm, output_layer)
+        if features_only:
+            return {"x": x, "padding_mask": pm, "features": features}
+        if not feature_mask:
+            pen = self._features_pen(B * T * self.embed)
+        if self.final_proj is None or self.num_classes is None:
+            raise RuntimeError("the masked-prediction head was removed (remove_pretraining_modules) or the model was "
+                               "built without dictionaries")
+        label_embs_list = self.label_embs_concat.split(self.num_classes, 0)
+        proj_x = self.compute_logits(x, self.final_proj.weight, bias=self.final_proj.bias, sim_type="dot", logit_temp=1.0)
+        if self.untie_final_proj:
+            proj_x_list = proj_x.chunk(len(self.num_classes), dim=-1)
+        else:
+            proj_x_list = [proj_x for _ in self.num_classes]
+        logit_list = [self.compute_logits(p, e).view(-1, n) for p, e, n in zip(proj_x_list, label_embs_list, self.num_classes)]
+        if pm is None:       # the reference evaluates ~padding_mask here (hubert.py:663)
+            raise TypeError("forward(features_only=False) needs a padding_mask (bad operand type for unary ~: 'NoneType')")
+        pad = pm
+        sel_m = torch.logical_and(mask_indices, ~pad).view(-1)
+        sel_u = torch.logical_and(~mask_indices, ~pad).view(-1)
+        return {
+            "logit_m_list": [lg[sel_m] for lg in logit_list],
+            "logit_u_list": [lg[sel_u] for lg in logit_list],
+            "target_m_list": [t.reshape(-1).to(x.device)[sel_m].long() for t in target_list],
+            "target_u_list": [t.reshape(-1).to(x.device)[sel_u].long() for t in target_list],
+            "padding_mask": pm,
+            "features_pen": pen,
+        }
+
+    def _encoder_forward(self, feats, padding_mask, output_layer):
+        """self.encoder(x, padding_mask, layer) on caller features through avh_encoder_forward."""
+        dev = feats.device
+        B, T, D = feats.shape
+        feats = feats.contiguous()
+        out = torch.empty(B, T, D, device=dev, dtype=feats.dtype)
+        pm_u8 = padding_mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8) if padding_mask is not None else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_encoder_forward(
+                self._ensure_handle(), ctypes.c_void_p(feats.data_ptr()), _DTYPES[feats.dtype],
+                ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None, B, T,
+                0 if output_layer is None else int(output_layer), ctypes.c_void_p(out.data_ptr()), _DTYPES[out.dtype],
+                ctypes.c_void_p(stream)))
+        return out

@@ -62,3 +62,34 @@ def to_dev(src, pm, device="cuda", dtype=None):
             v = v.to(device)
             out[k] = v.to(dtype) if dtype is not None else v
     return out, (pm.to(device) if pm is not None else None)
+
+
+def load_pretrain_case(name):
+    """Golden of the REAL AVHubertModel.forward(mask=True) (oracle/make_golden_pretrain.py): returns dict(oracle, head,
+    src, pm, targets, over, n_dicts, z) with the seeded encoder weights rebuilt and the stored head weights."""
+    from oracle import make_golden_pretrain as mg
+    from oracle import pretrain_oracle as po
+    B, T, lengths, over, n_dicts = mg.CASES[name]
+    z = np.load(os.path.join(GOLDEN, f"pretrain_{name}.npz"))
+    oracle = ao.build_oracle("tiny", seed=1234)
+    assert state_checksum(oracle.state_dict()) == str(z["checksum"]), "seeded weights changed: regenerate goldens"
+    src, pm, targets = mg.case_inputs(name, B, T, lengths, n_dicts)
+    head = po.Head(z["mask_emb"], z["final_proj_w"], z["final_proj_b"], z["label_embs"], mg.NUM_CLASSES[:n_dicts], **over)
+    return dict(oracle=oracle, head=head, src=src, pm=pm, targets=targets, over=over, n_dicts=n_dicts, z=z)
+
+
+def make_pretrain_device_model(c, dtype, device="cuda"):
+    """The product's AVHubertModel with the pretraining head of a golden case (dictionaries given, final_dim 32)."""
+    from multimodalvc_b200 import AVHubertConfig, AVHubertModel
+    from oracle import make_golden_pretrain as mg
+    import types
+    cfg = AVHubertConfig.named("tiny", final_dim=mg.FINAL_DIM, **c["over"])
+    m = AVHubertModel(cfg, types.SimpleNamespace(sample_rate=25), [list(range(n)) for n in mg.NUM_CLASSES[:c["n_dicts"]]])
+    sd = dict(c["oracle"].state_dict())
+    z = c["z"]
+    sd["mask_emb"] = torch.from_numpy(z["mask_emb"])
+    sd["final_proj.weight"], sd["final_proj.bias"] = torch.from_numpy(z["final_proj_w"]), torch.from_numpy(z["final_proj_b"])
+    sd["label_embs_concat"] = torch.from_numpy(z["label_embs"])
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and not missing.missing_keys, missing
+    return m.to(device=device, dtype=dtype).eval()

@@ -250,16 +250,17 @@ def test_hubert_encoder_ctc_head():
 
 
 def test_cuda_graph_replay_matches_direct_launches():
-    """The launch list is captured into a CUDA graph per distinct set of caller pointers (first call of a shape runs
-    directly, the second captures, later ones replay).  Replays, re-captures for new pointers and calls on another
-    stream must reproduce the direct results bit for bit, and must read the CURRENT contents of the buffers."""
+    """The plan-internal runs of the launch list are captured into CUDA graphs on the second call of a shape and
+    replayed afterwards WHATEVER tensors the caller passes (the steps that read caller pointers stay direct launches).
+    Replays with fresh input tensors, calls on another stream must reproduce the direct results bit for bit, and must
+    read the CURRENT contents of the buffers."""
     c = load_encoder_case("tiny_av_ragged")
     m = make_device_model(c["oracle"], c["over"], c["size"], torch.bfloat16)
     src, pm = to_dev(c["src"], c["pm"], dtype=torch.bfloat16)
     y0 = m.extract_finetune(src, pm)[0].clone()                  # direct
     outs = [m.extract_finetune(src, pm)[0].clone() for _ in range(3)]          # capture, replay, replay (fresh outputs)
     assert all(torch.equal(y0, y) for y in outs)
-    src2 = {k: v.clone() for k, v in src.items()}                # same values at new addresses -> new capture
+    src2 = {k: v.clone() for k, v in src.items()}                # same values at new addresses
     assert torch.equal(m.extract_finetune(src2, pm.clone())[0], y0)
     # same addresses, new contents: the graph must see them
     src2["video"].mul_(0.5)
@@ -269,8 +270,13 @@ def test_cuda_graph_replay_matches_direct_launches():
     assert torch.equal(m.extract_finetune(src3, pm)[0], y_half)
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
+    from multimodalvc_b200 import _lib
     with torch.cuda.stream(st):
         ys = [m.extract_finetune(src, pm)[0] for _ in range(3)]
+        g0 = _lib.load().avh_graph_launch_count()
+        fresh = {k: v.clone() for k, v in src.items()}           # new addresses on a capturable stream: still a replay
+        ys.append(m.extract_finetune(fresh, pm.clone())[0])
+        assert _lib.load().avh_graph_launch_count() >= g0 + 2    # graph segments, not ~200 direct launches
     st.synchronize()
     assert all(torch.equal(y0, y) for y in ys)
 
