@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag:
                 self.samples.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
                                      int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
-                time.sleep(0.002)
+                time.sleep(float(os.environ.get('AVH_BENCH_SAMPLE_S', '0.002')))
         except Exception as e:      # clocks are evidence, not part of the measurement: never fail the run
             self.err = str(e)
             self.ready.set()

@@ -70,8 +70,10 @@ typedef struct avh_config {
   int32_t compute_mode;            /* AVH_COMPUTE_* */
   int32_t frontend_chunk_frames;   /* video frames per lip-frontend pass; 0 = default */
   int32_t capture_stages;          /* non-zero: keep copies of intermediate stages for avh_read_stage (tests) */
-  int32_t reserved[4];             /* reserved[0] != 0: the handle holds a bare fairseq TransformerEncoder (state-dict keys
-                                      "encoder.*" only; avh_encoder_forward is its one forward entry point) */
+  int32_t reserved[4];             /* reserved[0] = 1: the handle holds a bare fairseq TransformerEncoder (state-dict keys
+                                      "encoder.*" only; avh_encoder_forward is its one forward entry point);
+                                      reserved[0] = 2: a Q-Former (avh_qformer_forward; reserved[1] = encoder_width,
+                                      reserved[2] = rows of query_tokens) */
 } avh_config;
 
 typedef struct avh_handle avh_handle;
@@ -171,6 +173,22 @@ AVH_API int avh_read_bn_stats(avh_handle* h, float* dst, int64_t capacity, void*
  * src/sub_model/modules.py:108-142 (Speech_Rate_Predictor, d = 256) is served this way. */
 AVH_API int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T,
                                 int output_layer, void* out, int out_dtype, void* stream);
+
+/* The Q-Former that compresses the fused AV features into query tokens in MMS-LLaMA:
+ * Qformer.bert(query_embeds=query_tokens[:, :Lq], attention_mask, encoder_hidden_states=enc, encoder_attention_mask)
+ * ['last_hidden_state'] (src/model.py:584-619 -> src/sub_model/Qformer.py:805-968, query-only path: self-attention over
+ * the queries, cross-attention to enc, *_query feed-forward, post-LN, eps 1e-12, erf GELU).
+ * Handle: avh_create with reserved[0] = 2, encoder_layers = qformer_layers, encoder_embed_dim = hidden size (heads x 64),
+ * encoder_ffn_embed_dim = intermediate size, reserved[1] = encoder_width (features of enc), reserved[2] = rows of
+ * query_tokens; avh_load_tensor with the BertModel-level state-dict keys ("embeddings.LayerNorm.*",
+ * "encoder.layer.{i}.attention.self.{query,key,value}.*", ".attention.output.{dense,LayerNorm}.*", ".crossattention.*",
+ * ".intermediate_query.dense.*", ".output_query.{dense,LayerNorm}.*") plus "query_tokens" [1, max_queries, hidden].
+ * enc [B,Lk,encoder_width] (device, any float dtype); enc_padding [B,Lk] bytes, 1 = padded frame (the reference passes
+ * the complement as a 0/1 long mask), or NULL; len_queries HOST int32 [B] valid queries per clip (rows beyond are masked
+ * as keys of the self-attention, as query_attn_mask does) or NULL; out [B,Lq,hidden].  Masked keys are dropped — the
+ * reference adds -10000 to their scores, which fp32 exp() turns into exactly 0 as long as one key is valid. */
+AVH_API int avh_qformer_forward(avh_handle* h, const void* enc, int enc_dtype, const uint8_t* enc_padding,
+                                const int32_t* len_queries, int B, int Lq, int Lk, void* out, int out_dtype, void* stream);
 
 /* extract_finetune for RAGGED batches without computing on pad frames (BASELINE config 3): same
  * padded tensors as avh_forward (video [B,1,T,88,88] or raw uint8, audio [B,F,T] + strides, out [B,T,D]) plus the HOST

@@ -153,6 +153,13 @@ struct LayerW {
   float *qkv_csum = nullptr, *fc1_csum = nullptr;
 };
 
+// Q-Former (src/sub_model/Qformer.py) handle: BERT-style post-LN layers over the query tokens, each = self-attention,
+// cross-attention to the AV features, feed-forward with the *_query weights
+struct QfLayerW {
+  LinearW sqkv, sout, cq, cout, fc1, fc2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *ln3_g = nullptr, *ln3_b = nullptr;
+};
+
 struct Step {
   std::function<int(cudaStream_t)> run;
   std::string name;       // kernel class for avh_profile_json
@@ -194,6 +201,9 @@ struct Plan {
   unsigned long long seed = 0;
   std::vector<unsigned char> layer_skip;
   bool enc_only = false;           // avh_encoder_forward: TransformerEncoder on caller-provided features [B,T,D]
+  int Lk = 0;                      // Q-Former plans: T = query rows per clip, Lk = AV feature rows per clip
+  unsigned char* qmask_dev = nullptr;    // Q-Former plans: [B*T] 1 = padded query, [B*Lk] 1 = padded AV frame
+  unsigned char* kmask_dev = nullptr;
   bool ragged = false;
   long long Nb = 0;
   int* rag = nullptr;
@@ -273,6 +283,10 @@ struct avh_handle {
   int pos_window = 64;            // input-channel window per 64-column N tile (64 or 128)
   int* pos_acol = nullptr;        // device [D/64] window start per N tile
   std::vector<LayerW> layers;
+  // Q-Former handles (cfg.reserved[0] == 2): reserved[1] = encoder_width, reserved[2] = rows of query_tokens
+  std::vector<QfLayerW> qf_layers;
+  LinearW qf_ckv;                  // cross-attention key / value projections of ALL layers: [L * 2D, encoder_width]
+  float *qf_emb_g = nullptr, *qf_emb_b = nullptr, *qf_tokens = nullptr;
   std::map<std::string, std::unique_ptr<Plan>> plans;
   long long plan_clock = 0;
   bool profiling = false;
@@ -419,9 +433,67 @@ void pack_ln_folded(Packer& pk, const std::vector<float>& w, const std::vector<f
   *csum = pk.upload_f(cs);
 }
 
+// several nn.Linear with the same input stacked along the output dim (fused q / k / v, the K / V of all layers)
+bool pack_linear_cat(Packer& pk, const std::vector<std::string>& prefixes, LinearW* lw) {
+  std::vector<float> wcat, bcat;
+  int k = -1, n = 0;
+  for (const std::string& pre : prefixes) {
+    const HostTensor* w = pk.get(pre + ".weight");
+    const HostTensor* b = pk.get(pre + ".bias");
+    if (!w || !b) return false;
+    if (k < 0) k = (int)w->shape[1];
+    if ((int)w->shape[1] != k) return false;
+    wcat.insert(wcat.end(), w->v.begin(), w->v.end());
+    bcat.insert(bcat.end(), b->v.begin(), b->v.end());
+    n += (int)w->shape[0];
+  }
+  const int kpad = round_up(k, 64);
+  std::vector<float> p((size_t)n * kpad, 0.f);
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < k; ++c) p[(size_t)r * kpad + c] = wcat[(size_t)r * k + c];
+  lw->w = pk.pack(p, n, k, kpad);
+  lw->bias = pk.upload_f(bcat);
+  return true;
+}
+
+// Q-Former weights, BertModel-level key names (src/sub_model/Qformer.py:52-111,379-486) + "query_tokens"
+bool pack_qformer(Packer& pk) {
+  avh_handle* h = pk.h;
+  const int L = h->cfg.encoder_layers;
+  bool ok = true;
+  auto ln = [&](const std::string& pre, float** g, float** b) {
+    const HostTensor* gw = pk.get(pre + ".weight");
+    const HostTensor* bw = pk.get(pre + ".bias");
+    if (gw && bw) { *g = pk.upload_f(gw->v); *b = pk.upload_f(bw->v); } else ok = false;
+  };
+  ln("embeddings.LayerNorm", &h->qf_emb_g, &h->qf_emb_b);
+  const HostTensor* qt = pk.get("query_tokens");
+  if (qt) h->qf_tokens = pk.upload_f(qt->v); else ok = false;
+  h->qf_layers.resize(L);
+  std::vector<std::string> kv;
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = "encoder.layer." + std::to_string(l) + ".";
+    QfLayerW& lw = h->qf_layers[l];
+    ok &= pack_linear_cat(pk, {pre + "attention.self.query", pre + "attention.self.key", pre + "attention.self.value"}, &lw.sqkv);
+    ok &= pack_linear(pk, pre + "attention.output.dense", &lw.sout);
+    ln(pre + "attention.output.LayerNorm", &lw.ln1_g, &lw.ln1_b);
+    ok &= pack_linear(pk, pre + "crossattention.self.query", &lw.cq);
+    kv.push_back(pre + "crossattention.self.key");
+    kv.push_back(pre + "crossattention.self.value");
+    ok &= pack_linear(pk, pre + "crossattention.output.dense", &lw.cout);
+    ln(pre + "crossattention.output.LayerNorm", &lw.ln2_g, &lw.ln2_b);
+    ok &= pack_linear(pk, pre + "intermediate_query.dense", &lw.fc1);
+    ok &= pack_linear(pk, pre + "output_query.dense", &lw.fc2);
+    ln(pre + "output_query.LayerNorm", &lw.ln3_g, &lw.ln3_b);
+  }
+  ok &= pack_linear_cat(pk, kv, &h->qf_ckv);
+  return ok;
+}
+
 bool pack_all(Packer& pk) {
   avh_handle* h = pk.h;
   const avh_config& c = h->cfg;
+  if (c.reserved[0] == 2) return pack_qformer(pk);
   const int D = c.encoder_embed_dim;
   const std::string R = "feature_extractor_video.resnet.";
   bool ok = true;
@@ -1407,10 +1479,163 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 
 // One plan (= workspace + launch list) per shape AND per CUDA stream: forwards enqueued on different streams
 // never share scratch memory, so a caller can keep several batches in flight on one device.
+// ============================================================================ Q-Former plan
+// Qformer.bert(query_embeds, attention_mask, encoder_hidden_states, encoder_attention_mask) (src/model.py:611-617 ->
+// src/sub_model/Qformer.py:805-968) for B clips x T query rows against Lk AV-feature rows each.  Post-LN BERT layers:
+// x = LN(dense(SelfAttn(x)) + x); x = LN(dense(CrossAttn(x, enc)) + x); x = LN(fc2(GELU(fc1(x))) + x), eps 1e-12.
+// Every Linear is a tcgen05 GEMM (the K / V projections of the AV features for ALL layers are one GEMM: they are
+// ~80 % of the block's FLOPs); attention is launch_attention_x (qformer.cu).
+bool build_qformer_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
+  Builder b;
+  b.h = h; b.plan = plan; b.sizing = sizing; b.P = h->P; b.f32 = (h->cfg.compute_mode == AVH_COMPUTE_FP32);
+  const avh_config& c = h->cfg;
+  const int P = b.P;
+  const bool f32 = b.f32;
+  const int B = plan->B, T = plan->T, Lk = plan->Lk, D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim;
+  const int Hh = c.encoder_attention_heads, Ew = c.reserved[1], L = c.encoder_layers;
+  const long long N = (long long)B * T, NK = (long long)B * Lk;
+  const size_t es = f32 ? 4 : 2;
+  const int act_dt = f32 ? DT_F32 : DT_BF16;
+  const float eps = 1e-12f;                                   // BertConfig.layer_norm_eps
+  Plan* pl = plan;
+  auto new_act = [&](long long rows, int C) {
+    Act a;
+    a.rows = rows; a.C = C;
+    a.data = b.alloc((size_t)rows * C * es);
+    a.op = f32 ? b.alloc((size_t)rows * C * 2 * P) : a.data;
+    return a;
+  };
+  auto sync_op = [&](const Act& a) {
+    if (!f32) return;
+    const float* src = reinterpret_cast<const float*>(a.data);
+    void* dst = a.op;
+    const long long rows = a.rows;
+    const int C = a.C, planes = P;
+    const std::string keep = b.tag;
+    b.tag = "split";
+    b.push([=](cudaStream_t s) { return launch_split_rows(src, C, dst, planes, rows, C, 0, 0, s); });
+    b.tag = keep;
+  };
+  b.sk_bytes = 0; b.sk_ws = nullptr; b.sk_flags = nullptr;
+  unsigned char* qm = reinterpret_cast<unsigned char*>(b.alloc((size_t)N + 16));
+  unsigned char* km = reinterpret_cast<unsigned char*>(b.alloc((size_t)NK + 16));
+  if (!sizing) { plan->qmask_dev = qm; plan->kmask_dev = km; }
+  float* x = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));       // hidden states (fp32)
+  float* tmp = reinterpret_cast<float*>(b.alloc((size_t)N * D * 4));     // dense(...) + residual, before the LayerNorm
+  float* emb = reinterpret_cast<float*>(b.alloc((size_t)T * D * 4));     // LayerNorm(query_tokens[:T])
+  Act hbuf = new_act(N, D), qkv = new_act(N, 3 * D), cq = new_act(N, D), ctx = new_act(N, D), ffn = new_act(N, F);
+  Act enc = new_act(NK, Ew), ckv = new_act(NK, 2 * D * L);
+  const bool hm = plan->has_mask;
+
+  // ---- AV features -> operand form (the only step that reads a caller pointer besides the output store)
+  b.tag = "load_features";
+  b.cur_direct = true;
+  {
+    void* dst = enc.data;
+    b.push([=](cudaStream_t s) { return launch_convert(pl->args.xin, pl->args.xin_dt, dst, act_dt, NK * Ew, s); });
+  }
+  b.cur_direct = false;
+  sync_op(enc);
+  // ---- embeddings: LayerNorm(query_embeds) (no position embeddings on the query-only path, Qformer.py:98-110)
+  {
+    const float* qt = h->qf_tokens; const float* g = h->qf_emb_g; const float* be = h->qf_emb_b;
+    b.tag = "layer_ln";
+    b.push([=](cudaStream_t s) { return launch_layernorm(qt, DT_F32, D, g, be, eps, emb, nullptr, DT_BF16, nullptr, T, D, s); });
+    b.push([=](cudaStream_t s) { return launch_rows_broadcast(emb, x, (long long)T * D, B, s); });
+  }
+  auto x_to_h = [&]() {
+    void* dst = hbuf.op;
+    const int planes = P;
+    b.tag = "split";
+    b.push([=](cudaStream_t s) { return launch_split_rows(x, D, dst, planes, N, D, 0, 0, s); });
+  };
+  auto post_ln = [&](const float* g, const float* be) {      // x = LayerNorm(tmp), then its operand copy
+    b.tag = "layer_ln";
+    b.push([=](cudaStream_t s) { return launch_layernorm(tmp, DT_F32, D, g, be, eps, x, nullptr, DT_BF16, nullptr, N, D, s); });
+  };
+  auto dense_res = [&](const Act& a, int K, const LinearW& w, const char* tag) {      // tmp = a W^T + b + x
+    Epilogue ep;
+    ep.C = tmp; ep.ldc = D; ep.c_fp32 = 1;
+    ep.col_bias = w.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+    b.tag = tag;
+    return b.gemm(a.op, N, P * K, w.w, N, {Tap{0, 0, 0}}, K / 64, K, ep);
+  };
+  x_to_h();
+  // ---- K / V of the AV features for every layer's cross-attention
+  {
+    Epilogue ep;
+    ep.C = ckv.data; ep.ldc = 2 * D * L; ep.c_fp32 = f32 ? 1 : 0;
+    ep.col_bias = h->qf_ckv.bias;
+    b.tag = "cross_kv_proj";
+    if (!b.gemm(enc.op, NK, P * Ew, h->qf_ckv.w, NK, {Tap{0, 0, 0}}, Ew / 64, Ew, ep)) return false;
+  }
+  const float scale = 0.125f;                                 // 1 / sqrt(attention_head_size = 64), Qformer.py:246
+  for (int l = 0; l < L; ++l) {
+    const QfLayerW& lw = h->qf_layers[l];
+    b.cur_layer = l;
+    {   // self-attention over the queries
+      Epilogue ep;
+      ep.C = qkv.data; ep.ldc = 3 * D; ep.c_fp32 = f32 ? 1 : 0;
+      ep.col_bias = lw.sqkv.bias;
+      b.tag = "qkv_proj";
+      if (!b.gemm(hbuf.op, N, P * D, lw.sqkv.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      const char* q = reinterpret_cast<const char*>(qkv.data);
+      void* o = ctx.data;
+      b.tag = "attention";
+      b.push([=](cudaStream_t s) {
+        return launch_attention_x(q, 3 * D, q + (size_t)D * es, 3 * D, q + (size_t)2 * D * es, 3 * D, act_dt, pl->qmask_dev, o, D,
+                                  act_dt, B, Hh, T, T, scale, s);
+      }, 4.0 * (double)B * Hh * (double)T * (double)T * 64.0);
+      sync_op(ctx);
+      if (!dense_res(ctx, D, lw.sout, "out_proj")) return false;
+      post_ln(lw.ln1_g, lw.ln1_b);
+      x_to_h();
+    }
+    {   // cross-attention to the AV features
+      Epilogue ep;
+      ep.C = cq.data; ep.ldc = D; ep.c_fp32 = f32 ? 1 : 0;
+      ep.col_bias = lw.cq.bias;
+      b.tag = "cross_q_proj";
+      if (!b.gemm(hbuf.op, N, P * D, lw.cq.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      const void* q = cq.data;
+      const char* kvp = reinterpret_cast<const char*>(ckv.data) + (size_t)l * 2 * D * es;
+      const long long ldkv = 2ll * D * L;
+      void* o = ctx.data;
+      b.tag = "cross_attention";
+      b.push([=](cudaStream_t s) {
+        return launch_attention_x(q, D, kvp, ldkv, kvp + (size_t)D * es, ldkv, act_dt, hm ? pl->kmask_dev : nullptr, o, D, act_dt,
+                                  B, Hh, T, Lk, scale, s);
+      }, 4.0 * (double)B * Hh * (double)T * (double)Lk * 64.0);
+      sync_op(ctx);
+      if (!dense_res(ctx, D, lw.cout, "cross_out_proj")) return false;
+      post_ln(lw.ln2_g, lw.ln2_b);
+      x_to_h();
+    }
+    {   // feed-forward of the query branch (intermediate_query / output_query, Qformer.py:482-485), erf GELU
+      Epilogue ep;
+      ep.C = ffn.data; ep.ldc = F; ep.c_fp32 = f32 ? 1 : 0;
+      ep.col_bias = lw.fc1.bias; ep.act = ACT_GELU;
+      b.tag = "fc1";
+      if (!b.gemm(hbuf.op, N, P * D, lw.fc1.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      sync_op(ffn);
+      if (!dense_res(ffn, F, lw.fc2, "fc2")) return false;
+      post_ln(lw.ln3_g, lw.ln3_b);
+      if (l + 1 < L) x_to_h();
+    }
+  }
+  b.cur_layer = -1;
+  b.tag = "output";
+  b.cur_direct = true;
+  b.push([=](cudaStream_t s) { return launch_convert(x, DT_F32, pl->args.out, pl->args.out_dt, N * D, s); });
+  b.cur_direct = false;
+  if (bytes_out) *bytes_out = b.sizer.used;
+  return true;
+}
+
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
-               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false) {
+               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false, int qf_lk = 0) {
   const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) + (enc_only ? "e:" : "") +
-                          (train ? "t:" : "") +
+                          (train ? "t:" : "") + (qf_lk > 0 ? "q" + std::to_string(qf_lk) + ":" : std::string()) +
                           std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
@@ -1439,10 +1664,12 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
   p->Nb = ragged_rows;
   p->enc_only = enc_only;
   p->train = train;
+  p->Lk = qf_lk;
   size_t bytes = 0;
-  if (!build_plan(h, p.get(), true, &bytes)) return nullptr;
+  auto build = qf_lk > 0 ? build_qformer_plan : build_plan;
+  if (!build(h, p.get(), true, &bytes)) return nullptr;
   if (p->arena.init(bytes + (1 << 20))) return nullptr;
-  if (!build_plan(h, p.get(), false, nullptr)) return nullptr;
+  if (!build(h, p.get(), false, nullptr)) return nullptr;
   if (p->ragged) {
     for (int i = 0; i < Plan::RAG_SLOTS; ++i) {
       if (cudaMallocHost(reinterpret_cast<void**>(&p->rag_host[i]), (size_t)p->rag_ints * 4) != cudaSuccess ||
@@ -1474,7 +1701,7 @@ bool ignorable_key(const std::string& k) {
 }
 bool known_prefix(const std::string& k) {
   static const char* pre[] = {"feature_extractor_video.", "feature_extractor_audio.", "layer_norm.",
-                              "post_extract_proj.", "encoder."};
+                              "post_extract_proj.", "encoder.", "embeddings.", "query_tokens"};
   for (const char* p : pre)
     if (k.rfind(p, 0) == 0) return true;
   return false;
@@ -1502,6 +1729,9 @@ int avh_create(const avh_config* cfg, int device, avh_handle** out) {
   AVH_CHECK(cfg->reserved[0] != 0 || (cfg->audio_feat_dim >= 1 && cfg->audio_feat_dim <= 1024), "bad audio_feat_dim");
   AVH_CHECK(cfg->modality_fuse == AVH_FUSE_CONCAT || cfg->modality_fuse == AVH_FUSE_ADD, "bad modality_fuse");
   AVH_CHECK(cfg->compute_mode == AVH_COMPUTE_BF16 || cfg->compute_mode == AVH_COMPUTE_FP32, "bad compute_mode");
+  AVH_CHECK(cfg->reserved[0] >= 0 && cfg->reserved[0] <= 2, "reserved[0] must be 0 (AV-HuBERT), 1 (TransformerEncoder) or 2 (Q-Former)");
+  AVH_CHECK(cfg->reserved[0] != 2 || (cfg->reserved[1] >= 64 && cfg->reserved[1] % 64 == 0 && cfg->reserved[2] >= 1),
+            "Q-Former handles need reserved[1] = encoder_width (multiple of 64) and reserved[2] = query_tokens rows");
   int ndev = 0;
   AVH_CUDA_OK(cudaGetDeviceCount(&ndev));
   AVH_CHECK(device >= 0 && device < ndev, "no such CUDA device");
@@ -1869,6 +2099,7 @@ int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t
   AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
   AVH_CHECK(x != nullptr && out != nullptr, "null argument");
   AVH_CHECK(x_dtype == AVH_F32 || x_dtype == AVH_F16 || x_dtype == AVH_BF16, "bad feature dtype");
+  AVH_CHECK(h->cfg.reserved[0] != 2, "this handle holds a Q-Former: use avh_qformer_forward");
   AVH_CHECK(B >= 1 && T >= 1 && (long long)B * T < (1ll << 24), "bad batch");
   AVH_CHECK(output_layer >= 0 && output_layer <= h->cfg.encoder_layers, "output_layer out of range");
   AVH_CUDA_OK(cudaSetDevice(h->device));
@@ -1881,6 +2112,40 @@ int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t
   p->args.mask = padding_mask;
   p->args.out = out; p->args.out_dt = out_dtype;
   return run_plan(h, p, s);
+}
+
+int avh_qformer_forward(avh_handle* h, const void* enc, int enc_dtype, const uint8_t* enc_padding, const int32_t* len_queries,
+                        int B, int Lq, int Lk, void* out, int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->cfg.reserved[0] == 2, "this handle does not hold a Q-Former");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(enc != nullptr && out != nullptr, "null argument");
+  AVH_CHECK(enc_dtype == AVH_F32 || enc_dtype == AVH_F16 || enc_dtype == AVH_BF16, "bad feature dtype");
+  AVH_CHECK(B >= 1 && Lq >= 1 && Lk >= 1 && (long long)B * Lk < (1ll << 24), "bad batch");
+  AVH_CHECK(Lq <= h->cfg.reserved[2], "more queries than query_tokens holds");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  avh::Plan* p = avh::get_plan(h, B, Lq, false, false, enc_padding != nullptr, 0, s, 0, false, false, Lk);
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  // query attention mask (src/model.py:588-590): row i of clip b is a key for the queries iff i < len_queries[b]
+  std::vector<unsigned char> qm((size_t)B * Lq, 0);
+  if (len_queries != nullptr)
+    for (int b = 0; b < B; ++b) {
+      AVH_CHECK(len_queries[b] >= 1 && len_queries[b] <= Lq, "len_queries must be in [1, Lq]");
+      for (int i = len_queries[b]; i < Lq; ++i) qm[(size_t)b * Lq + i] = 1;
+    }
+  AVH_CUDA_OK(cudaMemcpyAsync(p->qmask_dev, qm.data(), qm.size(), cudaMemcpyHostToDevice, s));      // pageable: staged before return
+  if (enc_padding != nullptr)
+    AVH_CUDA_OK(cudaMemcpyAsync(p->kmask_dev, enc_padding, (size_t)B * Lk, cudaMemcpyDeviceToDevice, s));
+  p->args = avh::CallArgs();
+  p->args.xin = enc; p->args.xin_dt = enc_dtype;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  const bool keep = p->has_mask;
+  p->has_mask = false;                 // run_plan's generic [B,T] mask staging does not apply (masks staged above)
+  const int rc = run_plan(h, p, s);
+  p->has_mask = keep;
+  return rc;
 }
 
 int avh_forward_ragged(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,

@@ -87,6 +87,7 @@ struct KernelParams {
 };
 
 // debug stall accounting (only when a trace buffer is attached): cycles a role spent blocked on an mbarrier
+#ifdef AVH_STALL_ACC
 #define AVH_WAIT_ACC(bar, parity, acc)                    \
   do {                                                    \
     if (p.trace == nullptr) mbar_wait((bar), (parity));   \
@@ -96,6 +97,14 @@ struct KernelParams {
       (acc) += clock64() - _c0;                           \
     }                                                     \
   } while (0)
+#else
+// production build: a plain wait (the run-time test sat between the MMAs of the issue loop: tools/ab_bench.sh)
+#define AVH_WAIT_ACC(bar, parity, acc) \
+  do {                                 \
+    mbar_wait((bar), (parity));        \
+    (void)(acc);                       \
+  } while (0)
+#endif
 
 #define AVH_TRACE(slot)                                                                            \
   do {                                                                                             \
@@ -881,6 +890,19 @@ double model_cycles(long long M, int N, int num_kb, int bn, int pair, int occ, i
   const long long nt = (N + bn - 1) / bn;
   const long long units = (long long)sms * occ / pair;
   const long long tiles = mt * nt;
+  static int model_env = -1;
+  if (model_env < 0) { const char* ev = std::getenv("AVH_GEMM_MODEL"); model_env = ev ? std::atoi(ev) : 0; }
+  if (model_env == 1 && !sk) {
+    // round-1 model (whole-step A/B, tools/ab_bench.sh): ~80 B/clk operand stream, no fill / tail asymmetry
+    const long long rounds = (tiles + units - 1) / units;
+    double kb1 = 415.0;
+    if (2.0 * bn > kb1) kb1 = 2.0 * bn;
+    const double pipe1 = occ * 4.0 * (bn / 2.0);
+    const double l2 = occ * (double)(A_STAGE_BYTES + (bn / pair) * BK * 2) / 80.0;
+    if (pipe1 > kb1) kb1 = pipe1;
+    if (l2 > kb1) kb1 = l2;
+    return rounds * (num_kb * kb1 + 400.0) + 8.0 * bn + 2500.0;
+  }
   double kblock = 415.0;
   if (2.0 * bn > kblock) kblock = 2.0 * bn;
   const double ingress = occ * (double)(A_STAGE_BYTES + (bn / pair) * BK * 2) / 66.0;

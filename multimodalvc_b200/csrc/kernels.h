@@ -90,6 +90,14 @@ int launch_logits(const void* F, int f_dt, long long ldf, const void* E, int e_d
 // *acc = sum of squares of x (float64; acc is zeroed first)
 int launch_sumsq(const void* x, int dt, long long n, double* acc, cudaStream_t stream);
 
+// ---- Q-Former (qformer.cu): softmax(scale Q K^T + key mask) V with separate Q / K / V matrices (row strides in elements),
+// head dim 64, heads side by side in the columns; key_pad [B, Lk] (1 = masked) or null; any float dtype in, o_dt out
+int launch_attention_x(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, int dt,
+                       const unsigned char* key_pad, void* O, long long ldo, int o_dt, int B, int H, int Lq, int Lk,
+                       float scale, cudaStream_t stream);
+// dst [B, per_clip] = src [per_clip] for every clip (fp32)
+int launch_rows_broadcast(const float* src, float* dst, long long per_clip, int B, cudaStream_t stream);
+
 // ---- audio frontend ---------------------------------------------------------------------------------
 struct FbankArgs {
   const int16_t* wav;          // concatenated clips
