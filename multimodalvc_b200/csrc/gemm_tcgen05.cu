@@ -144,7 +144,9 @@ struct SegIter {
 // ACT (ACT_*), RES (residual add), S2 (second PReLU), SCALE (per-column scale) and OUTF32 (fp32 output and
 // residual, else bf16) are compile-time when >= 0 and read from the Epilogue struct when -1.
 // LNF: LayerNorm folding (Epilogue::ln_mode): 0 none, 1 producer (centred bf16 copy + row partial sums), 2 consumer.
-template <int PAIR, int OCC, int ACT, int RES, int S2, int SCALE, int OUTF32, int LNF = 0>
+// SK: stream-K code compiled in (only the instantiations the planner picks for a stream-K launch carry it: with the
+// code in every kernel the epilogue spilled registers and the encoder GEMMs ran ~9 % slower — tools/ab_bench.sh).
+template <int PAIR, int OCC, int ACT, int RES, int S2, int SCALE, int OUTF32, int LNF = 0, int SK = 0>
 __global__ void __launch_bounds__(Occ<OCC>::NUM_THREADS, OCC)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2,
@@ -216,7 +218,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // 1.1 us between the wait and the first MMA); the A tiles (activations) follow after the wait.
   int pre_b = 0;
   if (PAIR == 1 && warp == 0) {
-    SegIter first(p.sk, unit, num_units, num_tiles, p.num_kb);
+    SegIter first(SK != 0 ? p.sk : 0, unit, num_units, num_tiles, p.num_kb);
     int t0, f_kb0 = 0, f_kb1 = 0;
     if (first.next(t0, f_kb0, f_kb1)) {
     const int n_blk0 = t0 / p.num_m_blk;
@@ -249,7 +251,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint32_t phase = 0;
     long long prod_wait = 0;
     const uint32_t stage_tx = (uint32_t)PAIR * (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
-    SegIter segs(p.sk, unit, num_units, num_tiles, p.num_kb);
+    SegIter segs(SK != 0 ? p.sk : 0, unit, num_units, num_tiles, p.num_kb);
     int tile, kb0, kb1;
     bool first_seg = true;
     for (; segs.next(tile, kb0, kb1); first_seg = false) {
@@ -288,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int it = 0;
       long long wait_full = 0, wait_tmem = 0;
-      SegIter segs(p.sk, unit, num_units, num_tiles, p.num_kb);
+      SegIter segs(SK != 0 ? p.sk : 0, unit, num_units, num_tiles, p.num_kb);
       int tile, kb0, kb1;
       for (; segs.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
@@ -339,7 +341,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const bool out_f32 = OUTF32 >= 0 ? OUTF32 != 0 : ep.c_fp32 != 0;
     const bool res_any = RES >= 0 ? RES != 0 : ep.R != nullptr;
     int it = 0;
-    SegIter segs(p.sk, unit, num_units, num_tiles, p.num_kb);
+    SegIter segs(SK != 0 ? p.sk : 0, unit, num_units, num_tiles, p.num_kb);
     int tile, kb0, kb1;
     for (; segs.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile % p.num_m_blk;
@@ -347,7 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = (m_blk * PAIR + cta_rank) * BM + q * 32;     // first row of this warp's quarter
-      if (p.sk && kb0 > 0) {
+      if (SK != 0 && p.sk && kb0 > 0) {
         // ---- stream-K, tail part of a tile owned by an earlier unit: raw fp32 accumulator -> workspace slot of this
         //      unit (thread = row, 128 contiguous bytes per 32-column chunk), then raise the flag
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -379,7 +381,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // stream-K owner of a tile whose K range continues in the following units: their partials are added (in unit
       // order) to the accumulator values before the epilogue math
       int sk_first = 0, sk_last = -1;
-      if (p.sk && kb1 < p.num_kb) {
+      if (SK != 0 && p.sk && kb1 < p.num_kb) {
         const long long U = (long long)num_tiles * p.num_kb;
         const long long tile_end = (long long)(tile + 1) * p.num_kb;
         sk_first = unit + 1;
@@ -512,7 +514,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             // stream-K owner: the first partial of this chunk is requested while the TMEM load is in flight (the
             // residual registers are free: stream-K is planned only for GEMMs without a separate residual operand)
-            const bool sk_add = c0 < BN && sk_last >= sk_first;
+            const bool sk_add = SK != 0 && c0 < BN && sk_last >= sk_first;
             if (sk_add) {
               const uint4* pp = reinterpret_cast<const uint4*>(p.sk_ws + ((size_t)sk_first * PAIR + cta_rank) * (size_t)BM * BN) +
                                 (size_t)((c0 >> 5) * 8) * BM + q * 32 + lane;
@@ -775,7 +777,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (it == 0) AVH_TRACE(7);
         AVH_TRACE(9);
       }
-      if (sk_last >= sk_first) {
+      if (SK != 0 && sk_last >= sk_first) {
         // every epilogue warp of this CTA has read its partial rows: hand the flags back (zero between launches)
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         if (threadIdx.x == 128)
@@ -1106,6 +1108,13 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   if (e.ln_mode == 1) fn = gemm_kernel<1, 1, ACT_NONE, 1, 0, 0, 1, 1>;                   // out_proj / fc2 producing xc + sums
   else if (e.ln_mode == 2 && act == ACT_GELU) fn = gemm_kernel<1, 1, ACT_GELU, 0, 0, 1, 0, 2>;   // fc1 on LayerNorm'd rows
   else if (e.ln_mode == 2) fn = gemm_kernel<1, 1, ACT_NONE, 0, 0, 1, 0, 2>;                      // qkv on LayerNorm'd rows
+  if (plan.sk != 0) {      // stream-K launches (AVH_GEMM_SK): single CTA per SM or CTA pairs, the three encoder epilogues
+    if (pair == 2) fn = gemm_kernel<2, 1, -1, -1, -1, -1, -1, 0, 1>;
+    else if (act == ACT_NONE && !res && !s2 && !scl && !f32) fn = gemm_kernel<1, 1, ACT_NONE, 0, 0, 0, 0, 0, 1>;
+    else if (act == ACT_GELU && !res && !s2 && !scl && !f32) fn = gemm_kernel<1, 1, ACT_GELU, 0, 0, 0, 0, 0, 1>;
+    else if (act == ACT_NONE && res && !s2 && !scl && f32) fn = gemm_kernel<1, 1, ACT_NONE, 1, 0, 0, 1, 0, 1>;
+    else fn = gemm_kernel<1, 1, -1, -1, -1, -1, -1, 0, 1>;
+  }
 #define AVH_SPEC(O, A, R, S, C, F)                                                                     \
   if (fn == nullptr && pair == 1 && occ == O && act == A && res == R && s2 == S && scl == C && f32 == F) \
     fn = gemm_kernel<1, O, A, R, S, C, F>;
