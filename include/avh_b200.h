@@ -73,7 +73,9 @@ typedef struct avh_config {
   int32_t reserved[4];             /* reserved[0] = 1: the handle holds a bare fairseq TransformerEncoder (state-dict keys
                                       "encoder.*" only; avh_encoder_forward is its one forward entry point);
                                       reserved[0] = 2: a Q-Former (avh_qformer_forward; reserved[1] = encoder_width,
-                                      reserved[2] = rows of query_tokens) */
+                                      reserved[2] = rows of query_tokens);
+                                      reserved[3] = 1: trainable encoder (also packs the transposed weights the
+                                      backward needs: avh_encoder_train_forward / avh_encoder_backward) */
 } avh_config;
 
 typedef struct avh_handle avh_handle;
@@ -173,6 +175,22 @@ AVH_API int avh_read_bn_stats(avh_handle* h, float* dst, int64_t capacity, void*
  * src/sub_model/modules.py:108-142 (Speech_Rate_Predictor, d = 256) is served this way. */
 AVH_API int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T,
                                 int output_layer, void* out, int out_dtype, void* stream);
+
+/* Training step of the TransformerEncoder (encoder part of BASELINE config 5; dropout and LayerDrop 0
+ * as that config states; pre-LN layers): forward with saved activations, then the backward of exactly that graph —
+ * wav2vec2.py:859-902 (positional conv + GELU + residual, index_put on padded frames), :974-992 (pre-LN layer),
+ * multihead_attention.py:170-192, the final LayerNorm (:862-863) — what torch.autograd computes for the reference module.
+ * Handle: any handle with encoder weights created with avh_config.reserved[3] = 1 (packs W^T for the dX = dY W GEMMs).
+ * avh_encoder_train_forward: as avh_encoder_forward (all layers + final LayerNorm); avh_encoder_backward: dout [B,T,D] =
+ * dL/d(out) (rows of padded frames are ignored), dx [B,T,D] = dL/d(x) (may be NULL), grads = fp32 [avh_encoder_grad_count]
+ * (may be NULL) in this order: per layer {q,k,v}_proj.weight, {q,k,v}_proj.bias, out_proj.weight, out_proj.bias,
+ * self_attn_layer_norm.{weight,bias}, fc1.weight, fc1.bias, fc2.weight, fc2.bias, final_layer_norm.{weight,bias}; then
+ * encoder.layer_norm.{weight,bias}; then pos_conv.0.{bias, weight_g, weight_v}.  Same stream as the forward. */
+AVH_API int avh_encoder_grad_count(avh_handle* h, int64_t* n_floats);
+AVH_API int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T,
+                                      void* out, int out_dtype, void* stream);
+AVH_API int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, float* grads,
+                                 int64_t grads_capacity, void* stream);
 
 /* The Q-Former that compresses the fused AV features into query tokens in MMS-LLaMA:
  * Qformer.bert(query_embeds=query_tokens[:, :Lq], attention_mask, encoder_hidden_states=enc, encoder_attention_mask)

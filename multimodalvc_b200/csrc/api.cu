@@ -146,6 +146,9 @@ struct LinearW {
 };
 struct LayerW {
   LinearW qkv, out, fc1, fc2;
+  // W^T packed K-major (rows = in features, K = out features): the B operand of dX = dY W in the backward pass; only
+  // packed for trainable handles (cfg.reserved[3] != 0), bias pointers unused
+  LinearW qkvT, outT, fc1T, fc2T;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   // LayerNorm folded into the consuming GEMM (bf16 mode, pre-LN): W' = W diag(gamma), csum[n] = sum_k bf16(W'[n,k]),
   // bias' [n] = b[n] + sum_k W[n,k] beta[k]
@@ -201,6 +204,15 @@ struct Plan {
   unsigned long long seed = 0;
   std::vector<unsigned char> layer_skip;
   bool enc_only = false;           // avh_encoder_forward: TransformerEncoder on caller-provided features [B,T,D]
+  // encoder training plans (avh_encoder_train_forward / avh_encoder_backward): steps [0, fwd_steps) are the forward
+  // with saved activations, the rest the backward; gradients accumulate in a plan-owned fp32 buffer
+  bool enc_train = false;
+  size_t fwd_steps = 0;
+  float* grads = nullptr;
+  long long grad_floats = 0;
+  float* dx_out = nullptr;         // gradient w.r.t. the input features [B*T, D] fp32
+  float* dy_in = nullptr;          // gradient w.r.t. the output, staged fp32 [B*T, D]
+  bool fwd_done = false;
   int Lk = 0;                      // Q-Former plans: T = query rows per clip, Lk = AV feature rows per clip
   unsigned char* qmask_dev = nullptr;    // Q-Former plans: [B*T] 1 = padded query, [B*Lk] 1 = padded AV frame
   unsigned char* kmask_dev = nullptr;
@@ -279,6 +291,8 @@ struct avh_handle {
   bool has_post_proj = false;
   float *fuse_ln_g = nullptr, *fuse_ln_b = nullptr, *enc_ln_g = nullptr, *enc_ln_b = nullptr;
   PackedW pos_w;
+  PackedW pos_wT;                 // trainable handles: the same windowed layout with in / out swapped inside every group
+  float *pos_v_raw = nullptr, *pos_g_raw = nullptr;     // trainable handles: weight_v [D, D/G, KT], weight_g [KT] (fp32)
   float* pos_bias = nullptr;
   int pos_window = 64;            // input-channel window per 64-column N tile (64 or 128)
   int* pos_acol = nullptr;        // device [D/64] window start per N tile
@@ -395,6 +409,31 @@ bool pack_conv(Packer& pk, const std::string& wkey, const std::string& bnkey, co
     for (int o = 0; o < cout; ++o) sl[o] = s->v[s->numel() == 1 ? 0 : o];
     cu->slope = pk.upload_f(sl);
   }
+  return true;
+}
+
+// the transpose of a packed Linear: [k, n] with K = n (zero padded to 64)
+bool pack_linear_T(Packer& pk, const std::vector<std::string>& prefixes, const std::vector<float>& scales, LinearW* lw) {
+  int k = -1, n = 0;
+  std::vector<const HostTensor*> ws;
+  for (const std::string& pre : prefixes) {
+    const HostTensor* w = pk.get(pre + ".weight");
+    if (!w) return false;
+    if (k < 0) k = (int)w->shape[1];
+    n += (int)w->shape[0];
+    ws.push_back(w);
+  }
+  const int npad = (n + 63) / 64 * 64;
+  std::vector<float> p((size_t)k * npad, 0.f);
+  int r0 = 0;
+  for (size_t t = 0; t < ws.size(); ++t) {
+    const int nn = (int)ws[t]->shape[0];
+    for (int r = 0; r < nn; ++r)
+      for (int c = 0; c < k; ++c) p[(size_t)c * npad + r0 + r] = ws[t]->v[(size_t)r * k + c] * scales[t];
+    r0 += nn;
+  }
+  lw->w = pk.pack(p, k, n, npad);
+  lw->bias = nullptr;
   return true;
 }
 
@@ -631,6 +670,23 @@ bool pack_all(Packer& pk) {
       h->pos_w = pk.pack(p, D, kpad, kpad);
       h->pos_bias = pk.upload_f(wb->v);
       h->pos_acol = pk.upload(acol);
+      if (c.reserved[3] != 0) {
+        // backward w.r.t. the input: dx[t, i] = sum_k sum_o dc[t + KT/2 - k, o] w[o, i, k] — row = input channel, the
+        // window holds the OUTPUT channels of the same groups (groups cover the same channel range on both sides)
+        std::vector<float> pt((size_t)D * kpad, 0.f);
+        for (int o = 0; o < D; ++o) {
+          const int g = o / cg;
+          for (int i = 0; i < cg; ++i) {
+            const int ig = g * cg + i, j = ig / 64;
+            const int col = o - acol[j];
+            for (int k = 0; k < KT; ++k)
+              pt[(size_t)ig * kpad + (size_t)k * window + col] = wv->v[((size_t)o * cg + i) * KT + k] * ratio[k];
+          }
+        }
+        h->pos_wT = pk.pack(pt, D, kpad, kpad);
+        h->pos_v_raw = pk.upload_f(wv->v);
+        h->pos_g_raw = pk.upload_f(wg->v);
+      }
     } else ok = false;
   }
   // ---- transformer layers: fused QKV with q scaling folded (multihead_attention.py:60, scaling = hd^-0.5)
@@ -670,6 +726,13 @@ bool pack_all(Packer& pk) {
         pack_ln_folded(pk, w1->v, bb1->v, (int)w1->shape[0], (int)w1->shape[1], g2->v, b2->v, &lw.fc1_ln, &lw.fc1_csum);
     }
     ok &= pack_linear(pk, pre + "fc2", &lw.fc2);
+    if (c.reserved[3] != 0) {      // trainable handle: W^T operands of the dgrad GEMMs (avh_encoder_backward)
+      ok &= pack_linear_T(pk, {pre + "self_attn.q_proj", pre + "self_attn.k_proj", pre + "self_attn.v_proj"},
+                          {qscale, 1.f, 1.f}, &lw.qkvT);
+      ok &= pack_linear_T(pk, {pre + "self_attn.out_proj"}, {1.f}, &lw.outT);
+      ok &= pack_linear_T(pk, {pre + "fc1"}, {1.f}, &lw.fc1T);
+      ok &= pack_linear_T(pk, {pre + "fc2"}, {1.f}, &lw.fc2T);
+    }
     const HostTensor* g1 = pk.get(pre + "self_attn_layer_norm.weight");
     const HostTensor* b1 = pk.get(pre + "self_attn_layer_norm.bias");
     const HostTensor* g2 = pk.get(pre + "final_layer_norm.weight");
@@ -1479,6 +1542,362 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 
 // One plan (= workspace + launch list) per shape AND per CUDA stream: forwards enqueued on different streams
 // never share scratch memory, so a caller can keep several batches in flight on one device.
+// ============================================================================ encoder training plan
+// TransformerEncoder forward with saved activations + its backward (pre-LN layers; dropout / LayerDrop 0 as BASELINE
+// config 5 states).  Forward: x0 = index_put(features, mask, 0); c = pos_conv(x0) + b; x1 = x0 + GELU(c); per layer
+// h1 = LN1(x); qkv = h1 Wqkv^T + b; ctx = Attn(qkv) (+ log-sum-exp per row); xm = x + ctx Wo^T + bo; h2 = LN2(xm);
+// u = h2 W1^T + b1; g = GELU(u); x' = xm + g W2^T + b2; y = LN(x_L).  Backward: the chain rule of exactly that graph
+// — every contraction on the tcgen05 GEMM (dX = dY W with W^T packed at finalisation; dW = dY^T X with both operands
+// transposed by transpose_split, K = tokens), the rest in backward_ops.cu.
+// Gradient layout (fp32, `grad_floats` values), in this order — the Python mirror walks the same list:
+//   per layer l: [q,k,v]_proj.weight (3 x [D,D], contiguous), [q,k,v]_proj.bias (3 x [D]), out_proj.weight [D,D],
+//   out_proj.bias [D], self_attn_layer_norm.{weight,bias}, fc1.weight [F,D], fc1.bias [F], fc2.weight [D,F], fc2.bias [D],
+//   final_layer_norm.{weight,bias};  then encoder.layer_norm.{weight,bias};  then pos_conv.0.bias [D],
+//   pos_conv.0.weight_g [KT], pos_conv.0.weight_v [D, D/G, KT].
+long long enc_layer_grad_floats(int D, int F) { return 4ll * D * D + 4ll * D + 2ll * D + 2ll * D * F + F + D + 2ll * D; }
+long long enc_grad_floats(const avh_config& c) {
+  const int D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim;
+  return c.encoder_layers * enc_layer_grad_floats(D, F) + 2ll * D + D + c.conv_pos +
+         (long long)D * (D / c.conv_pos_groups) * c.conv_pos;
+}
+
+// Weight gradients of the grouped positional convolution + weight-norm backward (wav2vec2.py:822-834):
+// dw[o, i, k] = sum_{b,t} dc[b,t,o] x0[b, t + k - KT/2, g(o) cg + i].  Per group one GEMM over K = the zero-gapped token
+// axis: A = rows [g cg, +cg) of dc^T, B = the (tap, input channel) rows of the group — shifted copies of x0^T — so that
+// N = KT cg; output [cg, KT cg] = dw of the group as (o, tap, in).  Then dg, dv of w = g v / ||v||.
+bool posconv_wgrad(Builder& b, avh_handle* h, Plan* plan, const float* dc, const float* x0, long long N, int B, int T,
+                   float* g_wg, float* g_wv) {
+  const avh_config& c = h->cfg;
+  const int D = c.encoder_embed_dim, KT = c.conv_pos, G = c.conv_pos_groups, cg = D / G, P = b.P;
+  const int Tp = T + 64;
+  const long long kp = ((long long)B * Tp + 63) / 64 * 64;
+  void* dcT = b.alloc((size_t)D * P * kp * 2);
+  void* x0T = b.alloc((size_t)D * P * kp * 2);
+  void* XS = b.alloc((size_t)KT * cg * P * kp * 2);
+  float* dw = reinterpret_cast<float*>(b.alloc((size_t)D * KT * cg * 4));
+  float* norms = reinterpret_cast<float*>(b.alloc((size_t)KT * 4));
+  const int planes = P;
+  b.tag = "transpose";
+  b.push([=](cudaStream_t s) { return launch_transpose_split(dc, DT_F32, D, N, D, dcT, planes, kp, 1.0f, s, T, Tp); });
+  b.push([=](cudaStream_t s) { return launch_transpose_split(x0, DT_F32, D, N, D, x0T, planes, kp, 1.0f, s, T, Tp); });
+  for (int g = 0; g < G; ++g) {
+    b.tag = "pos_conv_shift";
+    b.push([=](cudaStream_t s) { return launch_posconv_shift(x0T, XS, g, cg, KT, planes, kp, s); });
+    PackedW xw;
+    xw.w = reinterpret_cast<bf16*>(XS); xw.n = KT * cg; xw.k = (int)kp; xw.kpad = (int)kp;
+    Epilogue ep;
+    ep.C = dw + (size_t)g * cg * KT * cg; ep.ldc = (long long)KT * cg; ep.c_fp32 = 1;
+    const char* a = reinterpret_cast<const char*>(dcT) + (size_t)g * cg * P * kp * 2;
+    b.tag = "pos_conv_wgrad";
+    if (!b.gemm(a, cg, P * (int)kp, xw, cg, {Tap{0, 0, 0}}, (int)(kp / 64), (int)kp, ep)) return false;
+  }
+  const float* v = h->pos_v_raw; const float* gg = h->pos_g_raw;
+  b.tag = "weight_norm_bwd";
+  b.push([=](cudaStream_t s) { return launch_posconv_weightnorm_bwd(dw, v, gg, D, cg, KT, g_wg, g_wv, norms, s); });
+  (void)plan;
+  return true;
+}
+
+bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
+  Builder b;
+  b.h = h; b.plan = plan; b.sizing = sizing; b.P = h->P; b.f32 = (h->cfg.compute_mode == AVH_COMPUTE_FP32);
+  const avh_config& c = h->cfg;
+  const int P = b.P;
+  const bool f32 = b.f32;
+  const int B = plan->B, T = plan->T, D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim, Hh = c.encoder_attention_heads;
+  const int L = c.encoder_layers;
+  const long long N = (long long)B * T;
+  const long long Kp = (N + 63) / 64 * 64;                  // token count padded to whole K blocks (wgrad GEMMs)
+  const size_t es = f32 ? 4 : 2;
+  const int act_dt = f32 ? DT_F32 : DT_BF16;
+  Plan* pl = plan;
+  if (!c.layer_norm_first) { set_last_error("the encoder backward is built for pre-LN layers (layer_norm_first)"); return false; }
+  auto new_act = [&](long long rows, int C) {
+    Act a;
+    a.rows = rows; a.C = C;
+    a.data = b.alloc((size_t)rows * C * es);
+    a.op = f32 ? b.alloc((size_t)rows * C * 2 * P) : a.data;
+    return a;
+  };
+  auto sync_op = [&](const Act& a) {
+    if (!f32) return;
+    const float* src = reinterpret_cast<const float*>(a.data);
+    void* dst = a.op;
+    const long long rows = a.rows;
+    const int C = a.C, planes = P;
+    const std::string keep = b.tag;
+    b.tag = "split";
+    b.push([=](cudaStream_t s) { return launch_split_rows(src, C, dst, planes, rows, C, 0, 0, s); });
+    b.tag = keep;
+  };
+  auto f32buf = [&](long long n) { return reinterpret_cast<float*>(b.alloc((size_t)n * 4)); };
+  b.sk_bytes = 0; b.sk_ws = nullptr; b.sk_flags = nullptr;
+  {
+    unsigned char* md = reinterpret_cast<unsigned char*>(b.alloc((size_t)N + 16));
+    if (!sizing) plan->mask_dev = md;
+  }
+  const bool hm = plan->has_mask;
+  const long long GF = enc_grad_floats(c);
+  float* grads = f32buf(GF);
+  float* dy = f32buf(N * D);
+  float* dxo = f32buf(N * D);
+  if (!sizing) { plan->grads = grads; plan->grad_floats = GF; plan->dy_in = dy; plan->dx_out = dxo; }
+
+  // ---------------------------------------------------------------- saved activations
+  float* x0 = f32buf(N * D);
+  float* cpre = f32buf(N * D);                               // positional conv output before the GELU
+  std::vector<float*> xin(L + 1), xmid(L);
+  std::vector<Act> h1(L), qkv(L), ctx(L), h2(L), u(L), g(L);
+  std::vector<float*> lse(L);
+  for (int l = 0; l <= L; ++l) xin[l] = f32buf(N * D);
+  for (int l = 0; l < L; ++l) {
+    xmid[l] = f32buf(N * D);
+    h1[l] = new_act(N, D); qkv[l] = new_act(N, 3 * D); ctx[l] = new_act(N, D); h2[l] = new_act(N, D);
+    u[l] = new_act(N, F); g[l] = new_act(N, F);
+    lse[l] = f32buf((long long)B * Hh * T);
+  }
+
+  // ================================================================ forward
+  b.tag = "load_features";
+  b.cur_direct = true;
+  b.push([=](cudaStream_t s) { return launch_load_rows(pl->args.xin, pl->args.xin_dt, x0, hm ? pl->mask_dev : nullptr, N, D, s); });
+  b.cur_direct = false;
+  const int G = 64, Tp = T + G;
+  const long long pad_rows = (long long)B * Tp;
+  const int KT = c.conv_pos, win = h->pos_window;
+  void* xpad = b.alloc((size_t)pad_rows * P * D * 2);         // zero-gapped operand layout of the positional conv
+  {
+    const int planes = P;
+    b.tag = "pos_pad";
+    b.push([=](cudaStream_t s) { return launch_split_rows(x0, D, xpad, planes, N, D, T, Tp, s); });
+    std::vector<Tap> taps;
+    for (int k = 0; k < KT; ++k) taps.push_back(Tap{k - KT / 2, 0, k * win});
+    Epilogue ep;
+    ep.C = cpre; ep.ldc = D; ep.c_fp32 = 1;
+    ep.col_bias = h->pos_bias;
+    ep.map_mode = MAP_2LEVEL; ep.S2 = Tp; ep.S1 = Tp; ep.H = 1; ep.W = T; ep.O2 = T; ep.O1 = 0; ep.O0 = 0;
+    b.tag = "pos_conv";
+    if (!b.gemm(xpad, pad_rows, P * D, h->pos_w, pad_rows, taps, win / 64, D, ep, 64, h->pos_acol)) return false;
+    float* x1 = xin[0];
+    b.tag = "gelu";
+    b.push([=](cudaStream_t s) { return launch_gelu_fwd(cpre, DT_F32, x0, x1, DT_F32, N * D, s); });
+  }
+  auto ln_fwd = [&](const float* src, const float* gm, const float* be, const Act& dst) {
+    float* of = f32 ? reinterpret_cast<float*>(dst.data) : nullptr;
+    void* ol = f32 ? nullptr : dst.data;
+    b.tag = "layer_ln";
+    b.push([=](cudaStream_t s) { return launch_layernorm(src, DT_F32, D, gm, be, 1e-5f, of, ol, DT_BF16, nullptr, N, D, s); });
+    sync_op(dst);
+  };
+  for (int l = 0; l < L; ++l) {
+    const LayerW& lw = h->layers[l];
+    b.cur_layer = l;
+    float* x = xin[l];
+    ln_fwd(x, lw.ln1_g, lw.ln1_b, h1[l]);
+    {
+      Epilogue ep;
+      ep.C = qkv[l].data; ep.ldc = 3 * D; ep.c_fp32 = f32 ? 1 : 0; ep.col_bias = lw.qkv.bias;
+      b.tag = "qkv_proj";
+      if (!b.gemm(h1[l].op, N, P * D, lw.qkv.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      const char* q = reinterpret_cast<const char*>(qkv[l].data);
+      void* o = ctx[l].data;
+      float* ls = lse[l];
+      b.tag = "attention";
+      b.push([=](cudaStream_t s) {
+        return launch_attention_x(q, 3 * D, q + (size_t)D * es, 3 * D, q + (size_t)2 * D * es, 3 * D, act_dt,
+                                  hm ? pl->mask_dev : nullptr, o, D, act_dt, B, Hh, T, T, 1.0f, s, ls);
+      });
+      sync_op(ctx[l]);
+    }
+    {
+      Epilogue ep;
+      ep.C = xmid[l]; ep.ldc = D; ep.c_fp32 = 1; ep.col_bias = lw.out.bias; ep.R = x; ep.ldr = D; ep.r_fp32 = 1;
+      b.tag = "out_proj";
+      if (!b.gemm(ctx[l].op, N, P * D, lw.out.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+    }
+    ln_fwd(xmid[l], lw.ln2_g, lw.ln2_b, h2[l]);
+    {
+      Epilogue ep;
+      ep.C = u[l].data; ep.ldc = F; ep.c_fp32 = f32 ? 1 : 0; ep.col_bias = lw.fc1.bias;
+      b.tag = "fc1";
+      if (!b.gemm(h2[l].op, N, P * D, lw.fc1.w, N, {Tap{0, 0, 0}}, D / 64, D, ep)) return false;
+      const void* uu = u[l].data; void* gg = g[l].data;
+      b.tag = "gelu";
+      b.push([=](cudaStream_t s) { return launch_gelu_fwd(uu, act_dt, nullptr, gg, act_dt, N * F, s); });
+      sync_op(g[l]);
+    }
+    {
+      Epilogue ep;
+      ep.C = xin[l + 1]; ep.ldc = D; ep.c_fp32 = 1; ep.col_bias = lw.fc2.bias; ep.R = xmid[l]; ep.ldr = D; ep.r_fp32 = 1;
+      b.tag = "fc2";
+      if (!b.gemm(g[l].op, N, P * F, lw.fc2.w, N, {Tap{0, 0, 0}}, F / 64, F, ep)) return false;
+    }
+  }
+  b.cur_layer = -1;
+  {
+    float* xl = xin[L];
+    float* gm = h->enc_ln_g; float* be = h->enc_ln_b;
+    b.tag = "final_ln";
+    b.cur_direct = true;
+    b.push([=](cudaStream_t s) {
+      return launch_layernorm(xl, DT_F32, D, gm, be, 1e-5f, nullptr, pl->args.out, pl->args.out_dt, nullptr, N, D, s);
+    });
+    b.cur_direct = false;
+  }
+  if (!sizing) plan->fwd_steps = plan->steps.size();
+
+  // ================================================================ backward
+  float2* stats = reinterpret_cast<float2*>(b.alloc((size_t)N * 8));
+  float* Dbuf = f32buf((long long)B * Hh * T);
+  float* dx = f32buf(N * D);             // gradient of the residual stream (ping)
+  float* dxm = f32buf(N * D);            // ... at the middle of a layer (pong)
+  float* dh = f32buf(N * D);             // gradient of a LayerNorm output
+  Act dxa = new_act(N, D);               // operand form of dx / dxm
+  Act dga = new_act(N, F);               // dL/dg
+  Act dua = new_act(N, F);               // dL/du
+  Act dctx = new_act(N, D);
+  Act dqkv = new_act(N, 3 * D);
+  void* tA = b.alloc((size_t)std::max(3 * D, F) * P * Kp * 2);      // transposed dY operand
+  void* tB = b.alloc((size_t)std::max(D, F) * P * Kp * 2);          // transposed X operand
+  // fp32 [N, C] -> operand form (bf16 or split planes)
+  auto to_op = [&](const float* src, const Act& dst, int C) {
+    void* d = dst.op;
+    const int planes = P;
+    b.tag = "split";
+    b.push([=](cudaStream_t s) { return launch_split_rows(src, C, d, planes, N, C, 0, 0, s); });
+  };
+  // dX [N, n_in] = dY [N, n_out] W: A = dY operand, B = W^T (packed [n_in, n_out])
+  auto dgrad = [&](const void* dy_op, int n_out, const LinearW& wT, void* out, bool out_f32, const char* tag) {
+    Epilogue ep;
+    ep.C = out; ep.ldc = wT.w.n; ep.c_fp32 = out_f32 ? 1 : 0;
+    b.tag = tag;
+    return b.gemm(dy_op, N, P * n_out, wT.w, N, {Tap{0, 0, 0}}, wT.w.kpad / 64, n_out, ep);
+  };
+  // dW [n_out, n_in] = dY^T X (+ bias gradient = column sums of dY)
+  auto wgrad = [&](const void* dyv, int dy_dt, int n_out, const void* xv, int x_dt, int n_in, float* dW, float* db, const char* tag) {
+    const int planes = P;
+    b.tag = "transpose";
+    b.push([=](cudaStream_t s) { return launch_transpose_split(dyv, dy_dt, n_out, N, n_out, tA, planes, Kp, 1.0f, s); });
+    b.push([=](cudaStream_t s) { return launch_transpose_split(xv, x_dt, n_in, N, n_in, tB, planes, Kp, 1.0f, s); });
+    PackedW xw;
+    xw.w = reinterpret_cast<bf16*>(tB); xw.n = n_in; xw.k = (int)Kp; xw.kpad = (int)Kp;
+    Epilogue ep;
+    ep.C = dW; ep.ldc = n_in; ep.c_fp32 = 1;
+    b.tag = tag;
+    if (!b.gemm(tA, n_out, P * (int)Kp, xw, n_out, {Tap{0, 0, 0}}, (int)(Kp / 64), (int)Kp, ep)) return false;
+    if (db != nullptr) {
+      b.tag = "bias_grad";
+      b.push([=](cudaStream_t s) { return launch_colsum(dyv, dy_dt, n_out, N, n_out, db, 1.0f, s); });
+    }
+    return true;
+  };
+  const float qscale = 1.0f / std::sqrt(64.0f);
+  const long long LG = enc_layer_grad_floats(D, F);
+  b.tag = "load_grad";
+  b.cur_direct = true;
+  // (the caller's dL/dy is staged into `dy` by avh_encoder_backward before the steps run; pad rows zeroed there)
+  b.cur_direct = false;
+  {   // final LayerNorm
+    float* gfin = grads + (long long)L * LG;
+    float* xl = xin[L];
+    float* gm = h->enc_ln_g;
+    b.tag = "ln_bwd";
+    b.push([=](cudaStream_t s) { return launch_ln_bwd(xl, gm, dy, nullptr, dx, stats, gfin, gfin + D, N, D, 1e-5f, s); });
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerW& lw = h->layers[l];
+    b.cur_layer = l;
+    float* gl = grads + (long long)l * LG;
+    float* g_qkv_w = gl;                         // [3D, D]
+    float* g_qkv_b = g_qkv_w + 3ll * D * D;      // [3D]
+    float* g_out_w = g_qkv_b + 3ll * D;          // [D, D]
+    float* g_out_b = g_out_w + (long long)D * D;
+    float* g_ln1 = g_out_b + D;                  // gamma, beta
+    float* g_fc1_w = g_ln1 + 2ll * D;            // [F, D]
+    float* g_fc1_b = g_fc1_w + (long long)F * D;
+    float* g_fc2_w = g_fc1_b + F;                // [D, F]
+    float* g_fc2_b = g_fc2_w + (long long)D * F;
+    float* g_ln2 = g_fc2_b + D;
+    // ---- fc2: x' = xm + g W2^T + b2
+    if (!wgrad(dx, DT_F32, D, g[l].data, act_dt, F, g_fc2_w, g_fc2_b, "fc2_wgrad")) return false;
+    to_op(dx, dxa, D);
+    if (!dgrad(dxa.op, D, lw.fc2T, dga.data, f32, "fc2_dgrad")) return false;
+    {
+      const void* uu = u[l].data; const void* dgv = dga.data; void* duv = dua.data;
+      b.tag = "gelu_bwd";
+      b.push([=](cudaStream_t s) { return launch_gelu_bwd(uu, act_dt, dgv, act_dt, duv, act_dt, N * F, s); });
+      sync_op(dua);
+    }
+    // ---- fc1: u = h2 W1^T + b1
+    if (!wgrad(dua.data, act_dt, F, h2[l].data, act_dt, D, g_fc1_w, g_fc1_b, "fc1_wgrad")) return false;
+    if (!dgrad(dua.op, F, lw.fc1T, dh, true, "fc1_dgrad")) return false;
+    {   // LN2: dxm = dx + dLN(dh; xm)
+      float* xm = xmid[l]; float* gm = lw.ln2_g;
+      b.tag = "ln_bwd";
+      b.push([=](cudaStream_t s) { return launch_ln_bwd(xm, gm, dh, dx, dxm, stats, g_ln2, g_ln2 + D, N, D, 1e-5f, s); });
+    }
+    // ---- out_proj: xm = x + ctx Wo^T + bo
+    if (!wgrad(dxm, DT_F32, D, ctx[l].data, act_dt, D, g_out_w, g_out_b, "out_wgrad")) return false;
+    to_op(dxm, dxa, D);
+    if (!dgrad(dxa.op, D, lw.outT, dctx.data, f32, "out_dgrad")) return false;
+    {   // attention
+      const char* q = reinterpret_cast<const char*>(qkv[l].data);
+      char* dq = reinterpret_cast<char*>(dqkv.data);
+      const void* dO = dctx.data; const void* O = ctx[l].data;
+      float* ls = lse[l];
+      b.tag = "attention_bwd";
+      b.push([=](cudaStream_t s) {
+        return launch_attention_bwd(q, 3 * D, q + (size_t)D * es, 3 * D, q + (size_t)2 * D * es, 3 * D, act_dt, dO, O, D, act_dt, ls,
+                                    hm ? pl->mask_dev : nullptr, dq, dq + (size_t)D * es, dq + (size_t)2 * D * es, 3 * D, act_dt,
+                                    Dbuf, B, Hh, T, s);
+      });
+      sync_op(dqkv);
+    }
+    // ---- qkv: [q', k, v] = h1 Wqkv'^T + b' with q' = s q (the scaling is folded into Wq', bq')
+    if (!wgrad(dqkv.data, act_dt, 3 * D, h1[l].data, act_dt, D, g_qkv_w, g_qkv_b, "qkv_wgrad")) return false;
+    b.tag = "scale";
+    b.push([=](cudaStream_t s) {     // d/dWq = s d/dWq', d/dbq = s d/dbq'
+      if (launch_scale(g_qkv_w, (long long)D * D, qscale, s)) return 1;
+      return launch_scale(g_qkv_b, D, qscale, s);
+    });
+    if (!dgrad(dqkv.op, 3 * D, lw.qkvT, dh, true, "qkv_dgrad")) return false;
+    {   // LN1: dx = dxm + dLN(dh; x)
+      float* xl = xin[l]; float* gm = lw.ln1_g;
+      b.tag = "ln_bwd";
+      b.push([=](cudaStream_t s) { return launch_ln_bwd(xl, gm, dh, dxm, dx, stats, g_ln1, g_ln1 + D, N, D, 1e-5f, s); });
+    }
+  }
+  b.cur_layer = -1;
+  // ---- positional conv block: x1 = x0 + GELU(c), c = conv(x0) + bias  (pos-conv weight gradients: see posconv_bwd)
+  {
+    float* gpos = grads + (long long)L * LG + 2ll * D;       // bias [D], weight_g [KT], weight_v [D, D/G, KT]
+    float* dc = dh;                                          // dL/dc = dx * GELU'(c)
+    b.tag = "gelu_bwd";
+    b.push([=](cudaStream_t s) { return launch_gelu_bwd(cpre, DT_F32, dx, DT_F32, dc, DT_F32, N * D, s); });
+    b.tag = "bias_grad";
+    b.push([=](cudaStream_t s) { return launch_colsum(dc, DT_F32, D, N, D, gpos, 1.0f, s); });
+    // dgrad: dx0[t, i] = dx[t, i] + sum_k sum_o dc[t + 64 - k, o] w[o, i, k]: the same shifted-row GEMM over the
+    // zero-gapped layout with the taps mirrored and the weights transposed inside every group (pos_wT)
+    void* dcpad = b.alloc((size_t)pad_rows * P * D * 2);     // zero-gapped operand layout of dL/dc (gap rows stay zero)
+    const int planes = P;
+    b.tag = "pos_pad";
+    b.push([=](cudaStream_t s) { return launch_split_rows(dc, D, dcpad, planes, N, D, T, Tp, s); });
+    std::vector<Tap> taps;
+    for (int k = 0; k < KT; ++k) taps.push_back(Tap{KT / 2 - k, 0, k * win});
+    Epilogue ep;
+    ep.C = dxo; ep.ldc = D; ep.c_fp32 = 1;
+    ep.R = dx; ep.ldr = D; ep.r_fp32 = 1;
+    if (hm) ep.row_zero = MASK_SENTINEL;                     // x0 = index_put(features, mask, 0): no gradient into pad rows
+    ep.map_mode = MAP_2LEVEL; ep.S2 = Tp; ep.S1 = Tp; ep.H = 1; ep.W = T; ep.O2 = T; ep.O1 = 0; ep.O0 = 0;
+    b.tag = "pos_conv_dgrad";
+    if (!b.gemm(dcpad, pad_rows, P * D, h->pos_wT, pad_rows, taps, win / 64, D, ep, 64, h->pos_acol)) return false;
+    // weight gradients of the grouped convolution + weight-norm backward
+    if (!posconv_wgrad(b, h, plan, dc, x0, N, B, T, gpos + D, gpos + D + KT)) return false;
+  }
+  if (bytes_out) *bytes_out = b.sizer.used;
+  return true;
+}
+
 // ============================================================================ Q-Former plan
 // Qformer.bert(query_embeds, attention_mask, encoder_hidden_states, encoder_attention_mask) (src/model.py:611-617 ->
 // src/sub_model/Qformer.py:805-968) for B clips x T query rows against Lk AV-feature rows each.  Post-LN BERT layers:
@@ -1633,9 +2052,11 @@ bool build_qformer_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_ou
 }
 
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
-               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false, int qf_lk = 0) {
+               cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false, int qf_lk = 0,
+               bool enc_train = false) {
   const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) + (enc_only ? "e:" : "") +
                           (train ? "t:" : "") + (qf_lk > 0 ? "q" + std::to_string(qf_lk) + ":" : std::string()) +
+                          (enc_train ? "g:" : "") +
                           std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
@@ -1665,8 +2086,9 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
   p->enc_only = enc_only;
   p->train = train;
   p->Lk = qf_lk;
+  p->enc_train = enc_train;
   size_t bytes = 0;
-  auto build = qf_lk > 0 ? build_qformer_plan : build_plan;
+  auto build = qf_lk > 0 ? build_qformer_plan : (enc_train ? build_encoder_train_plan : build_plan);
   if (!build(h, p.get(), true, &bytes)) return nullptr;
   if (p->arena.init(bytes + (1 << 20))) return nullptr;
   if (!build(h, p.get(), false, nullptr)) return nullptr;
@@ -2112,6 +2534,71 @@ int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t
   p->args.mask = padding_mask;
   p->args.out = out; p->args.out_dt = out_dtype;
   return run_plan(h, p, s);
+}
+
+static int run_steps(avh_handle* h, avh::Plan* p, size_t begin, size_t end, cudaStream_t s) {
+  (void)h;
+  for (size_t i = begin; i < end; ++i)
+    if (p->steps[i].run(s)) {
+      if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
+      return 1;
+    }
+  return 0;
+}
+
+int avh_encoder_grad_count(avh_handle* h, int64_t* n_floats) {
+  AVH_CHECK(h != nullptr && n_floats != nullptr, "null argument");
+  AVH_CHECK(h->cfg.reserved[0] != 2, "this handle holds a Q-Former");
+  *n_floats = avh::enc_grad_floats(h->cfg);
+  return 0;
+}
+
+int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T, void* out,
+                              int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(h->cfg.reserved[0] != 2, "this handle holds a Q-Former");
+  AVH_CHECK(h->cfg.reserved[3] != 0, "handle not created as trainable (avh_config.reserved[3] = 1 packs the backward's operands)");
+  AVH_CHECK(x != nullptr && out != nullptr, "null argument");
+  AVH_CHECK(x_dtype == AVH_F32 || x_dtype == AVH_F16 || x_dtype == AVH_BF16, "bad feature dtype");
+  AVH_CHECK(B >= 1 && T >= 1 && (long long)B * T < (1ll << 24), "bad batch");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  avh::Plan* p = avh::get_plan(h, B, T, false, false, padding_mask != nullptr, 0, s, 0, true, false, 0, true);
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  p->args = avh::CallArgs();
+  p->args.xin = x; p->args.xin_dt = x_dtype;
+  p->args.mask = padding_mask;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  if (padding_mask != nullptr)
+    AVH_CUDA_OK(cudaMemcpyAsync(p->mask_dev, padding_mask, (size_t)B * T, cudaMemcpyDeviceToDevice, s));
+  p->fwd_done = false;
+  if (run_steps(h, p, 0, p->fwd_steps, s)) return 1;
+  p->fwd_done = true;
+  return 0;
+}
+
+int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, float* grads,
+                         int64_t grads_capacity, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(dout != nullptr, "null argument");
+  avh::Plan* p = h->last_plan;
+  AVH_CHECK(p != nullptr && p->enc_train && p->fwd_done, "avh_encoder_backward follows avh_encoder_train_forward on the same handle");
+  AVH_CHECK(grads == nullptr || grads_capacity >= p->grad_floats, "gradient buffer too small (avh_encoder_grad_count)");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AVH_CHECK(s == p->stream, "backward must run on the stream of its forward");
+  const long long N = (long long)p->B * p->T;
+  const int D = h->cfg.encoder_embed_dim;
+  // dL/dy -> fp32, rows of padded frames zeroed (the reference's loss never reads them)
+  if (avh::launch_load_rows(dout, dout_dtype, p->dy_in, p->has_mask ? p->mask_dev : nullptr, N, D, s)) return 1;
+  if (run_steps(h, p, p->fwd_steps, p->steps.size(), s)) return 1;
+  if (dx != nullptr && avh::launch_convert(p->dx_out, avh::DT_F32, dx, dx_dtype, N * D, s)) return 1;
+  if (grads != nullptr)
+    AVH_CUDA_OK(cudaMemcpyAsync(grads, p->grads, (size_t)p->grad_floats * 4, cudaMemcpyDeviceToDevice, s));
+  p->fwd_done = false;
+  return 0;
 }
 
 int avh_qformer_forward(avh_handle* h, const void* enc, int enc_dtype, const uint8_t* enc_padding, const int32_t* len_queries,

@@ -2,6 +2,7 @@
 // return 0 on success / 1 with avh::set_last_error on failure).
 #pragma once
 #include <cuda_runtime.h>
+#include <vector_types.h>
 #include <stdint.h>
 
 namespace avh {
@@ -94,9 +95,33 @@ int launch_sumsq(const void* x, int dt, long long n, double* acc, cudaStream_t s
 // head dim 64, heads side by side in the columns; key_pad [B, Lk] (1 = masked) or null; any float dtype in, o_dt out
 int launch_attention_x(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, int dt,
                        const unsigned char* key_pad, void* O, long long ldo, int o_dt, int B, int H, int Lq, int Lk,
-                       float scale, cudaStream_t stream);
+                       float scale, cudaStream_t stream, float* lse = nullptr);      // lse [B, H, Lq]: log-sum-exp per query row
 // dst [B, per_clip] = src [per_clip] for every clip (fp32)
 int launch_rows_broadcast(const float* src, float* dst, long long per_clip, int B, cudaStream_t stream);
+
+// ---- backward of the Transformer encoder (backward_ops.cu)
+// in [rows, C] -> bf16 [C, planes * kpad] (transposed GEMM operand over K = rows, zero padded), values times `scale`
+// T > 0: K index (b * Tp + t) holds input row b * T + t, the gaps t in [T, Tp) are zeros (the positional conv's layout)
+int launch_transpose_split(const void* in, int dt, long long ld, long long rows, int C, void* out, int planes, long long kpad,
+                           float scale, cudaStream_t stream, int T = 0, int Tp = 0);
+int launch_scale(float* p, long long n, float s, cudaStream_t stream);
+// positional-conv weight gradient helpers: shifted copies of the transposed input for one group; weight-norm backward
+int launch_posconv_shift(const void* XT, void* XS, int g, int cg, int KT, int planes, long long kp, cudaStream_t stream);
+int launch_posconv_weightnorm_bwd(const float* dw, const float* v, const float* g, int D, int cg, int KT, float* dg, float* dv,
+                                  float* norms, cudaStream_t stream);
+// out[c] = scale * sum_r in[r, c]  (bias gradients)
+int launch_colsum(const void* in, int dt, long long ld, long long rows, int C, float* out, float scale, cudaStream_t stream);
+// out = (res ? res : 0) + gelu(u);  du = dg * gelu'(u)
+int launch_gelu_fwd(const void* u, int u_dt, const float* res, void* out, int out_dt, long long n, cudaStream_t stream);
+int launch_gelu_bwd(const void* u, int u_dt, const void* dg, int dg_dt, void* du, int du_dt, long long n, cudaStream_t stream);
+// LayerNorm backward: dx_out = (res ? res : 0) + dLN/dx(dy), dgamma, dbeta; stats = scratch [rows] float2
+int launch_ln_bwd(const float* x, const float* gamma, const float* dy, const float* res, float* dx_out, float2* stats,
+                  float* dgamma, float* dbeta, long long rows, int C, float eps, cudaStream_t stream);
+// attention backward (self-attention over L rows per clip, heads of 64 channels side by side); Dbuf = scratch [B, H, L]
+int launch_attention_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, int dt,
+                         const void* dO, const void* O, long long ldo, int o_dt, const float* lse, const unsigned char* key_pad,
+                         void* dQ, void* dK, void* dV, long long ldd, int d_dt, float* Dbuf, int B, int H, int L,
+                         cudaStream_t stream);
 
 // ---- audio frontend ---------------------------------------------------------------------------------
 struct FbankArgs {

@@ -32,7 +32,7 @@ __device__ __forceinline__ float ldx(const void* p, int dt, long long i) {
 __global__ void __launch_bounds__(256)
 attention_x_kernel(const void* __restrict__ Q, long long ldq, const void* __restrict__ K, long long ldk,
                    const void* __restrict__ V, long long ldv, int dt, const unsigned char* __restrict__ key_pad,
-                   void* __restrict__ O, long long ldo, int o_dt, int Lq, int Lk, float scale) {
+                   void* __restrict__ O, long long ldo, int o_dt, int Lq, int Lk, float scale, float* __restrict__ lse) {
   __shared__ __align__(16) float Ks[AX_KT][AX_HD];
   __shared__ __align__(16) float Vs[AX_KT][AX_HD];
   __shared__ unsigned char dead[AX_KT];
@@ -123,6 +123,10 @@ attention_x_kernel(const void* __restrict__ Q, long long ldq, const void* __rest
     }
     __syncthreads();
   }
+  // log-sum-exp of every query row for the backward pass ([B, H, Lq]; +inf for a row without a live key: P = 0)
+  if (lse != nullptr && threadIdx.x < AX_QT && q0 + threadIdx.x < Lq)
+    lse[((long long)b * gridDim.y + h) * Lq + q0 + threadIdx.x] =
+        Ls[threadIdx.x] > 0.f ? Ms[threadIdx.x] + __logf(Ls[threadIdx.x]) : INFINITY;
   for (int e = threadIdx.x; e < AX_QT * AX_HD; e += 256) {
     const int r = e / AX_HD, d = e % AX_HD;
     if (q0 + r >= Lq) continue;
@@ -148,11 +152,11 @@ rows_broadcast_kernel(const float* __restrict__ src, float* __restrict__ dst, lo
 
 int launch_attention_x(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, int dt,
                        const unsigned char* key_pad, void* O, long long ldo, int o_dt, int B, int H, int Lq, int Lk,
-                       float scale, cudaStream_t stream) {
+                       float scale, cudaStream_t stream, float* lse) {
   AVH_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "bad attention shape");
   AVH_CHECK(B <= 65535 && H <= 65535, "batch / head count exceeds the grid limits");
   dim3 grid((Lq + AX_QT - 1) / AX_QT, H, B);
-  attention_x_kernel<<<grid, 256, 0, stream>>>(Q, ldq, K, ldk, V, ldv, dt, key_pad, O, ldo, o_dt, Lq, Lk, scale);
+  attention_x_kernel<<<grid, 256, 0, stream>>>(Q, ldq, K, ldk, V, ldv, dt, key_pad, O, ldo, o_dt, Lq, Lk, scale, lse);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

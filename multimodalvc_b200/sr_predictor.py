@@ -8,8 +8,11 @@
   ReLU on the token's output.  Same attribute / state-dict names as the reference (``sr_token``, ``linear.*``,
   ``encoder.*``, ``sr_predictor.*``).
 
-Inference only (eval mode: LayerDrop and dropout are identity, as in the reference's ``self.training`` gates); no CPU
-path.
+Inference by default (eval mode: LayerDrop and dropout are identity, as in the reference's ``self.training`` gates).
+``TransformerEncoder(args, trainable=True)`` also differentiates: in ``.train()`` with gradients enabled ``forward`` is a
+``torch.autograd.Function`` whose backward is the library's (``avh_encoder_train_forward`` / ``avh_encoder_backward``:
+SURVEY row A18, encoder part of BASELINE config 5 — dropout / LayerDrop must be 0, pre-LN layers), so ``loss.backward()``
+fills ``.grad`` of the input and of every encoder parameter.  No CPU path.
 """
 import ctypes
 from types import SimpleNamespace
@@ -22,12 +25,65 @@ from .hubert import _DTYPES, _EncoderParams
 from .hubert_asr import _project
 
 
+class _EncoderTrainFn(torch.autograd.Function):
+    """y = encoder(x, padding_mask) with the library's forward (activations saved in the handle's plan) and backward.
+    The parameters are passed only so that autograd routes their gradients; the arithmetic uses the packed copies."""
+
+    @staticmethod
+    def forward(ctx, enc, x, pm_u8, *params):
+        handle = enc._ensure_handle()
+        dev = x.device
+        B, T, D = x.shape
+        out_dtype = enc.layer_norm.weight.dtype if enc.layer_norm.weight.dtype in _DTYPES else torch.float32
+        out = torch.empty(B, T, D, device=dev, dtype=out_dtype)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_encoder_train_forward(
+                handle, ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype],
+                ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None, B, T,
+                ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
+        ctx.enc, ctx.handle, ctx.x_dtype, ctx.stream = enc, handle, x.dtype, stream
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        enc = ctx.enc
+        dev = dout.device
+        dout = dout.contiguous()
+        if dout.dtype not in _DTYPES:
+            dout = dout.float()
+        lib = _lib.load()
+        n = ctypes.c_int64()
+        _lib.check(lib.avh_encoder_grad_count(ctx.handle, ctypes.byref(n)))
+        flat = torch.empty(n.value, device=dev, dtype=torch.float32)
+        dx = torch.empty(dout.shape, device=dev, dtype=ctx.x_dtype)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if stream != ctx.stream:
+                raise RuntimeError("the encoder backward must run on the CUDA stream of its forward")
+            _lib.check(lib.avh_encoder_backward(
+                ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], ctypes.c_void_p(dx.data_ptr()),
+                _DTYPES[dx.dtype], ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+        grads, off = [], 0
+        for shape, dt in zip(ctx.shapes, ctx.dtypes):
+            k = 1
+            for d in shape:
+                k *= d
+            grads.append(flat[off:off + k].view(shape).to(dt))
+            off += k
+        assert off == n.value
+        return (None, dx, None, *grads)
+
+
 class TransformerEncoder(nn.Module):
     """``TransformerEncoder(args)`` with the reference's argument names (encoder_embed_dim, encoder_ffn_embed_dim,
     encoder_attention_heads, encoder_layers, conv_pos, conv_pos_groups, layer_norm_first, activation_fn='gelu')."""
 
-    def __init__(self, args):
+    def __init__(self, args, trainable=False):
         super().__init__()
+        self.trainable = bool(trainable)
         if getattr(args, "activation_fn", "gelu") != "gelu":
             raise NotImplementedError("only activation_fn='gelu' is implemented")
         if args.encoder_embed_dim != 64 * args.encoder_attention_heads:
@@ -81,6 +137,7 @@ class TransformerEncoder(nn.Module):
                 conv_pos=a.conv_pos, conv_pos_groups=a.conv_pos_groups, compute_mode=mode, frontend_chunk_frames=0,
                 capture_stages=0)
             cc.reserved[0] = 1                    # bare TransformerEncoder: only "encoder.*" weights
+            cc.reserved[3] = 1 if self.trainable else 0      # also pack the backward's transposed operands
             hp = ctypes.c_void_p()
             _lib.check(lib.avh_create(ctypes.byref(cc), key[0], ctypes.byref(hp)))
             self._handle, self._handle_key = hp, key
@@ -98,11 +155,60 @@ class TransformerEncoder(nn.Module):
         self._dirty = False
         return self._handle
 
-    @torch.no_grad()
+    def grad_parameters(self):
+        """The parameters in the order avh_encoder_backward writes their gradients (include/avh_b200.h)."""
+        out = []
+        for layer in self.layers:
+            a = layer.self_attn
+            out += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.q_proj.bias, a.k_proj.bias, a.v_proj.bias,
+                    a.out_proj.weight, a.out_proj.bias, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias,
+                    layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias,
+                    layer.final_layer_norm.weight, layer.final_layer_norm.bias]
+        out += [self.layer_norm.weight, self.layer_norm.bias]
+        pc = self.pos_conv[0]
+        out += [pc.bias, pc.weight_g, pc.weight_v]
+        return out
+
+    def _forward_train(self, x, padding_mask, layer):
+        a = self.args
+        if not self.trainable:
+            raise RuntimeError("build the module with trainable=True to differentiate through it (or call .eval())")
+        if layer is not None:
+            raise NotImplementedError("the training-mode forward runs the whole stack (layer=None)")
+        if not self.layer_norm_first:
+            raise NotImplementedError("the device backward is built for pre-LN layers (layer_norm_first=True)")
+        for name in ("dropout", "attention_dropout", "activation_dropout", "encoder_layerdrop"):
+            if float(getattr(a, name, 0.0) or 0.0) != 0.0:
+                raise NotImplementedError(f"{name} must be 0 for the device training step (BASELINE config 5 sets "
+                                          "dropout / layerdrop 0)")
+        dev = self.layer_norm.weight.device
+        if x.device != dev or x.dim() != 3 or x.size(2) != self.embedding_dim:
+            raise ValueError(f"x must be [B,T,{self.embedding_dim}] on {dev}, got {tuple(x.shape)} on {x.device}")
+        B, T, _ = x.shape
+        if x.dtype not in _DTYPES:
+            x = x.float()
+        x = x.contiguous()
+        pm = None
+        if padding_mask is not None:
+            if tuple(padding_mask.shape) != (B, T):
+                raise ValueError(f"padding_mask must be [{B},{T}]")
+            pm = padding_mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
+        if any(p._version != v for p, v in zip(self.parameters(), getattr(self, "_versions", []))) or not hasattr(self, "_versions"):
+            self._dirty = True                                   # an optimizer step changed the weights: re-pack
+        self._ensure_handle()
+        self._versions = [p._version for p in self.parameters()]
+        return _EncoderTrainFn.apply(self, x, pm, *self.grad_parameters()), []
+
     def forward(self, x, padding_mask=None, layer=None):
         """wav2vec2.py:859-902: returns (x [B,T,D], layer_results) — layer_results is empty (nobody on this path reads
         it; the reference fills it with per-layer tensors only for tgt_layer / feature dumping)."""
-        if self.training:
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(x, padding_mask, layer)
+        with torch.no_grad():
+            return self._forward_eval(x, padding_mask, layer)
+
+    def _forward_eval(self, x, padding_mask=None, layer=None):
+        if self.training and not self.trainable:
             raise RuntimeError("TransformerEncoder on the device path is inference-only: call .eval()")
         handle = self._ensure_handle()
         dev = self.layer_norm.weight.device

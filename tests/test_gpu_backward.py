@@ -1,0 +1,132 @@
+"""Backward of the TransformerEncoder on the device (encoder part of BASELINE config 5):
+avh_encoder_train_forward / avh_encoder_backward through the autograd wrapper of multimodalvc_b200.TransformerEncoder
+(trainable=True) against torch.autograd on the CPU oracle's restatement of wav2vec2.py:816-1014 — gradient w.r.t. the
+input features and w.r.t. EVERY parameter (attention, FFN, LayerNorms, weight-normed grouped positional conv).
+Gate: max |g - g_ref| / max |g_ref| <= 2e-3 per tensor in the fp32-faithful mode; cosine in bf16 mode."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import avhubert_oracle as ao
+
+from helpers import cosine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(D, F, H, L, groups, seed):
+    from multimodalvc_b200.sr_predictor import TransformerEncoder
+    cfg = ao.OracleConfig(encoder_layers=L, encoder_embed_dim=D, encoder_ffn_embed_dim=F, encoder_attention_heads=H,
+                          layer_norm_first=True, conv_pos=128, conv_pos_groups=groups)
+    torch.manual_seed(seed)
+    ref = ao._Encoder(cfg)
+    ao.randomize_norm_stats(ref)
+    with torch.no_grad():            # weights large enough that every path carries gradient signal
+        for m in ref.modules():
+            if isinstance(m, torch.nn.Linear):
+                m.weight.mul_(3.0)
+    enc = TransformerEncoder(SimpleNamespace(encoder_embed_dim=D, encoder_ffn_embed_dim=F, encoder_attention_heads=H,
+                                             encoder_layers=L, conv_pos=128, conv_pos_groups=groups, layer_norm_first=True,
+                                             activation_fn="gelu", dropout=0.0, attention_dropout=0.0,
+                                             activation_dropout=0.0, encoder_layerdrop=0.0), trainable=True)
+    enc.load_state_dict(ref.state_dict(), strict=True)
+    return ref, enc
+
+
+def _case(B, T, D, lengths, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, D, generator=g)
+    pm = None
+    if lengths is not None:
+        pm = torch.arange(T)[None, :] >= torch.tensor(lengths)[:, None]
+    w = torch.randn(B, T, D, generator=g)
+    if pm is not None:
+        w = w.masked_fill(pm.unsqueeze(-1), 0.0)         # the loss reads valid positions only (config 5)
+    return x, pm, w
+
+
+def _loss(y, w, pm):
+    valid = y if pm is None else y.masked_fill(pm.unsqueeze(-1), 0.0)
+    return (valid * w).sum() / w.numel() + valid.pow(2).mean()
+
+
+def _reference_grads(ref, x, pm, w):
+    ref.train()
+    ref.zero_grad()
+    xr = x.clone().requires_grad_(True)
+    y = ref(xr, pm)
+    _loss(y, w, pm).backward()
+    return y.detach(), xr.grad, {n: p.grad.clone() for n, p in ref.named_parameters()}
+
+
+@pytest.mark.parametrize("shape", [
+    dict(D=128, F=256, H=2, L=2, groups=16, B=3, T=37, lengths=[37, 20, 29]),        # 8 channels per conv group
+    dict(D=256, F=1024, H=4, L=2, groups=16, B=2, T=150, lengths=None),               # the Speech_Rate_Predictor's encoder
+    dict(D=1024, F=4096, H=16, L=1, groups=16, B=2, T=70, lengths=[70, 51]),          # Large layer shape, 64 per group
+])
+def test_encoder_backward_matches_autograd_fp32(shape):
+    ref, enc = _pair(shape["D"], shape["F"], shape["H"], shape["L"], shape["groups"], seed=7)
+    x, pm, w = _case(shape["B"], shape["T"], shape["D"], shape["lengths"], seed=8)
+    y_ref, dx_ref, g_ref = _reference_grads(ref, x, pm, w)
+    enc = enc.cuda().train()
+    xd = x.cuda().requires_grad_(True)
+    pmd = pm.cuda() if pm is not None else None
+    y, _ = enc(xd, pmd)
+    valid = slice(None) if pm is None else ~pm
+    assert rel_err(y.detach().cpu()[valid], y_ref[valid]) < 2e-3
+    _loss(y, w.cuda(), pmd).backward()
+    assert rel_err(xd.grad.cpu(), dx_ref) < 2e-3, ("dx", rel_err(xd.grad.cpu(), dx_ref))
+    if pm is not None:
+        assert not xd.grad.cpu()[pm].any()                 # index_put(x, padding_mask, 0): no gradient into padded frames
+    worst = {}
+    for n, p in enc.named_parameters():
+        assert p.grad is not None, n
+        if n.endswith("k_proj.bias"):
+            # softmax is invariant to a shift of every key by the same vector: this gradient is exactly 0 in exact
+            # arithmetic (autograd returns ~1e-9 noise) — judged on the scale of the q_proj.bias gradient beside it
+            scale = g_ref[n.replace("k_proj", "q_proj")].abs().max().item()
+            worst[n] = (p.grad.cpu() - g_ref[n]).abs().max().item() / scale
+            continue
+        worst[n] = rel_err(p.grad.cpu(), g_ref[n])
+    bad = {n: e for n, e in worst.items() if e > 2e-3}
+    assert not bad, bad
+    # a second step through the same plan (saved activations are overwritten, gradients rewritten) is identical
+    enc.zero_grad()
+    xd2 = x.cuda().requires_grad_(True)
+    y2, _ = enc(xd2, pmd)
+    _loss(y2, w.cuda(), pmd).backward()
+    assert torch.equal(xd2.grad, xd.grad)
+
+
+def test_encoder_backward_bf16_and_optimizer_step():
+    ref, enc = _pair(256, 1024, 4, 2, 16, seed=3)
+    x, pm, w = _case(4, 60, 256, [60, 44, 60, 31], seed=4)
+    _, dx_ref, g_ref = _reference_grads(ref, x, pm, w)
+    enc = enc.cuda().bfloat16().train()
+    xd = x.cuda().bfloat16().requires_grad_(True)
+    y, _ = enc(xd, pm.cuda())
+    _loss(y.float(), w.cuda(), pm.cuda()).backward()
+    assert cosine(xd.grad.float().cpu(), dx_ref) > 0.99
+    for n, p in enc.named_parameters():
+        if n.endswith("k_proj.bias"):
+            continue                                        # exactly 0 in exact arithmetic (see above)
+        assert cosine(p.grad.float().cpu(), g_ref[n]) > 0.98, (n, cosine(p.grad.float().cpu(), g_ref[n]))
+    # an optimizer step changes the weights in place: the next forward must see them
+    enc = enc.float()
+    opt = torch.optim.SGD(enc.parameters(), lr=0.5)
+    xf = x.cuda().requires_grad_(True)
+    y0, _ = enc(xf, pm.cuda())
+    l0 = _loss(y0, w.cuda(), pm.cuda())
+    l0.backward()
+    opt.step()
+    opt.zero_grad()
+    y1, _ = enc(x.cuda().requires_grad_(True), pm.cuda())
+    l1 = _loss(y1, w.cuda(), pm.cuda())
+    assert l1.item() < l0.item()                            # a gradient step on the library's gradients lowers the loss
+    with pytest.raises(NotImplementedError):
+        enc(x.cuda().requires_grad_(True), pm.cuda(), layer=0)
+    from multimodalvc_b200.sr_predictor import TransformerEncoder
+    frozen = TransformerEncoder(enc.args).cuda().train()
+    with pytest.raises(RuntimeError):
+        frozen(x.cuda().requires_grad_(True), pm.cuda())
