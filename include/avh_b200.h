@@ -192,6 +192,16 @@ AVH_API int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype,
 AVH_API int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, float* grads,
                                  int64_t grads_capacity, void* stream);
 
+/* The trainable tail of AVHubertModel.extract_finetune when the feature extractors are frozen (feature_grad_mult <= 0: the
+ * reference runs them under no_grad, avhubert/hubert.py:538-547): fused [B,T,E] = the concatenated / summed extractor
+ * outputs BEFORE the fusion LayerNorm (avh_read_stage "fused"), then layer_norm -> post_extract_proj -> index_put ->
+ * encoder (hubert.py:719-745) with saved activations; avh_encoder_backward then returns, after the encoder's gradients
+ * in the order above, post_extract_proj.{weight,bias} (concat fusion only) and layer_norm.{weight,bias}; its dx is the
+ * gradient at the ENCODER input (post_extract_proj output).  AV-HuBERT handle created with reserved[3] = 1. */
+AVH_API int avh_tail_grad_count(avh_handle* h, int64_t* n_floats);
+AVH_API int avh_tail_train_forward(avh_handle* h, const void* fused, int dtype, const uint8_t* padding_mask, int B, int T,
+                                   void* out, int out_dtype, void* stream);
+
 /* The Q-Former that compresses the fused AV features into query tokens in MMS-LLaMA:
  * Qformer.bert(query_embeds=query_tokens[:, :Lq], attention_mask, encoder_hidden_states=enc, encoder_attention_mask)
  * ['last_hidden_state'] (src/model.py:584-619 -> src/sub_model/Qformer.py:805-968, query-only path: self-attention over

@@ -207,6 +207,7 @@ struct Plan {
   // encoder training plans (avh_encoder_train_forward / avh_encoder_backward): steps [0, fwd_steps) are the forward
   // with saved activations, the rest the backward; gradients accumulate in a plan-owned fp32 buffer
   bool enc_train = false;
+  bool tail = false;               // the trainable tail of AV-HuBERT: fusion LayerNorm + post_extract_proj in front of the encoder
   size_t fwd_steps = 0;
   float* grads = nullptr;
   long long grad_floats = 0;
@@ -288,6 +289,7 @@ struct avh_handle {
   PackedW stem_wf;          // stem weights in the K order of the fused kernel (stem_fused.cu)
   BlockW blocks[4][2];
   LinearW proj_v, proj_a, post_proj;
+  LinearW post_projT;             // trainable handles: post_extract_proj^T for the backward
   bool has_post_proj = false;
   float *fuse_ln_g = nullptr, *fuse_ln_b = nullptr, *enc_ln_g = nullptr, *enc_ln_b = nullptr;
   PackedW pos_w;
@@ -635,6 +637,7 @@ bool pack_all(Packer& pk) {
   }
   h->has_post_proj = !enc_only && (c.modality_fuse == AVH_FUSE_CONCAT);
   if (h->has_post_proj) ok &= pack_linear(pk, "post_extract_proj", &h->post_proj);
+  if (h->has_post_proj && c.reserved[3] != 0) ok &= pack_linear_T(pk, {"post_extract_proj"}, {1.f}, &h->post_projT);
   // ---- positional conv: weight-norm(dim=2) fold, grouped -> per-N-tile windowed dense K-major
   {
     const HostTensor* wg = pk.get("encoder.pos_conv.0.weight_g");
@@ -1555,10 +1558,13 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 //   final_layer_norm.{weight,bias};  then encoder.layer_norm.{weight,bias};  then pos_conv.0.bias [D],
 //   pos_conv.0.weight_g [KT], pos_conv.0.weight_v [D, D/G, KT].
 long long enc_layer_grad_floats(int D, int F) { return 4ll * D * D + 4ll * D + 2ll * D + 2ll * D * F + F + D + 2ll * D; }
-long long enc_grad_floats(const avh_config& c) {
+long long enc_grad_floats(const avh_config& c, bool tail = false) {
   const int D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim;
-  return c.encoder_layers * enc_layer_grad_floats(D, F) + 2ll * D + D + c.conv_pos +
-         (long long)D * (D / c.conv_pos_groups) * c.conv_pos;
+  const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
+  long long n = c.encoder_layers * enc_layer_grad_floats(D, F) + 2ll * D + D + c.conv_pos +
+                (long long)D * (D / c.conv_pos_groups) * c.conv_pos;
+  if (tail) n += (E != D ? (long long)D * E + D : 0) + 2ll * E;      // post_extract_proj.{weight,bias}, layer_norm.{weight,bias}
+  return n;
 }
 
 // Weight gradients of the grouped positional convolution + weight-norm backward (wav2vec2.py:822-834):
@@ -1637,7 +1643,9 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
     if (!sizing) plan->mask_dev = md;
   }
   const bool hm = plan->has_mask;
-  const long long GF = enc_grad_floats(c);
+  const bool tail = plan->tail;
+  const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
+  const long long GF = enc_grad_floats(c, tail);
   float* grads = f32buf(GF);
   float* dy = f32buf(N * D);
   float* dxo = f32buf(N * D);
@@ -1658,10 +1666,41 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   }
 
   // ================================================================ forward
-  b.tag = "load_features";
-  b.cur_direct = true;
-  b.push([=](cudaStream_t s) { return launch_load_rows(pl->args.xin, pl->args.xin_dt, x0, hm ? pl->mask_dev : nullptr, N, D, s); });
-  b.cur_direct = false;
+  float* fused = nullptr;                 // tail: the caller's fused features [N, E] (fp32 copy) and their LayerNorm
+  Act fln;
+  if (tail) {
+    // AVHubertModel.extract_finetune after the (frozen) feature extractors: features = layer_norm(fused);
+    // features = post_extract_proj(features) (concat fusion); index_put(padded frames, 0)   (hubert.py:719-727, wav2vec2.py:869)
+    fused = f32buf(N * E);
+    fln = new_act(N, E);
+    b.tag = "load_features";
+    b.cur_direct = true;
+    b.push([=](cudaStream_t s) { return launch_load_rows(pl->args.xin, pl->args.xin_dt, fused, nullptr, N, E, s); });
+    b.cur_direct = false;
+    float* of = f32 ? reinterpret_cast<float*>(fln.data) : nullptr;
+    void* ol = f32 ? nullptr : fln.data;
+    float* gm = h->fuse_ln_g; float* be = h->fuse_ln_b;
+    b.tag = "fuse_ln";
+    if (h->has_post_proj) {
+      b.push([=](cudaStream_t s) { return launch_layernorm(fused, DT_F32, E, gm, be, 1e-5f, of, ol, DT_BF16, nullptr, N, E, s); });
+      sync_op(fln);
+      Epilogue ep;
+      ep.C = x0; ep.ldc = D; ep.c_fp32 = 1;
+      ep.col_bias = h->post_proj.bias;
+      if (hm) ep.row_zero = MASK_SENTINEL;
+      b.tag = "post_extract_proj";
+      if (!b.gemm(fln.op, N, P * E, h->post_proj.w, N, {Tap{0, 0, 0}}, E / 64, E, ep)) return false;
+    } else {
+      b.push([=](cudaStream_t s) {
+        return launch_layernorm(fused, DT_F32, E, gm, be, 1e-5f, x0, nullptr, DT_BF16, hm ? pl->mask_dev : nullptr, N, E, s);
+      });
+    }
+  } else {
+    b.tag = "load_features";
+    b.cur_direct = true;
+    b.push([=](cudaStream_t s) { return launch_load_rows(pl->args.xin, pl->args.xin_dt, x0, hm ? pl->mask_dev : nullptr, N, D, s); });
+    b.cur_direct = false;
+  }
   const int G = 64, Tp = T + G;
   const long long pad_rows = (long long)B * Tp;
   const int KT = c.conv_pos, win = h->pos_window;
@@ -1758,7 +1797,7 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   Act dctx = new_act(N, D);
   Act dqkv = new_act(N, 3 * D);
   void* tA = b.alloc((size_t)std::max(3 * D, F) * P * Kp * 2);      // transposed dY operand
-  void* tB = b.alloc((size_t)std::max(D, F) * P * Kp * 2);          // transposed X operand
+  void* tB = b.alloc((size_t)std::max(std::max(D, F), E) * P * Kp * 2);      // transposed X operand
   // fp32 [N, C] -> operand form (bf16 or split planes)
   auto to_op = [&](const float* src, const Act& dst, int C) {
     void* d = dst.op;
@@ -1893,6 +1932,27 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
     if (!b.gemm(dcpad, pad_rows, P * D, h->pos_wT, pad_rows, taps, win / 64, D, ep, 64, h->pos_acol)) return false;
     // weight gradients of the grouped convolution + weight-norm backward
     if (!posconv_wgrad(b, h, plan, dc, x0, N, B, T, gpos + D, gpos + D + KT)) return false;
+    if (tail) {
+      // dxo = dL/dx0 (rows of padded frames already zero).  post_extract_proj: x0 = fln Wp^T + bp; then the fusion LayerNorm
+      // (its input comes from the frozen extractors: only dgamma / dbeta are needed)
+      float* gt = gpos + D + KT + (long long)D * (D / c.conv_pos_groups) * KT;
+      float* dfl = nullptr;
+      float* g_ln = gt;
+      if (h->has_post_proj) {
+        float* g_pw = gt; float* g_pb = gt + (long long)D * E;
+        g_ln = g_pb + D;
+        if (!wgrad(dxo, DT_F32, D, fln.data, act_dt, E, g_pw, g_pb, "post_proj_wgrad")) return false;
+        to_op(dxo, dxa, D);
+        dfl = f32buf(N * E);
+        if (!dgrad(dxa.op, D, h->post_projT, dfl, true, "post_proj_dgrad")) return false;
+      } else {
+        dfl = dxo;
+      }
+      float* scratch = f32buf(N * E);
+      float* gm = h->fuse_ln_g;
+      b.tag = "ln_bwd";
+      b.push([=](cudaStream_t s) { return launch_ln_bwd(fused, gm, dfl, nullptr, scratch, stats, g_ln, g_ln + E, N, E, 1e-5f, s); });
+    }
   }
   if (bytes_out) *bytes_out = b.sizer.used;
   return true;
@@ -2053,10 +2113,10 @@ bool build_qformer_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_ou
 
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
                cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false, int qf_lk = 0,
-               bool enc_train = false) {
+               bool enc_train = false, bool tail = false) {
   const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) + (enc_only ? "e:" : "") +
                           (train ? "t:" : "") + (qf_lk > 0 ? "q" + std::to_string(qf_lk) + ":" : std::string()) +
-                          (enc_train ? "g:" : "") +
+                          (enc_train ? (tail ? "gt:" : "g:") : "") +
                           std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
@@ -2087,6 +2147,7 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
   p->train = train;
   p->Lk = qf_lk;
   p->enc_train = enc_train;
+  p->tail = tail;
   size_t bytes = 0;
   auto build = qf_lk > 0 ? build_qformer_plan : (enc_train ? build_encoder_train_plan : build_plan);
   if (!build(h, p.get(), true, &bytes)) return nullptr;
@@ -2553,8 +2614,29 @@ int avh_encoder_grad_count(avh_handle* h, int64_t* n_floats) {
   return 0;
 }
 
+static int encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T, void* out,
+                                 int out_dtype, void* stream, bool tail);
+
+int avh_tail_grad_count(avh_handle* h, int64_t* n_floats) {
+  AVH_CHECK(h != nullptr && n_floats != nullptr, "null argument");
+  AVH_CHECK(h->cfg.reserved[0] == 0, "the trainable tail belongs to an AV-HuBERT handle");
+  *n_floats = avh::enc_grad_floats(h->cfg, true);
+  return 0;
+}
+
+int avh_tail_train_forward(avh_handle* h, const void* fused, int dtype, const uint8_t* padding_mask, int B, int T, void* out,
+                           int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr && h->cfg.reserved[0] == 0, "the trainable tail belongs to an AV-HuBERT handle");
+  return encoder_train_forward(h, fused, dtype, padding_mask, B, T, out, out_dtype, stream, true);
+}
+
 int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T, void* out,
                               int out_dtype, void* stream) {
+  return encoder_train_forward(h, x, x_dtype, padding_mask, B, T, out, out_dtype, stream, false);
+}
+
+static int encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T, void* out,
+                                 int out_dtype, void* stream, bool tail) {
   AVH_CHECK(h != nullptr, "null handle");
   AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
   AVH_CHECK(h->cfg.reserved[0] != 2, "this handle holds a Q-Former");
@@ -2564,7 +2646,7 @@ int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const u
   AVH_CHECK(B >= 1 && T >= 1 && (long long)B * T < (1ll << 24), "bad batch");
   AVH_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  avh::Plan* p = avh::get_plan(h, B, T, false, false, padding_mask != nullptr, 0, s, 0, true, false, 0, true);
+  avh::Plan* p = avh::get_plan(h, B, T, false, false, padding_mask != nullptr, 0, s, 0, true, false, 0, true, tail);
   if (p == nullptr) return 1;
   h->last_plan = p;
   p->args = avh::CallArgs();

@@ -79,6 +79,8 @@ class AVHubertConfig:
     compute_dtype: str = "auto"        # "auto": fp32 module -> fp32-faithful mode, half/bf16 module -> bf16 mode
     frontend_chunk_frames: int = 0     # 0 = library default
     capture_stages: bool = False       # keep intermediate stages readable (tests)
+    trainable: bool = False            # also pack the backward's operands: extract_finetune in .train() with gradients
+                                       # enabled differentiates the tail (fusion LayerNorm, post_extract_proj, encoder)
     ragged: str = "dense"              # "dense": compute on the padded [B,T] batch, every output position as the
                                        # reference's; "packed": bf16 mode, frames/tokens of ragged batches packed back to
                                        # back (no work on pad frames), output rows at pad positions are zeros
@@ -187,6 +189,58 @@ class _EncoderParams(nn.Module):         # wav2vec2.py:816-857
                 m.bias.data.zero_()
 
 
+class _TailTrainFn(torch.autograd.Function):
+    """y = encoder(post_extract_proj(layer_norm(fused))) with the library's forward (activations saved in the plan) and
+    backward; the parameters are arguments only so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, model, fused, pm_u8, *params):
+        handle = model._ensure_handle()
+        dev = fused.device
+        B, T, _ = fused.shape
+        out_dtype = model.encoder.layer_norm.weight.dtype
+        if out_dtype not in _DTYPES:
+            out_dtype = torch.float32
+        out = torch.empty(B, T, model.encoder_embed_dim, device=dev, dtype=out_dtype)
+        fused = fused.contiguous()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_tail_train_forward(
+                handle, ctypes.c_void_p(fused.data_ptr()), _DTYPES[fused.dtype],
+                ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None, B, T,
+                ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
+        ctx.handle, ctx.stream = handle, stream
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dev = dout.device
+        dout = dout.contiguous()
+        if dout.dtype not in _DTYPES:
+            dout = dout.float()
+        lib = _lib.load()
+        n = ctypes.c_int64()
+        _lib.check(lib.avh_tail_grad_count(ctx.handle, ctypes.byref(n)))
+        flat = torch.empty(n.value, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if stream != ctx.stream:
+                raise RuntimeError("the backward must run on the CUDA stream of its forward")
+            _lib.check(lib.avh_encoder_backward(ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], None, 0,
+                                                ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+        grads, off = [], 0
+        for shape, dt in zip(ctx.shapes, ctx.dtypes):
+            k = 1
+            for d in shape:
+                k *= d
+            grads.append(flat[off:off + k].view(shape).to(dt))
+            off += k
+        assert off == n.value
+        return (None, None, None, *grads)
+
+
 class AVHubertModel(nn.Module):
     """Drop-in for the reference ``AVHubertModel`` on the ``extract_finetune`` path."""
 
@@ -233,6 +287,7 @@ class AVHubertModel(nn.Module):
         self._video_geo = None
         self._eval_stale = False
         self._host_keepalive = {}
+        self._param_versions = None
         # normalisation of raw uint8 video (task config image_mean / image_std, hubert_pretraining.py:144-149)
         self.image_mean, self.image_std = 0.421, 0.165
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
@@ -317,6 +372,7 @@ class AVHubertModel(nn.Module):
                 layer_norm_first=int(bool(c.layer_norm_first)), conv_pos=c.conv_pos, conv_pos_groups=c.conv_pos_groups,
                 compute_mode=key[1], frontend_chunk_frames=int(c.frontend_chunk_frames),
                 capture_stages=int(bool(c.capture_stages)))
+            cc.reserved[3] = 1 if c.trainable else 0
             hp = ctypes.c_void_p()
             _lib.check(lib.avh_create(ctypes.byref(cc), key[0], ctypes.byref(hp)))
             self._handle, self._handle_key = hp, key
@@ -439,8 +495,60 @@ class AVHubertModel(nn.Module):
         lengths = (~pm).sum(1).tolist()
         return lengths if min(lengths) >= 1 else None
 
-    @torch.no_grad()
+    def tail_parameters(self):
+        """Parameters of the trainable tail in the order avh_encoder_backward writes their gradients."""
+        out = []
+        for layer in self.encoder.layers:
+            a = layer.self_attn
+            out += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.q_proj.bias, a.k_proj.bias, a.v_proj.bias,
+                    a.out_proj.weight, a.out_proj.bias, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias,
+                    layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias,
+                    layer.final_layer_norm.weight, layer.final_layer_norm.bias]
+        out += [self.encoder.layer_norm.weight, self.encoder.layer_norm.bias]
+        pc = self.encoder.pos_conv[0]
+        out += [pc.bias, pc.weight_g, pc.weight_v]
+        if self.post_extract_proj is not None:
+            out += [self.post_extract_proj.weight, self.post_extract_proj.bias]
+        out += [self.layer_norm.weight, self.layer_norm.bias]
+        return out
+
+    def _extract_finetune_trainable(self, source, padding_mask, mask, output_layer):
+        """Fine-tuning step with frozen feature extractors (feature_grad_mult <= 0: the reference runs them under
+        no_grad, hubert.py:538-547).  Extractors + fusion run as in the training-mode forward (batch-statistics
+        BatchNorm), the fused features feed the differentiable tail: layer_norm -> post_extract_proj -> encoder."""
+        c = self.cfg
+        if c.feature_grad_mult > 0:
+            raise NotImplementedError("feature_grad_mult > 0 needs the backward of the lip ResNet / modality projections, "
+                                      "which is not built; set feature_grad_mult = 0 (frozen feature extractors)")
+        if output_layer is not None:
+            raise NotImplementedError("the training step runs the whole encoder (output_layer=None)")
+        if not c.layer_norm_first:
+            raise NotImplementedError("the device backward is built for pre-LN layers (layer_norm_first=True)")
+        for name in ("dropout_input", "dropout", "activation_dropout", "attention_dropout", "encoder_layerdrop"):
+            if float(getattr(c, name)) != 0.0:
+                raise NotImplementedError(f"{name} must be 0 for the device training step (BASELINE config 5)")
+        if self._param_versions != [p._version for p in self.parameters()]:
+            self._dirty = True                                   # an optimizer step changed the weights: re-pack
+        with torch.no_grad():
+            y1, pm = self._extract_finetune_nograd(source, padding_mask, mask=mask, output_layer=1)
+            B, T, _ = y1.shape
+            fused = self.read_stage("fused", B * T * self.embed).view(B, T, self.embed)
+        self._param_versions = [p._version for p in self.parameters()]
+        dev = fused.device
+        pm_u8 = pm.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8) if pm is not None else None
+        return _TailTrainFn.apply(self, fused, pm_u8, *self.tail_parameters()), pm
+
     def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None, lengths=None):
+        """avhubert/hubert.py:694-745 (see _extract_finetune_nograd).  In .train() with gradients enabled and
+        cfg.trainable, the call is differentiable w.r.t. the tail's parameters (fusion LayerNorm, post_extract_proj,
+        encoder): SURVEY row A18 with the feature extractors frozen."""
+        if self.training and torch.is_grad_enabled() and self.cfg.trainable:
+            return self._extract_finetune_trainable(source, padding_mask, mask, output_layer)
+        return self._extract_finetune_nograd(source, padding_mask, mask=mask, ret_conv=ret_conv, output_layer=output_layer,
+                                             lengths=lengths)
+
+    @torch.no_grad()
+    def _extract_finetune_nograd(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None, lengths=None):
         """avhubert/hubert.py:694-745.  source = {'audio': [B,F,T] | None, 'video': [B,1,T,88,88] | None};
         padding_mask bool [B,T] (True = padded).  Returns (x [B,T,D], padding_mask).  With cfg.ragged == "packed" (bf16
         mode) ragged batches run packed; `lengths` (valid frames per clip) may be given to skip reading the mask back."""

@@ -130,3 +130,59 @@ def test_encoder_backward_bf16_and_optimizer_step():
     frozen = TransformerEncoder(enc.args).cuda().train()
     with pytest.raises(RuntimeError):
         frozen(x.cuda().requires_grad_(True), pm.cuda())
+
+
+@pytest.mark.parametrize("fuse", ["concat", "add"])
+def test_avhubert_finetune_step_with_frozen_extractors(fuse):
+    """AVHubertModel.extract_finetune in .train() with gradients enabled (cfg.trainable, feature_grad_mult = 0: the
+    reference runs the feature extractors under no_grad, hubert.py:538-547): forward through the training-mode
+    extractors (batch-statistics BatchNorm), gradients of the fusion LayerNorm, post_extract_proj and the whole encoder
+    against torch.autograd on the oracle wired the same way."""
+    from multimodalvc_b200 import AVHubertConfig, AVHubertModel
+    o = ao.build_oracle("tiny", seed=1234, modality_fuse=fuse).train()
+    with torch.no_grad():
+        for mod in o.encoder.modules():
+            if isinstance(mod, torch.nn.Linear):
+                mod.weight.mul_(3.0)
+    B, T, lengths = 3, 30, [30, 21, 26]
+    src, pm = ao.synthetic_inputs(B, T, lengths=lengths, seed=13)
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(B, T, 128, generator=g).masked_fill(pm.unsqueeze(-1), 0.0)
+    cfg = AVHubertConfig.named("tiny", modality_fuse=fuse, feature_grad_mult=0.0, trainable=True, dropout=0.0,
+                               attention_dropout=0.0, activation_dropout=0.0, encoder_layerdrop=0.0, dropout_input=0.0)
+    m = AVHubertModel(cfg)
+    m.remove_pretraining_modules()
+    m.load_state_dict(o.state_dict(), strict=False)
+    m = m.cuda().train()
+    # reference: extractors under no_grad (train-mode BatchNorm), the rest differentiable
+    with torch.no_grad():
+        fv = o.feature_extractor_video(src["video"])
+        fa = o.feature_extractor_audio(src["audio"])
+        fused = (torch.cat([fa, fv], dim=1) if fuse == "concat" else fa + fv).transpose(1, 2)
+    feats = o.layer_norm(fused)
+    if o.post_extract_proj is not None:
+        feats = o.post_extract_proj(feats)
+    y_ref = o.encoder(feats, pm)
+    o.zero_grad()
+    _loss(y_ref, w, pm).backward()
+    y, pm_out = m.extract_finetune({k: v.cuda() for k, v in src.items()}, pm.cuda())
+    assert y.requires_grad and torch.equal(pm_out.cpu(), pm)
+    assert rel_err(y.detach().cpu()[~pm], y_ref.detach()[~pm]) < 2e-3
+    _loss(y, w.cuda(), pm.cuda()).backward()
+    ref_grads = {n: p.grad for n, p in o.named_parameters()}
+    checked = 0
+    for n, p in m.named_parameters():
+        if n.startswith("feature_extractor") or n == "mask_emb":
+            assert p.grad is None, n                          # frozen: no gradient flows into the extractors
+            continue
+        assert p.grad is not None, n
+        if n.endswith("k_proj.bias"):
+            scale = ref_grads[n.replace("k_proj", "q_proj")].abs().max().item()
+            assert (p.grad.cpu() - ref_grads[n]).abs().max().item() < 2e-3 * scale
+        else:
+            assert rel_err(p.grad.cpu(), ref_grads[n]) < 2e-3, (n, rel_err(p.grad.cpu(), ref_grads[n]))
+        checked += 1
+    assert checked >= 16 * 2 + 5 + (2 if fuse == "concat" else 0) + 2
+    m2 = AVHubertModel(AVHubertConfig.named("tiny", trainable=True)).cuda().train()      # feature_grad_mult = 1 (default)
+    with pytest.raises(NotImplementedError):
+        m2.extract_finetune({k: v.cuda() for k, v in src.items()}, pm.cuda())
