@@ -258,6 +258,8 @@ def main():
                     help="seconds of back-to-back steps for the `sustained` leg after the timed region (0 = skip)")
     ap.add_argument("--config3-passes", type=int, default=5, help="timed passes over the 64 ragged clips of config 3 (0 = skip)")
     ap.add_argument("--config3-tokens", type=int, default=4800, help="packed frames per ragged sub-batch")
+    ap.add_argument("--config5-steps", type=int, default=5,
+                    help="timed fine-tuning steps of BASELINE config 5 (forward + backward + gradient all-reduce; 0 = skip)")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-class breakdown here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -515,15 +517,62 @@ def main():
                 "sub_batches_rank0": [[len(sb), sum(lengths3[i] for i in sb)] for sb in subs],
                 "pad_fraction_if_dense_rank0": 1.0 - frames_mine / float(padded_dense)}
 
+    # ---- BASELINE config 5 (the part of it that is built): Large, B = 8 clips x 150 frames per GPU, bf16, dropout /
+    #      LayerDrop 0, loss = mean(x^2); forward + backward + gradient all-reduce per step.  The feature extractors are
+    #      FROZEN (feature_grad_mult = 0, the reference then runs them under no_grad): the lip-ResNet backward is not built.
+    cfg5 = None
+    if args.config5_steps > 0:
+        from multimodalvc_b200.distributed import GradientAllReducer
+        m5 = AVHubertModel(AVHubertConfig.named("large", feature_grad_mult=0.0, trainable=True, dropout=0.0,
+                                                attention_dropout=0.0, activation_dropout=0.0, encoder_layerdrop=0.0,
+                                                dropout_input=0.0))
+        m5.remove_pretraining_modules()
+        m5 = m5.to(dev, torch.bfloat16).train()
+        tail = m5.tail_parameters()
+        reducer = GradientAllReducer(tail) if world > 1 else None
+        g5 = torch.Generator().manual_seed(500 + rank)
+        v5 = torch.randn(8, 1, T_FRAMES, 88, 88, generator=g5).to(dev, torch.bfloat16)
+        a5 = torch.randn(8, 104, T_FRAMES, generator=g5).to(dev, torch.bfloat16)
+
+        def step5():
+            y5, _ = m5.extract_finetune({"audio": a5, "video": v5}, None)
+            loss = y5.float().pow(2).mean()
+            loss.backward()
+            if reducer is not None:
+                reducer.all_reduce_grads()
+            return loss
+
+        for _ in range(2):
+            step5()
+            for p5 in tail:
+                p5.grad = None
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.config5_steps):
+            loss5 = step5()
+            for p5 in tail:
+                p5.grad = None
+        t1.record()
+        torch.cuda.synchronize(dev)
+        barrier()
+        cfg5 = {"ms": t0.elapsed_time(t1), "loss": float(loss5.item()),
+                "grad_elements": int(sum(p5.numel() for p5 in tail))}
+        del m5, reducer, tail
+        torch.cuda.empty_cache()
+
     # ---- max over ranks
     ms_sus = sustained[1] if sustained else 0.0
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, cfg3["ms"] if cfg3 else 0.0], device=dev,
-                         dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, cfg3["ms"] if cfg3 else 0.0,
+                          cfg5["ms"] if cfg5 else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3 = t.tolist()
+        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3, ms_c5 = t.tolist()
         if cfg3:
             cfg3["ms"] = ms_c3
+        if cfg5:
+            cfg5["ms"] = ms_c5
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -654,6 +703,18 @@ def main():
                 "frames": cfg3["frames_all"], "config2_frames_per_s": fps2, "frac_of_config2_frame_rate": fps3 / fps2,
                 "sub_batches_rank0_clips_frames": cfg3["sub_batches_rank0"],
                 "pad_fraction_if_dense_rank0": cfg3["pad_fraction_if_dense_rank0"]}
+        if cfg5:
+            sec5 = cfg5["ms"] * 1e-3 / args.config5_steps
+            line["config5"] = {
+                "workload": "BASELINE config 5, frozen-extractor form: AV-HuBERT Large fine-tuning step, 8 clips x 150 frames "
+                            "per GPU, bf16, dropout / LayerDrop 0, loss = mean(x^2); forward (training-mode extractors with "
+                            "batch-statistics BatchNorm, then LayerNorm + post_extract_proj + 24 encoder layers with saved "
+                            "activations) + backward of that tail + bucketed gradient all-reduce (NCCL) at N > 1",
+                "clips_per_s": world * 8 / sec5, "ms_per_step": sec5 * 1e3, "steps": args.config5_steps,
+                "grad_elements": cfg5["grad_elements"], "loss": cfg5["loss"],
+                "not_included": "backward of the lip ResNet / modality projections (feature_grad_mult = 0 freezes them, as "
+                                "the reference does under no_grad); optimizer step (weights are re-packed on the host after "
+                                "an update)"}
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"classes": prof, "total_ms": total_prof_ms}, f, indent=1, sort_keys=True)

@@ -9,6 +9,7 @@
 //   ln_stats + ln_bwd_dx + ln_bwd_params   LayerNorm backward (fairseq/fairseq/modules/layer_norm.py:51-56 -> F.layer_norm)
 //   attention_bwd_dq / attention_bwd_dkv  softmax attention backward with the probabilities recomputed from the saved
 //                               log-sum-exp of every query row (fairseq/fairseq/modules/multihead_attention.py:170-192)
+#include "attn_tile.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -63,20 +64,21 @@ transpose_split_kernel(const void* __restrict__ in, int dt, long long ld, long l
 }
 
 // out[c] = scale * sum_r in[r, c]: one CTA per 32 columns, 8 row phases, fixed summation order
-__global__ void __launch_bounds__(256)
+constexpr int CS_PH = 32;      // row phases of the column reductions (1024 threads = 32 columns x 32 phases)
+__global__ void __launch_bounds__(1024)
 colsum_kernel(const void* __restrict__ in, int dt, long long ld, long long rows, int C, float* __restrict__ out, float scale) {
-  __shared__ float part[8][33];
+  __shared__ float part[CS_PH][33];
   const int j = threadIdx.x % 32, ph = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + j;
   float s = 0.f;
   if (c < C)
-    for (long long r = ph; r < rows; r += 8) s += ldb(in, dt, r * ld + c);
+    for (long long r = ph; r < rows; r += CS_PH) s += ldb(in, dt, r * ld + c);
   part[ph][j] = s;
   __syncthreads();
   if (ph == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][j];
+    for (int k = 0; k < CS_PH; ++k) t += part[k][j];
     out[c] = t * scale;
   }
 }
@@ -143,15 +145,15 @@ ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
 }
 // dgamma[c] = sum_r dy[r,c] xhat[r,c], dbeta[c] = sum_r dy[r,c]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 ln_bwd_params_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float2* __restrict__ stats,
                      long long rows, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float pg[8][33], pb[8][33];
+  __shared__ float pg[CS_PH][33], pb[CS_PH][33];
   const int j = threadIdx.x % 32, ph = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + j;
   float sg = 0.f, sb = 0.f;
   if (c < C)
-    for (long long r = ph; r < rows; r += 8) {
+    for (long long r = ph; r < rows; r += CS_PH) {
       const float2 st = stats[r];
       const float d = dy[r * C + c];
       sg += d * (x[r * C + c] - st.x) * st.y;
@@ -162,7 +164,7 @@ ln_bwd_params_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   if (ph == 0 && c < C) {
     float tg = 0.f, tb = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { tg += pg[k][j]; tb += pb[k][j]; }
+    for (int k = 0; k < CS_PH; ++k) { tg += pg[k][j]; tb += pb[k][j]; }
     dgamma[c] = tg; dbeta[c] = tb;
   }
 }
@@ -189,12 +191,8 @@ attention_bwd_dq_kernel(const void* __restrict__ Q, long long ldq, const void* _
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int qi = q0 + lane;
   const bool ok = qi < L;
-  for (int e = threadIdx.x; e < AB_T * AB_HD; e += 256) {
-    const int r = e / AB_HD, d = e % AB_HD;
-    const long long row = (long long)b * L + q0 + r;
-    Qs[r][d] = q0 + r < L ? ldb(Q, dt, row * ldq + h * AB_HD + d) : 0.f;
-    Gs[r][d] = q0 + r < L ? ldb(dO, o_dt, row * ldo + h * AB_HD + d) : 0.f;
-  }
+  attn_load_tile<AB_T, AB_HD + 1, 256>(Q, dt, ldq, (long long)b * L, q0, L, h * AB_HD, &Qs[0][0]);
+  attn_load_tile<AB_T, AB_HD + 1, 256>(dO, o_dt, ldo, (long long)b * L, q0, L, h * AB_HD, &Gs[0][0]);
   __syncthreads();
   float acc[AB_HD];
   float D = 0.f;
@@ -212,13 +210,8 @@ attention_bwd_dq_kernel(const void* __restrict__ Q, long long ldq, const void* _
   if (w == 0 && ok) Dbuf[((long long)b * H + h) * L + qi] = D;
   for (int k0 = 0; k0 < L; k0 += AB_KT) {
     __syncthreads();
-    for (int e = threadIdx.x; e < AB_KT * AB_HD; e += 256) {
-      const int r = e / AB_HD, d = e % AB_HD;
-      const int key = k0 + r;
-      const long long row = (long long)b * L + key;
-      Ks[r][d] = key < L ? ldb(K, dt, row * ldk + h * AB_HD + d) : 0.f;
-      Vs[r][d] = key < L ? ldb(V, dt, row * ldv + h * AB_HD + d) : 0.f;
-    }
+    attn_load_tile<AB_KT, AB_HD, 256>(K, dt, ldk, (long long)b * L, k0, L, h * AB_HD, &Ks[0][0]);
+    attn_load_tile<AB_KT, AB_HD, 256>(V, dt, ldv, (long long)b * L, k0, L, h * AB_HD, &Vs[0][0]);
     if (threadIdx.x < AB_KT) {
       const int key = k0 + threadIdx.x;
       dead[threadIdx.x] = (key >= L || (key_pad != nullptr && key_pad[(long long)b * L + key] != 0)) ? 1 : 0;
@@ -269,25 +262,15 @@ attention_bwd_dkv_kernel(const void* __restrict__ Q, long long ldq, const void* 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int kj = j0 + lane;
   const bool live = kj < L && !(key_pad != nullptr && key_pad[(long long)b * L + kj] != 0);
-  for (int e = threadIdx.x; e < AB_T * AB_HD; e += 256) {
-    const int r = e / AB_HD, d = e % AB_HD;
-    const int key = j0 + r;
-    const long long row = (long long)b * L + key;
-    Ks[r][d] = key < L ? ldb(K, dt, row * ldk + h * AB_HD + d) : 0.f;
-    Vs[r][d] = key < L ? ldb(V, dt, row * ldv + h * AB_HD + d) : 0.f;
-  }
+  attn_load_tile<AB_T, AB_HD + 1, 256>(K, dt, ldk, (long long)b * L, j0, L, h * AB_HD, &Ks[0][0]);
+  attn_load_tile<AB_T, AB_HD + 1, 256>(V, dt, ldv, (long long)b * L, j0, L, h * AB_HD, &Vs[0][0]);
   float dk[AB_HD], dv[AB_HD];
 #pragma unroll
   for (int d = 0; d < AB_HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
   for (int i0 = 0; i0 < L; i0 += AB_KT) {
     __syncthreads();
-    for (int e = threadIdx.x; e < AB_KT * AB_HD; e += 256) {
-      const int r = e / AB_HD, d = e % AB_HD;
-      const int qi = i0 + r;
-      const long long row = (long long)b * L + qi;
-      Qs[r][d] = qi < L ? ldb(Q, dt, row * ldq + h * AB_HD + d) : 0.f;
-      Gs[r][d] = qi < L ? ldb(dO, o_dt, row * ldo + h * AB_HD + d) : 0.f;
-    }
+    attn_load_tile<AB_KT, AB_HD, 256>(Q, dt, ldq, (long long)b * L, i0, L, h * AB_HD, &Qs[0][0]);
+    attn_load_tile<AB_KT, AB_HD, 256>(dO, o_dt, ldo, (long long)b * L, i0, L, h * AB_HD, &Gs[0][0]);
     if (threadIdx.x < AB_KT) {
       const int qi = i0 + threadIdx.x;
       Ls[threadIdx.x] = qi < L ? lse[((long long)b * H + h) * L + qi] : INFINITY;     // exp(s - inf) = 0: no contribution
@@ -447,7 +430,7 @@ int launch_transpose_split(const void* in, int dt, long long ld, long long rows,
 
 int launch_colsum(const void* in, int dt, long long ld, long long rows, int C, float* out, float scale, cudaStream_t stream) {
   if (C <= 0) return 0;
-  colsum_kernel<<<(C + 31) / 32, 256, 0, stream>>>(in, dt, ld, rows, C, out, scale);
+  colsum_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(in, dt, ld, rows, C, out, scale);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -477,7 +460,7 @@ int launch_ln_bwd(const float* x, const float* gamma, const float* dy, const flo
   AVH_CHECK(stats != nullptr, "ln_bwd needs the per-row statistics buffer");
   ln_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, gamma, dy, res, dx_out, stats, rows, C, eps);
   AVH_CUDA_OK(cudaGetLastError());
-  ln_bwd_params_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, dy, stats, rows, C, dgamma, dbeta);
+  ln_bwd_params_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(x, dy, stats, rows, C, dgamma, dbeta);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(2);
   return 0;

@@ -11,6 +11,7 @@
 //    (Qformer.py:797-801), which exp() turns into exactly 0 in fp32 whenever one key is valid.
 //  * rows_broadcast_kernel: hidden states of every clip start as the same LayerNorm(query_tokens) rows
 //    (BertEmbeddings with query_embeds only, Qformer.py:98-110).
+#include "attn_tile.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -41,22 +42,22 @@ attention_x_kernel(const void* __restrict__ Q, long long ldq, const void* __rest
   const int qi = q0 + lane;
   const bool q_ok = qi < Lq;
   float q[AX_HD], acc[AX_HD];
+  {   // the CTA's 32 query rows: coalesced load into shared memory (padded rows), then one row per thread
+    float* stage = &Ks[0][0];                                   // [32][65] fits the 64 x 64 key tile
+    attn_load_tile<AX_QT, AX_HD + 1, 256>(Q, dt, ldq, (long long)b * Lq, q0, Lq, h * AX_HD, stage);
+    __syncthreads();
 #pragma unroll
-  for (int d = 0; d < AX_HD; ++d) {
-    q[d] = q_ok ? ldx(Q, dt, ((long long)b * Lq + qi) * ldq + h * AX_HD + d) * scale : 0.f;
-    acc[d] = 0.f;
+    for (int d = 0; d < AX_HD; ++d) {
+      q[d] = stage[lane * (AX_HD + 1) + d] * scale;
+      acc[d] = 0.f;
+    }
   }
+  (void)q_ok;
   float m = -INFINITY, l = 0.f;
   for (int k0 = 0; k0 < Lk; k0 += AX_KT) {
     __syncthreads();
-    for (int e = threadIdx.x; e < AX_KT * AX_HD; e += 256) {
-      const int r = e / AX_HD, d = e % AX_HD;
-      const int key = k0 + r;
-      const bool ok = key < Lk;
-      const long long row = (long long)b * Lk + key;
-      Ks[r][d] = ok ? ldx(K, dt, row * ldk + h * AX_HD + d) : 0.f;
-      Vs[r][d] = ok ? ldx(V, dt, row * ldv + h * AX_HD + d) : 0.f;
-    }
+    attn_load_tile<AX_KT, AX_HD, 256>(K, dt, ldk, (long long)b * Lk, k0, Lk, h * AX_HD, &Ks[0][0]);
+    attn_load_tile<AX_KT, AX_HD, 256>(V, dt, ldv, (long long)b * Lk, k0, Lk, h * AX_HD, &Vs[0][0]);
     if (threadIdx.x < AX_KT) {
       const int key = k0 + threadIdx.x;
       dead[threadIdx.x] = (key >= Lk || (key_pad != nullptr && key_pad[(long long)b * Lk + key] != 0)) ? 1 : 0;

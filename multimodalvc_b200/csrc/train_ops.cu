@@ -32,41 +32,66 @@ __device__ __forceinline__ void st_any(void* out, int dt, long long i, float v) 
 }
 
 // ---- per-channel sums over the rows of [rows, C]; rows with (r % period) >= valid are skipped (the gap frames of the
-// stem's clip-padded row space; period = 0: no such gaps), and with S > 0 only the H x H image of the padded S x S layout
-constexpr int BN_ROWS_PER_CTA = 2048;     // few double atomics per channel: ~rows / 2048 CTAs
+// stem's clip-padded row space; period = 0: no such gaps), and with S > 0 only the H x H image of the padded S x S layout.
+// Thread = (row phase, group of 8 channels): one 16-byte (bf16) / two 16-byte (fp32) loads per row and thread, the row's
+// validity worked out ONCE per row in 32-bit arithmetic (the first version did 64-bit divisions per element: 1.5 ms per
+// BatchNorm at 8 clips), float64 partial sums per thread, one smem reduction and one double atomic per channel per CTA.
+constexpr int BN_ROWS_PER_CTA = 2048;
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const void* __restrict__ raw, int dt, long long rows, int C, long long period, long long valid, int S,
                 int H, double* __restrict__ sums) {
   pdl_launch_dependents();
   pdl_wait();
-  // thread = (channel c, row phase): 256 threads cover C channels x (256 / C) row phases (C = 64..512, power of two)
-  const int c = threadIdx.x % C;
-  const int phases = 256 / C > 0 ? 256 / C : 1;
-  const int ph = threadIdx.x / C;
+  extern __shared__ double sh[];                 // [phases][C][2]
+  const int groups = C >> 3;                     // threads per row
+  const int phases = 256 / groups > 0 ? 256 / groups : 1;
+  const int gi = threadIdx.x % groups, ph = threadIdx.x / groups;
   const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_CTA;
   const long long r1 = r0 + BN_ROWS_PER_CTA < rows ? r0 + BN_ROWS_PER_CTA : rows;
-  __shared__ double s1[256], s2[256];
-  for (int cc = c; cc < C; cc += 256) {          // C > 256: each thread walks several channels
-    double a = 0.0, b2 = 0.0;
-    if (ph < phases) {
+  const unsigned int SS = (unsigned int)(S * S);
+  for (int g0 = 0; g0 < groups; g0 += 256) {     // C > 2048 never happens; loop kept for generality
+    const int g = g0 + gi;
+    double a[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = 0.0; q[k] = 0.0; }
+    if (ph < phases && g < groups) {
       for (long long r = r0 + ph; r < r1; r += phases) {
-        if (period > 0 && (r % period) >= valid) continue;
-        if (S > 0) {                                   // padded S x S layout: only the H x H image counts
-          const int rem = (int)(r % ((long long)S * S));
-          if ((rem / S) >= H || (rem % S) >= H) continue;
+        if (period > 0 && (unsigned long long)r % (unsigned long long)period >= (unsigned long long)valid) continue;
+        if (S > 0) {
+          const unsigned int rem = (unsigned int)((unsigned long long)r % SS);
+          if (rem / (unsigned int)S >= (unsigned int)H || rem % (unsigned int)S >= (unsigned int)H) continue;
         }
-        const float v = ld_any(raw, dt, r * C + cc);
-        a += (double)v;
-        b2 += (double)v * (double)v;
+        float v[8];
+        if (dt == DT_BF16) {
+          const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + r * C + g * 8);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+        } else if (dt == DT_F32) {
+          const float4 u0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw) + r * C + g * 8);
+          const float4 u1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw) + r * C + g * 8 + 4);
+          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = ld_any(raw, dt, r * C + g * 8 + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] += (double)v[k]; q[k] += (double)v[k] * (double)v[k]; }
       }
     }
-    s1[threadIdx.x] = a;
-    s2[threadIdx.x] = b2;
+    if (ph < phases && g < groups) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sh[((size_t)ph * C + g * 8 + k) * 2] = a[k];
+        sh[((size_t)ph * C + g * 8 + k) * 2 + 1] = q[k];
+      }
+    }
     __syncthreads();
-    if (ph == 0) {
-      for (int k = 1; k < phases; ++k) { a += s1[threadIdx.x + k * C]; b2 += s2[threadIdx.x + k * C]; }
-      atomicAdd(&sums[cc], a);
-      atomicAdd(&sums[C + cc], b2);
+    for (int c = threadIdx.x; c < C; c += 256) {
+      double ta = 0.0, tq = 0.0;
+      for (int p2 = 0; p2 < phases; ++p2) { ta += sh[((size_t)p2 * C + c) * 2]; tq += sh[((size_t)p2 * C + c) * 2 + 1]; }
+      atomicAdd(&sums[c], ta);
+      atomicAdd(&sums[C + c], tq);
     }
     __syncthreads();
   }
@@ -93,30 +118,68 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
   sums[C + c] = 0.0;
 }
 
-// out = act2(act1(raw * scale + bias) + res); rows outside the H x H image of the padded S x S layout are zeros
-__global__ void bn_apply_kernel(const void* __restrict__ raw, void* __restrict__ out, int dt, long long rows, int C,
-                                const float* __restrict__ scale, const float* __restrict__ bias,
-                                const float* __restrict__ slope1, const void* __restrict__ res,
-                                const float* __restrict__ slope2, int S, int H) {
+// out = act2(act1(raw * scale + bias) + res); rows outside the H x H image of the padded S x S layout are zeros.
+// Thread = 8 consecutive channels of one row (C % 8 == 0): 16-byte accesses, the row's validity computed once.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const void* __restrict__ raw, void* __restrict__ out, int dt, long long rows, int C,
+                const float* __restrict__ scale, const float* __restrict__ bias,
+                const float* __restrict__ slope1, const void* __restrict__ res,
+                const float* __restrict__ slope2, int S, int H) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const long long r = i / C;
-  const int c = (int)(i - r * C);
+  const int groups = C >> 3;
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= rows * groups) return;
+  const long long r = gidx / groups;
+  const int c0 = (int)(gidx - r * groups) * 8;
   bool ok = true;
   if (S > 0) {
-    const int rem = (int)(r % ((long long)S * S));
-    ok = (rem / S) < H && (rem % S) < H;
+    const unsigned int rem = (unsigned int)((unsigned long long)r % (unsigned int)(S * S));
+    ok = rem / (unsigned int)S < (unsigned int)H && rem % (unsigned int)S < (unsigned int)H;
   }
-  float v = 0.f;
+  const long long i0 = r * C + c0;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 0.f;
   if (ok) {
-    v = fmaf(ld_any(raw, dt, i), scale[c], bias[c]);
-    if (slope1 != nullptr) v = v > 0.f ? v : v * slope1[c];
-    if (res != nullptr) v += ld_any(res, dt, i);
-    if (slope2 != nullptr) v = v > 0.f ? v : v * slope2[c];
+    float x[8], rr[8];
+    if (dt == DT_BF16) {
+      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + i0);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+      if (res != nullptr) {
+        const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + i0);
+        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(g2[k]); rr[2 * k] = f.x; rr[2 * k + 1] = f.y; }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        x[k] = ld_any(raw, dt, i0 + k);
+        rr[k] = res != nullptr ? ld_any(res, dt, i0 + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = fmaf(x[k], scale[c0 + k], bias[c0 + k]);
+      if (slope1 != nullptr) t = t > 0.f ? t : t * slope1[c0 + k];
+      if (res != nullptr) t += rr[k];
+      if (slope2 != nullptr) t = t > 0.f ? t : t * slope2[c0 + k];
+      v[k] = t;
+    }
   }
-  st_any(out, dt, i, v);
+  if (dt == DT_BF16) {
+    uint4 u;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + i0) = u;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st_any(out, dt, i0 + k, v[k]);
+  }
 }
 
 // ---- Philox4x32-10 (Salmon et al.): counter = (element block, site), key = seed
@@ -167,9 +230,13 @@ inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per);
 
 int launch_bn_stats(const void* raw, int dt, long long rows, int C, long long period, long long valid, int S, int H,
                     double* sums, cudaStream_t stream) {
-  AVH_CHECK(C >= 1 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "bn_stats: channel count must divide or be a multiple of 256");
+  AVH_CHECK(C >= 8 && C % 8 == 0 && C <= 2048 && (C / 8 <= 256 ? 256 % (C / 8) == 0 : false),
+            "bn_stats: channel count must be a multiple of 8 whose 8-channel groups divide 256");
   if (rows <= 0) return 0;
-  AVH_CUDA_OK(launch_pdl(bn_stats_kernel, dim3(blocks_for(rows, BN_ROWS_PER_CTA)), dim3(256), 0, stream, raw, dt, rows, C,
+  const int phases = 256 / (C / 8);
+  const size_t smem = (size_t)phases * C * 2 * sizeof(double);
+  AVH_CHECK(smem <= 48 * 1024, "bn_stats: shared-memory reduction buffer too large");
+  AVH_CUDA_OK(launch_pdl(bn_stats_kernel, dim3(blocks_for(rows, BN_ROWS_PER_CTA)), dim3(256), smem, stream, raw, dt, rows, C,
                          period, valid, S, H, sums));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
@@ -189,7 +256,8 @@ int launch_bn_apply(const void* raw, void* out, int dt, long long rows, int C, c
                     const float* slope1, const void* res, const float* slope2, int S, int H, cudaStream_t stream) {
   const long long n = rows * C;
   if (n <= 0) return 0;
-  AVH_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, stream, raw, out, dt, rows, C, scale, bias,
+  AVH_CHECK(C % 8 == 0, "bn_apply: channel count must be a multiple of 8");
+  AVH_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(blocks_for(n / 8, 256)), dim3(256), 0, stream, raw, out, dt, rows, C, scale, bias,
                          slope1, res, slope2, S, H));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);

@@ -67,6 +67,9 @@ class _EncoderTrainFn(torch.autograd.Function):
                 ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], ctypes.c_void_p(dx.data_ptr()),
                 _DTYPES[dx.dtype], ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
         grads, off = [], 0
+        same = ctx.dtypes[0] if all(dt == ctx.dtypes[0] for dt in ctx.dtypes) else None
+        if same is not None:
+            flat = flat.to(same)                           # one conversion for the whole buffer, the gradients are views
         for shape, dt in zip(ctx.shapes, ctx.dtypes):
             k = 1
             for d in shape:
