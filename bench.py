@@ -280,7 +280,10 @@ def main():
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    affinity = pin_host_thread(local_rank, world) if world > 1 else {"pinned": False, "note": "single rank: left to the OS"}
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    # AVH_BENCH_PIN=0 leaves placement to the OS; the CPU-baseline leg gets every core back (below)
+    affinity = (pin_host_thread(local_rank, world) if os.environ.get("AVH_BENCH_PIN", "1") != "0"
+                else {"pinned": False, "note": "AVH_BENCH_PIN=0: left to the OS"})
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL announces its version on stdout at the first collective; stdout carries exactly ONE JSON line
@@ -719,6 +722,8 @@ def main():
             with open(args.profile_json, "w") as f:
                 json.dump({"classes": prof, "total_ms": total_prof_ms}, f, indent=1, sort_keys=True)
         if world == 1 and not args.no_cpu_baseline:
+            if full_affinity is not None:
+                os.sched_setaffinity(0, full_affinity)      # the CPU arm uses all the host cores it can
             # the oracle is the CHECKER here: same 16 clips, same (bf16-rounded) weights -> CPU time + parity of the
             # benchmarked output
             cores = os.cpu_count() or 1

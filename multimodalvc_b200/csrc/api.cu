@@ -958,7 +958,7 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
     float *bn_scale = nullptr, *bn_bias = nullptr;
     if (train) {
       bn_raw = b.alloc((size_t)CB * (T + 2) * 1936 * 64 * es);          // the stem's map is the largest
-      bn_sums = reinterpret_cast<double*>(b.alloc(2 * 512 * sizeof(double)));
+      bn_sums = reinterpret_cast<double*>(b.alloc((size_t)BN_SLOTS * 2 * 512 * sizeof(double)));
       bn_scale = reinterpret_cast<float*>(b.alloc(512 * 4));
       bn_bias = reinterpret_cast<float*>(b.alloc(512 * 4));
     }

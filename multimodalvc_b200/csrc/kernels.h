@@ -68,6 +68,7 @@ int launch_ln_center_stats(const float* in, void* xc, float* mu, void* part, int
 int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int pitch, int fp32, cudaStream_t stream);
 
 // ---- training-mode forward (train_ops.cu): BatchNorm with batch statistics, Philox dropout
+constexpr int BN_SLOTS = 16;     // `sums` of bn_stats / bn_finalize holds BN_SLOTS x 2 x C doubles (zero before the first use)
 int launch_bn_stats(const void* raw, int dt, long long rows, int C, long long period, long long valid, int S, int H,
                     double* sums, cudaStream_t stream);
 int launch_bn_finalize(double* sums, double count, const float* gamma, const float* beta, float eps, float momentum,

@@ -37,6 +37,8 @@ __device__ __forceinline__ void st_any(void* out, int dt, long long i, float v) 
 // validity worked out ONCE per row in 32-bit arithmetic (the first version did 64-bit divisions per element: 1.5 ms per
 // BatchNorm at 8 clips), float64 partial sums per thread, one smem reduction and one double atomic per channel per CTA.
 constexpr int BN_ROWS_PER_CTA = 2048;
+// the per-channel double atomics of ~300 CTAs on 2 C addresses serialised (175 us per BatchNorm): CTAs spread their
+// partial sums over BN_SLOTS copies of the accumulators, bn_finalize adds the copies
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const void* __restrict__ raw, int dt, long long rows, int C, long long period, long long valid, int S,
                 int H, double* __restrict__ sums) {
@@ -90,8 +92,9 @@ bn_stats_kernel(const void* __restrict__ raw, int dt, long long rows, int C, lon
     for (int c = threadIdx.x; c < C; c += 256) {
       double ta = 0.0, tq = 0.0;
       for (int p2 = 0; p2 < phases; ++p2) { ta += sh[((size_t)p2 * C + c) * 2]; tq += sh[((size_t)p2 * C + c) * 2 + 1]; }
-      atomicAdd(&sums[c], ta);
-      atomicAdd(&sums[C + c], tq);
+      double* slot = sums + (size_t)(blockIdx.x % BN_SLOTS) * 2 * C;
+      atomicAdd(&slot[c], ta);
+      atomicAdd(&slot[C + c], tq);
     }
     __syncthreads();
   }
@@ -105,8 +108,14 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mean = sums[c] / count;
-  double var = sums[C + c] / count - mean * mean;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < BN_SLOTS; ++k) {
+    double* slot = sums + (size_t)k * 2 * C;
+    s1 += slot[c]; s2 += slot[C + c];
+    slot[c] = 0.0; slot[C + c] = 0.0;      // ready for the next BatchNorm that uses this scratch
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
   const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
   scale[c] = sc;
@@ -114,8 +123,6 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
   const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
   rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
   rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
-  sums[c] = 0.0;                 // ready for the next BatchNorm that uses this scratch
-  sums[C + c] = 0.0;
 }
 
 // out = act2(act1(raw * scale + bias) + res); rows outside the H x H image of the padded S x S layout are zeros.
