@@ -1743,6 +1743,8 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
       float* ls = lse[l];
       b.tag = "attention";
       b.push([=](cudaStream_t s) {
+        if (!f32)      // bf16 mode: the mma.sync forward kernel, also writing the log-sum-exp of every query row
+          return launch_attention(q, hm ? pl->mask_dev : nullptr, o, B, T, D, Hh, 0, s, ls);
         return launch_attention_x(q, 3 * D, q + (size_t)D * es, 3 * D, q + (size_t)2 * D * es, 3 * D, act_dt,
                                   hm ? pl->mask_dev : nullptr, o, D, act_dt, B, Hh, T, T, 1.0f, s, ls);
       });
@@ -1886,6 +1888,8 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
       float* ls = lse[l];
       b.tag = "attention_bwd";
       b.push([=](cudaStream_t s) {
+        if (!f32)      // bf16 mode: tensor-core backward (attention.cu); fp32 mode: the fp32 CUDA-core kernels
+          return launch_attention_bwd_tc(q, dO, O, ls, hm ? pl->mask_dev : nullptr, dq, Dbuf, B, T, D, Hh, s);
         return launch_attention_bwd(q, 3 * D, q + (size_t)D * es, 3 * D, q + (size_t)2 * D * es, 3 * D, act_dt, dO, O, D, act_dt, ls,
                                     hm ? pl->mask_dev : nullptr, dq, dq + (size_t)D * es, dq + (size_t)2 * D * es, 3 * D, act_dt,
                                     Dbuf, B, Hh, T, s);

@@ -10,8 +10,12 @@ namespace avh {
 enum { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 
 // Self-attention core on the fused QKV projection [B*T, 3*D] -> context [B*T, D]; bf16 or fp32 I/O.
+// lse (optional, training): fp32 [B, H, T] log-sum-exp of every query row's scores
 int launch_attention(const void* qkv, const unsigned char* kpm, void* out, int B, int T, int D, int H, int fp32,
-                     cudaStream_t stream);
+                     cudaStream_t stream, float* lse = nullptr);
+// backward of the above in bf16 mode (mma.sync): dO, O bf16 [B*T, D]; dqkv bf16 [B*T, 3*D] (dQ | dK | dV); Dbuf scratch [B,H,T]
+int launch_attention_bwd_tc(const void* qkv, const void* dO, const void* O, const float* lse, const unsigned char* kpm,
+                            void* dqkv, float* Dbuf, int B, int T, int D, int H, cudaStream_t stream);
 
 // LayerNorm over the last dim C of [rows, C] (row stride ld_in); optional fp32 and low-precision outputs
 // (both dense [rows, C]); rows flagged in row_zero (may be null) are written as zeros.

@@ -57,12 +57,19 @@ bn_stats_kernel(const void* __restrict__ raw, int dt, long long rows, int C, lon
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a[k] = 0.0; q[k] = 0.0; }
     if (ph < phases && g < groups) {
+      // position of the row inside its period / image, advanced incrementally (no division in the loop but one 32-bit one)
+      unsigned long long rp = period > 0 ? (unsigned long long)(r0 + ph) % (unsigned long long)period : 0ull;
+      unsigned int rs = S > 0 ? (unsigned int)((unsigned long long)(r0 + ph) % SS) : 0u;
       for (long long r = r0 + ph; r < r1; r += phases) {
-        if (period > 0 && (unsigned long long)r % (unsigned long long)period >= (unsigned long long)valid) continue;
+        const bool in_period = period <= 0 || rp < (unsigned long long)valid;
+        bool in_image = true;
         if (S > 0) {
-          const unsigned int rem = (unsigned int)((unsigned long long)r % SS);
-          if (rem / (unsigned int)S >= (unsigned int)H || rem % (unsigned int)S >= (unsigned int)H) continue;
+          const unsigned int y = rs / (unsigned int)S, x = rs - y * (unsigned int)S;
+          in_image = y < (unsigned int)H && x < (unsigned int)H;
         }
+        if (period > 0) { rp += phases; while (rp >= (unsigned long long)period) rp -= period; }
+        if (S > 0) { rs += phases; while (rs >= SS) rs -= SS; }
+        if (!in_period || !in_image) continue;
         float v[8];
         if (dt == DT_BF16) {
           const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + r * C + g * 8);
@@ -140,9 +147,10 @@ bn_apply_kernel(const void* __restrict__ raw, void* __restrict__ out, int dt, lo
   const long long r = gidx / groups;
   const int c0 = (int)(gidx - r * groups) * 8;
   bool ok = true;
-  if (S > 0) {
-    const unsigned int rem = (unsigned int)((unsigned long long)r % (unsigned int)(S * S));
-    ok = rem / (unsigned int)S < (unsigned int)H && rem % (unsigned int)S < (unsigned int)H;
+  if (S > 0) {      // rows < 2^32 (checked by the launcher): 32-bit arithmetic
+    const unsigned int rem = (unsigned int)r % (unsigned int)(S * S);
+    const unsigned int y = rem / (unsigned int)S;
+    ok = y < (unsigned int)H && rem - y * (unsigned int)S < (unsigned int)H;
   }
   const long long i0 = r * C + c0;
   float v[8];
@@ -263,7 +271,7 @@ int launch_bn_apply(const void* raw, void* out, int dt, long long rows, int C, c
                     const float* slope1, const void* res, const float* slope2, int S, int H, cudaStream_t stream) {
   const long long n = rows * C;
   if (n <= 0) return 0;
-  AVH_CHECK(C % 8 == 0, "bn_apply: channel count must be a multiple of 8");
+  AVH_CHECK(C % 8 == 0 && rows < (1ll << 32), "bn_apply: channel count must be a multiple of 8, rows < 2^32");
   AVH_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(blocks_for(n / 8, 256)), dim3(256), 0, stream, raw, out, dt, rows, C, scale, bias,
                          slope1, res, slope2, S, H));
   AVH_CUDA_OK(cudaGetLastError());

@@ -64,6 +64,8 @@ def _reference_grads(ref, x, pm, w):
     dict(D=128, F=256, H=2, L=2, groups=16, B=3, T=37, lengths=[37, 20, 29]),        # 8 channels per conv group
     dict(D=256, F=1024, H=4, L=2, groups=16, B=2, T=150, lengths=None),               # the Speech_Rate_Predictor's encoder
     dict(D=1024, F=4096, H=16, L=1, groups=16, B=2, T=70, lengths=[70, 51]),          # Large layer shape, 64 per group
+    dict(D=128, F=256, H=2, L=1, groups=16, B=1, T=3, lengths=None),                  # a clip shorter than every tile
+    dict(D=128, F=256, H=2, L=1, groups=16, B=2, T=161, lengths=[161, 1]),            # one valid frame; > 160 keys
 ])
 def test_encoder_backward_matches_autograd_fp32(shape):
     ref, enc = _pair(shape["D"], shape["F"], shape["H"], shape["L"], shape["groups"], seed=7)

@@ -76,6 +76,15 @@ def test_compute_logits_kernel_matches_oracle():
         assert (got - po.compute_logits(fb.float(), e, "cosine", 0.1)).abs().max().item() < 1e-4
     with pytest.raises(RuntimeError):
         m.compute_logits(torch.randn(2, 3, 8), torch.randn(4, 8))          # CPU tensors: no CPU path
+    # the C entry point refuses an in-place substitution (sources must be read from the un-substituted tensor)
+    import ctypes
+    from multimodalvc_b200 import _lib
+    x = torch.zeros(1, 4, 8, device="cuda")
+    code = torch.full((4,), -1, dtype=torch.int32, device="cuda")
+    vp = ctypes.c_void_p
+    rc = _lib.load().avh_mask_substitute(vp(x.data_ptr()), _lib.AVH_F32, 0, None, 1, 4, 8, vp(code.data_ptr()), None, 0, None,
+                                         vp(x.data_ptr()), _lib.AVH_F32, None)
+    assert rc != 0 and b"out of place" in _lib.load().avh_last_error()
 
 
 @pytest.mark.parametrize("name", list(mg.CASES))

@@ -86,6 +86,8 @@ def test_device_qformer_bert_masks_and_errors():
     assert rel_err(y.cpu(), y_ref) < 2e-3
     y_nomask = m.bert(lq, enc.cuda(), None)
     assert rel_err(y_nomask.cpu(), o.bert(lq, enc, torch.ones(2, 70))) < 2e-3
+    one = m.bert([1], enc[:1, :1].cuda(), None)                          # one query, one frame
+    assert rel_err(one.cpu(), o.bert([1], enc[:1, :1], torch.ones(1, 1))) < 2e-3
     with pytest.raises(ValueError):
         m.bert([3], enc.cuda(), None)                                    # one length per sample
     with pytest.raises(ValueError):
