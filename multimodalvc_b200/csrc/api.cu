@@ -2300,14 +2300,74 @@ int avh_finalize_weights(avh_handle* h) {
   return 0;
 }
 
-static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
-  static int graphs_env = -1;
-  if (graphs_env < 0) {
-    const char* ev = std::getenv("AVH_GRAPHS");
-    const char* dbg = std::getenv("AVH_STEM_DBG");
-    const char* dbg2 = std::getenv("AVH_WIN_DBG");
-    graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr || dbg2 != nullptr) ? 0 : 1;
+static int graphs_env = -1;      // 1 = CUDA-graph replay of the plan-internal runs of a launch list (AVH_GRAPHS=0: off)
+static void read_graphs_env() {
+  if (graphs_env >= 0) return;
+  const char* ev = std::getenv("AVH_GRAPHS");
+  const char* dbg = std::getenv("AVH_STEM_DBG");
+  const char* dbg2 = std::getenv("AVH_WIN_DBG");
+  graphs_env = ((ev != nullptr && ev[0] == '0') || dbg != nullptr || dbg2 != nullptr) ? 0 : 1;
+}
+
+// capture every maximal run of plan-internal steps (they only enqueue kernels / async copies) into its own graph
+static bool capture_segments(avh::Plan* p, cudaStream_t s) {
+  bool ok = true;
+  size_t i = 0;
+  while (ok && i < p->steps.size()) {
+    if (p->steps[i].direct) { ++i; continue; }
+    size_t j = i;
+    while (j < p->steps.size() && !p->steps[j].direct) ++j;
+    const long long before = avh::g_launches.load();
+    cudaGraph_t graph = nullptr;
+    ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      for (size_t k = i; k < j; ++k)
+        if (p->steps[k].run(s)) { ok = false; break; }
+      if (cudaStreamEndCapture(s, &graph) != cudaSuccess || graph == nullptr) ok = false;
+    }
+    const int captured = (int)(avh::g_launches.load() - before);
+    avh::count_launch(-captured);            // captured launches have not run
+    cudaGraphExec_t exec = nullptr;
+    if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (ok) p->segments.push_back(avh::Plan::Segment{i, j, exec, captured});
+    i = j;
   }
+  if (ok) p->segments_ready = true;
+  else {
+    // capture is not available for this launch list on this driver: remember, clear the error, run directly
+    p->drop_graphs();
+    cudaGetLastError();
+    avh::g_err.clear();
+    graphs_env = 0;
+  }
+  return ok;
+}
+
+// steps [begin, end) through the captured segments (direct steps launched in between); segments never straddle the range
+static int replay_range(avh::Plan* p, size_t begin, size_t end, cudaStream_t s) {
+  size_t i = begin, sg = 0;
+  while (sg < p->segments.size() && p->segments[sg].begin < begin) ++sg;
+  while (i < end) {
+    if (sg < p->segments.size() && p->segments[sg].begin == i && p->segments[sg].end <= end) {
+      AVH_CUDA_OK(cudaGraphLaunch(p->segments[sg].exec, s));
+      avh::count_launch(p->segments[sg].kernels);
+      avh::g_graph_launches.fetch_add(1, std::memory_order_relaxed);
+      i = p->segments[sg].end;
+      ++sg;
+    } else {
+      if (p->steps[i].run(s)) {
+        if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
+        return 1;
+      }
+      ++i;
+    }
+  }
+  return 0;
+}
+
+static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
+  read_graphs_env();
   // the caller's padding mask -> plan-owned copy (every later read is pointer-independent)
   if (p->has_mask && p->args.mask != nullptr)
     AVH_CUDA_OK(cudaMemcpyAsync(p->mask_dev, p->args.mask, (size_t)p->B * p->T, cudaMemcpyDeviceToDevice, s));
@@ -2316,58 +2376,8 @@ static int run_plan(avh_handle* h, avh::Plan* p, cudaStream_t s) {
   if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) cudaStreamIsCapturing(s, &cap_status);
   const bool graphs_ok = graphs_env == 1 && !h->profiling && !p->train && s != nullptr && s != cudaStreamLegacy &&
                          s != cudaStreamPerThread && cap_status == cudaStreamCaptureStatusNone;
-  if (graphs_ok && !p->segments_ready && p->direct_runs >= 1) {
-    // second forward of this plan: capture every run of plan-internal steps (they only enqueue kernels / async copies)
-    bool ok = true;
-    size_t i = 0;
-    while (ok && i < p->steps.size()) {
-      if (p->steps[i].direct) { ++i; continue; }
-      size_t j = i;
-      while (j < p->steps.size() && !p->steps[j].direct) ++j;
-      const long long before = avh::g_launches.load();
-      cudaGraph_t graph = nullptr;
-      ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-      if (ok) {
-        for (size_t k = i; k < j; ++k)
-          if (p->steps[k].run(s)) { ok = false; break; }
-        if (cudaStreamEndCapture(s, &graph) != cudaSuccess || graph == nullptr) ok = false;
-      }
-      const int captured = (int)(avh::g_launches.load() - before);
-      avh::count_launch(-captured);            // captured launches have not run
-      cudaGraphExec_t exec = nullptr;
-      if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
-      if (graph != nullptr) cudaGraphDestroy(graph);
-      if (ok) p->segments.push_back(avh::Plan::Segment{i, j, exec, captured});
-      i = j;
-    }
-    if (ok) p->segments_ready = true;
-    else {
-      // capture is not available for this launch list on this driver: remember, clear the error, run directly
-      p->drop_graphs();
-      cudaGetLastError();
-      avh::g_err.clear();
-      graphs_env = 0;
-    }
-  }
-  if (graphs_ok && graphs_env == 1 && p->segments_ready) {
-    size_t i = 0, sg = 0;
-    while (i < p->steps.size()) {
-      if (sg < p->segments.size() && p->segments[sg].begin == i) {
-        AVH_CUDA_OK(cudaGraphLaunch(p->segments[sg].exec, s));
-        avh::count_launch(p->segments[sg].kernels);
-        avh::g_graph_launches.fetch_add(1, std::memory_order_relaxed);
-        i = p->segments[sg].end;
-        ++sg;
-      } else {
-        if (p->steps[i].run(s)) {
-          if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");
-          return 1;
-        }
-        ++i;
-      }
-    }
-    return 0;
-  }
+  if (graphs_ok && !p->segments_ready && p->direct_runs >= 1) capture_segments(p, s);      // second forward of this plan
+  if (graphs_ok && graphs_env == 1 && p->segments_ready) return replay_range(p, 0, p->steps.size(), s);
   ++p->direct_runs;
   if (h->profiling) {
     while (h->prof_events.size() < 2 * p->steps.size()) {
@@ -2603,6 +2613,16 @@ int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t
 
 static int run_steps(avh_handle* h, avh::Plan* p, size_t begin, size_t end, cudaStream_t s) {
   (void)h;
+  read_graphs_env();
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) cudaStreamIsCapturing(s, &cap_status);
+  const bool graphs_ok = graphs_env == 1 && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+                         cap_status == cudaStreamCaptureStatusNone;
+  // training plans: the first step of a shape runs directly (it also configures the kernels), the second captures the
+  // forward and the backward launch lists (the direct final-LayerNorm store separates them), later ones replay
+  if (graphs_ok && begin == 0 && !p->segments_ready && p->direct_runs >= 1) capture_segments(p, s);
+  if (graphs_ok && graphs_env == 1 && p->segments_ready) return replay_range(p, begin, end, s);
+  if (begin == 0) ++p->direct_runs;
   for (size_t i = begin; i < end; ++i)
     if (p->steps[i].run(s)) {
       if (avh::g_err.empty()) avh::set_last_error("kernel launch failed");

@@ -41,15 +41,15 @@ constexpr int BN_ROWS_PER_CTA = 2048;
 // partial sums over BN_SLOTS copies of the accumulators, bn_finalize adds the copies
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const void* __restrict__ raw, int dt, long long rows, int C, long long period, long long valid, int S,
-                int H, double* __restrict__ sums) {
+                int H, double* __restrict__ sums, int rows_per_cta) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ double sh[];                 // [phases][C][2]
   const int groups = C >> 3;                     // threads per row
   const int phases = 256 / groups > 0 ? 256 / groups : 1;
   const int gi = threadIdx.x % groups, ph = threadIdx.x / groups;
-  const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_CTA;
-  const long long r1 = r0 + BN_ROWS_PER_CTA < rows ? r0 + BN_ROWS_PER_CTA : rows;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
   const unsigned int SS = (unsigned int)(S * S);
   for (int g0 = 0; g0 < groups; g0 += 256) {     // C > 2048 never happens; loop kept for generality
     const int g = g0 + gi;
@@ -251,8 +251,14 @@ int launch_bn_stats(const void* raw, int dt, long long rows, int C, long long pe
   const int phases = 256 / (C / 8);
   const size_t smem = (size_t)phases * C * 2 * sizeof(double);
   AVH_CHECK(smem <= 48 * 1024, "bn_stats: shared-memory reduction buffer too large");
-  AVH_CUDA_OK(launch_pdl(bn_stats_kernel, dim3(blocks_for(rows, BN_ROWS_PER_CTA)), dim3(256), smem, stream, raw, dt, rows, C,
-                         period, valid, S, H, sums));
+  // rows per CTA: enough CTAs to fill the machine (a thread has ONE 16-byte load in flight: the small maps of layers 3-4
+  // gave 10-30 CTAs at 2048 rows each and ran at a few GB/s per CTA), never more than BN_ROWS_PER_CTA
+  long long rpc = (rows + 4 * 148 - 1) / (4 * 148);
+  rpc = (rpc + phases - 1) / phases * phases;
+  if (rpc < 4 * phases) rpc = 4 * phases;
+  if (rpc > BN_ROWS_PER_CTA) rpc = BN_ROWS_PER_CTA;
+  AVH_CUDA_OK(launch_pdl(bn_stats_kernel, dim3(blocks_for(rows, (int)rpc)), dim3(256), smem, stream, raw, dt, rows, C,
+                         period, valid, S, H, sums, (int)rpc));
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
