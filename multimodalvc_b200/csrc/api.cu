@@ -2140,6 +2140,22 @@ Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool
     if (h->prof_plan == victim->second.get()) h->prof_plan = nullptr;
     h->plans.erase(victim);
   }
+  if (enc_train) {
+    // training plans keep every activation of the step (GBs for Large): at most two of them live per handle
+    for (;;) {
+      int n_train = 0;
+      auto victim = h->plans.end();
+      for (auto jt = h->plans.begin(); jt != h->plans.end(); ++jt)
+        if (jt->second->enc_train) {
+          ++n_train;
+          if (victim == h->plans.end() || jt->second->last_use < victim->second->last_use) victim = jt;
+        }
+      if (n_train < 2) break;
+      if (h->last_plan == victim->second.get()) h->last_plan = nullptr;
+      if (h->prof_plan == victim->second.get()) h->prof_plan = nullptr;
+      h->plans.erase(victim);
+    }
+  }
   std::unique_ptr<Plan> p(new Plan());
   p->last_use = ++h->plan_clock;
   p->stream = stream;

@@ -188,3 +188,20 @@ def test_avhubert_finetune_step_with_frozen_extractors(fuse):
     m2 = AVHubertModel(AVHubertConfig.named("tiny", trainable=True)).cuda().train()      # feature_grad_mult = 1 (default)
     with pytest.raises(NotImplementedError):
         m2.extract_finetune({k: v.cuda() for k, v in src.items()}, pm.cuda())
+
+
+def test_training_plans_are_evicted_and_rebuilt():
+    """Training plans keep GBs of activations: at most two live per handle (LRU).  A shape that was evicted is rebuilt
+    and gives bit-identical gradients."""
+    ref, enc = _pair(128, 256, 2, 2, 16, seed=5)
+    enc = enc.cuda().train()
+    grads = {}
+    for T in (20, 24, 28, 20):
+        x, pm, w = _case(2, T, 128, [T, T - 5], seed=T)
+        xd = x.cuda().requires_grad_(True)
+        y, _ = enc(xd, pm.cuda())
+        _loss(y, w.cuda(), pm.cuda()).backward()
+        if T in grads:
+            assert torch.equal(grads[T], xd.grad)
+        grads[T] = xd.grad.clone()
+        enc.zero_grad()
