@@ -182,7 +182,7 @@ AVH_API int avh_encoder_forward(avh_handle* h, const void* x, int x_dtype, const
  * multihead_attention.py:170-192, the final LayerNorm (:862-863) — what torch.autograd computes for the reference module.
  * Handle: any handle with encoder weights created with avh_config.reserved[3] = 1 (packs W^T for the dX = dY W GEMMs).
  * avh_encoder_train_forward: as avh_encoder_forward (all layers + final LayerNorm); avh_encoder_backward: dout [B,T,D] =
- * dL/d(out) (rows of padded frames are ignored), dx [B,T,D] = dL/d(x) (may be NULL), grads = fp32 [avh_encoder_grad_count]
+ * dL/d(out) (every row counts, padded frames too, as under autograd), dx [B,T,D] = dL/d(x) (may be NULL), grads = fp32 [avh_encoder_grad_count]
  * (may be NULL) in this order: per layer {q,k,v}_proj.weight, {q,k,v}_proj.bias, out_proj.weight, out_proj.bias,
  * self_attn_layer_norm.{weight,bias}, fc1.weight, fc1.bias, fc2.weight, fc2.bias, final_layer_norm.{weight,bias}; then
  * encoder.layer_norm.{weight,bias}; then pos_conv.0.{bias, weight_g, weight_v}.  Same stream as the forward. */

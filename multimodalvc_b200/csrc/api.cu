@@ -1836,7 +1836,7 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   const long long LG = enc_layer_grad_floats(D, F);
   b.tag = "load_grad";
   b.cur_direct = true;
-  // (the caller's dL/dy is staged into `dy` by avh_encoder_backward before the steps run; pad rows zeroed there)
+  // (the caller's dL/dy is staged into `dy` by avh_encoder_backward before the steps run)
   b.cur_direct = false;
   {   // final LayerNorm
     float* gfin = grads + (long long)L * LG;
@@ -2713,8 +2713,9 @@ int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype, void* 
   AVH_CHECK(s == p->stream, "backward must run on the stream of its forward");
   const long long N = (long long)p->B * p->T;
   const int D = h->cfg.encoder_embed_dim;
-  // dL/dy -> fp32, rows of padded frames zeroed (the reference's loss never reads them)
-  if (avh::launch_load_rows(dout, dout_dtype, p->dy_in, p->has_mask ? p->mask_dev : nullptr, N, D, s)) return 1;
+  // dL/dy -> fp32.  Rows of padded frames are taken as given, as autograd does: the dense forward computed those rows
+  // (their queries attend to the valid keys), so a loss that reads them sends gradient through them too
+  if (avh::launch_load_rows(dout, dout_dtype, p->dy_in, nullptr, N, D, s)) return 1;
   if (run_steps(h, p, p->fwd_steps, p->steps.size(), s)) return 1;
   if (dx != nullptr && avh::launch_convert(p->dx_out, avh::DT_F32, dx, dx_dtype, N * D, s)) return 1;
   if (grads != nullptr)

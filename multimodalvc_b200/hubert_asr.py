@@ -36,12 +36,93 @@ class HubertEncoderWrapper(nn.Module):
         return encoder_out
 
 
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the library's GEMM, differentiable: dX = dY W, dW = dY^T X (both through the same GEMM entry
+    point; the operand transposes are copies), db = column sums."""
+
+    @staticmethod
+    def forward(ctx, x, lin, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.lin = lin
+        return _project(x, lin)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        B, T, D = x.shape
+        N = weight.size(0)
+        dy2 = dy.reshape(B * T, N)
+        dx = _matmul_nt(dy2, weight.detach().t().contiguous()).view(B, T, D).to(x.dtype)        # [M,N] x [D,N]^T
+        dw = _matmul_nt(dy2.t().contiguous(), x.reshape(B * T, D).t().contiguous()).to(weight.dtype)   # [N,M] x [D,M]^T
+        db = dy2.float().sum(0).to(weight.dtype)
+        return dx, None, dw, db
+
+
+def _matmul_nt(a, b):
+    """a [M,K] @ b[N,K]^T -> fp32 [M,N] on avh_gemm_bf16; fp32 inputs run in split precision (hi + mid planes, three
+    products), K padded to 8 and N to 32 with zeros."""
+    M, K = a.shape
+    N = b.size(0)
+    Kp, Np = (K + 7) // 8 * 8, (N + 31) // 32 * 32
+    dev = a.device
+    af = torch.zeros(M, Kp, device=dev, dtype=torch.float32)
+    af[:, :K] = a.float()
+    bf = torch.zeros(Np, Kp, device=dev, dtype=torch.float32)
+    bf[:N, :K] = b.float()
+    split = a.dtype == torch.float32
+    a_hi, b_hi = af.to(torch.bfloat16), bf.to(torch.bfloat16)
+    out = torch.empty(M, Np, device=dev, dtype=torch.float32)
+    vp = ctypes.c_void_p
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        stream = vp(torch.cuda.current_stream(dev).cuda_stream)
+
+        def gemm(aa, bb, res):
+            _lib.check(lib.avh_gemm_bf16(vp(aa.data_ptr()), vp(bb.data_ptr()), M, Np, Kp, None, 0,
+                                         vp(out.data_ptr()) if res else None, 1, vp(out.data_ptr()), 1, 0, 0, 0, stream))
+        if split:
+            a_mid = (af - a_hi.float()).to(torch.bfloat16)
+            b_mid = (bf - b_hi.float()).to(torch.bfloat16)
+            gemm(a_mid, b_hi, False)
+            gemm(a_hi, b_mid, True)
+            gemm(a_hi, b_hi, True)
+        else:
+            gemm(a_hi, b_hi, False)
+    return out[:, :N]
+
+
+class _DropoutFn(torch.autograd.Function):
+    """nn.Dropout on the library's Philox stream (avh_dropout): the mask is a pure function of (seed, site, element), so
+    the backward applies the same call to the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return _DropoutFn._apply(x, p, seed)
+
+    @staticmethod
+    def _apply(x, p, seed):
+        y = x.contiguous().clone()
+        from .hubert import _DTYPES
+        with torch.cuda.device(y.device):
+            stream = torch.cuda.current_stream(y.device).cuda_stream
+            _lib.check(_lib.load().avh_dropout(ctypes.c_void_p(y.data_ptr()), _DTYPES[y.dtype], y.numel(), float(p),
+                                               int(seed), 7, ctypes.c_void_p(stream)))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _DropoutFn._apply(dy, ctx.p, ctx.seed), None, None
+
+
 class HubertEncoder(nn.Module):
     """avhubert/hubert_asr.py:251-372 around an already-built ``AVHubertModel`` (the reference builds it from the
     checkpoint's config through the fairseq task, :299-305; here the caller passes it in).  ``forward`` =
-    extract_finetune (no grad: the device path is inference-only) -> T x B x C -> final_dropout (identity in eval)
-    -> optional ``proj`` (CTC vocabulary head ``Linear(d, len(tgt_dict))`` or ``Linear(d, decoder_embed_dim)``).
-    The projection runs on the library's tcgen05 GEMM (bf16 operands, fp32 accumulation)."""
+    extract_finetune -> T x B x C -> final_dropout -> optional ``proj`` (CTC vocabulary head ``Linear(d,
+    len(tgt_dict))`` or ``Linear(d, decoder_embed_dim)``) on the library's tcgen05 GEMM.  Training (:329-354): the
+    backbone runs under no_grad until ``num_updates`` reaches ``freeze_finetune_updates``, afterwards with gradients
+    (needs the backbone built with ``cfg.trainable`` and frozen feature extractors: SURVEY row A18); ``mask`` =
+    ``apply_mask and self.training``; the head is always differentiable."""
 
     def __init__(self, w2v_model, tgt_dict_size=None, decoder_embed_dim=None, final_dropout=0.0, apply_mask=False,
                  freeze_finetune_updates=0):
@@ -63,13 +144,31 @@ class HubertEncoder(nn.Module):
     def set_num_updates(self, num_updates):
         self.num_updates = num_updates
 
-    @torch.no_grad()
     def forward(self, source, padding_mask, tbc=True, **kwargs):
-        if self.training:
-            raise RuntimeError("HubertEncoder on the device path is inference-only: call .eval()")
-        x, padding_mask = self.w2v_model.extract_finetune(source=source, padding_mask=padding_mask, mask=False)
-        if self.proj is not None:
-            x = _project(x, self.proj)
+        if not (self.training and torch.is_grad_enabled()):
+            with torch.no_grad():
+                x, padding_mask = self.w2v_model.extract_finetune(source=source, padding_mask=padding_mask,
+                                                                  mask=self.apply_mask and self.training)
+                if self.training and self.final_dropout.p > 0:
+                    x = _DropoutFn._apply(x, self.final_dropout.p, int(torch.randint(0, 2 ** 62, (1,)).item()))
+                if self.proj is not None:
+                    x = _project(x, self.proj)
+        else:
+            ft = self.freeze_finetune_updates <= self.num_updates
+            if ft and not self.w2v_model.cfg.trainable and any(p.requires_grad for p in self.w2v_model.parameters()):
+                raise RuntimeError("fine-tuning the backbone needs AVHubertConfig(trainable=True, feature_grad_mult=0): "
+                                   "build it that way, or freeze its parameters (requires_grad_(False))")
+            if ft and self.w2v_model.cfg.trainable:
+                x, padding_mask = self.w2v_model.extract_finetune(source=source, padding_mask=padding_mask,
+                                                                  mask=self.apply_mask)
+            else:
+                with torch.no_grad():
+                    x, padding_mask = self.w2v_model.extract_finetune(source=source, padding_mask=padding_mask,
+                                                                      mask=self.apply_mask)
+            if self.final_dropout.p > 0:
+                x = _DropoutFn.apply(x, self.final_dropout.p, int(torch.randint(0, 2 ** 62, (1,)).item()))
+            if self.proj is not None:
+                x = _LinearFn.apply(x, self.proj, self.proj.weight, self.proj.bias)
         if tbc:
             x = x.transpose(0, 1)                 # B x T x C -> T x B x C
         return {

@@ -205,3 +205,66 @@ def test_training_plans_are_evicted_and_rebuilt():
             assert torch.equal(grads[T], xd.grad)
         grads[T] = xd.grad.clone()
         enc.zero_grad()
+
+
+def test_hubert_encoder_ctc_head_trains_with_freeze_gating():
+    """HubertEncoder.forward in training (avhubert/hubert_asr.py:329-354): below freeze_finetune_updates the backbone runs
+    under no_grad and only the head gets gradients; from there on the tail of the backbone trains too.  Gradients of
+    the head (library GEMM forward and backward) and of the tail against torch.autograd on the oracle."""
+    from multimodalvc_b200 import AVHubertConfig, AVHubertModel
+    from multimodalvc_b200.hubert_asr import HubertEncoder
+    o = ao.build_oracle("tiny", seed=1234).train()
+    B, T, lengths, V = 2, 24, [24, 17], 40
+    src, pm = ao.synthetic_inputs(B, T, lengths=lengths, seed=17)
+    torch.manual_seed(3)
+    head = torch.nn.Linear(128, V)
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(T, B, V, generator=g)
+    cfg = AVHubertConfig.named("tiny", feature_grad_mult=0.0, trainable=True, dropout=0.0, attention_dropout=0.0,
+                               activation_dropout=0.0, encoder_layerdrop=0.0, dropout_input=0.0)
+    m = AVHubertModel(cfg)
+    m.load_state_dict(o.state_dict(), strict=False)
+    enc = HubertEncoder(m, tgt_dict_size=V, final_dropout=0.0, freeze_finetune_updates=5)
+    enc.proj.load_state_dict(head.state_dict())
+    enc = enc.cuda().train()
+    # reference
+    with torch.no_grad():
+        fv = o.feature_extractor_video(src["video"])
+        fa = o.feature_extractor_audio(src["audio"])
+        fused = torch.cat([fa, fv], dim=1).transpose(1, 2)
+    def ref_step(backbone_grad):
+        o.zero_grad(); head.zero_grad()
+        with torch.enable_grad() if backbone_grad else torch.no_grad():
+            y = o.encoder(o.post_extract_proj(o.layer_norm(fused)), pm)
+        out = head(y.detach() if not backbone_grad else y).transpose(0, 1)
+        (out * w).sum().backward()
+        return out.detach()
+    dsrc = {k: v.cuda() for k, v in src.items()}
+    # (1) num_updates < freeze: head only
+    out_ref = ref_step(False)
+    res = enc(dsrc, pm.cuda())
+    assert rel_err(res["encoder_out"].detach().cpu(), out_ref) < 2e-3
+    (res["encoder_out"] * w.cuda()).sum().backward()
+    assert rel_err(enc.proj.weight.grad.cpu(), head.weight.grad) < 2e-3
+    assert rel_err(enc.proj.bias.grad.cpu(), head.bias.grad) < 2e-3
+    assert all(p.grad is None for p in m.parameters())
+    # (2) num_updates >= freeze: the backbone's tail too
+    enc.zero_grad()
+    enc.set_num_updates(5)
+    ref_step(True)
+    res = enc(dsrc, pm.cuda())
+    (res["encoder_out"] * w.cuda()).sum().backward()
+    assert rel_err(enc.proj.weight.grad.cpu(), head.weight.grad) < 2e-3
+    ref_grads = {n: p.grad for n, p in o.named_parameters()}
+    for n in ("encoder.layers.0.fc1.weight", "encoder.layers.1.self_attn.q_proj.weight", "post_extract_proj.weight",
+              "layer_norm.bias", "encoder.pos_conv.0.weight_v"):
+        assert rel_err(dict(m.named_parameters())[n].grad.cpu(), ref_grads[n]) < 2e-3, n
+    # (3) final_dropout on the library's Philox stream: zeros in the output <-> zeros in the gradient
+    enc2 = HubertEncoder(m, final_dropout=0.5, freeze_finetune_updates=100).cuda().train()
+    x_probe = torch.ones(2, 5, 128, device="cuda", requires_grad=True)
+    from multimodalvc_b200.hubert_asr import _DropoutFn
+    y = _DropoutFn.apply(x_probe, 0.5, 1234)
+    y.sum().backward()
+    assert torch.equal(y.detach() == 0, x_probe.grad == 0) and 0.3 < (y == 0).float().mean().item() < 0.7
+    assert torch.allclose(y[y != 0], torch.full_like(y[y != 0], 2.0))
+    assert enc2(dsrc, pm.cuda())["encoder_out"].shape == (T, B, 128)
