@@ -258,6 +258,8 @@ def main():
                     help="seconds of back-to-back steps for the `sustained` leg after the timed region (0 = skip)")
     ap.add_argument("--config3-passes", type=int, default=5, help="timed passes over the 64 ragged clips of config 3 (0 = skip)")
     ap.add_argument("--config3-tokens", type=int, default=4800, help="packed frames per ragged sub-batch")
+    ap.add_argument("--config4-passes", type=int, default=2,
+                    help="timed passes over the 32 noisy 24 s clips of BASELINE config 4 (0 = skip)")
     ap.add_argument("--config5-steps", type=int, default=5,
                     help="timed fine-tuning steps of BASELINE config 5 (forward + backward + gradient all-reduce; 0 = skip)")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-class breakdown here")
@@ -520,6 +522,47 @@ def main():
                 "sub_batches_rank0": [[len(sb), sum(lengths3[i] for i in sb)] for sb in subs],
                 "pad_fraction_if_dense_rank0": 1.0 - frames_mine / float(padded_dense)}
 
+    # ---- BASELINE config 4: noisy evaluation — 32 clips x 24 s (600 frames) per GPU, babble noise mixed at -5 / 0 / 5 dB
+    #      on the device (add_noise), log-fbank + stack + LayerNorm + collate (avh_fbank), then the Large forward, as 4
+    #      sub-batches of 8 clips (4800 frames each).  Waveforms, noise and uint8 frames device-resident.
+    cfg4 = None
+    if args.config4_passes > 0:
+        from multimodalvc_b200 import audio as avh_audio
+        import numpy as np
+        T4, NB4, SUB4 = 600, 32, 8
+        r4 = np.random.RandomState(400 + rank)
+        babble = np.mean([np.clip(np.round(3000.0 * r4.randn(T4 * 640)), -32768, 32767) for _ in range(30)], axis=0)
+        noise4 = torch.from_numpy(babble.astype(np.float32)).to(dev)
+        subs4 = []
+        for j in range(NB4 // SUB4):
+            wav = torch.from_numpy(np.clip(np.round(3000.0 * r4.randn(SUB4 * T4 * 640)), -32768, 32767).astype(np.int16)).to(dev)
+            offs = (torch.arange(SUB4 + 1, dtype=torch.int64) * (T4 * 640)).to(dev)
+            vid = torch.randint(0, 256, (SUB4, 1, T4, 88, 88), dtype=torch.uint8,
+                                generator=torch.Generator().manual_seed(410 + rank * 8 + j)).to(dev)
+            subs4.append((wav, offs, vid, (-5.0, 0.0, 5.0, 0.0)[j]))
+
+        def pass4(k):
+            for j, (wav, offs, vid, snr) in enumerate(subs4):
+                with torch.cuda.stream(streams[(k * len(subs4) + j) % S]):
+                    mixed = avh_audio.add_noise_packed(wav, offs, noise4, snr)
+                    a4, _ = avh_audio.logfbank_stack_collate_packed(mixed, offs, T4)
+                    model.extract_finetune({"audio": a4.to(torch.bfloat16), "video": vid}, None)
+
+        for k in range(2):
+            pass4(k)
+        join()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        fork(d0)
+        for k in range(args.config4_passes):
+            pass4(k)
+        join()
+        d1.record()
+        barrier()
+        cfg4 = {"ms": d0.elapsed_time(d1)}
+        del subs4
+
     # ---- BASELINE config 5 (the part of it that is built): Large, B = 8 clips x 150 frames per GPU, bf16, dropout /
     #      LayerDrop 0, loss = mean(x^2); forward + backward + gradient all-reduce per step.  The feature extractors are
     #      FROZEN (feature_grad_mult = 0, the reference then runs them under no_grad): the lip-ResNet backward is not built.
@@ -569,9 +612,11 @@ def main():
     ms_sus = sustained[1] if sustained else 0.0
     if world > 1:
         t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, cfg3["ms"] if cfg3 else 0.0,
-                          cfg5["ms"] if cfg5 else 0.0], device=dev, dtype=torch.float64)
+                          cfg5["ms"] if cfg5 else 0.0, cfg4["ms"] if cfg4 else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3, ms_c5 = t.tolist()
+        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3, ms_c5, ms_c4 = t.tolist()
+        if cfg4:
+            cfg4["ms"] = ms_c4
         if cfg3:
             cfg3["ms"] = ms_c3
         if cfg5:
@@ -706,6 +751,18 @@ def main():
                 "frames": cfg3["frames_all"], "config2_frames_per_s": fps2, "frac_of_config2_frame_rate": fps3 / fps2,
                 "sub_batches_rank0_clips_frames": cfg3["sub_batches_rank0"],
                 "pad_fraction_if_dense_rank0": cfg3["pad_fraction_if_dense_rank0"]}
+        if cfg4:
+            sec4 = cfg4["ms"] * 1e-3 / args.config4_passes
+            fps4 = world * 32 * 600 / sec4
+            line["config4"] = {
+                "workload": "BASELINE config 4: Large, 32 clips x 24 s (600 frames) per GPU, babble noise mixed at -5 / 0 / 5 dB "
+                            "(add_noise on the device), log-fbank + stack + LayerNorm + collate (avh_fbank), uint8 frames "
+                            "normalised on the device, forward as 4 sub-batches of 8 clips; device-resident waveforms / frames",
+                "clips_per_s": world * 32 / sec4, "frames_per_s": fps4, "ms_per_pass": sec4 * 1e3,
+                "passes": args.config4_passes, "config2_frames_per_s": value * T_FRAMES,
+                "frac_of_config2_frame_rate": fps4 / (value * T_FRAMES),
+                "note": "attention grows with T (600 keys per query instead of 150): 790.5 GFLOP per 24 s clip against "
+                        "4 x 190.99 for four 6 s clips"}
         if cfg5:
             sec5 = cfg5["ms"] * 1e-3 / args.config5_steps
             line["config5"] = {

@@ -8,6 +8,7 @@ for rep in 1 2; do
     extra=""
     grep -q "config3-passes" $d/bench.py && extra="--config3-passes 0"
     grep -q "config5-steps" $d/bench.py && extra="$extra --config5-steps 0"
+    grep -q "config4-passes" $d/bench.py && extra="$extra --config4-passes 0"
     line=$(cd $d && python bench.py --no-cpu-baseline --sustain-s 2 --steps 50 --warmup 3 $extra 2>/dev/null | tail -1)
     python - "$d" "$rep" "$line" >> $out <<'PY'
 import sys, json

@@ -6,7 +6,7 @@ out=$1; shift
 for rep in 1 2; do
   for e in "$@"; do
     envs=""; [ "$e" != "-" ] && envs="$e"
-    line=$(env $envs python bench.py --no-cpu-baseline --sustain-s 2 --steps 50 --warmup 3 --config3-passes 0 --config5-steps 0 2>/dev/null | tail -1)
+    line=$(env $envs python bench.py --no-cpu-baseline --sustain-s 2 --steps 50 --warmup 3 --config3-passes 0 --config5-steps 0 --config4-passes 0 2>/dev/null | tail -1)
     python - "$e" "$rep" "$line" >> $out <<'PY'
 import sys, json
 d, rep, line = sys.argv[1:4]
