@@ -202,6 +202,21 @@ AVH_API int avh_tail_grad_count(avh_handle* h, int64_t* n_floats);
 AVH_API int avh_tail_train_forward(avh_handle* h, const void* fused, int dtype, const uint8_t* padding_mask, int B, int T,
                                    void* out, int out_dtype, void* stream);
 
+/* The whole fine-tuning step (feature_grad_mult > 0, BASELINE config 5 as stated): lip ResNet (training-mode BatchNorm:
+ * batch statistics, running statistics updated with bn_momentum — read them back with avh_read_bn_stats), modality
+ * projections, fusion, encoder, with saved activations; avh_encoder_backward then also returns, after the tail's
+ * gradients, those of the feature extractors (scaled by feature_grad_mult as fairseq's GradMultiply does,
+ * avhubert/hubert.py:538-547): feature_extractor_audio.proj.{weight [D, round_up(F,64)], bias} (when audio is given),
+ * feature_extractor_video.proj.{weight, bias}, frontend3D.0.weight as [64, 5, 64] (dt, kh*7+kw zero-padded to 64),
+ * frontend3D.1.{weight,bias}, frontend3D.2.weight, and per BasicBlock conv1.weight as [C, kh, kw, Cin], bn1.{weight,
+ * bias}, relu1.weight, conv2.weight, bn2.{weight,bias}, relu2.weight, downsample.0.weight [C, Cin], downsample.1.{weight,
+ * bias} (first block of layers 2-4).  Correctness-first path: every convolution is explicit patches -> one GEMM.
+ * video [B,1,T,88,88] float (or NULL), audio [B,F,T] + strides (or NULL).  Its dx output is not defined (pass NULL). */
+AVH_API int avh_full_grad_count(avh_handle* h, int has_video, int has_audio, int64_t* n_floats);
+AVH_API int avh_full_train_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                                   const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T,
+                                   float feature_grad_mult, float bn_momentum, void* out, int out_dtype, void* stream);
+
 /* The Q-Former that compresses the fused AV features into query tokens in MMS-LLaMA:
  * Qformer.bert(query_embeds=query_tokens[:, :Lq], attention_mask, encoder_hidden_states=enc, encoder_attention_mask)
  * ['last_hidden_state'] (src/model.py:584-619 -> src/sub_model/Qformer.py:805-968, query-only path: self-attention over

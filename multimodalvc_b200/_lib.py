@@ -21,7 +21,7 @@ EXPORTS = [
     "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward", "avh_forward_train", "avh_bn_stats_count", "avh_read_bn_stats", "avh_dropout", "avh_interp_linear", "avh_graph_launch_count",
     "avh_mask_substitute", "avh_compute_logits", "avh_sum_squares", "avh_qformer_forward",
     "avh_encoder_grad_count", "avh_encoder_train_forward", "avh_encoder_backward",
-    "avh_tail_grad_count", "avh_tail_train_forward",
+    "avh_tail_grad_count", "avh_tail_train_forward", "avh_full_grad_count", "avh_full_train_forward",
 ]
 
 
@@ -85,6 +85,9 @@ def load():
     lib.avh_interp_linear.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp]
     lib.avh_encoder_grad_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.avh_tail_grad_count.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.avh_full_grad_count.argtypes = [vp, i32, i32, ctypes.POINTER(i64)]
+    lib.avh_full_train_forward.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(i64), vp, i32, i32, ctypes.c_float, ctypes.c_float,
+                                           vp, i32, vp]
     lib.avh_tail_train_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp]
     lib.avh_encoder_train_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp]
     lib.avh_encoder_backward.argtypes = [vp, vp, i32, vp, i32, vp, i64, vp]

@@ -129,6 +129,7 @@ struct ConvUnit {         // conv + folded eval-mode BatchNorm (+ PReLU)
   // training-mode BatchNorm: affine parameters and the running statistics the batch statistics update (device, fp32)
   float *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;
   int cin = 0, cout = 0, ks = 3, stride = 1;
+  PackedW wT;               // trainable handles: [K = ks*ks*cin rows, cout] — the B operand of d_col = d_raw W
 };
 struct BlockW {
   ConvUnit c1, c2, ds;
@@ -207,12 +208,14 @@ struct Plan {
   // encoder training plans (avh_encoder_train_forward / avh_encoder_backward): steps [0, fwd_steps) are the forward
   // with saved activations, the rest the backward; gradients accumulate in a plan-owned fp32 buffer
   bool enc_train = false;
-  bool tail = false;               // the trainable tail of AV-HuBERT: fusion LayerNorm + post_extract_proj in front of the encoder
+  int tail = 0;                    // 1: trainable tail of AV-HuBERT (fusion LayerNorm + post_extract_proj + encoder) on caller-provided
+                                   // fused features; 2: the whole model (lip ResNet + projections computed in the plan, feature_grad_mult > 0)
   size_t fwd_steps = 0;
   float* grads = nullptr;
   long long grad_floats = 0;
   float* dx_out = nullptr;         // gradient w.r.t. the input features [B*T, D] fp32
   float* dy_in = nullptr;          // gradient w.r.t. the output, staged fp32 [B*T, D]
+  float fgm = 1.f;                 // mode 2: feature_grad_mult (GradMultiply on the extractor outputs), set per call
   bool fwd_done = false;
   int Lk = 0;                      // Q-Former plans: T = query rows per clip, Lk = AV feature rows per clip
   unsigned char* qmask_dev = nullptr;    // Q-Former plans: [B*T] 1 = padded query, [B*Lk] 1 = padded AV frame
@@ -290,6 +293,7 @@ struct avh_handle {
   BlockW blocks[4][2];
   LinearW proj_v, proj_a, post_proj;
   LinearW post_projT;             // trainable handles: post_extract_proj^T for the backward
+  LinearW proj_vT;                // ... and feature_extractor_video.proj^T (gradient into the ResNet features)
   bool has_post_proj = false;
   float *fuse_ln_g = nullptr, *fuse_ln_b = nullptr, *enc_ln_g = nullptr, *enc_ln_b = nullptr;
   PackedW pos_w;
@@ -395,6 +399,13 @@ bool pack_conv(Packer& pk, const std::string& wkey, const std::string& bnkey, co
     for (int c = 0; c < cin; ++c)
       for (int t = 0; t < ks * ks; ++t) packed[(size_t)o * K + (size_t)t * cin + c] = w->v[((size_t)o * cin + c) * ks * ks + t];
   cu->w = pk.pack(packed, cout, K, K);
+  if (pk.h->cfg.reserved[3] != 0 && pk.h->cfg.reserved[0] == 0) {
+    const int cp = round_up(cout, 64);
+    std::vector<float> pt((size_t)K * cp, 0.f);
+    for (int o = 0; o < cout; ++o)
+      for (int k = 0; k < K; ++k) pt[(size_t)k * cp + o] = packed[(size_t)o * K + k];
+    cu->wT = pk.pack(pt, K, cout, cp);
+  }
   std::vector<float> sc(cout), bi(cout);
   for (int o = 0; o < cout; ++o) {
     const float inv = 1.0f / std::sqrt(v->v[o] + 1e-5f);      // nn.BatchNorm eps default
@@ -630,6 +641,7 @@ bool pack_all(Packer& pk) {
   // ---- modality projections, fusion LN, post_extract_proj
   if (!enc_only) {
     ok &= pack_linear(pk, "feature_extractor_video.proj", &h->proj_v);
+    if (c.reserved[3] != 0) ok &= pack_linear_T(pk, {"feature_extractor_video.proj"}, {1.f}, &h->proj_vT);
     ok &= pack_linear(pk, "feature_extractor_audio.proj", &h->proj_a);
     const HostTensor* g = pk.get("layer_norm.weight");
     const HostTensor* b = pk.get("layer_norm.bias");
@@ -802,9 +814,10 @@ struct Builder {
 
   // enqueue one GEMM; returns false on planning failure
   bool gemm(const void* A, long long a_rows, int a_cols, const PackedW& W, long long M, const std::vector<Tap>& taps,
-            int chunks, int a_plane_stride, Epilogue ep, int block_n = 0, const int* a_col_nblk = nullptr) {
+            int chunks, int a_plane_stride, Epilogue ep, int block_n = 0, const int* a_col_nblk = nullptr,
+            long long lda = 0) {
     GemmProblem pr;
-    pr.A = A; pr.a_rows = a_rows; pr.a_cols = a_cols; pr.lda = a_cols;
+    pr.A = A; pr.a_rows = a_rows; pr.a_cols = a_cols; pr.lda = lda > 0 ? lda : a_cols;
     pr.B = W.w; pr.b_rows = W.n; pr.b_cols = P * W.kpad; pr.ldb = (long long)P * W.kpad;
     pr.M = M; pr.N = W.n;
     pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
@@ -1558,12 +1571,14 @@ bool build_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
 //   final_layer_norm.{weight,bias};  then encoder.layer_norm.{weight,bias};  then pos_conv.0.bias [D],
 //   pos_conv.0.weight_g [KT], pos_conv.0.weight_v [D, D/G, KT].
 long long enc_layer_grad_floats(int D, int F) { return 4ll * D * D + 4ll * D + 2ll * D + 2ll * D * F + F + D + 2ll * D; }
-long long enc_grad_floats(const avh_config& c, bool tail = false) {
+long long frontend_grad_floats(const avh_config& c, bool has_video, bool has_audio);
+long long enc_grad_floats(const avh_config& c, int tail = 0, bool has_video = true, bool has_audio = true) {
   const int D = c.encoder_embed_dim, F = c.encoder_ffn_embed_dim;
   const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
   long long n = c.encoder_layers * enc_layer_grad_floats(D, F) + 2ll * D + D + c.conv_pos +
                 (long long)D * (D / c.conv_pos_groups) * c.conv_pos;
   if (tail) n += (E != D ? (long long)D * E + D : 0) + 2ll * E;      // post_extract_proj.{weight,bias}, layer_norm.{weight,bias}
+  if (tail == 2) n += frontend_grad_floats(c, has_video, has_audio);
   return n;
 }
 
@@ -1602,6 +1617,31 @@ bool posconv_wgrad(Builder& b, avh_handle* h, Plan* plan, const float* dc, const
   b.push([=](cudaStream_t s) { return launch_posconv_weightnorm_bwd(dw, v, gg, D, cg, KT, g_wg, g_wv, norms, s); });
   (void)plan;
   return true;
+}
+
+// Gradients of the feature extractors (mode 2), after the tail's: feature_extractor_audio.proj.{weight [D, Fp], bias}
+// (Fp = audio_feat_dim rounded up to 64, the columns past audio_feat_dim are zero), feature_extractor_video.proj.{weight
+// [D,512], bias}, then the ResNet: frontend3D.0.weight as [64, 5, 64] (dt, kh*7+kw padded to 64), frontend3D.1.{weight,bias},
+// frontend3D.2.weight; per BasicBlock conv1.weight [C, 3,3,Cin] (tap-major, channel-minor), bn1.{weight,bias},
+// relu1.weight, conv2.weight, bn2.{weight,bias}, relu2.weight, and for the first block of layers 2-4 downsample.0.weight
+// [C, Cin], downsample.1.{weight,bias}.  The Python mirror permutes the conv weights back to [C, Cin, kh, kw].
+long long frontend_grad_floats(const avh_config& c, bool has_video, bool has_audio) {
+  const int D = c.encoder_embed_dim;
+  long long n = 0;
+  if (has_audio) n += (long long)D * round_up(c.audio_feat_dim, 64) + D;
+  if (has_video) {
+    n += (long long)D * 512 + D + 64 * 320 + 3 * 64;
+    int cin = 64;
+    for (int L = 0; L < 4; ++L) {
+      const int C = 64 << L;
+      for (int bi = 0; bi < 2; ++bi) {
+        n += (long long)C * 9 * cin + 3 * C + (long long)C * 9 * C + 3 * C;
+        if (L > 0 && bi == 0) n += (long long)C * cin + 2 * C;
+        cin = C;
+      }
+    }
+  }
+  return n;
 }
 
 bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_out) {
@@ -1643,9 +1683,10 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
     if (!sizing) plan->mask_dev = md;
   }
   const bool hm = plan->has_mask;
-  const bool tail = plan->tail;
+  const int tail = plan->tail;
+  const bool full = tail == 2;
   const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
-  const long long GF = enc_grad_floats(c, tail);
+  const long long GF = enc_grad_floats(c, tail, plan->has_video, plan->has_audio);
   float* grads = f32buf(GF);
   float* dy = f32buf(N * D);
   float* dxo = f32buf(N * D);
@@ -1668,15 +1709,162 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   // ================================================================ forward
   float* fused = nullptr;                 // tail: the caller's fused features [N, E] (fp32 copy) and their LayerNorm
   Act fln;
-  if (tail) {
-    // AVHubertModel.extract_finetune after the (frozen) feature extractors: features = layer_norm(fused);
-    // features = post_extract_proj(features) (concat fusion); index_put(padded frames, 0)   (hubert.py:719-727, wav2vec2.py:869)
+  // ---- mode 2: the feature extractors inside the plan, every convolution as explicit patches -> GEMM on dense NHWC maps
+  struct ConvSave {                      // what the backward of one conv + BatchNorm (+ residual) (+ PReLU) needs
+    const ConvUnit* cu = nullptr;
+    Act in, raw, res, out;               // input map, raw conv output, residual added after the BatchNorm, block output
+    int H = 0, Ho = 0, pad = 0;
+    float* stat = nullptr;               // batch mean | rstd
+    const float* slope = nullptr;        // PReLU after (BatchNorm + residual), or null
+  };
+  std::vector<ConvSave> convs;           // forward order: stem, then per block conv1, [downsample], conv2
+  Act feat, arows, act0, p0;
+  const long long nfr = N;               // frames
+  void* colbuf = nullptr;
+  double* bn_sums = nullptr;
+  float *bn_scale = nullptr, *bn_bias = nullptr;
+  const int v_off = c.modality_fuse == AVH_FUSE_CONCAT ? D : 0;
+  const int Fa = c.audio_feat_dim, Fp = round_up(Fa > 0 ? Fa : 64, 64);
+  static const int HSd[5] = {22, 22, 11, 6, 3};
+  if (full) {
     fused = f32buf(N * E);
     fln = new_act(N, E);
-    b.tag = "load_features";
-    b.cur_direct = true;
-    b.push([=](cudaStream_t s) { return launch_load_rows(pl->args.xin, pl->args.xin_dt, fused, nullptr, N, E, s); });
-    b.cur_direct = false;
+    bn_sums = reinterpret_cast<double*>(b.alloc((size_t)BN_SLOTS * 3 * 512 * sizeof(double)));
+    bn_scale = f32buf(512); bn_bias = f32buf(512);
+    if (plan->has_video) {
+      size_t colbytes = (size_t)nfr * 1936 * 320 * P * 2;
+      colbytes = std::max(colbytes, (size_t)nfr * 484 * 576 * P * 2);
+      colbuf = b.alloc(colbytes);
+      auto bn_fwd = [&](ConvSave& cs, long long rows, const float* slope1, const Act* res, const float* slope2, const Act& out) {
+        const ConvUnit* cu = cs.cu;
+        const int Cc = cu->cout;
+        const void* rawp = cs.raw.data; void* outp = out.data;
+        const void* resp = res ? res->data : nullptr;
+        const float *gm = cu->gamma, *bt = cu->beta;
+        float *rm = cu->rmean, *rv = cu->rvar;
+        float* st = f32buf(2 * Cc);
+        cs.stat = st; cs.out = out; cs.slope = slope1 ? slope1 : slope2;
+        if (res) cs.res = *res;
+        b.tag = "bn_train";
+        b.push([=](cudaStream_t s) { return launch_bn_stats(rawp, act_dt, rows, Cc, 0, 0, 0, 0, bn_sums, s); });
+        b.push([=](cudaStream_t s) {
+          return launch_bn_finalize(bn_sums, (double)rows, gm, bt, 1e-5f, pl->bn_momentum, rm, rv, bn_scale, bn_bias, Cc, s);
+        });
+        b.push([=](cudaStream_t s) { return launch_bn_stat_from_affine(bn_scale, bn_bias, gm, bt, Cc, st, s); });
+        b.push([=](cudaStream_t s) {
+          return launch_bn_apply(rawp, outp, act_dt, rows, Cc, bn_scale, bn_bias, slope1, resp, slope2, 0, 0, s);
+        });
+        sync_op(out);
+      };
+      auto conv_fwd = [&](const ConvUnit& cu, const Act& in, int H, int pad, ConvSave* cs) -> bool {
+        const int Ho = (H + 2 * pad - cu.ks) / cu.stride + 1;
+        const int K = cu.ks * cu.ks * cu.cin;
+        const long long rows = nfr * Ho * Ho;
+        cs->cu = &cu; cs->in = in; cs->H = H; cs->Ho = Ho; cs->pad = pad;
+        cs->raw = new_act(rows, cu.cout);
+        const void* xin = in.data;
+        const int planes = P, ks = cu.ks, st = cu.stride, cin = cu.cin;
+        b.tag = "im2col";
+        b.push([=](cudaStream_t s) { return launch_im2col2d(xin, act_dt, nfr, H, cin, ks, st, pad, Ho, colbuf, planes, s); });
+        Epilogue ep;
+        ep.C = cs->raw.data; ep.ldc = cu.cout; ep.c_fp32 = f32 ? 1 : 0;
+        b.tag = "conv_gemm";
+        return b.gemm(colbuf, rows, P * K, cu.w, rows, {Tap{0, 0, 0}}, K / 64, K, ep);
+      };
+      // stem: Conv3d as patches [frames * 1936, 5 * 64] x the packed stem weights
+      {
+        ConvSave cs;
+        cs.cu = &h->stem; cs.H = 88; cs.Ho = 44;
+        const long long rows = nfr * 1936;
+        cs.raw = new_act(rows, 64);
+        const int planes = P;
+        b.tag = "stem_patches";
+        b.cur_direct = true;
+        b.push([=](cudaStream_t s) { return launch_im2col_stem(pl->args.video, pl->args.video_dt, B, T, colbuf, planes, s); });
+        b.cur_direct = false;
+        Epilogue ep;
+        ep.C = cs.raw.data; ep.ldc = 64; ep.c_fp32 = f32 ? 1 : 0;
+        b.tag = "stem_gemm";
+        if (!b.gemm(colbuf, rows, P * 320, h->stem.w, rows, {Tap{0, 0, 0}}, 5, 320, ep)) return false;
+        act0 = new_act(rows, 64);
+        bn_fwd(cs, rows, h->stem.slope, nullptr, nullptr, act0);
+        convs.push_back(cs);
+        p0 = new_act(nfr * 484, 64);
+        const void* a0 = act0.data; void* pp = p0.data;
+        b.tag = "maxpool";
+        b.push([=](cudaStream_t s) { return launch_maxpool_dense(a0, pp, act_dt, nfr, 44, 64, 22, s); });
+        sync_op(p0);
+      }
+      Act cur = p0;
+      int H = 22;
+      for (int L = 0; L < 4; ++L)
+        for (int bi = 0; bi < 2; ++bi) {
+          const BlockW& bw = h->blocks[L][bi];
+          ConvSave c1, c2, cd;
+          if (!conv_fwd(bw.c1, cur, H, 1, &c1)) return false;
+          const int Ho = c1.Ho, Cc = bw.c1.cout;
+          const long long rows = nfr * Ho * Ho;
+          Act a1 = new_act(rows, Cc);
+          bn_fwd(c1, rows, bw.c1.slope, nullptr, nullptr, a1);
+          convs.push_back(c1);
+          Act resid = cur;
+          if (bw.has_ds) {
+            if (!conv_fwd(bw.ds, cur, H, 0, &cd)) return false;
+            Act dso = new_act(rows, Cc);
+            bn_fwd(cd, rows, nullptr, nullptr, nullptr, dso);
+            convs.push_back(cd);
+            resid = dso;
+          }
+          if (!conv_fwd(bw.c2, a1, Ho, 1, &c2)) return false;
+          Act outb = new_act(rows, Cc);
+          bn_fwd(c2, rows, nullptr, &resid, bw.slope2, outb);
+          convs.push_back(c2);
+          cur = outb;
+          H = Ho;
+          (void)HSd;
+        }
+      feat = new_act(N, 512);
+      if (!sizing) plan->stages["resnet"] = {feat.data, {act_dt, N * 512}};
+      {
+        const void* src = cur.data; void* dst = feat.data;
+        b.tag = "avgpool";
+        b.push([=](cudaStream_t s) { return launch_avgpool_dense(src, dst, act_dt, nfr, 9, 512, s); });
+        sync_op(feat);
+      }
+      Epilogue ep;
+      ep.C = fused + v_off; ep.ldc = E; ep.c_fp32 = 1; ep.col_bias = h->proj_v.bias;
+      b.tag = "proj_video";
+      if (!b.gemm(feat.op, N, P * 512, h->proj_v.w, N, {Tap{0, 0, 0}}, 512 / 64, 512, ep)) return false;
+    }
+    if (plan->has_audio) {
+      arows = new_act(N, Fp);
+      void* dst = arows.data;
+      b.tag = "audio_rows";
+      b.cur_direct = true;
+      b.push([=](cudaStream_t s) {
+        return launch_bct_to_rows(pl->args.audio, pl->args.audio_dt, pl->args.as[0], pl->args.as[1], pl->args.as[2], B, Fa, T, dst,
+                                  act_dt, Fp, s);
+      });
+      b.cur_direct = false;
+      sync_op(arows);
+      Epilogue ep;
+      ep.C = fused; ep.ldc = E; ep.c_fp32 = 1; ep.col_bias = h->proj_a.bias;
+      if (c.modality_fuse == AVH_FUSE_ADD && plan->has_video) { ep.R = ep.C; ep.ldr = E; ep.r_fp32 = 1; }
+      b.tag = "proj_audio";
+      if (!b.gemm(arows.op, N, P * Fp, h->proj_a.w, N, {Tap{0, 0, 0}}, Fp / 64, Fp, ep)) return false;
+    }
+  }
+  if (tail) {
+    // AVHubertModel.extract_finetune after the feature extractors: features = layer_norm(fused);
+    // features = post_extract_proj(features) (concat fusion); index_put(padded frames, 0)   (hubert.py:719-727, wav2vec2.py:869)
+    if (!full) {
+      fused = f32buf(N * E);
+      fln = new_act(N, E);
+      b.tag = "load_features";
+      b.cur_direct = true;
+      b.push([=](cudaStream_t s) { return launch_load_rows(pl->args.xin, pl->args.xin_dt, fused, nullptr, N, E, s); });
+      b.cur_direct = false;
+    }
     float* of = f32 ? reinterpret_cast<float*>(fln.data) : nullptr;
     void* ol = f32 ? nullptr : fln.data;
     float* gm = h->fuse_ln_g; float* be = h->fuse_ln_b;
@@ -1952,10 +2140,220 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
       } else {
         dfl = dxo;
       }
-      float* scratch = f32buf(N * E);
+      float* dfused = f32buf(N * E);       // dL/d(fused): used by mode 2, a by-product otherwise
       float* gm = h->fuse_ln_g;
       b.tag = "ln_bwd";
-      b.push([=](cudaStream_t s) { return launch_ln_bwd(fused, gm, dfl, nullptr, scratch, stats, g_ln, g_ln + E, N, E, 1e-5f, s); });
+      b.push([=](cudaStream_t s) { return launch_ln_bwd(fused, gm, dfl, nullptr, dfused, stats, g_ln, g_ln + E, N, E, 1e-5f, s); });
+      if (full) {
+        // ============================================================ backward of the feature extractors (mode 2)
+        float* gf = g_ln + 2ll * E;                         // frontend gradients follow layer_norm.{weight,bias}
+        b.tag = "scale";
+        b.push([=](cudaStream_t s) {                        // GradMultiply on the extractor outputs (grad_multiply.py:105-114)
+          return pl->fgm != 1.f ? launch_scale(dfused, N * E, pl->fgm, s) : 0;
+        });
+        // generic dW [n_out, n_in] (+)= dY^T X over `rows` rows; X either a plain matrix (x_op = false) or an operand-form
+        // matrix [rows, P * n_in] (planes side by side); K = rows is cut into segments the GEMM's K-step table holds
+        long long max_rows = N;
+        long long max_a = (long long)D * ((N + 63) / 64 * 64), max_b = (long long)std::max(Fp, 512) * ((N + 63) / 64 * 64);
+        if (plan->has_video) {
+          max_rows = nfr * 1936;
+          max_a = std::max(max_a, 64ll * ((nfr * 1936 + 63) / 64 * 64));
+          max_b = std::max(max_b, 320ll * ((nfr * 1936 + 63) / 64 * 64));
+          int cin = 64, Hh2 = 22;
+          for (int L = 0; L < 4; ++L) {
+            const int C = 64 << L;
+            const int Ho = L == 0 ? 22 : (Hh2 + 2 - 3) / 2 + 1;
+            const long long kp = (nfr * Ho * Ho + 63) / 64 * 64;
+            max_a = std::max(max_a, (long long)C * kp);
+            max_b = std::max(max_b, (long long)9 * std::max(cin, C) * kp);
+            cin = C; Hh2 = Ho;
+          }
+        }
+        void* ftA = b.alloc((size_t)max_a * P * 2);
+        void* ftB = b.alloc((size_t)max_b * P * 2);
+        auto wgrad_rows = [&](const float* dyv, long long ld_dy, int n_out, const void* xv, int x_dt, long long ld_x, bool x_op,
+                              int n_in, long long rows, float* dW, float* db, const char* tag) -> bool {
+          const long long kp = (rows + 63) / 64 * 64;
+          const int planes = P;
+          b.tag = "transpose";
+          b.push([=](cudaStream_t s) { return launch_transpose_split(dyv, DT_F32, ld_dy, rows, n_out, ftA, planes, kp, 1.0f, s); });
+          if (x_op) {
+            for (int pp = 0; pp < P; ++pp) {
+              const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xv) + (long long)pp * n_in;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ftB) + (long long)pp * kp;
+              b.push([=](cudaStream_t s) {
+                return launch_transpose_split(src, DT_BF16, ld_x, rows, n_in, dst, 1, kp, 1.0f, s, 0, 0, (long long)planes * kp);
+              });
+            }
+          } else {
+            b.push([=](cudaStream_t s) { return launch_transpose_split(xv, x_dt, ld_x, rows, n_in, ftB, planes, kp, 1.0f, s); });
+          }
+          const long long seg = (f32 ? 256 : 768) * 64;
+          for (long long k0 = 0; k0 < kp; k0 += seg) {
+            const long long kl = std::min(seg, kp - k0);
+            PackedW xw;
+            xw.w = reinterpret_cast<bf16*>(ftB) + k0; xw.n = n_in; xw.k = (int)kp; xw.kpad = (int)kp;
+            Epilogue ep;
+            ep.C = dW; ep.ldc = n_in; ep.c_fp32 = 1;
+            if (k0 > 0) { ep.R = dW; ep.ldr = n_in; ep.r_fp32 = 1; }
+            b.tag = tag;
+            const char* a = reinterpret_cast<const char*>(ftA) + (size_t)k0 * 2;
+            if (!b.gemm(a, n_out, (int)(P * kp - k0), xw, n_out, {Tap{0, 0, 0}}, (int)(kl / 64), (int)kp, ep, 0, nullptr, P * kp))
+              return false;
+          }
+          if (db != nullptr) {
+            b.tag = "bias_grad";
+            b.push([=](cudaStream_t s) { return launch_colsum(dyv, DT_F32, ld_dy, rows, n_out, db, 1.0f, s); });
+          }
+          return true;
+        };
+        if (plan->has_audio) {
+          float* g_w = gf; float* g_b = g_w + (long long)D * Fp;
+          gf = g_b + D;
+          if (!wgrad_rows(dfused, E, D, arows.data, act_dt, Fp, false, Fp, N, g_w, g_b, "proj_audio_wgrad")) return false;
+        }
+        if (plan->has_video) {
+          float* g_w = gf; float* g_b = g_w + (long long)D * 512;
+          gf = g_b + D;
+          if (!wgrad_rows(dfused + v_off, E, D, feat.data, act_dt, 512, false, 512, N, g_w, g_b, "proj_video_wgrad")) return false;
+          // d(feat) = d(fused_video) Wv
+          {
+            void* d = dxa.op;
+            const float* src = dfused + v_off;
+            const int planes = P;
+            b.tag = "split";
+            b.push([=](cudaStream_t s) { return launch_split_rows(src, E, d, planes, N, D, 0, 0, s); });
+          }
+          float* dfeat = f32buf(N * 512);
+          if (!dgrad(dxa.op, D, h->proj_vT, dfeat, true, "proj_video_dgrad")) return false;
+          // gradient slots of the ResNet, in forward (state-dict) order
+          float* g_stem_w = gf; float* g_stem_bn = g_stem_w + 64 * 320; float* g_stem_slope = g_stem_bn + 128;
+          gf = g_stem_slope + 64;
+          struct BlockG { float *c1w, *bn1, *s1, *c2w, *bn2, *s2, *dsw, *dsbn; };
+          BlockG bg[4][2];
+          {
+            int cin = 64;
+            for (int L = 0; L < 4; ++L) {
+              const int C = 64 << L;
+              for (int bi = 0; bi < 2; ++bi) {
+                BlockG& g = bg[L][bi];
+                g.c1w = gf; gf += (long long)C * 9 * cin;
+                g.bn1 = gf; gf += 2 * C;
+                g.s1 = gf; gf += C;
+                g.c2w = gf; gf += (long long)C * 9 * C;
+                g.bn2 = gf; gf += 2 * C;
+                g.s2 = gf; gf += C;
+                g.dsw = nullptr; g.dsbn = nullptr;
+                if (L > 0 && bi == 0) { g.dsw = gf; gf += (long long)C * cin; g.dsbn = gf; gf += 2 * C; }
+                cin = C;
+              }
+            }
+          }
+          float* tot = f32buf(3 * 512);
+          size_t dcol_elems = 0, dop_elems = 0;
+          for (const ConvSave& cs : convs) {
+            if (cs.cu == &h->stem) continue;
+            const long long rows = nfr * cs.Ho * cs.Ho;
+            dcol_elems = std::max(dcol_elems, (size_t)rows * cs.cu->ks * cs.cu->ks * cs.cu->cin);
+            dop_elems = std::max(dop_elems, (size_t)rows * cs.cu->cout);
+          }
+          float* dcol = f32buf((long long)dcol_elems);
+          void* dop = b.alloc(dop_elems * P * 2);
+          // BatchNorm (+ residual) (+ PReLU) backward of one saved conv: dz -> d_raw (returned), d_res, parameter gradients
+          auto bn_bwd = [&](const ConvSave& cs, const float* dz, float* d_res, int res_acc, float* g_bn, float* g_slope) {
+            const long long rows = nfr * cs.Ho * cs.Ho;
+            const int Cc = cs.cu->cout;
+            float* d_raw = f32buf(rows * Cc);
+            const void* rawp = cs.raw.data;
+            const void* resp = cs.res.data;
+            const float* st = cs.stat; const float* gm = cs.cu->gamma; const float* bt = cs.cu->beta; const float* sl = cs.slope;
+            b.tag = "bn_bwd";
+            b.push([=](cudaStream_t s) {
+              return launch_bn_act_bwd(rawp, act_dt, resp, dz, st, gm, bt, sl, rows, Cc, bn_sums, tot, d_raw, d_res, res_acc,
+                                       g_bn, g_bn + Cc, g_slope, s);
+            });
+            return d_raw;
+          };
+          // conv backward: dW = d_raw^T col(x); dx (+)= col2im(d_raw W)
+          auto conv_bwd = [&](const ConvSave& cs, const float* d_raw, float* dW, float* dx, int dx_acc) -> bool {
+            const ConvUnit& cu = *cs.cu;
+            const int K = cu.ks * cu.ks * cu.cin, Cc = cu.cout;
+            const long long rows = nfr * cs.Ho * cs.Ho;
+            const void* xin = cs.in.data;
+            const int planes = P, ks = cu.ks, st = cu.stride, cin = cu.cin, H = cs.H, Ho = cs.Ho, pad = cs.pad;
+            b.tag = "im2col";
+            b.push([=](cudaStream_t s) { return launch_im2col2d(xin, act_dt, nfr, H, cin, ks, st, pad, Ho, colbuf, planes, s); });
+            if (!wgrad_rows(d_raw, Cc, Cc, colbuf, DT_BF16, (long long)P * K, true, K, rows, dW, nullptr, "conv_wgrad")) return false;
+            if (dx == nullptr) return true;
+            b.tag = "split";
+            b.push([=](cudaStream_t s) { return launch_split_rows(d_raw, Cc, dop, planes, rows, Cc, 0, 0, s); });
+            Epilogue ep;
+            ep.C = dcol; ep.ldc = K; ep.c_fp32 = 1;
+            b.tag = "conv_dgrad";
+            if (!b.gemm(dop, rows, P * Cc, cu.wT, rows, {Tap{0, 0, 0}}, cu.wT.kpad / 64, Cc, ep)) return false;
+            b.tag = "col2im";
+            b.push([=](cudaStream_t s) { return launch_col2im2d(dcol, DT_F32, nfr, H, cin, ks, st, pad, Ho, dx, dx_acc, s); });
+            return true;
+          };
+          // avgpool
+          float* dcur = f32buf(nfr * 9 * 512);
+          b.tag = "avgpool_bwd";
+          {
+            float* dc4 = dcur;
+            b.push([=](cudaStream_t s) { return launch_avgpool_bwd(dfeat, dc4, nfr, 9, 512, s); });
+          }
+          // blocks in reverse; convs = [stem, (c1, [ds], c2) x 8]
+          int ci = (int)convs.size() - 1;
+          for (int L = 3; L >= 0; --L)
+            for (int bi = 1; bi >= 0; --bi) {
+              const BlockW& bw = h->blocks[L][bi];
+              const BlockG& g = bg[L][bi];
+              const ConvSave& c2 = convs[ci];
+              const ConvSave* cd = bw.has_ds ? &convs[ci - 1] : nullptr;
+              const ConvSave& c1 = convs[ci - (bw.has_ds ? 2 : 1)];
+              ci -= bw.has_ds ? 3 : 2;
+              const long long rows_out = nfr * c2.Ho * c2.Ho;
+              const long long rows_in = nfr * c1.H * c1.H;
+              float* d_res = f32buf(rows_out * c2.cu->cout);
+              float* d_raw2 = bn_bwd(c2, dcur, d_res, 0, g.bn2, g.s2);
+              float* d_a1 = f32buf(rows_out * c2.cu->cin);
+              if (!conv_bwd(c2, d_raw2, g.c2w, d_a1, 0)) return false;
+              float* d_raw1 = bn_bwd(c1, d_a1, nullptr, 0, g.bn1, g.s1);
+              float* d_in = f32buf(rows_in * c1.cu->cin);
+              if (!sizing && L == 3 && bi == 1) {      // gradient maps of the last block, for the kink-attribution test
+                plan->stages["grad_layer4_1_conv2_in"] = {d_a1, {DT_F32, rows_out * 512}};
+                plan->stages["grad_layer4_1_conv1_out"] = {d_raw1, {DT_F32, rows_out * 512}};
+              }
+              if (!conv_bwd(c1, d_raw1, g.c1w, d_in, 0)) return false;
+              if (cd != nullptr) {
+                float* d_rawd = bn_bwd(*cd, d_res, nullptr, 0, g.dsbn, nullptr);
+                if (!conv_bwd(*cd, d_rawd, g.dsw, d_in, 1)) return false;
+              } else {
+                const long long n_el = rows_in * c1.cu->cin;
+                b.tag = "add";
+                b.push([=](cudaStream_t s) { return launch_add_f32(d_in, d_res, n_el, s); });
+              }
+              dcur = d_in;
+            }
+          // max-pool, stem BatchNorm + PReLU, stem weights
+          {
+            const ConvSave& cs = convs[0];
+            float* d_act0 = f32buf(nfr * 1936 * 64);
+            const void* a0 = act0.data;
+            float* dp0 = dcur;
+            b.tag = "maxpool_bwd";
+            b.push([=](cudaStream_t s) { return launch_maxpool_bwd(a0, act_dt, dp0, d_act0, nfr, 44, 64, 22, s); });
+            float* d_raw0 = bn_bwd(cs, d_act0, nullptr, 0, g_stem_bn, g_stem_slope);
+            const int planes = P;
+            b.tag = "stem_patches";
+            b.cur_direct = true;
+            b.push([=](cudaStream_t s) { return launch_im2col_stem(pl->args.video, pl->args.video_dt, B, T, colbuf, planes, s); });
+            b.cur_direct = false;
+            if (!wgrad_rows(d_raw0, 64, 64, colbuf, DT_BF16, (long long)P * 320, true, 320, nfr * 1936, g_stem_w, nullptr, "stem_wgrad"))
+              return false;
+          }
+        }
+      }
     }
   }
   if (bytes_out) *bytes_out = b.sizer.used;
@@ -2117,10 +2515,10 @@ bool build_qformer_plan(avh_handle* h, Plan* plan, bool sizing, size_t* bytes_ou
 
 Plan* get_plan(avh_handle* h, int B, int T, bool has_video, bool has_audio, bool has_mask, int output_layer,
                cudaStream_t stream, long long ragged_rows = 0, bool enc_only = false, bool train = false, int qf_lk = 0,
-               bool enc_train = false, bool tail = false) {
+               bool enc_train = false, int tail = 0) {
   const std::string key = (ragged_rows > 0 ? "r" + std::to_string(ragged_rows) + ":" : std::string()) + (enc_only ? "e:" : "") +
                           (train ? "t:" : "") + (qf_lk > 0 ? "q" + std::to_string(qf_lk) + ":" : std::string()) +
-                          (enc_train ? (tail ? "gt:" : "g:") : "") +
+                          (enc_train ? (tail == 2 ? "gf:" : (tail ? "gt:" : "g:")) : "") +
                           std::to_string(B) + "x" + std::to_string(T) + (has_video ? "v" : "-") +
                           (has_audio ? "a" : "-") + (has_mask ? "m" : "-") + std::to_string(output_layer) + "@" +
                           std::to_string(reinterpret_cast<uintptr_t>(stream));
@@ -2673,6 +3071,48 @@ int avh_tail_train_forward(avh_handle* h, const void* fused, int dtype, const ui
 int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T, void* out,
                               int out_dtype, void* stream) {
   return encoder_train_forward(h, x, x_dtype, padding_mask, B, T, out, out_dtype, stream, false);
+}
+
+int avh_full_grad_count(avh_handle* h, int has_video, int has_audio, int64_t* n_floats) {
+  AVH_CHECK(h != nullptr && n_floats != nullptr, "null argument");
+  AVH_CHECK(h->cfg.reserved[0] == 0, "the full training step belongs to an AV-HuBERT handle");
+  *n_floats = avh::enc_grad_floats(h->cfg, 2, has_video != 0, has_audio != 0);
+  return 0;
+}
+
+int avh_full_train_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,
+                           const int64_t* audio_strides, const uint8_t* padding_mask, int B, int T, float feature_grad_mult,
+                           float bn_momentum, void* out, int out_dtype, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights)");
+  AVH_CHECK(h->cfg.reserved[0] == 0, "the full training step belongs to an AV-HuBERT handle");
+  AVH_CHECK(h->cfg.reserved[3] != 0, "handle not created as trainable (avh_config.reserved[3] = 1)");
+  AVH_CHECK(video != nullptr || audio != nullptr, "both modalities are None");
+  AVH_CHECK(out != nullptr, "null argument");
+  AVH_CHECK(video == nullptr || video_dtype == AVH_F32 || video_dtype == AVH_F16 || video_dtype == AVH_BF16,
+            "the training step takes normalised float video");
+  AVH_CHECK(audio == nullptr || audio_strides != nullptr, "audio strides required");
+  AVH_CHECK(B >= 1 && T >= 1 && (long long)B * T < (1ll << 20), "bad batch");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  avh::Plan* p = avh::get_plan(h, B, T, video != nullptr, audio != nullptr, padding_mask != nullptr, 0, s, 0, false, false, 0,
+                               true, 2);
+  if (p == nullptr) return 1;
+  h->last_plan = p;
+  p->args = avh::CallArgs();
+  p->args.video = video; p->args.video_dt = video_dtype;
+  p->args.audio = audio; p->args.audio_dt = audio_dtype;
+  if (audio) for (int i = 0; i < 3; ++i) p->args.as[i] = audio_strides[i];
+  p->args.mask = padding_mask;
+  p->args.out = out; p->args.out_dt = out_dtype;
+  p->bn_momentum = bn_momentum;
+  p->fgm = feature_grad_mult;
+  if (padding_mask != nullptr)
+    AVH_CUDA_OK(cudaMemcpyAsync(p->mask_dev, padding_mask, (size_t)B * T, cudaMemcpyDeviceToDevice, s));
+  p->fwd_done = false;
+  if (run_steps(h, p, 0, p->fwd_steps, s)) return 1;
+  p->fwd_done = true;
+  return 0;
 }
 
 static int encoder_train_forward(avh_handle* h, const void* x, int x_dtype, const uint8_t* padding_mask, int B, int T, void* out,

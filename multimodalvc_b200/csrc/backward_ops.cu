@@ -33,7 +33,7 @@ __device__ __forceinline__ void stb(void* out, int dt, long long i, float v) {
 // (plane 0 = bf16 round, plane 1 = bf16 of the remainder); columns r in [rows, kpad) are zero.  32 x 32 tiles through smem.
 __global__ void __launch_bounds__(256)
 transpose_split_kernel(const void* __restrict__ in, int dt, long long ld, long long rows, int C, __nv_bfloat16* __restrict__ out,
-                       int planes, long long kpad, float scale, int T, int Tp) {
+                       int planes, long long kpad, float scale, int T, int Tp, long long out_ld) {
   __shared__ float tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;      // OUTPUT column (= K index) of the tile
   const int c0 = blockIdx.y * 32;
@@ -58,8 +58,8 @@ transpose_split_kernel(const void* __restrict__ in, int dt, long long ld, long l
     if (c >= C || r >= kpad) continue;
     const float v = tile[i][j];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    out[(long long)c * planes * kpad + r] = hi;
-    if (planes > 1) out[(long long)c * planes * kpad + kpad + r] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    out[(long long)c * out_ld + r] = hi;
+    if (planes > 1) out[(long long)c * out_ld + kpad + r] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
@@ -418,13 +418,13 @@ int launch_posconv_weightnorm_bwd(const float* dw, const float* v, const float* 
 }
 
 int launch_transpose_split(const void* in, int dt, long long ld, long long rows, int C, void* out, int planes, long long kpad,
-                           float scale, cudaStream_t stream, int T, int Tp) {
+                           float scale, cudaStream_t stream, int T, int Tp, long long out_ld) {
   AVH_CHECK(kpad % 64 == 0 && (T > 0 ? kpad >= rows / T * Tp : kpad >= rows),
             "transpose_split: K padding must cover the rows and be a multiple of 64");
   if (C <= 0) return 0;
   dim3 grid((unsigned)((kpad + 31) / 32), (unsigned)((C + 31) / 32));
   transpose_split_kernel<<<grid, 256, 0, stream>>>(in, dt, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), planes, kpad, scale,
-                                                   T, Tp);
+                                                   T, Tp, out_ld > 0 ? out_ld : (long long)planes * kpad);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

@@ -108,7 +108,8 @@ int launch_rows_broadcast(const float* src, float* dst, long long per_clip, int 
 // in [rows, C] -> bf16 [C, planes * kpad] (transposed GEMM operand over K = rows, zero padded), values times `scale`
 // T > 0: K index (b * Tp + t) holds input row b * T + t, the gaps t in [T, Tp) are zeros (the positional conv's layout)
 int launch_transpose_split(const void* in, int dt, long long ld, long long rows, int C, void* out, int planes, long long kpad,
-                           float scale, cudaStream_t stream, int T = 0, int Tp = 0);
+                           float scale, cudaStream_t stream, int T = 0, int Tp = 0, long long out_ld = 0);      // out_ld: row stride
+                                                                                    // of `out` when it differs from planes * kpad
 int launch_scale(float* p, long long n, float s, cudaStream_t stream);
 // positional-conv weight gradient helpers: shifted copies of the transposed input for one group; weight-norm backward
 int launch_posconv_shift(const void* XT, void* XS, int g, int cg, int KT, int planes, long long kp, cudaStream_t stream);
@@ -127,6 +128,26 @@ int launch_attention_bwd(const void* Q, long long ldq, const void* K, long long 
                          const void* dO, const void* O, long long ldo, int o_dt, const float* lse, const unsigned char* key_pad,
                          void* dQ, void* dK, void* dV, long long ldd, int d_dt, float* Dbuf, int B, int H, int L,
                          cudaStream_t stream);
+
+// ---- training step of the lip ResNet on dense NHWC maps (frontend_train.cu)
+int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int planes, cudaStream_t stream);
+int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* col, int planes,
+                    cudaStream_t stream);
+int launch_col2im2d(const void* dcol, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, float* dx,
+                    int accumulate, cudaStream_t stream);
+int launch_maxpool_dense(const void* x, void* y, int dt, long long n, int H, int C, int Ho, cudaStream_t stream);
+int launch_maxpool_bwd(const void* x, int dt, const float* dy, float* dx, long long n, int H, int C, int Ho, cudaStream_t stream);
+int launch_avgpool_dense(const void* x, void* y, int dt, long long n, int HW, int C, cudaStream_t stream);
+int launch_avgpool_bwd(const float* dy, float* dx, long long n, int HW, int C, cudaStream_t stream);
+// stat [2*C] = batch mean, rstd recovered from bn_finalize's (scale, bias)
+int launch_bn_stat_from_affine(const float* scale, const float* bias, const float* gamma, const float* beta, int C, float* stat,
+                               cudaStream_t stream);
+// BatchNorm(batch stats) [+ residual] [+ PReLU] backward on [rows, C]: d_raw, d_res (optional, = or +=), dgamma, dbeta, dslope;
+// sums = BN_SLOTS x 3 x C doubles (zero before the first use), tot = 3 x C floats scratch
+int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz, const float* stat, const float* gamma,
+                      const float* beta, const float* slope, long long rows, int C, double* sums, float* tot, float* d_raw,
+                      float* d_res, int res_accumulate, float* dgamma, float* dbeta, float* dslope, cudaStream_t stream);
+int launch_add_f32(float* a, const float* b, long long n, cudaStream_t stream);
 
 // ---- audio frontend ---------------------------------------------------------------------------------
 struct FbankArgs {

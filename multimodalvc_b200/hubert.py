@@ -244,6 +244,63 @@ class _TailTrainFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+class _FullTrainFn(torch.autograd.Function):
+    """The whole fine-tuning step (feature_grad_mult > 0): lip ResNet + projections + fusion + encoder with the library's
+    forward (activations saved in the plan) and backward; `spec` = [(buffer shape, to_param)] describes how the flat
+    gradient buffer maps onto the parameters that follow."""
+
+    @staticmethod
+    def forward(ctx, model, video, audio, pm_u8, fgm, spec, *params):
+        handle = model._ensure_handle()
+        ref = video if video is not None else audio
+        dev = ref.device
+        B, T = (video.size(0), video.size(2)) if video is not None else (audio.size(0), audio.size(2))
+        out_dtype = model.encoder.layer_norm.weight.dtype
+        if out_dtype not in _DTYPES:
+            out_dtype = torch.float32
+        out = torch.empty(B, T, model.encoder_embed_dim, device=dev, dtype=out_dtype)
+        strides = (ctypes.c_int64 * 3)(*audio.stride()) if audio is not None else None
+        vp = ctypes.c_void_p
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().avh_full_train_forward(
+                handle, vp(video.data_ptr()) if video is not None else None, _DTYPES[video.dtype] if video is not None else 0,
+                vp(audio.data_ptr()) if audio is not None else None, _DTYPES[audio.dtype] if audio is not None else 0, strides,
+                vp(pm_u8.data_ptr()) if pm_u8 is not None else None, B, T, float(fgm), 0.1, vp(out.data_ptr()),
+                _DTYPES[out_dtype], vp(stream)))
+        ctx.handle, ctx.stream, ctx.spec = handle, stream, spec
+        ctx.flags = (int(video is not None), int(audio is not None))
+        ctx.keep = (video, audio)                      # the backward re-reads the frames (stem patches are recomputed)
+        ctx.dtypes = [p.dtype for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dev = dout.device
+        dout = dout.contiguous()
+        if dout.dtype not in _DTYPES:
+            dout = dout.float()
+        lib = _lib.load()
+        n = ctypes.c_int64()
+        _lib.check(lib.avh_full_grad_count(ctx.handle, ctx.flags[0], ctx.flags[1], ctypes.byref(n)))
+        flat = torch.empty(n.value, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if stream != ctx.stream:
+                raise RuntimeError("the backward must run on the CUDA stream of its forward")
+            _lib.check(lib.avh_encoder_backward(ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], None, 0,
+                                                ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+        grads, off = [], 0
+        for (shape, to_param), dt in zip(ctx.spec, ctx.dtypes):
+            k = 1
+            for d in shape:
+                k *= d
+            grads.append(to_param(flat[off:off + k].view(shape)).to(dt))
+            off += k
+        assert off == n.value, (off, n.value)
+        return (None, None, None, None, None, None, *grads)
+
+
 class AVHubertModel(nn.Module):
     """Drop-in for the reference ``AVHubertModel`` on the ``extract_finetune`` path."""
 
@@ -515,14 +572,83 @@ class AVHubertModel(nn.Module):
         out += [self.layer_norm.weight, self.layer_norm.bias]
         return out
 
+    def full_parameters(self, has_video, has_audio):
+        """(parameters, spec) of the whole training step in the order avh_encoder_backward writes their gradients; spec =
+        (shape of the gradient inside the flat buffer, map onto the parameter's own layout)."""
+        same = lambda g: g
+        params = self.tail_parameters()
+        spec = [(tuple(p.shape), same) for p in params]
+        D = self.encoder_embed_dim
+        if has_audio:
+            lin = self.feature_extractor_audio.proj
+            Fa = lin.in_features
+            Fp = (Fa + 63) // 64 * 64
+            params += [lin.weight, lin.bias]
+            spec += [((D, Fp), lambda g, Fa=Fa: g[:, :Fa]), ((D,), same)]
+        if has_video:
+            fe = self.feature_extractor_video
+            params += [fe.proj.weight, fe.proj.bias]
+            spec += [((D, 512), same), ((D,), same)]
+            st = fe.resnet.frontend3D
+            params += [st[0].weight, st[1].weight, st[1].bias, st[2].weight]
+            spec += [((64, 5, 64), lambda g: g[:, :, :49].reshape(64, 1, 5, 7, 7)), ((64,), same), ((64,), same), ((64,), same)]
+            cin = 64
+            for i in range(1, 5):
+                C = 64 << (i - 1)
+                for blk in getattr(fe.resnet.trunk, f"layer{i}"):
+                    params += [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.relu1.weight,
+                               blk.conv2.weight, blk.bn2.weight, blk.bn2.bias, blk.relu2.weight]
+                    spec += [((C, 3, 3, cin), lambda g: g.permute(0, 3, 1, 2)), ((C,), same), ((C,), same), ((C,), same),
+                             ((C, 3, 3, C), lambda g: g.permute(0, 3, 1, 2)), ((C,), same), ((C,), same), ((C,), same)]
+                    if blk.downsample is not None:
+                        params += [blk.downsample[0].weight, blk.downsample[1].weight, blk.downsample[1].bias]
+                        spec += [((C, cin), lambda g, C=C, cin=cin: g.reshape(C, cin, 1, 1)), ((C,), same), ((C,), same)]
+                    cin = C
+        return params, spec
+
+    def _extract_finetune_full(self, source, padding_mask, mask):
+        """The whole model differentiable (feature_grad_mult > 0, hubert.py:538-547 with GradMultiply): SURVEY row A18 /
+        BASELINE config 5 as stated."""
+        c = self.cfg
+        if mask and c.masking_type == "input":
+            with torch.no_grad():
+                v, _ = self.apply_input_mask(source["video"], padding_mask, None)
+                a, _ = self.apply_input_mask(source["audio"], padding_mask, None)
+            source = {"audio": a, "video": v}
+        if self._param_versions != [p._version for p in self.parameters()]:
+            self._dirty = True
+        handle = self._ensure_handle()
+        self._param_versions = [p._version for p in self.parameters()]
+        dev = self.encoder.layer_norm.weight.device
+        video, video_dt, audio, pm_u8, pm, B, T = self._check_inputs(handle, source["video"], source["audio"], padding_mask, dev)
+        if video is not None and video_dt == _U8:
+            raise NotImplementedError("the training step takes normalised float video")
+        params, spec = self.full_parameters(video is not None, audio is not None)
+        y = _FullTrainFn.apply(self, video, audio, pm_u8, float(c.feature_grad_mult), spec, *params)
+        if video is not None:          # running statistics of the training-mode BatchNorms back into the module's buffers
+            with torch.no_grad():
+                lib = _lib.load()
+                n = ctypes.c_int64()
+                _lib.check(lib.avh_bn_stats_count(handle, ctypes.byref(n)))
+                flat = torch.empty(n.value, device=dev, dtype=torch.float32)
+                with torch.cuda.device(dev):
+                    stream = torch.cuda.current_stream(dev).cuda_stream
+                    _lib.check(lib.avh_read_bn_stats(handle, ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+                off = 0
+                for bn in self._bn_modules():
+                    C = bn.num_features
+                    bn.running_mean.copy_(flat[off:off + C])
+                    bn.running_var.copy_(flat[off + C:off + 2 * C])
+                    bn.num_batches_tracked += 1
+                    off += 2 * C
+                self._eval_stale = True
+        return y, pm
+
     def _extract_finetune_trainable(self, source, padding_mask, mask, output_layer):
         """Fine-tuning step with frozen feature extractors (feature_grad_mult <= 0: the reference runs them under
         no_grad, hubert.py:538-547).  Extractors + fusion run as in the training-mode forward (batch-statistics
         BatchNorm), the fused features feed the differentiable tail: layer_norm -> post_extract_proj -> encoder."""
         c = self.cfg
-        if c.feature_grad_mult > 0:
-            raise NotImplementedError("feature_grad_mult > 0 needs the backward of the lip ResNet / modality projections, "
-                                      "which is not built; set feature_grad_mult = 0 (frozen feature extractors)")
         if output_layer is not None:
             raise NotImplementedError("the training step runs the whole encoder (output_layer=None)")
         if not c.layer_norm_first:
@@ -530,6 +656,8 @@ class AVHubertModel(nn.Module):
         for name in ("dropout_input", "dropout", "activation_dropout", "attention_dropout", "encoder_layerdrop"):
             if float(getattr(c, name)) != 0.0:
                 raise NotImplementedError(f"{name} must be 0 for the device training step (BASELINE config 5)")
+        if c.feature_grad_mult > 0:
+            return self._extract_finetune_full(source, padding_mask, mask)
         if self._param_versions != [p._version for p in self.parameters()]:
             self._dirty = True                                   # an optimizer step changed the weights: re-pack
         with torch.no_grad():
