@@ -563,58 +563,72 @@ def main():
         cfg4 = {"ms": d0.elapsed_time(d1)}
         del subs4
 
-    # ---- BASELINE config 5 (the part of it that is built): Large, B = 8 clips x 150 frames per GPU, bf16, dropout /
-    #      LayerDrop 0, loss = mean(x^2); forward + backward + gradient all-reduce per step.  The feature extractors are
-    #      FROZEN (feature_grad_mult = 0, the reference then runs them under no_grad): the lip-ResNet backward is not built.
+    # ---- BASELINE config 5: Large, B = 8 clips x 150 frames per GPU, bf16, dropout / LayerDrop 0, loss = mean(x^2);
+    #      forward + backward + gradient all-reduce per step.  Two forms: the whole model differentiable
+    #      (feature_grad_mult = 0.1: lip ResNet, projections, encoder) and the frozen-extractor form (feature_grad_mult = 0,
+    #      the reference then runs the extractors under no_grad).
     cfg5 = None
+    cfg5_frozen = None
     if args.config5_steps > 0:
         from multimodalvc_b200.distributed import GradientAllReducer
-        m5 = AVHubertModel(AVHubertConfig.named("large", feature_grad_mult=0.0, trainable=True, dropout=0.0,
-                                                attention_dropout=0.0, activation_dropout=0.0, encoder_layerdrop=0.0,
-                                                dropout_input=0.0))
-        m5.remove_pretraining_modules()
-        m5 = m5.to(dev, torch.bfloat16).train()
-        tail = m5.tail_parameters()
-        reducer = GradientAllReducer(tail) if world > 1 else None
         g5 = torch.Generator().manual_seed(500 + rank)
         v5 = torch.randn(8, 1, T_FRAMES, 88, 88, generator=g5).to(dev, torch.bfloat16)
         a5 = torch.randn(8, 104, T_FRAMES, generator=g5).to(dev, torch.bfloat16)
 
-        def step5():
-            y5, _ = m5.extract_finetune({"audio": a5, "video": v5}, None)
-            loss = y5.float().pow(2).mean()
-            loss.backward()
-            if reducer is not None:
-                reducer.all_reduce_grads()
-            return loss
+        def config5_leg(fgm):
+            m5 = AVHubertModel(AVHubertConfig.named("large", feature_grad_mult=fgm, trainable=True, dropout=0.0,
+                                                    attention_dropout=0.0, activation_dropout=0.0, encoder_layerdrop=0.0,
+                                                    dropout_input=0.0))
+            m5.remove_pretraining_modules()
+            m5 = m5.to(dev, torch.bfloat16).train()
+            params = m5.full_parameters(True, True)[0] if fgm > 0 else m5.tail_parameters()
+            reducer = GradientAllReducer(params) if world > 1 else None
 
-        for _ in range(2):
-            step5()
-            for p5 in tail:
-                p5.grad = None
-        torch.cuda.synchronize(dev)
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(args.config5_steps):
-            loss5 = step5()
-            for p5 in tail:
-                p5.grad = None
-        t1.record()
-        torch.cuda.synchronize(dev)
-        barrier()
-        cfg5 = {"ms": t0.elapsed_time(t1), "loss": float(loss5.item()),
-                "grad_elements": int(sum(p5.numel() for p5 in tail))}
-        del m5, reducer, tail
-        torch.cuda.empty_cache()
+            def step5():
+                y5, _ = m5.extract_finetune({"audio": a5, "video": v5}, None)
+                loss = y5.float().pow(2).mean()
+                loss.backward()
+                if reducer is not None:
+                    reducer.all_reduce_grads()
+                return loss
+
+            for _ in range(2):
+                step5()
+                for p5 in params:
+                    p5.grad = None
+            torch.cuda.synchronize(dev)
+            barrier()
+            _lib.reset_launch_count()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(args.config5_steps):
+                loss5 = step5()
+                for p5 in params:
+                    p5.grad = None
+            t1.record()
+            torch.cuda.synchronize(dev)
+            barrier()
+            out = {"ms": t0.elapsed_time(t1), "loss": float(loss5.item()),
+                   "grad_elements": int(sum(p5.numel() for p5 in params)),
+                   "launches_per_step": int(_lib.launch_count()) // args.config5_steps,
+                   "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+            del m5, reducer, params
+            torch.cuda.empty_cache()
+            return out
+
+        cfg5 = config5_leg(0.1)
+        cfg5_frozen = config5_leg(0.0)
 
     # ---- max over ranks
     ms_sus = sustained[1] if sustained else 0.0
     if world > 1:
         t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, cfg3["ms"] if cfg3 else 0.0,
-                          cfg5["ms"] if cfg5 else 0.0, cfg4["ms"] if cfg4 else 0.0], device=dev, dtype=torch.float64)
+                          cfg5["ms"] if cfg5 else 0.0, cfg4["ms"] if cfg4 else 0.0,
+                          cfg5_frozen["ms"] if cfg5_frozen else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3, ms_c5, ms_c4 = t.tolist()
+        ms, ms_e2e, ms_e2e_u8, ms_e2e_raw, ms_sus, ms_c3, ms_c5, ms_c4, ms_c5f = t.tolist()
+        if cfg5_frozen:
+            cfg5_frozen["ms"] = ms_c5f
         if cfg4:
             cfg4["ms"] = ms_c4
         if cfg3:
@@ -766,15 +780,23 @@ def main():
         if cfg5:
             sec5 = cfg5["ms"] * 1e-3 / args.config5_steps
             line["config5"] = {
-                "workload": "BASELINE config 5, frozen-extractor form: AV-HuBERT Large fine-tuning step, 8 clips x 150 frames "
-                            "per GPU, bf16, dropout / LayerDrop 0, loss = mean(x^2); forward (training-mode extractors with "
-                            "batch-statistics BatchNorm, then LayerNorm + post_extract_proj + 24 encoder layers with saved "
-                            "activations) + backward of that tail + bucketed gradient all-reduce (NCCL) at N > 1",
+                "workload": "BASELINE config 5: AV-HuBERT Large fine-tuning step with the whole model differentiable "
+                            "(feature_grad_mult = 0.1), 8 clips x 150 frames per GPU, bf16, dropout / LayerDrop 0, loss = "
+                            "mean(x^2); forward (lip ResNet as patch GEMMs with batch-statistics BatchNorm, projections, "
+                            "fusion LayerNorm, post_extract_proj, 24 encoder layers, activations saved) + backward of all of "
+                            "it + bucketed gradient all-reduce (NCCL) at N > 1",
                 "clips_per_s": world * 8 / sec5, "ms_per_step": sec5 * 1e3, "steps": args.config5_steps,
                 "grad_elements": cfg5["grad_elements"], "loss": cfg5["loss"],
-                "not_included": "backward of the lip ResNet / modality projections (feature_grad_mult = 0 freezes them, as "
-                                "the reference does under no_grad); optimizer step (weights are re-packed on the host after "
-                                "an update)"}
+                "launches_per_step": cfg5["launches_per_step"], "peak_mem_gb": cfg5["peak_mem_gb"],
+                "not_included": "optimizer step (weights are re-packed on the host after an update)"}
+        if cfg5_frozen:
+            sec5 = cfg5_frozen["ms"] * 1e-3 / args.config5_steps
+            line["config5_frozen"] = {
+                "workload": "config 5 with the feature extractors frozen (feature_grad_mult = 0, reference: no_grad): "
+                            "training-mode extractor forward, backward of fusion LayerNorm + post_extract_proj + encoder",
+                "clips_per_s": world * 8 / sec5, "ms_per_step": sec5 * 1e3, "steps": args.config5_steps,
+                "grad_elements": cfg5_frozen["grad_elements"], "loss": cfg5_frozen["loss"],
+                "launches_per_step": cfg5_frozen["launches_per_step"]}
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"classes": prof, "total_ms": total_prof_ms}, f, indent=1, sort_keys=True)

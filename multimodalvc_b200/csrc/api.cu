@@ -777,6 +777,8 @@ struct Builder {
   Sizer sizer;
   int P;
   bool f32;      // fp32-faithful mode
+  bool linear_k = false;         // next gemm(): plain K loop without a step table (bf16 mode, single zero tap)
+  int force_sk = 0;              // next gemm(): GemmProblem::streamk
   float* sk_ws = nullptr;        // stream-K workspace of the plan's GEMMs (launches of a plan are serialised on its stream)
   size_t sk_bytes = 0;
   int* sk_flags = nullptr;
@@ -820,7 +822,13 @@ struct Builder {
     pr.A = A; pr.a_rows = a_rows; pr.a_cols = a_cols; pr.lda = lda > 0 ? lda : a_cols;
     pr.B = W.w; pr.b_rows = W.n; pr.b_cols = P * W.kpad; pr.ldb = (long long)P * W.kpad;
     pr.M = M; pr.N = W.n;
-    pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
+    if (linear_k && !f32 && taps.size() == 1 && taps[0].a_col == 0 && taps[0].a_row_off == 0 && taps[0].b_col == 0) {
+      pr.ktable = nullptr;          // K step kb reads columns 64 kb of both operands: no table, no limit on the K extent
+      pr.num_kb = chunks;
+    } else {
+      pr.ktable = ktable(taps, chunks, a_plane_stride, W.kpad, &pr.num_kb);
+    }
+    pr.streamk = force_sk;
     pr.a_col_nblk = a_col_nblk;
     pr.block_n = block_n;
     pr.sk_ws = sk_ws; pr.sk_ws_bytes = sk_bytes; pr.sk_flags = sk_flags;
@@ -1685,6 +1693,13 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   const bool hm = plan->has_mask;
   const int tail = plan->tail;
   const bool full = tail == 2;
+  if (full && !f32) {
+    // stream-K workspace for the weight-gradient GEMMs of the lip ResNet (a handful of output tiles, K = pixels): one
+    // fp32 partial tile per SM + flags (zero from the arena's initial fill; the kernels hand the flags back as zeros)
+    b.sk_bytes = (size_t)device_sm_count() * 128 * 256 * 4;
+    b.sk_ws = reinterpret_cast<float*>(b.alloc(b.sk_bytes));
+    b.sk_flags = reinterpret_cast<int*>(b.alloc(4096));
+  }
   const int E = c.modality_fuse == AVH_FUSE_CONCAT ? 2 * D : D;
   const long long GF = enc_grad_floats(c, tail, plan->has_video, plan->has_audio);
   float* grads = f32buf(GF);
@@ -1721,6 +1736,8 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   Act feat, arows, act0, p0;
   const long long nfr = N;               // frames
   void* colbuf = nullptr;
+  void* stemcol = nullptr;
+  unsigned char* pool_arg = nullptr;     // bf16 mode: window position of every max-pool maximum
   double* bn_sums = nullptr;
   float *bn_scale = nullptr, *bn_bias = nullptr;
   const int v_off = c.modality_fuse == AVH_FUSE_CONCAT ? D : 0;
@@ -1732,9 +1749,9 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
     bn_sums = reinterpret_cast<double*>(b.alloc((size_t)BN_SLOTS * 3 * 512 * sizeof(double)));
     bn_scale = f32buf(512); bn_bias = f32buf(512);
     if (plan->has_video) {
-      size_t colbytes = (size_t)nfr * 1936 * 320 * P * 2;
-      colbytes = std::max(colbytes, (size_t)nfr * 484 * 576 * P * 2);
-      colbuf = b.alloc(colbytes);
+      colbuf = b.alloc((size_t)nfr * 484 * 576 * P * 2);
+      stemcol = b.alloc((size_t)nfr * 1936 * 320 * P * 2);      // stem patches: kept for the weight gradient
+      if (!f32) pool_arg = reinterpret_cast<unsigned char*>(b.alloc((size_t)nfr * 484 * 64));
       auto bn_fwd = [&](ConvSave& cs, long long rows, const float* slope1, const Act* res, const float* slope2, const Act& out) {
         const ConvUnit* cu = cs.cu;
         const int Cc = cu->cout;
@@ -1780,19 +1797,19 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
         const int planes = P;
         b.tag = "stem_patches";
         b.cur_direct = true;
-        b.push([=](cudaStream_t s) { return launch_im2col_stem(pl->args.video, pl->args.video_dt, B, T, colbuf, planes, s); });
+        b.push([=](cudaStream_t s) { return launch_im2col_stem(pl->args.video, pl->args.video_dt, B, T, stemcol, planes, s); });
         b.cur_direct = false;
         Epilogue ep;
         ep.C = cs.raw.data; ep.ldc = 64; ep.c_fp32 = f32 ? 1 : 0;
         b.tag = "stem_gemm";
-        if (!b.gemm(colbuf, rows, P * 320, h->stem.w, rows, {Tap{0, 0, 0}}, 5, 320, ep)) return false;
+        if (!b.gemm(stemcol, rows, P * 320, h->stem.w, rows, {Tap{0, 0, 0}}, 5, 320, ep)) return false;
         act0 = new_act(rows, 64);
         bn_fwd(cs, rows, h->stem.slope, nullptr, nullptr, act0);
         convs.push_back(cs);
         p0 = new_act(nfr * 484, 64);
         const void* a0 = act0.data; void* pp = p0.data;
         b.tag = "maxpool";
-        b.push([=](cudaStream_t s) { return launch_maxpool_dense(a0, pp, act_dt, nfr, 44, 64, 22, s); });
+        b.push([=](cudaStream_t s) { return launch_maxpool_dense(a0, pp, act_dt, nfr, 44, 64, 22, s, pool_arg); });
         sync_op(p0);
       }
       Act cur = p0;
@@ -2171,35 +2188,61 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
         }
         void* ftA = b.alloc((size_t)max_a * P * 2);
         void* ftB = b.alloc((size_t)max_b * P * 2);
-        auto wgrad_rows = [&](const float* dyv, long long ld_dy, int n_out, const void* xv, int x_dt, long long ld_x, bool x_op,
+        // x_mode: 0 = xv [rows, n_in] values (x_dt), 1 = xv operand planes (bf16 [rows, P * n_in]), 2 = ftB already holds
+        // the transposed operand (im2colT)
+        auto wgrad_rows = [&](const float* dyv, long long ld_dy, int n_out, const void* xv, int x_dt, long long ld_x, int x_mode,
                               int n_in, long long rows, float* dW, float* db, const char* tag) -> bool {
           const long long kp = (rows + 63) / 64 * 64;
           const int planes = P;
           b.tag = "transpose";
-          b.push([=](cudaStream_t s) { return launch_transpose_split(dyv, DT_F32, ld_dy, rows, n_out, ftA, planes, kp, 1.0f, s); });
-          if (x_op) {
+          if (!f32 && n_out % 8 == 0 && ld_dy % 8 == 0) {
+            b.push([=](cudaStream_t s) { return launch_transposeT(dyv, DT_F32, ld_dy, rows, n_out, ftA, kp, kp, s); });
+          } else {
+            b.push([=](cudaStream_t s) { return launch_transpose_split(dyv, DT_F32, ld_dy, rows, n_out, ftA, planes, kp, 1.0f, s); });
+          }
+          if (x_mode == 1) {
             for (int pp = 0; pp < P; ++pp) {
               const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xv) + (long long)pp * n_in;
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ftB) + (long long)pp * kp;
-              b.push([=](cudaStream_t s) {
-                return launch_transpose_split(src, DT_BF16, ld_x, rows, n_in, dst, 1, kp, 1.0f, s, 0, 0, (long long)planes * kp);
-              });
+              if (!f32 && n_in % 8 == 0 && ld_x % 8 == 0)
+                b.push([=](cudaStream_t s) { return launch_transposeT(src, DT_BF16, ld_x, rows, n_in, dst, kp, kp, s); });
+              else
+                b.push([=](cudaStream_t s) {
+                  return launch_transpose_split(src, DT_BF16, ld_x, rows, n_in, dst, 1, kp, 1.0f, s, 0, 0, (long long)planes * kp);
+                });
             }
-          } else {
-            b.push([=](cudaStream_t s) { return launch_transpose_split(xv, x_dt, ld_x, rows, n_in, ftB, planes, kp, 1.0f, s); });
+          } else if (x_mode == 0) {
+            if (!f32 && x_dt == DT_BF16 && n_in % 8 == 0 && ld_x % 8 == 0)
+              b.push([=](cudaStream_t s) { return launch_transposeT(xv, DT_BF16, ld_x, rows, n_in, ftB, kp, kp, s); });
+            else
+              b.push([=](cudaStream_t s) { return launch_transpose_split(xv, x_dt, ld_x, rows, n_in, ftB, planes, kp, 1.0f, s); });
           }
-          const long long seg = (f32 ? 256 : 768) * 64;
-          for (long long k0 = 0; k0 < kp; k0 += seg) {
-            const long long kl = std::min(seg, kp - k0);
+          if (!f32) {
+            // bf16 mode: ONE launch over the whole K extent (no step table), stream-K over the SMs: the output is a handful
+            // of tiles (dW of a 64-channel conv: 1 x 5) while K is the pixel count (580 800 in layer1 at 8 x 150 frames)
             PackedW xw;
-            xw.w = reinterpret_cast<bf16*>(ftB) + k0; xw.n = n_in; xw.k = (int)kp; xw.kpad = (int)kp;
+            xw.w = reinterpret_cast<bf16*>(ftB); xw.n = n_in; xw.k = (int)kp; xw.kpad = (int)kp;
             Epilogue ep;
             ep.C = dW; ep.ldc = n_in; ep.c_fp32 = 1;
-            if (k0 > 0) { ep.R = dW; ep.ldr = n_in; ep.r_fp32 = 1; }
             b.tag = tag;
-            const char* a = reinterpret_cast<const char*>(ftA) + (size_t)k0 * 2;
-            if (!b.gemm(a, n_out, (int)(P * kp - k0), xw, n_out, {Tap{0, 0, 0}}, (int)(kl / 64), (int)kp, ep, 0, nullptr, P * kp))
-              return false;
+            b.linear_k = true; b.force_sk = 1;
+            const bool ok = b.gemm(ftA, n_out, (int)kp, xw, n_out, {Tap{0, 0, 0}}, (int)(kp / 64), (int)kp, ep, 0, nullptr, kp);
+            b.linear_k = false; b.force_sk = 0;
+            if (!ok) return false;
+          } else {
+            const long long seg = 256 * 64;
+            for (long long k0 = 0; k0 < kp; k0 += seg) {
+              const long long kl = std::min(seg, kp - k0);
+              PackedW xw;
+              xw.w = reinterpret_cast<bf16*>(ftB) + k0; xw.n = n_in; xw.k = (int)kp; xw.kpad = (int)kp;
+              Epilogue ep;
+              ep.C = dW; ep.ldc = n_in; ep.c_fp32 = 1;
+              if (k0 > 0) { ep.R = dW; ep.ldr = n_in; ep.r_fp32 = 1; }
+              b.tag = tag;
+              const char* a = reinterpret_cast<const char*>(ftA) + (size_t)k0 * 2;
+              if (!b.gemm(a, n_out, (int)(P * kp - k0), xw, n_out, {Tap{0, 0, 0}}, (int)(kl / 64), (int)kp, ep, 0, nullptr, P * kp))
+                return false;
+            }
           }
           if (db != nullptr) {
             b.tag = "bias_grad";
@@ -2210,12 +2253,12 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
         if (plan->has_audio) {
           float* g_w = gf; float* g_b = g_w + (long long)D * Fp;
           gf = g_b + D;
-          if (!wgrad_rows(dfused, E, D, arows.data, act_dt, Fp, false, Fp, N, g_w, g_b, "proj_audio_wgrad")) return false;
+          if (!wgrad_rows(dfused, E, D, arows.data, act_dt, Fp, 0, Fp, N, g_w, g_b, "proj_audio_wgrad")) return false;
         }
         if (plan->has_video) {
           float* g_w = gf; float* g_b = g_w + (long long)D * 512;
           gf = g_b + D;
-          if (!wgrad_rows(dfused + v_off, E, D, feat.data, act_dt, 512, false, 512, N, g_w, g_b, "proj_video_wgrad")) return false;
+          if (!wgrad_rows(dfused + v_off, E, D, feat.data, act_dt, 512, 0, 512, N, g_w, g_b, "proj_video_wgrad")) return false;
           // d(feat) = d(fused_video) Wv
           {
             void* d = dxa.op;
@@ -2282,17 +2325,24 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
             const void* xin = cs.in.data;
             const int planes = P, ks = cu.ks, st = cu.stride, cin = cu.cin, H = cs.H, Ho = cs.Ho, pad = cs.pad;
             b.tag = "im2col";
-            b.push([=](cudaStream_t s) { return launch_im2col2d(xin, act_dt, nfr, H, cin, ks, st, pad, Ho, colbuf, planes, s); });
-            if (!wgrad_rows(d_raw, Cc, Cc, colbuf, DT_BF16, (long long)P * K, true, K, rows, dW, nullptr, "conv_wgrad")) return false;
+            if (!f32) {
+              // bf16 mode: the patches are written transposed straight from the map (no patch matrix, no transpose pass)
+              const long long kp = (rows + 63) / 64 * 64;
+              b.push([=](cudaStream_t s) { return launch_im2colT(xin, nfr, H, cin, ks, st, pad, Ho, ftB, kp, s); });
+              if (!wgrad_rows(d_raw, Cc, Cc, nullptr, DT_BF16, 0, 2, K, rows, dW, nullptr, "conv_wgrad")) return false;
+            } else {
+              b.push([=](cudaStream_t s) { return launch_im2col2d(xin, act_dt, nfr, H, cin, ks, st, pad, Ho, colbuf, planes, s); });
+              if (!wgrad_rows(d_raw, Cc, Cc, colbuf, DT_BF16, (long long)P * K, 1, K, rows, dW, nullptr, "conv_wgrad")) return false;
+            }
             if (dx == nullptr) return true;
             b.tag = "split";
             b.push([=](cudaStream_t s) { return launch_split_rows(d_raw, Cc, dop, planes, rows, Cc, 0, 0, s); });
             Epilogue ep;
-            ep.C = dcol; ep.ldc = K; ep.c_fp32 = 1;
+            ep.C = dcol; ep.ldc = K; ep.c_fp32 = f32 ? 1 : 0;        // bf16 mode: patch gradients in bf16 (half the traffic)
             b.tag = "conv_dgrad";
             if (!b.gemm(dop, rows, P * Cc, cu.wT, rows, {Tap{0, 0, 0}}, cu.wT.kpad / 64, Cc, ep)) return false;
             b.tag = "col2im";
-            b.push([=](cudaStream_t s) { return launch_col2im2d(dcol, DT_F32, nfr, H, cin, ks, st, pad, Ho, dx, dx_acc, s); });
+            b.push([=](cudaStream_t s) { return launch_col2im2d(dcol, act_dt, nfr, H, cin, ks, st, pad, Ho, dx, dx_acc, s); });
             return true;
           };
           // avgpool
@@ -2342,14 +2392,9 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
             const void* a0 = act0.data;
             float* dp0 = dcur;
             b.tag = "maxpool_bwd";
-            b.push([=](cudaStream_t s) { return launch_maxpool_bwd(a0, act_dt, dp0, d_act0, nfr, 44, 64, 22, s); });
+            b.push([=](cudaStream_t s) { return launch_maxpool_bwd(a0, act_dt, dp0, d_act0, nfr, 44, 64, 22, s, pool_arg); });
             float* d_raw0 = bn_bwd(cs, d_act0, nullptr, 0, g_stem_bn, g_stem_slope);
-            const int planes = P;
-            b.tag = "stem_patches";
-            b.cur_direct = true;
-            b.push([=](cudaStream_t s) { return launch_im2col_stem(pl->args.video, pl->args.video_dt, B, T, colbuf, planes, s); });
-            b.cur_direct = false;
-            if (!wgrad_rows(d_raw0, 64, 64, colbuf, DT_BF16, (long long)P * 320, true, 320, nfr * 1936, g_stem_w, nullptr, "stem_wgrad"))
+            if (!wgrad_rows(d_raw0, 64, 64, stemcol, DT_BF16, (long long)P * 320, 1, 320, nfr * 1936, g_stem_w, nullptr, "stem_wgrad"))
               return false;
           }
         }

@@ -422,6 +422,12 @@ int launch_transpose_split(const void* in, int dt, long long ld, long long rows,
   AVH_CHECK(kpad % 64 == 0 && (T > 0 ? kpad >= rows / T * Tp : kpad >= rows),
             "transpose_split: K padding must cover the rows and be a multiple of 64");
   if (C <= 0) return 0;
+  {
+    const long long old_ = out_ld > 0 ? out_ld : (long long)planes * kpad;
+    if (planes == 1 && scale == 1.0f && T == 0 && (dt == DT_BF16 || dt == DT_F32) && C % 8 == 0 && ld % 8 == 0 && old_ % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+      return launch_transposeT(in, dt, ld, rows, C, out, kpad, old_, stream);       // 64 x 64 tiles, 16-byte accesses
+  }
   dim3 grid((unsigned)((kpad + 31) / 32), (unsigned)((C + 31) / 32));
   transpose_split_kernel<<<grid, 256, 0, stream>>>(in, dt, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), planes, kpad, scale,
                                                    T, Tp, out_ld > 0 ? out_ld : (long long)planes * kpad);

@@ -269,6 +269,391 @@ add_f32_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) 
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) a[i] += b[i];
 }
 
+
+// ================= bf16-mode fast paths: 16-byte vectors along the channel axis, 64 x 64 smem-tile transposes =================
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+// im2col2d, one 16-byte vector (8 channels of one tap) per thread
+__global__ void __launch_bounds__(256)
+im2col2d_vec_kernel(const __nv_bfloat16* __restrict__ x, long long n, int H, int C, int ks, int stride, int pad, int Ho,
+                    __nv_bfloat16* __restrict__ col) {
+  const int C8 = C / 8, K8 = ks * ks * C8;
+  const long long total = n * Ho * Ho * K8;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const long long row = idx / K8;
+    const int k8 = (int)(idx % K8), tap = k8 / C8, c8 = k8 % C8, kh = tap / ks, kw = tap % ks;
+    const int pix = (int)(row % (Ho * Ho)), oy = pix / Ho, ox = pix % Ho;
+    const long long f = row / (Ho * Ho);
+    const int y = oy * stride + kh - pad, xx = ox * stride + kw - pad;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && xx >= 0 && xx < H) v = __ldg(reinterpret_cast<const uint4*>(x + ((f * H + y) * H + xx) * C) + c8);
+    reinterpret_cast<uint4*>(col)[idx] = v;
+  }
+}
+// the 64 x 64 tile store shared by the transposing kernels: tile[i][(j ^ (i/8 % 8)) * 8 + e] holds element (row i, column
+// 8 j + e); output row (c0 + c) receives the 8 consecutive K indices r0 + 8 g .. + 7 as one 16-byte store
+__device__ __forceinline__ void store_tile_T(const __nv_bfloat16 (*tile)[72], __nv_bfloat16* __restrict__ out, long long out_row0,
+                                             int c_lim, long long out_ld, long long r0) {
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int c = v / 8, g = v % 8;
+    if (c >= c_lim) continue;
+    __align__(16) __nv_bfloat16 w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) w[q] = tile[g * 8 + q][(((c >> 3) ^ g) << 3) + (c & 7)];
+    *reinterpret_cast<uint4*>(out + (out_row0 + c) * out_ld + r0 + g * 8) = *reinterpret_cast<const uint4*>(w);
+  }
+}
+// patches written TRANSPOSED for the weight-gradient GEMM (K = pixels): colT[(tap * C + c), r] = x[patch r, tap, c], columns
+// r in [rows, kp) zero.  grid (kp / 64, C / 64, ks * ks)
+__global__ void __launch_bounds__(256)
+im2colT_kernel(const __nv_bfloat16* __restrict__ x, long long n, int H, int C, int ks, int stride, int pad, int Ho,
+               __nv_bfloat16* __restrict__ colT, long long kp) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];
+  const long long rows = n * Ho * Ho;
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64, tap = blockIdx.z, kh = tap / ks, kw = tap % ks;
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int i = v / 8, j = v % 8;
+    const long long r = r0 + i;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) {
+      const int pix = (int)(r % (Ho * Ho)), oy = pix / Ho, ox = pix % Ho;
+      const long long f = r / (Ho * Ho);
+      const int y = oy * stride + kh - pad, xx = ox * stride + kw - pad;
+      if (y >= 0 && y < H && xx >= 0 && xx < H)
+        val = __ldg(reinterpret_cast<const uint4*>(x + ((f * H + y) * H + xx) * C + c0) + j);
+    }
+    *reinterpret_cast<uint4*>(&tile[i][(j ^ ((i >> 3) & 7)) << 3]) = val;
+  }
+  __syncthreads();
+  store_tile_T(tile, colT, (long long)tap * C + c0, 64, kp, r0);
+}
+// in [rows, C] (row stride ld; bf16 or fp32) -> out bf16 [C, out_ld], out[c, r] = in[r, c], columns r in [rows, kp) zero.
+// grid (kp / 64, ceil(C / 64)); C and ld multiples of 8
+template <bool F32>
+__global__ void __launch_bounds__(256)
+transposeT_kernel(const void* __restrict__ in, long long ld, long long rows, int C, __nv_bfloat16* __restrict__ out,
+                  long long out_ld) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int i = v / 8, j = v % 8;
+    const long long r = r0 + i;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows && c0 + j * 8 < C) {
+      if (F32) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + r * ld + c0 + j * 8);
+        const float4 a = __ldg(src), b2 = __ldg(src + 1);
+        __nv_bfloat162 h[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                               __floats2bfloat162_rn(b2.x, b2.y), __floats2bfloat162_rn(b2.z, b2.w)};
+        val = *reinterpret_cast<const uint4*>(h);
+      } else {
+        val = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + r * ld + c0) + j);
+      }
+    }
+    *reinterpret_cast<uint4*>(&tile[i][(j ^ ((i >> 3) & 7)) << 3]) = val;
+  }
+  __syncthreads();
+  store_tile_T(tile, out, c0, C - c0 < 64 ? C - c0 : 64, out_ld, r0);
+}
+// col2im as a gather, vectors along the channel axis (dcol bf16: 8 channels, fp32: 4 channels per thread)
+template <bool F32>
+__global__ void __launch_bounds__(256)
+col2im2d_vec_kernel(const void* __restrict__ dcol, long long n, int H, int C, int ks, int stride, int pad, int Ho,
+                    float* __restrict__ dx, int accumulate) {
+  constexpr int V = F32 ? 4 : 8;
+  const int CV = C / V;
+  const long long K = (long long)ks * ks * C;
+  const long long total = n * H * H * CV;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int cv = (int)(idx % CV);
+    const long long p = idx / CV;
+    const int xx = (int)(p % H), y = (int)((p / H) % H);
+    const long long f = p / ((long long)H * H);
+    float s[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) s[e] = 0.f;
+    for (int kh = 0; kh < ks; ++kh) {
+      const int ny = y + pad - kh;
+      if (ny < 0 || ny % stride != 0) continue;
+      const int oy = ny / stride;
+      if (oy >= Ho) continue;
+      for (int kw = 0; kw < ks; ++kw) {
+        const int nx = xx + pad - kw;
+        if (nx < 0 || nx % stride != 0) continue;
+        const int ox = nx / stride;
+        if (ox >= Ho) continue;
+        const long long off = ((f * Ho + oy) * Ho + ox) * K + (long long)(kh * ks + kw) * C + cv * V;
+        if (F32) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dcol) + off));
+          s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
+        } else {
+          float t[8];
+          bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(dcol) + off)), t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s[e] += t[e];
+        }
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dx + p * C + cv * V);
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) {
+      float4 w = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+      if (accumulate) { const float4 old = o[q]; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
+      o[q] = w;
+    }
+  }
+}
+// stem patches, bf16 video: one 16-byte vector (8 consecutive patch columns) per thread
+__global__ void __launch_bounds__(256)
+im2col_stem_vec_kernel(const __nv_bfloat16* __restrict__ video, int B, int T, __nv_bfloat16* __restrict__ col) {
+  const long long total = (long long)B * T * 1936 * 40;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const long long row = idx / 40;
+  const int v = (int)(idx % 40), d = v / 8, jv = v % 8;
+  const int pix = (int)(row % 1936), oy = pix / 44, ox = pix % 44;
+  const long long f = row / 1936;
+  const int t = (int)(f % T) + d - 2;
+  __align__(16) __nv_bfloat16 w[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) w[q] = __float2bfloat16_rn(0.f);
+  if (t >= 0 && t < T && jv < 7) {
+    const __nv_bfloat16* img = video + ((f / T) * T + t) * 7744;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = jv * 8 + q;
+      if (j < 49) {
+        const int kh = j / 7, kw = j % 7, y = 2 * oy + kh - 3, x = 2 * ox + kw - 3;
+        if (y >= 0 && y < 88 && x >= 0 && x < 88) w[q] = img[y * 88 + x];
+      }
+    }
+  }
+  reinterpret_cast<uint4*>(col)[idx] = *reinterpret_cast<const uint4*>(w);
+}
+// max-pool backward, bf16 maps, 8 channels per thread
+__global__ void __launch_bounds__(256)
+maxpool_bwd_vec_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n,
+                       int H, int C, int Ho) {
+  const int C8 = C / 8;
+  const long long total = n * H * H * C8;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int c8 = (int)(idx % C8);
+    const long long p = idx / C8;
+    const int xx = (int)(p % H), y = (int)((p / H) % H);
+    const long long f = p / ((long long)H * H);
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    for (int oy = (y + 1) / 2 - 1; oy <= (y + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= Ho || 2 * oy - 1 > y || 2 * oy + 1 < y) continue;
+      for (int ox = (xx + 1) / 2 - 1; ox <= (xx + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= Ho || 2 * ox - 1 > xx || 2 * ox + 1 < xx) continue;
+        float m[8];
+        int arg[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; arg[e] = -1; }
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const int yy = 2 * oy + kh - 1, x2 = 2 * ox + kw - 1;
+            if (yy < 0 || yy >= H || x2 < 0 || x2 >= H) continue;
+            float t[8];
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + ((f * H + yy) * H + x2) * C) + c8), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (t[e] > m[e]) { m[e] = t[e]; arg[e] = kh * 3 + kw; }
+          }
+        const int mine = (y - (2 * oy - 1)) * 3 + (xx - (2 * ox - 1));
+        const float4* g = reinterpret_cast<const float4*>(dy + ((f * Ho + oy) * Ho + ox) * C + c8 * 8);
+        const float4 g0 = __ldg(g), g1 = __ldg(g + 1);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (arg[e] == mine) s[e] += gv[e];
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dx + p * C + c8 * 8);
+    o[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o[1] = make_float4(s[4], s[5], s[6], s[7]);
+  }
+}
+// max-pool forward, bf16 maps, 8 channels per thread; `arg` (optional, [n,Ho,Ho,C] bytes) keeps the window position
+// (kh*3+kw, first maximum in scan order) so that the backward is a pure gather
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ yout, unsigned char* __restrict__ arg_out,
+                       long long n, int H, int C, int Ho) {
+  const int C8 = C / 8;
+  const long long total = n * Ho * Ho * C8;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int c8 = (int)(idx % C8);
+    const long long p = idx / C8;
+    const int ox = (int)(p % Ho), oy = (int)((p / Ho) % Ho);
+    const long long f = p / ((long long)Ho * Ho);
+    float m[8];
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; arg[e] = 0; }
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int yy = 2 * oy + kh - 1, xx = 2 * ox + kw - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= H) continue;
+        float t[8];
+        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + ((f * H + yy) * H + xx) * C) + c8), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (t[e] > m[e]) { m[e] = t[e]; arg[e] = kh * 3 + kw; }
+      }
+    __align__(16) __nv_bfloat16 w[8];
+    __align__(8) unsigned char a8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { w[e] = __float2bfloat16_rn(m[e]); a8[e] = (unsigned char)arg[e]; }
+    reinterpret_cast<uint4*>(yout)[idx] = *reinterpret_cast<const uint4*>(w);
+    if (arg_out != nullptr) reinterpret_cast<uint2*>(arg_out)[idx] = *reinterpret_cast<const uint2*>(a8);
+  }
+}
+__global__ void __launch_bounds__(256)
+maxpool_bwd_arg_kernel(const unsigned char* __restrict__ arg, const float* __restrict__ dy, float* __restrict__ dx, long long n,
+                       int H, int C, int Ho) {
+  const int C8 = C / 8;
+  const long long total = n * H * H * C8;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int c8 = (int)(idx % C8);
+    const long long p = idx / C8;
+    const int xx = (int)(p % H), y = (int)((p / H) % H);
+    const long long f = p / ((long long)H * H);
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    for (int oy = (y + 1) / 2 - 1; oy <= (y + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= Ho || 2 * oy - 1 > y || 2 * oy + 1 < y) continue;
+      for (int ox = (xx + 1) / 2 - 1; ox <= (xx + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= Ho || 2 * ox - 1 > xx || 2 * ox + 1 < xx) continue;
+        const long long o = ((f * Ho + oy) * Ho + ox) * C + c8 * 8;
+        const uint2 au = __ldg(reinterpret_cast<const uint2*>(arg + o));
+        const unsigned char* a8 = reinterpret_cast<const unsigned char*>(&au);
+        const int mine = (y - (2 * oy - 1)) * 3 + (xx - (2 * ox - 1));
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy + o)), g1 = __ldg(reinterpret_cast<const float4*>(dy + o) + 1);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if ((int)a8[e] == mine) s[e] += gv[e];
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(dx + p * C + c8 * 8);
+    o4[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o4[1] = make_float4(s[4], s[5], s[6], s[7]);
+  }
+}
+// BatchNorm + residual + PReLU backward, bf16 maps: 8 channels per thread.  reduce: lane = channel group, 256 / (C / 8) row
+// phases, fp32 partials per thread (<= BWD_ROWS_PER_CTA_MAX / phases rows), summed across phases and CTAs in double.
+__device__ __forceinline__ void bn_dv8(const __nv_bfloat16* raw, const __nv_bfloat16* res, const float* dz, long long off,
+                                       const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                       const float* slope, bool has_slope, float* dv, float* v, float* xh, float* dzv) {
+  float r[8], rs[8];
+  bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(raw + off)), r);
+  if (res != nullptr) bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(res + off)), rs);
+  const float4 d0 = __ldg(reinterpret_cast<const float4*>(dz + off)), d1 = __ldg(reinterpret_cast<const float4*>(dz + off) + 1);
+  const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    xh[e] = (r[e] - mean[e]) * rstd[e];
+    v[e] = fmaf(xh[e], gamma[e], beta[e]) + (res != nullptr ? rs[e] : 0.f);
+    dzv[e] = d[e];
+    dv[e] = has_slope ? (v[e] > 0.f ? d[e] : d[e] * slope[e]) : d[e];
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_vec_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ res,
+                             const float* __restrict__ dz, const float* __restrict__ stat, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, const float* __restrict__ slope, long long rows, int C,
+                             int rows_per_cta, double* __restrict__ sums) {
+  extern __shared__ float shf[];                 // [phases][C][3]
+  const int lanes = C / 8, phases = 256 / lanes;
+  const int l = threadIdx.x % lanes, ph = threadIdx.x / lanes, c0 = l * 8;
+  float mean[8], rstd[8], gm[8], bt[8], sl[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mean[e] = stat[c0 + e]; rstd[e] = stat[C + c0 + e]; gm[e] = gamma[c0 + e]; bt[e] = beta[c0 + e];
+    sl[e] = slope != nullptr ? slope[c0 + e] : 0.f;
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float a[8], b2[8], s3[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; b2[e] = 0.f; s3[e] = 0.f; }
+  for (long long r = r0 + ph; r < r1; r += phases) {
+    float dv[8], v[8], xh[8], d[8];
+    bn_dv8(raw, res, dz, r * C + c0, mean, rstd, gm, bt, sl, slope != nullptr, dv, v, xh, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[e] += dv[e];
+      b2[e] = fmaf(dv[e], xh[e], b2[e]);
+      if (slope != nullptr && v[e] <= 0.f) s3[e] = fmaf(d[e], v[e], s3[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    shf[((size_t)ph * C + c0 + e) * 3] = a[e];
+    shf[((size_t)ph * C + c0 + e) * 3 + 1] = b2[e];
+    shf[((size_t)ph * C + c0 + e) * 3 + 2] = s3[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int p2 = 0; p2 < phases; ++p2) {
+      t0 += (double)shf[((size_t)p2 * C + c) * 3]; t1 += (double)shf[((size_t)p2 * C + c) * 3 + 1];
+      t2 += (double)shf[((size_t)p2 * C + c) * 3 + 2];
+    }
+    double* slot = sums + (size_t)(blockIdx.x % BN_SLOTS) * 3 * C;
+    atomicAdd(&slot[c], t0);
+    atomicAdd(&slot[C + c], t1);
+    atomicAdd(&slot[2 * C + c], t2);
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ res,
+                            const float* __restrict__ dz, const float* __restrict__ stat, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, const float* __restrict__ slope, const float* __restrict__ tot,
+                            long long rows, int C, float* __restrict__ d_raw, float* __restrict__ d_res, int res_accumulate) {
+  const int C8 = C / 8;
+  const long long total = rows * C8;
+  const float inv_rows = 1.0f / (float)rows;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int c0 = (int)(idx % C8) * 8;
+    float mean[8], rstd[8], gm[8], bt[8], sl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mean[e] = stat[c0 + e]; rstd[e] = stat[C + c0 + e]; gm[e] = gamma[c0 + e]; bt[e] = beta[c0 + e];
+      sl[e] = slope != nullptr ? slope[c0 + e] : 0.f;
+    }
+    float dv[8], v[8], xh[8], d[8], o[8];
+    const long long off = idx * 8;
+    bn_dv8(raw, res, dz, off, mean, rstd, gm, bt, sl, slope != nullptr, dv, v, xh, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      o[e] = gm[e] * rstd[e] * (dv[e] - tot[c0 + e] * inv_rows - xh[e] * tot[C + c0 + e] * inv_rows);
+    float4* dst = reinterpret_cast<float4*>(d_raw + off);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    if (d_res != nullptr) {
+      float4* dr = reinterpret_cast<float4*>(d_res + off);
+      if (res_accumulate) {
+        const float4 p0 = dr[0], p1 = dr[1];
+        dv[0] += p0.x; dv[1] += p0.y; dv[2] += p0.z; dv[3] += p0.w; dv[4] += p1.x; dv[5] += p1.y; dv[6] += p1.z; dv[7] += p1.w;
+      }
+      dr[0] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+      dr[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
+    }
+  }
+}
+
 inline unsigned grid_for(long long n) {
   const long long b = (n + 255) / 256;
   return (unsigned)(b < 148 * 32 ? (b > 0 ? b : 1) : 148 * 32);
@@ -279,6 +664,13 @@ inline unsigned grid_for(long long n) {
 int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int planes, cudaStream_t stream) {
   const long long total = (long long)B * T * 1936 * 320;
   AVH_CHECK((total + 255) / 256 < (1ll << 31), "stem patch matrix too large");
+  if (dt == DT_BF16 && planes == 1) {
+    im2col_stem_vec_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(video), B, T, reinterpret_cast<__nv_bfloat16*>(col));
+    AVH_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
   im2col_stem_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(video, dt, B, T, reinterpret_cast<__nv_bfloat16*>(col),
                                                                          planes);
   AVH_CUDA_OK(cudaGetLastError());
@@ -287,6 +679,13 @@ int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int p
 }
 int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* col, int planes,
                     cudaStream_t stream) {
+  if (dt == DT_BF16 && planes == 1 && C % 8 == 0) {
+    im2col2d_vec_kernel<<<grid_for(n * Ho * Ho * ks * ks * (C / 8)), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), n, H, C, ks, stride, pad, Ho, reinterpret_cast<__nv_bfloat16*>(col));
+    AVH_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
   im2col2d_kernel<<<grid_for(n * Ho * Ho * ks * ks * C), 256, 0, stream>>>(x, dt, n, H, C, ks, stride, pad, Ho,
                                                                           reinterpret_cast<__nv_bfloat16*>(col), planes);
   AVH_CUDA_OK(cudaGetLastError());
@@ -295,19 +694,38 @@ int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, in
 }
 int launch_col2im2d(const void* dcol, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, float* dx,
                     int accumulate, cudaStream_t stream) {
+  if (dt == DT_BF16 && C % 8 == 0)
+    col2im2d_vec_kernel<false><<<grid_for(n * H * H * (C / 8)), 256, 0, stream>>>(dcol, n, H, C, ks, stride, pad, Ho, dx, accumulate);
+  else if (dt == DT_F32 && C % 4 == 0)
+    col2im2d_vec_kernel<true><<<grid_for(n * H * H * (C / 4)), 256, 0, stream>>>(dcol, n, H, C, ks, stride, pad, Ho, dx, accumulate);
+  else
   col2im2d_kernel<<<grid_for(n * H * H * C), 256, 0, stream>>>(dcol, dt, n, H, C, ks, stride, pad, Ho, dx, accumulate);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
 }
-int launch_maxpool_dense(const void* x, void* y, int dt, long long n, int H, int C, int Ho, cudaStream_t stream) {
-  maxpool_fwd_kernel<<<grid_for(n * Ho * Ho * C), 256, 0, stream>>>(x, y, dt, n, H, C, Ho);
+int launch_maxpool_dense(const void* x, void* y, int dt, long long n, int H, int C, int Ho, cudaStream_t stream,
+                         unsigned char* arg) {
+  if (dt == DT_BF16 && C % 8 == 0) {
+    maxpool_fwd_vec_kernel<<<grid_for(n * Ho * Ho * (C / 8)), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), arg, n, H, C, Ho);
+  } else {
+    AVH_CHECK(arg == nullptr, "max-pool window positions are kept for bf16 maps only");
+    maxpool_fwd_kernel<<<grid_for(n * Ho * Ho * C), 256, 0, stream>>>(x, y, dt, n, H, C, Ho);
+  }
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
 }
-int launch_maxpool_bwd(const void* x, int dt, const float* dy, float* dx, long long n, int H, int C, int Ho, cudaStream_t stream) {
-  maxpool_bwd_kernel<<<grid_for(n * H * H * C), 256, 0, stream>>>(x, dt, dy, dx, n, H, C, Ho);
+int launch_maxpool_bwd(const void* x, int dt, const float* dy, float* dx, long long n, int H, int C, int Ho, cudaStream_t stream,
+                       const unsigned char* arg) {
+  if (arg != nullptr && C % 8 == 0)
+    maxpool_bwd_arg_kernel<<<grid_for(n * H * H * (C / 8)), 256, 0, stream>>>(arg, dy, dx, n, H, C, Ho);
+  else if (dt == DT_BF16 && C % 8 == 0)
+    maxpool_bwd_vec_kernel<<<grid_for(n * H * H * (C / 8)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), dy, dx, n, H,
+                                                                             C, Ho);
+  else
+    maxpool_bwd_kernel<<<grid_for(n * H * H * C), 256, 0, stream>>>(x, dt, dy, dx, n, H, C, Ho);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -336,6 +754,26 @@ int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz,
                       float* d_res, int res_accumulate, float* dgamma, float* dbeta, float* dslope, cudaStream_t stream) {
   AVH_CHECK(C >= 32 && C <= 512 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "bn backward: channel count must divide or double 256");
   if (rows <= 0) return 0;
+  if (dt == DT_BF16) {
+    const int phases = 256 / (C / 8);
+    long long rpc = (rows + 4 * 148 - 1) / (4 * 148);
+    rpc = (rpc + phases - 1) / phases * phases;
+    if (rpc < 4 * phases) rpc = 4 * phases;
+    if (rpc > BWD_ROWS_PER_CTA_MAX) rpc = BWD_ROWS_PER_CTA_MAX;
+    const size_t smem = (size_t)phases * C * 3 * sizeof(float);
+    const __nv_bfloat16* rw = reinterpret_cast<const __nv_bfloat16*>(raw);
+    const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(res);
+    bn_act_bwd_reduce_vec_kernel<<<(unsigned)((rows + rpc - 1) / rpc), 256, smem, stream>>>(rw, rs, dz, stat, gamma, beta, slope,
+                                                                                          rows, C, (int)rpc, sums);
+    AVH_CUDA_OK(cudaGetLastError());
+    bn_act_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, tot, dgamma, dbeta, dslope);
+    AVH_CUDA_OK(cudaGetLastError());
+    bn_act_bwd_apply_vec_kernel<<<grid_for(rows * (C / 8)), 256, 0, stream>>>(rw, rs, dz, stat, gamma, beta, slope, tot, rows, C,
+                                                                            d_raw, d_res, res_accumulate);
+    AVH_CUDA_OK(cudaGetLastError());
+    count_launch(3);
+    return 0;
+  }
   const int phases = 256 / C > 0 ? 256 / C : 1;
   long long rpc = (rows + 4 * 148 - 1) / (4 * 148);
   rpc = (rpc + phases - 1) / phases * phases;
@@ -357,6 +795,30 @@ int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz,
 int launch_add_f32(float* a, const float* b, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
   add_f32_kernel<<<grid_for(n), 256, 0, stream>>>(a, b, n);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+int launch_im2colT(const void* x, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* colT, long long kp,
+                   cudaStream_t stream) {
+  AVH_CHECK(C % 64 == 0 && kp % 64 == 0 && kp >= n * Ho * Ho, "transposed patches: channels / K padding must be multiples of 64");
+  dim3 grid((unsigned)(kp / 64), (unsigned)(C / 64), (unsigned)(ks * ks));
+  im2colT_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, H, C, ks, stride, pad, Ho,
+                                           reinterpret_cast<__nv_bfloat16*>(colT), kp);
+  AVH_CUDA_OK(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+int launch_transposeT(const void* in, int dt, long long ld, long long rows, int C, void* out, long long kp, long long out_ld,
+                      cudaStream_t stream) {
+  AVH_CHECK((dt == DT_BF16 || dt == DT_F32) && C % 8 == 0 && ld % 8 == 0 && kp % 64 == 0 && kp >= rows && out_ld % 8 == 0,
+            "tile transpose: bf16 / fp32 input, channel count and strides multiples of 8");
+  dim3 grid((unsigned)(kp / 64), (unsigned)((C + 63) / 64));
+  if (dt == DT_F32)
+    transposeT_kernel<true><<<grid, 256, 0, stream>>>(in, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), out_ld);
+  else
+    transposeT_kernel<false><<<grid, 256, 0, stream>>>(in, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), out_ld);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

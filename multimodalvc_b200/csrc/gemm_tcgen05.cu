@@ -966,7 +966,7 @@ int gemm_plan(const GemmProblem& pr, GemmPlan* plan) {
   if (sk_env == 2) sk_env = -1;      // -1 = model decides
   // stream-K needs the TMA epilogue (tile rows = output rows), no LayerNorm folding and a workspace
   const Epilogue& e0 = pr.ep;
-  const bool sk_possible = pr.sk_ws != nullptr && pr.sk_flags != nullptr && pr.streamk >= 0 && sk_env != 0 &&
+  const bool sk_possible = pr.sk_ws != nullptr && pr.sk_flags != nullptr && pr.streamk >= 0 && (sk_env != 0 || pr.streamk == 1) &&
                            e0.ln_mode == 0 && e0.row_map == nullptr && e0.map_mode != MAP_2LEVEL && e0.row_zero == nullptr &&
                            (e0.R == nullptr || (e0.R == e0.C && e0.slope2 == nullptr && e0.c_fp32));
   int sk = 0;

@@ -133,10 +133,16 @@ int launch_attention_bwd(const void* Q, long long ldq, const void* K, long long 
 int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int planes, cudaStream_t stream);
 int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* col, int planes,
                     cudaStream_t stream);
+int launch_im2colT(const void* x, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* colT, long long kp,
+                   cudaStream_t stream);          // bf16 x -> bf16 colT [ks*ks*C, kp] (transposed patches)
+int launch_transposeT(const void* in, int dt, long long ld, long long rows, int C, void* out, long long kp, long long out_ld,
+                      cudaStream_t stream);       // [rows, C] bf16 / fp32 -> bf16 [C, out_ld] (64 x 64 tiles)
 int launch_col2im2d(const void* dcol, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, float* dx,
                     int accumulate, cudaStream_t stream);
-int launch_maxpool_dense(const void* x, void* y, int dt, long long n, int H, int C, int Ho, cudaStream_t stream);
-int launch_maxpool_bwd(const void* x, int dt, const float* dy, float* dx, long long n, int H, int C, int Ho, cudaStream_t stream);
+int launch_maxpool_dense(const void* x, void* y, int dt, long long n, int H, int C, int Ho, cudaStream_t stream,
+                         unsigned char* arg = nullptr);     // arg: window position of every maximum (bf16 maps), for the backward
+int launch_maxpool_bwd(const void* x, int dt, const float* dy, float* dx, long long n, int H, int C, int Ho, cudaStream_t stream,
+                       const unsigned char* arg = nullptr);
 int launch_avgpool_dense(const void* x, void* y, int dt, long long n, int HW, int C, cudaStream_t stream);
 int launch_avgpool_bwd(const float* dy, float* dx, long long n, int HW, int C, cudaStream_t stream);
 // stat [2*C] = batch mean, rstd recovered from bn_finalize's (scale, bias)

@@ -107,14 +107,18 @@ class GradientAllReducer:
                 offset += n
                 nonzero = False
                 o = 0
+                dsts, srcs = [], []
                 for p in bucket:
                     sz = p.numel()
                     if p.grad is not None:
-                        flat[o:o + sz].copy_(p.grad.detach().reshape(-1))
+                        dsts.append(flat[o:o + sz].view_as(p))
+                        srcs.append(p.grad.detach())
                         nonzero = True
                     else:
                         flat[o:o + sz].zero_()
                     o += sz
+                if dsts:
+                    torch._foreach_copy_(dsts, srcs)          # one multi-tensor copy per bucket, not one kernel per parameter
                 pending.append((self._reduce_async(flat, nonzero), flat, bucket))
                 issued += 1
             # copy the averaged gradients back into their original place (reference :114-121)
@@ -122,11 +126,15 @@ class GradientAllReducer:
                 if work is not None:
                     work.wait()
                 o = 0
+                dsts, srcs = [], []
                 for p in bucket:
                     sz = p.numel()
                     if p.grad is not None:
-                        p.grad.detach().copy_(flat[o:o + sz].view_as(p))
+                        dsts.append(p.grad.detach())
+                        srcs.append(flat[o:o + sz].view_as(p))
                     else:
                         p.grad = flat[o:o + sz].view_as(p).clone()
                     o += sz
+                if dsts:
+                    torch._foreach_copy_(dsts, srcs)
         return issued

@@ -231,14 +231,18 @@ class _TailTrainFn(torch.autograd.Function):
             _lib.check(lib.avh_encoder_backward(ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], None, 0,
                                                 ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
         grads, off = [], 0
-        same = ctx.dtypes[0] if all(dt == ctx.dtypes[0] for dt in ctx.dtypes) else None
-        if same is not None:
-            flat = flat.to(same)                           # one conversion for the whole buffer, the gradients are views
+        converted = {torch.float32: flat}
+
+        def flat_of(dt):            # ONE conversion of the flat buffer per parameter dtype (not one kernel per parameter)
+            if dt not in converted:
+                converted[dt] = flat.to(dt)
+            return converted[dt]
+
         for shape, dt in zip(ctx.shapes, ctx.dtypes):
             k = 1
             for d in shape:
                 k *= d
-            grads.append(flat[off:off + k].view(shape).to(dt))
+            grads.append(flat_of(dt)[off:off + k].view(shape))
             off += k
         assert off == n.value
         return (None, None, None, *grads)
@@ -291,11 +295,18 @@ class _FullTrainFn(torch.autograd.Function):
             _lib.check(lib.avh_encoder_backward(ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], None, 0,
                                                 ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
         grads, off = [], 0
+        converted = {torch.float32: flat}
+
+        def flat_of(dt):            # ONE conversion of the flat buffer per parameter dtype (not one kernel per parameter)
+            if dt not in converted:
+                converted[dt] = flat.to(dt)
+            return converted[dt]
+
         for (shape, to_param), dt in zip(ctx.spec, ctx.dtypes):
             k = 1
             for d in shape:
                 k *= d
-            grads.append(to_param(flat[off:off + k].view(shape)).to(dt))
+            grads.append(to_param(flat_of(dt)[off:off + k].view(shape)))
             off += k
         assert off == n.value, (off, n.value)
         return (None, None, None, None, None, None, *grads)

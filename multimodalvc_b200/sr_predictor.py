@@ -67,14 +67,18 @@ class _EncoderTrainFn(torch.autograd.Function):
                 ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], ctypes.c_void_p(dx.data_ptr()),
                 _DTYPES[dx.dtype], ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
         grads, off = [], 0
-        same = ctx.dtypes[0] if all(dt == ctx.dtypes[0] for dt in ctx.dtypes) else None
-        if same is not None:
-            flat = flat.to(same)                           # one conversion for the whole buffer, the gradients are views
+        converted = {torch.float32: flat}
+
+        def flat_of(dt):            # ONE conversion of the flat buffer per parameter dtype (not one kernel per parameter)
+            if dt not in converted:
+                converted[dt] = flat.to(dt)
+            return converted[dt]
+
         for shape, dt in zip(ctx.shapes, ctx.dtypes):
             k = 1
             for d in shape:
                 k *= d
-            grads.append(flat[off:off + k].view(shape).to(dt))
+            grads.append(flat_of(dt)[off:off + k].view(shape))
             off += k
         assert off == n.value
         return (None, dx, None, *grads)

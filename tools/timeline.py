@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--fgm", type=float, default=0.0, help="with --train: feature_grad_mult (> 0 = whole-model step)")
     ap.add_argument("--train", action="store_true", help="profile the fine-tuning step of BASELINE config 5 (frozen extractors) instead")
     args = ap.parse_args()
     import torch
@@ -43,7 +44,7 @@ def main():
 
     if args.train:
         del model
-        m5 = AVHubertModel(AVHubertConfig.named("large", feature_grad_mult=0.0, trainable=True, dropout=0.0, attention_dropout=0.0,
+        m5 = AVHubertModel(AVHubertConfig.named("large", feature_grad_mult=args.fgm, trainable=True, dropout=0.0, attention_dropout=0.0,
                                                 activation_dropout=0.0, encoder_layerdrop=0.0, dropout_input=0.0))
         m5.remove_pretraining_modules()
         m5 = m5.to(dev, torch.bfloat16).train()
@@ -52,7 +53,7 @@ def main():
         def step(i):
             y5, _ = m5.extract_finetune({"audio": a5, "video": v5}, None)
             y5.float().pow(2).mean().backward()
-            for p5 in m5.tail_parameters():
+            for p5 in m5.parameters():
                 p5.grad = None
 
     for i in range(4):
