@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: one bench step = the launches between two
-stem_fused_kernel launches; per kernel name: launches, total us, share of the step.  usage: ncu_summary.py launches.csv"""
+stem_fused_kernel launches (or launches of the kernel named by the second argument, e.g. im2col_stem for the training
+step); per kernel name: launches, total us, share of the step.  usage: ncu_summary.py launches.csv [delimiter kernel]"""
 import collections
 import csv
 import re
@@ -18,7 +19,8 @@ def main():
         unit = r.get("Metric Unit", "ns")
         us = val / 1000.0 if unit in ("ns", "nsecond") else (val if unit in ("us", "usecond") else val * 1000.0)
         rows.append((r["Kernel Name"], us))
-    stems = [i for i, (n, _) in enumerate(rows) if "stem_fused_kernel" in n]
+    delim = sys.argv[2] if len(sys.argv) > 2 else "stem_fused_kernel"
+    stems = [i for i, (n, _) in enumerate(rows) if delim in n]
     if len(stems) >= 2:
         rows = rows[stems[-2]:stems[-1]]
     agg = collections.OrderedDict()
