@@ -582,7 +582,7 @@ def main():
             m5.remove_pretraining_modules()
             m5 = m5.to(dev, torch.bfloat16).train()
             params = m5.full_parameters(True, True)[0] if fgm > 0 else m5.tail_parameters()
-            reducer = GradientAllReducer(params) if world > 1 else None
+            reducer = GradientAllReducer(params).attach(m5) if world > 1 else None      # buckets reduced during the backward
 
             def step5():
                 y5, _ = m5.extract_finetune({"audio": a5, "video": v5}, None)

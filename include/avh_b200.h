@@ -191,6 +191,18 @@ AVH_API int avh_encoder_train_forward(avh_handle* h, const void* x, int x_dtype,
                                       void* out, int out_dtype, void* stream);
 AVH_API int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, float* grads,
                                  int64_t grads_capacity, void* stream);
+/* The same backward with the gradients handed over BUCKET BY BUCKET, so that the gradient all-reduce of the training
+ * configuration (fairseq legacy_distributed_data_parallel.py:76-165) overlaps the rest of the backward:
+ * the flat buffer is cut into buckets in the order the backward completes them (four encoder layers each, last layers
+ * first; then final LayerNorm + positional conv + fusion tail; then the feature extractors).  As soon as a bucket is
+ * final it is converted into `grads` (fp32 / bf16 / fp16 [avh_encoder_grad_count], same element offsets) and an event is
+ * recorded; avh_grad_bucket_wait makes another stream wait for bucket k of the last avh_encoder_backward_buckets call
+ * (the caller then issues its collective there).  Bucket geometry is a property of the last training forward's plan. */
+AVH_API int avh_encoder_backward_buckets(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, void* grads,
+                                         int grads_dtype, int64_t grads_capacity, void* stream);
+AVH_API int avh_grad_bucket_count(avh_handle* h, int32_t* count);
+AVH_API int avh_grad_bucket_range(avh_handle* h, int k, int64_t* begin, int64_t* end);       /* [begin, end) elements */
+AVH_API int avh_grad_bucket_wait(avh_handle* h, int k, void* stream);
 
 /* The trainable tail of AVHubertModel.extract_finetune when the feature extractors are frozen (feature_grad_mult <= 0: the
  * reference runs them under no_grad, avhubert/hubert.py:538-547): fused [B,T,E] = the concatenated / summed extractor

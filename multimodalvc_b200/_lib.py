@@ -21,6 +21,7 @@ EXPORTS = [
     "avh_release_stream", "avh_attention_bf16", "avh_forward_ragged", "avh_encoder_forward", "avh_forward_train", "avh_bn_stats_count", "avh_read_bn_stats", "avh_dropout", "avh_interp_linear", "avh_graph_launch_count",
     "avh_mask_substitute", "avh_compute_logits", "avh_sum_squares", "avh_qformer_forward",
     "avh_encoder_grad_count", "avh_encoder_train_forward", "avh_encoder_backward",
+    "avh_encoder_backward_buckets", "avh_grad_bucket_count", "avh_grad_bucket_range", "avh_grad_bucket_wait",
     "avh_tail_grad_count", "avh_tail_train_forward", "avh_full_grad_count", "avh_full_train_forward",
 ]
 
@@ -91,6 +92,10 @@ def load():
     lib.avh_tail_train_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp]
     lib.avh_encoder_train_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp]
     lib.avh_encoder_backward.argtypes = [vp, vp, i32, vp, i32, vp, i64, vp]
+    lib.avh_encoder_backward_buckets.argtypes = [vp, vp, i32, vp, i32, vp, i32, i64, vp]
+    lib.avh_grad_bucket_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.avh_grad_bucket_range.argtypes = [vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.avh_grad_bucket_wait.argtypes = [vp, i32, vp]
     lib.avh_qformer_forward.argtypes = [vp, vp, i32, vp, ctypes.POINTER(ctypes.c_int32), i32, i32, i32, vp, i32, vp]
     lib.avh_mask_substitute.argtypes = [vp, i32, i32, ctypes.POINTER(i64), i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]
     lib.avh_compute_logits.argtypes = [vp, i32, i64, vp, i32, i64, vp, i64, i32, i32, i32, ctypes.c_float, vp, i64, vp]

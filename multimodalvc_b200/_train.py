@@ -1,0 +1,55 @@
+"""Host side of the device backward shared by the three autograd wrappers (TransformerEncoder, the fusion tail, the whole
+AVHubertModel): one call into the library that fills a flat gradient buffer in the parameters' dtype bucket by bucket,
+and — when a GradientAllReducer is attached to the module — the all-reduce of every bucket issued on a side stream as
+soon as the library has recorded the bucket's event, so that the collective overlaps the rest of the backward
+(fairseq legacy_distributed_data_parallel.py:76-165 does the reduction after the backward; same result)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def backward_flat(handle, dout, dx, n_floats, dtypes, fwd_stream, owner):
+    """Runs the library backward of the last training forward on `handle`.  Returns {dtype: flat gradient buffer}: when
+    every parameter has the same dtype the buffer is written in that dtype directly (and all-reduced bucket by bucket if
+    `owner._grad_sync` is an active GradientAllReducer); otherwise fp32, converted once per dtype on demand."""
+    dev = dout.device
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    single = dtypes[0] if dtypes and all(d == dtypes[0] for d in dtypes) and dtypes[0] in _DTYPES else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if stream != fwd_stream:
+            raise RuntimeError("the backward must run on the CUDA stream of its forward")
+        dxp = vp(dx.data_ptr()) if dx is not None else None
+        dxd = _DTYPES[dx.dtype] if dx is not None else 0
+        if single is None:
+            flat = torch.empty(n_floats, device=dev, dtype=torch.float32)
+            _lib.check(lib.avh_encoder_backward(handle, vp(dout.data_ptr()), _DTYPES[dout.dtype], dxp, dxd, vp(flat.data_ptr()),
+                                                n_floats, vp(stream)))
+            return _FlatGrads(flat)
+        flat = torch.empty(n_floats, device=dev, dtype=single)
+        _lib.check(lib.avh_encoder_backward_buckets(handle, vp(dout.data_ptr()), _DTYPES[dout.dtype], dxp, dxd,
+                                                    vp(flat.data_ptr()), _DTYPES[single], n_floats, vp(stream)))
+        sync = getattr(owner, "_grad_sync", None)
+        reduced = sync is not None and sync.reduce_buckets(lib, handle, flat)
+    out = _FlatGrads(flat)
+    out.reduced = bool(reduced)
+    return out
+
+
+class _FlatGrads:
+    """The flat buffer in one dtype, other dtypes converted once on demand."""
+
+    def __init__(self, flat):
+        self.base = flat
+        self.by_dtype = {flat.dtype: flat}
+        self.reduced = False
+
+    def of(self, dt):
+        if dt not in self.by_dtype:
+            self.by_dtype[dt] = self.base.to(dt)
+        return self.by_dtype[dt]

@@ -184,6 +184,8 @@ struct CallArgs {          // per-call pointers the steps read through the plan
   const void* xin = nullptr; // encoder-only plans: features [B,T,D]
   int xin_dt = 0;
   int pitch = 0;             // ragged plans: time pitch of the caller's padded tensors (baked into captured launches)
+  void* grads_out = nullptr; // training backward: the caller's gradient buffer, filled bucket by bucket (never captured)
+  int grads_dt = 0;
   // graph-cache key: the INPUT pointers (the output is written by the last step, which stays outside the graph)
   bool operator<(const CallArgs& o) const {
     return std::tie(video, video_dt, audio, audio_dt, as[0], as[1], as[2], mask, pitch, xin, xin_dt) <
@@ -227,6 +229,10 @@ struct Plan {
   static constexpr int RAG_SLOTS = 4;
   int* rag_host[RAG_SLOTS] = {nullptr, nullptr, nullptr, nullptr};      // pinned mirrors, used round robin
   cudaEvent_t rag_done[RAG_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  // training plans: gradient buckets in the order the backward completes them ([begin, end) floats of the flat buffer)
+  // and one event per bucket, recorded right after the bucket was copied into the caller's buffer
+  struct GradBucket { long long begin, end; cudaEvent_t ev; };
+  std::vector<GradBucket> buckets;
   int rag_next = 0;
   int* pos_row_map = nullptr;
 
@@ -272,6 +278,8 @@ struct Plan {
       if (rag_host[i]) cudaFreeHost(rag_host[i]);
       if (rag_done[i]) cudaEventDestroy(rag_done[i]);
     }
+    for (GradBucket& gb : buckets)
+      if (gb.ev) cudaEventDestroy(gb.ev);
     arena.release();
   }
 };
@@ -1706,6 +1714,34 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   float* dy = f32buf(N * D);
   float* dxo = f32buf(N * D);
   if (!sizing) { plan->grads = grads; plan->grad_floats = GF; plan->dy_in = dy; plan->dx_out = dxo; }
+  // gradient bucket [begin, end) of the flat buffer is final here: a direct (never captured) step hands it to the caller —
+  // converted into the caller's buffer when avh_encoder_backward_buckets runs the plan — and records the bucket's event,
+  // so that an all-reduce on another stream can start while the rest of the backward still runs
+  auto grad_mark = [&](long long begin, long long end) {
+    if (end <= begin) return;
+    int k = -1;
+    if (!sizing) {
+      Plan::GradBucket gb{begin, end, nullptr};
+      cudaEventCreateWithFlags(&gb.ev, cudaEventDisableTiming);
+      plan->buckets.push_back(gb);
+      k = (int)plan->buckets.size() - 1;
+    }
+    const std::string keep = b.tag;
+    b.tag = "grad_bucket";
+    b.cur_direct = true;
+    b.push([=](cudaStream_t s) {
+      const CallArgs& a = pl->args;
+      if (a.grads_out == nullptr) return 0;
+      const Plan::GradBucket& gb = pl->buckets[k];
+      const size_t es = a.grads_dt == DT_F32 ? 4 : 2;
+      if (launch_convert(pl->grads + gb.begin, DT_F32, reinterpret_cast<char*>(a.grads_out) + (size_t)gb.begin * es, a.grads_dt,
+                         gb.end - gb.begin, s))
+        return 1;
+      return cudaEventRecord(gb.ev, s) == cudaSuccess ? 0 : 1;
+    });
+    b.cur_direct = false;
+    b.tag = keep;
+  };
 
   // ---------------------------------------------------------------- saved activations
   float* x0 = f32buf(N * D);
@@ -2114,6 +2150,10 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
       b.tag = "ln_bwd";
       b.push([=](cudaStream_t s) { return launch_ln_bwd(xl, gm, dh, dxm, dx, stats, g_ln1, g_ln1 + D, N, D, 1e-5f, s); });
     }
+    if (l % 4 == 0) {      // layers l .. l+3 are final: one gradient bucket (Large: 4 x 12.6 M floats)
+      b.cur_layer = -1;
+      grad_mark((long long)l * LG, (long long)std::min(L, l + 4) * LG);
+    }
   }
   b.cur_layer = -1;
   // ---- positional conv block: x1 = x0 + GELU(c), c = conv(x0) + bias  (pos-conv weight gradients: see posconv_bwd)
@@ -2161,6 +2201,8 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
       float* gm = h->fuse_ln_g;
       b.tag = "ln_bwd";
       b.push([=](cudaStream_t s) { return launch_ln_bwd(fused, gm, dfl, nullptr, dfused, stats, g_ln, g_ln + E, N, E, 1e-5f, s); });
+      // final LayerNorm, positional conv, post_extract_proj, fusion LayerNorm: one bucket; the feature extractors' another
+      grad_mark((long long)L * LG, full ? (g_ln + 2ll * E) - grads : GF);
       if (full) {
         // ============================================================ backward of the feature extractors (mode 2)
         float* gf = g_ln + 2ll * E;                         // frontend gradients follow layer_norm.{weight,bias}
@@ -2398,7 +2440,10 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
               return false;
           }
         }
+        grad_mark((g_ln + 2ll * E) - grads, GF);         // modality projections + lip ResNet
       }
+    } else {
+      grad_mark((long long)L * LG, GF);                  // final LayerNorm + positional conv
     }
   }
   if (bytes_out) *bytes_out = b.sizer.used;
@@ -3201,11 +3246,62 @@ int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype, void* 
   // dL/dy -> fp32.  Rows of padded frames are taken as given, as autograd does: the dense forward computed those rows
   // (their queries attend to the valid keys), so a loss that reads them sends gradient through them too
   if (avh::launch_load_rows(dout, dout_dtype, p->dy_in, nullptr, N, D, s)) return 1;
+  p->args.grads_out = nullptr;
   if (run_steps(h, p, p->fwd_steps, p->steps.size(), s)) return 1;
   if (dx != nullptr && avh::launch_convert(p->dx_out, avh::DT_F32, dx, dx_dtype, N * D, s)) return 1;
   if (grads != nullptr)
     AVH_CUDA_OK(cudaMemcpyAsync(grads, p->grads, (size_t)p->grad_floats * 4, cudaMemcpyDeviceToDevice, s));
   p->fwd_done = false;
+  return 0;
+}
+
+int avh_encoder_backward_buckets(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, void* grads,
+                                 int grads_dtype, int64_t grads_capacity, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  AVH_CHECK(dout != nullptr && grads != nullptr, "null argument");
+  AVH_CHECK(grads_dtype == AVH_F32 || grads_dtype == AVH_BF16 || grads_dtype == AVH_F16, "bad gradient dtype");
+  avh::Plan* p = h->last_plan;
+  AVH_CHECK(p != nullptr && p->enc_train && p->fwd_done, "avh_encoder_backward_buckets follows a training forward on the same handle");
+  AVH_CHECK(grads_capacity >= p->grad_floats, "gradient buffer too small (avh_encoder_grad_count)");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AVH_CHECK(s == p->stream, "backward must run on the stream of its forward");
+  const long long N = (long long)p->B * p->T;
+  const int D = h->cfg.encoder_embed_dim;
+  if (avh::launch_load_rows(dout, dout_dtype, p->dy_in, nullptr, N, D, s)) return 1;
+  p->args.grads_out = grads;
+  p->args.grads_dt = grads_dtype;
+  const int rc = run_steps(h, p, p->fwd_steps, p->steps.size(), s);
+  p->args.grads_out = nullptr;
+  if (rc) return 1;
+  if (dx != nullptr && avh::launch_convert(p->dx_out, avh::DT_F32, dx, dx_dtype, N * D, s)) return 1;
+  p->fwd_done = false;
+  return 0;
+}
+
+int avh_grad_bucket_count(avh_handle* h, int32_t* count) {
+  AVH_CHECK(h != nullptr && count != nullptr, "null argument");
+  avh::Plan* p = h->last_plan;
+  AVH_CHECK(p != nullptr && p->enc_train, "no training plan on this handle yet (run a training forward first)");
+  *count = (int32_t)p->buckets.size();
+  return 0;
+}
+
+int avh_grad_bucket_range(avh_handle* h, int k, int64_t* begin, int64_t* end) {
+  AVH_CHECK(h != nullptr && begin != nullptr && end != nullptr, "null argument");
+  avh::Plan* p = h->last_plan;
+  AVH_CHECK(p != nullptr && p->enc_train && k >= 0 && k < (int)p->buckets.size(), "bucket index out of range");
+  *begin = p->buckets[k].begin;
+  *end = p->buckets[k].end;
+  return 0;
+}
+
+int avh_grad_bucket_wait(avh_handle* h, int k, void* stream) {
+  AVH_CHECK(h != nullptr, "null handle");
+  avh::Plan* p = h->last_plan;
+  AVH_CHECK(p != nullptr && p->enc_train && k >= 0 && k < (int)p->buckets.size(), "bucket index out of range");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  AVH_CUDA_OK(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), p->buckets[k].ev, 0));
   return 0;
 }
 

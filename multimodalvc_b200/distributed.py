@@ -37,6 +37,8 @@ class GradientAllReducer:
         self.bucket_bytes = int(bucket_bytes)
         self.buffer: Optional[torch.Tensor] = None
         self.accumulate_grads = False
+        self._side = None                 # stream the overlapped bucket reductions are issued from
+        self._presynced = set()           # ids of parameters whose gradients the backward already averaged this step
 
     @contextmanager
     def no_sync(self):
@@ -47,6 +49,52 @@ class GradientAllReducer:
             yield
         finally:
             self.accumulate_grads = old
+
+    # ------------------------------------------------------------------------------- overlap with the device backward
+    def attach(self, module):
+        """Overlap the reduction with `module`'s device backward (TransformerEncoder / AVHubertModel with trainable
+        weights): the library hands the flat gradient buffer over bucket by bucket (avh_encoder_backward_buckets) and every
+        bucket's all-reduce is issued from a side stream as soon as its event is recorded.  all_reduce_grads() then only
+        reduces what the backward did not cover (other modules' parameters).  Returns self."""
+        module._grad_sync = self
+        return self
+
+    def reduce_buckets(self, lib, handle, flat) -> bool:
+        """Called by the backward (multimodalvc_b200/_train.py) right after the library call returned (all launches are
+        enqueued, none needs to have run).  Averages `flat` over the group in place, bucket by bucket; the caller's stream
+        waits for the last collective before anything reads the gradients.  False = nothing done (single rank, no_sync,
+        or not an NCCL group): all_reduce_grads() will do the work."""
+        import ctypes
+        if self.accumulate_grads or self.world_size == 1 or not flat.is_cuda:
+            return False
+        if dist.get_backend(self.process_group) != "nccl":
+            return False
+        from . import _lib
+        n = ctypes.c_int32()
+        _lib.check(lib.avh_grad_bucket_count(handle, ctypes.byref(n)))
+        if n.value == 0:
+            return False
+        dev = flat.device
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        flat.record_stream(self._side)
+        works, covered = [], 0
+        for k in range(n.value):
+            b, e = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(lib.avh_grad_bucket_range(handle, k, ctypes.byref(b), ctypes.byref(e)))
+            _lib.check(lib.avh_grad_bucket_wait(handle, k, ctypes.c_void_p(self._side.cuda_stream)))
+            with torch.cuda.stream(self._side):        # the collective is ordered after the side stream, i.e. after the event
+                works.append(self._reduce_async(flat[b.value:e.value], True))
+            covered += e.value - b.value
+        if covered != flat.numel():
+            raise RuntimeError("gradient buckets do not cover the flat buffer")
+        for w in works:
+            if w is not None:
+                w.wait()                               # the current stream waits; the host does not
+        return True
+
+    def mark_reduced(self, params):
+        self._presynced.update(id(p) for p in params)
 
     # ------------------------------------------------------------------------------------------------ helpers
     def _reduce_async(self, flat: torch.Tensor, nonzero: bool):
@@ -88,8 +136,9 @@ class GradientAllReducer:
         if self.accumulate_grads:
             return 0
         by_device = {}
+        presynced, self._presynced = self._presynced, set()
         for p in self.params:
-            if not p.requires_grad or hasattr(p, "expert"):
+            if not p.requires_grad or hasattr(p, "expert") or id(p) in presynced:
                 continue
             if p.grad is not None and p.grad.requires_grad:
                 raise RuntimeError("gradient all-reduce only works with gradients that don't require grad")

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, masking
+from ._train import backward_flat
 
 _DTYPES = {torch.float32: _lib.AVH_F32, torch.float16: _lib.AVH_F16, torch.bfloat16: _lib.AVH_BF16}
 _U8 = _lib.AVH_U8        # raw uint8 video frames (normalised + centre-cropped on the device)
@@ -209,7 +210,7 @@ class _TailTrainFn(torch.autograd.Function):
                 handle, ctypes.c_void_p(fused.data_ptr()), _DTYPES[fused.dtype],
                 ctypes.c_void_p(pm_u8.data_ptr()) if pm_u8 is not None else None, B, T,
                 ctypes.c_void_p(out.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(stream)))
-        ctx.handle, ctx.stream = handle, stream
+        ctx.handle, ctx.stream, ctx.model, ctx.params = handle, stream, model, params
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.dtypes = [p.dtype for p in params]
         return out
@@ -223,28 +224,17 @@ class _TailTrainFn(torch.autograd.Function):
         lib = _lib.load()
         n = ctypes.c_int64()
         _lib.check(lib.avh_tail_grad_count(ctx.handle, ctypes.byref(n)))
-        flat = torch.empty(n.value, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            if stream != ctx.stream:
-                raise RuntimeError("the backward must run on the CUDA stream of its forward")
-            _lib.check(lib.avh_encoder_backward(ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], None, 0,
-                                                ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+        flat = backward_flat(ctx.handle, dout, None, n.value, ctx.dtypes, ctx.stream, ctx.model)
         grads, off = [], 0
-        converted = {torch.float32: flat}
-
-        def flat_of(dt):            # ONE conversion of the flat buffer per parameter dtype (not one kernel per parameter)
-            if dt not in converted:
-                converted[dt] = flat.to(dt)
-            return converted[dt]
-
         for shape, dt in zip(ctx.shapes, ctx.dtypes):
             k = 1
             for d in shape:
                 k *= d
-            grads.append(flat_of(dt)[off:off + k].view(shape))
+            grads.append(flat.of(dt)[off:off + k].view(shape))
             off += k
         assert off == n.value
+        if flat.reduced:
+            ctx.model._grad_sync.mark_reduced(ctx.params)
         return (None, None, None, *grads)
 
 
@@ -273,6 +263,7 @@ class _FullTrainFn(torch.autograd.Function):
                 vp(pm_u8.data_ptr()) if pm_u8 is not None else None, B, T, float(fgm), 0.1, vp(out.data_ptr()),
                 _DTYPES[out_dtype], vp(stream)))
         ctx.handle, ctx.stream, ctx.spec = handle, stream, spec
+        ctx.model, ctx.params = model, params
         ctx.flags = (int(video is not None), int(audio is not None))
         ctx.keep = (video, audio)                      # the backward re-reads the frames (stem patches are recomputed)
         ctx.dtypes = [p.dtype for p in params]
@@ -287,28 +278,17 @@ class _FullTrainFn(torch.autograd.Function):
         lib = _lib.load()
         n = ctypes.c_int64()
         _lib.check(lib.avh_full_grad_count(ctx.handle, ctx.flags[0], ctx.flags[1], ctypes.byref(n)))
-        flat = torch.empty(n.value, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            if stream != ctx.stream:
-                raise RuntimeError("the backward must run on the CUDA stream of its forward")
-            _lib.check(lib.avh_encoder_backward(ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], None, 0,
-                                                ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+        flat = backward_flat(ctx.handle, dout, None, n.value, ctx.dtypes, ctx.stream, ctx.model)
         grads, off = [], 0
-        converted = {torch.float32: flat}
-
-        def flat_of(dt):            # ONE conversion of the flat buffer per parameter dtype (not one kernel per parameter)
-            if dt not in converted:
-                converted[dt] = flat.to(dt)
-            return converted[dt]
-
         for (shape, to_param), dt in zip(ctx.spec, ctx.dtypes):
             k = 1
             for d in shape:
                 k *= d
-            grads.append(to_param(flat_of(dt)[off:off + k].view(shape)))
+            grads.append(to_param(flat.of(dt)[off:off + k].view(shape)))
             off += k
         assert off == n.value, (off, n.value)
+        if flat.reduced:
+            ctx.model._grad_sync.mark_reduced(ctx.params)
         return (None, None, None, None, None, None, *grads)
 
 

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._train import backward_flat
 from .hubert import _DTYPES, _EncoderParams
 from .hubert_asr import _project
 
@@ -45,6 +46,7 @@ class _EncoderTrainFn(torch.autograd.Function):
         ctx.enc, ctx.handle, ctx.x_dtype, ctx.stream = enc, handle, x.dtype, stream
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.dtypes = [p.dtype for p in params]
+        ctx.params = params
         return out
 
     @staticmethod
@@ -57,30 +59,18 @@ class _EncoderTrainFn(torch.autograd.Function):
         lib = _lib.load()
         n = ctypes.c_int64()
         _lib.check(lib.avh_encoder_grad_count(ctx.handle, ctypes.byref(n)))
-        flat = torch.empty(n.value, device=dev, dtype=torch.float32)
         dx = torch.empty(dout.shape, device=dev, dtype=ctx.x_dtype)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            if stream != ctx.stream:
-                raise RuntimeError("the encoder backward must run on the CUDA stream of its forward")
-            _lib.check(lib.avh_encoder_backward(
-                ctx.handle, ctypes.c_void_p(dout.data_ptr()), _DTYPES[dout.dtype], ctypes.c_void_p(dx.data_ptr()),
-                _DTYPES[dx.dtype], ctypes.c_void_p(flat.data_ptr()), n.value, ctypes.c_void_p(stream)))
+        flat = backward_flat(ctx.handle, dout, dx, n.value, ctx.dtypes, ctx.stream, enc)
         grads, off = [], 0
-        converted = {torch.float32: flat}
-
-        def flat_of(dt):            # ONE conversion of the flat buffer per parameter dtype (not one kernel per parameter)
-            if dt not in converted:
-                converted[dt] = flat.to(dt)
-            return converted[dt]
-
         for shape, dt in zip(ctx.shapes, ctx.dtypes):
             k = 1
             for d in shape:
                 k *= d
-            grads.append(flat_of(dt)[off:off + k].view(shape))
+            grads.append(flat.of(dt)[off:off + k].view(shape))
             off += k
         assert off == n.value
+        if flat.reduced:
+            enc._grad_sync.mark_reduced(ctx.params)
         return (None, dx, None, *grads)
 
 

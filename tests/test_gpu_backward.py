@@ -445,3 +445,19 @@ def test_full_finetune_step_bf16_and_sgd():
         opt.step()
         losses.append(loss.item())
     assert losses[2] < losses[1] < losses[0], losses
+
+
+def test_overlapped_gradient_allreduce_two_gpus():
+    """SURVEY row A19 overlapped with A18: with GradientAllReducer.attach(model) the backward hands the gradients over
+    bucket by bucket and every bucket is all-reduced (NCCL, side stream) while the rest of the backward runs; the result
+    is bit-identical to the reduction after the backward (2 ranks).  Worker: tests/dist_overlap_worker.py."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(here, "dist_overlap_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
