@@ -201,6 +201,17 @@ AVH_API int avh_encoder_backward(avh_handle* h, const void* dout, int dout_dtype
 AVH_API int avh_encoder_backward_buckets(avh_handle* h, const void* dout, int dout_dtype, void* dx, int dx_dtype, void* grads,
                                          int grads_dtype, int64_t grads_capacity, void* stream);
 AVH_API int avh_grad_bucket_count(avh_handle* h, int32_t* count);
+/* After an optimizer step on a trainable handle (avh_config.reserved[3] = 1): rewrite, IN PLACE and on the device, every
+ * packed tensor the TRAINING plans read (K-major bf16 planes of every Linear / convolution and their transposes, biases,
+ * LayerNorm / BatchNorm affine parameters, PReLU slopes, the weight-normed positional convolution) from the caller's
+ * device-resident parameters: names[i] = state-dict key (the reference's names, as avh_load_tensor), ptrs[i] = device
+ * pointer of the contiguous tensor, dtypes[i] = AVH_F32 / AVH_F16 / AVH_BF16, numels[i] = element count.  Plans and
+ * captured graphs stay valid (no pointer moves); nothing crosses the host (avh_finalize_weights re-packs through the
+ * host: seconds for the Large model).  The eval-only packed forms (BatchNorm folded with the running statistics,
+ * LayerNorm folded into the QKV / fc1 weights, the fused stem order) are NOT refreshed: before the next eval-mode
+ * forward reload the state dict and call avh_finalize_weights.  Enqueued on `stream`. */
+AVH_API int avh_refresh_weights_device(avh_handle* h, const char* const* names, const void* const* ptrs, const int32_t* dtypes,
+                                       const int64_t* numels, int32_t count, void* stream);
 AVH_API int avh_grad_bucket_range(avh_handle* h, int k, int64_t* begin, int64_t* end);       /* [begin, end) elements */
 AVH_API int avh_grad_bucket_wait(avh_handle* h, int k, void* stream);
 

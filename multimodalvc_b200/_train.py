@@ -53,3 +53,28 @@ class _FlatGrads:
         if dt not in self.by_dtype:
             self.by_dtype[dt] = self.base.to(dt)
         return self.by_dtype[dt]
+
+
+def refresh_weights_device(handle, module, prefix=""):
+    """After an optimizer step: rewrite the packed weights the training plans read from `module`'s device-resident
+    parameters, in place and on the device (avh_refresh_weights_device) — plans and captured graphs stay valid, nothing
+    crosses the host.  `prefix` maps the module's parameter names onto the state-dict keys the handle was loaded with."""
+    lib = _lib.load()
+    names, tensors = [], []
+    for name, p in module.named_parameters():
+        t = p.detach()
+        if not t.is_floating_point():
+            continue
+        if t.dtype not in _DTYPES:
+            t = t.float()
+        names.append((prefix + name).encode())
+        tensors.append(t.contiguous())
+    n = len(names)
+    c_names = (ctypes.c_char_p * n)(*names)
+    c_ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    c_dts = (ctypes.c_int32 * n)(*[_DTYPES[t.dtype] for t in tensors])
+    c_num = (ctypes.c_int64 * n)(*[t.numel() for t in tensors])
+    dev = tensors[0].device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.avh_refresh_weights_device(handle, c_names, c_ptrs, c_dts, c_num, n, ctypes.c_void_p(stream)))

@@ -310,6 +310,20 @@ struct avh_handle {
   float* pos_bias = nullptr;
   int pos_window = 64;            // input-channel window per 64-column N tile (64 or 128)
   int* pos_acol = nullptr;        // device [D/64] window start per N tile
+  float* pos_ratio = nullptr;     // trainable handles: device scratch [KT] of the weight-norm ratios (refresh on the device)
+  // trainable handles: how every packed tensor the TRAINING plans read derives from a state-dict entry, recorded by the
+  // packers; avh_refresh_weights_device replays the list with device kernels (refresh.cu)
+  struct RefreshJob {
+    std::string src;              // state-dict key
+    int form = 0;                 // RJ_*
+    void* dst = nullptr;
+    long long n = 0, k = 0;       // source [n, k] (matrix forms), n elements (vector), cout / cin (conv)
+    long long ld = 0;             // elements of one plane of a destination row
+    long long off = 0;            // destination row offset (matrix), column offset (transposed matrix)
+    float scale = 1.f;
+    int ks = 0;                   // conv: taps per side
+  };
+  std::vector<RefreshJob> refresh_jobs;
   std::vector<LayerW> layers;
   // Q-Former handles (cfg.reserved[0] == 2): reserved[1] = encoder_width, reserved[2] = rows of query_tokens
   std::vector<QfLayerW> qf_layers;
@@ -338,6 +352,8 @@ namespace {
 int dtype_size(int dt) { return dt == AVH_F32 ? 4 : (dt == AVH_U8 ? 1 : 2); }
 
 // ============================================================================ weight folding / packing
+enum { RJ_MATRIX = 0, RJ_MATRIX_T, RJ_VEC, RJ_CONV, RJ_CONV_T, RJ_STEM, RJ_POS, RJ_POS_T, RJ_VEC_OFF };
+
 struct Packer {
   avh_handle* h;
   Arena* arena;      // null during sizing
@@ -385,6 +401,16 @@ struct Packer {
     return out;
   }
   float* upload_f(const std::vector<float>& v) { return upload(v); }
+  // record how a packed destination derives from a state-dict entry (trainable handles, real pass only)
+  bool recording() const { return arena != nullptr && h->cfg.reserved[3] != 0; }
+  void job(const std::string& src, int form, void* dst, long long n, long long k, long long ld, long long off = 0, float scale = 1.f,
+           int ks = 0) {
+    if (!recording() || dst == nullptr) return;
+    avh_handle::RefreshJob j;
+    j.src = src; j.form = form; j.dst = dst; j.n = n; j.k = k; j.ld = ld; j.off = off; j.scale = scale; j.ks = ks;
+    h->refresh_jobs.push_back(j);
+  }
+  void job_vec(const std::string& src, float* dst, long long n, float scale = 1.f) { job(src, RJ_VEC, dst, n, 0, 0, 0, scale); }
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -407,12 +433,14 @@ bool pack_conv(Packer& pk, const std::string& wkey, const std::string& bnkey, co
     for (int c = 0; c < cin; ++c)
       for (int t = 0; t < ks * ks; ++t) packed[(size_t)o * K + (size_t)t * cin + c] = w->v[((size_t)o * cin + c) * ks * ks + t];
   cu->w = pk.pack(packed, cout, K, K);
+  pk.job(wkey, RJ_CONV, cu->w.w, cout, cin, K, 0, 1.f, ks);
   if (pk.h->cfg.reserved[3] != 0 && pk.h->cfg.reserved[0] == 0) {
     const int cp = round_up(cout, 64);
     std::vector<float> pt((size_t)K * cp, 0.f);
     for (int o = 0; o < cout; ++o)
       for (int k = 0; k < K; ++k) pt[(size_t)k * cp + o] = packed[(size_t)o * K + k];
     cu->wT = pk.pack(pt, K, cout, cp);
+    pk.job(wkey, RJ_CONV_T, cu->wT.w, cout, cin, cp, 0, 1.f, ks);
   }
   std::vector<float> sc(cout), bi(cout);
   for (int o = 0; o < cout; ++o) {
@@ -424,11 +452,14 @@ bool pack_conv(Packer& pk, const std::string& wkey, const std::string& bnkey, co
   cu->bias = pk.upload_f(bi);
   cu->gamma = pk.upload_f(g->v); cu->beta = pk.upload_f(b->v);
   cu->rmean = pk.upload_f(m->v); cu->rvar = pk.upload_f(v->v);
+  pk.job_vec(bnkey + ".weight", cu->gamma, cout);
+  pk.job_vec(bnkey + ".bias", cu->beta, cout);
   cu->slope = nullptr;
   if (s) {
     std::vector<float> sl(cout);
     for (int o = 0; o < cout; ++o) sl[o] = s->v[s->numel() == 1 ? 0 : o];
     cu->slope = pk.upload_f(sl);
+    pk.job_vec(prelu_key, cu->slope, cout);
   }
   return true;
 }
@@ -455,6 +486,11 @@ bool pack_linear_T(Packer& pk, const std::vector<std::string>& prefixes, const s
   }
   lw->w = pk.pack(p, k, n, npad);
   lw->bias = nullptr;
+  r0 = 0;
+  for (size_t t = 0; t < ws.size(); ++t) {
+    pk.job(prefixes[t] + ".weight", RJ_MATRIX_T, lw->w.w, ws[t]->shape[0], k, npad, r0, scales[t]);
+    r0 += (int)ws[t]->shape[0];
+  }
   return true;
 }
 
@@ -470,6 +506,8 @@ bool pack_linear(Packer& pk, const std::string& prefix, LinearW* lw, float wscal
   std::vector<float> bb(b->v);
   for (auto& x : bb) x *= wscale;
   lw->bias = pk.upload_f(bb);
+  pk.job(prefix + ".weight", RJ_MATRIX, lw->w.w, n, k, kpad, 0, wscale);
+  pk.job_vec(prefix + ".bias", lw->bias, n, wscale);
   return true;
 }
 
@@ -572,6 +610,7 @@ bool pack_all(Packer& pk) {
         for (int dt = 0; dt < 5; ++dt)
           for (int k = 0; k < 49; ++k) p[(size_t)o * 320 + dt * 64 + k] = w->v[(size_t)o * 245 + dt * 49 + k];
       h->stem.w = pk.pack(p, 64, 245, 320);
+      pk.job(R + "frontend3D.0.weight", RJ_STEM, h->stem.w.w, 64, 245, 320);
       std::vector<float> pf((size_t)64 * 320, 0.f);     // fused stem kernel: K = dt*64 + kh*8 + kw
       for (int o = 0; o < 64; ++o)
         for (int dt = 0; dt < 5; ++dt)
@@ -592,6 +631,9 @@ bool pack_all(Packer& pk) {
       h->stem.slope = pk.upload_f(sl);
       h->stem.gamma = pk.upload_f(g->v); h->stem.beta = pk.upload_f(b->v);
       h->stem.rmean = pk.upload_f(m->v); h->stem.rvar = pk.upload_f(v->v);
+      pk.job_vec(R + "frontend3D.1.weight", h->stem.gamma, 64);
+      pk.job_vec(R + "frontend3D.1.bias", h->stem.beta, 64);
+      pk.job_vec(R + "frontend3D.2.weight", h->stem.slope, 64);
     } else ok = false;
   }
   // ---- ResNet-18 trunk (avhubert/resnet.py:77-129)
@@ -644,6 +686,7 @@ bool pack_all(Packer& pk) {
         std::vector<float> sl(cout);
         for (int o = 0; o < cout; ++o) sl[o] = s2->v[s2->numel() == 1 ? 0 : o];
         bw.slope2 = pk.upload_f(sl);
+        pk.job_vec(pre + "relu2.weight", bw.slope2, cout);
       } else ok = false;
     }
   // ---- modality projections, fusion LN, post_extract_proj
@@ -653,7 +696,11 @@ bool pack_all(Packer& pk) {
     ok &= pack_linear(pk, "feature_extractor_audio.proj", &h->proj_a);
     const HostTensor* g = pk.get("layer_norm.weight");
     const HostTensor* b = pk.get("layer_norm.bias");
-    if (g && b) { h->fuse_ln_g = pk.upload_f(g->v); h->fuse_ln_b = pk.upload_f(b->v); } else ok = false;
+    if (g && b) {
+      h->fuse_ln_g = pk.upload_f(g->v); h->fuse_ln_b = pk.upload_f(b->v);
+      pk.job_vec("layer_norm.weight", h->fuse_ln_g, (long long)g->v.size());
+      pk.job_vec("layer_norm.bias", h->fuse_ln_b, (long long)b->v.size());
+    } else ok = false;
   }
   h->has_post_proj = !enc_only && (c.modality_fuse == AVH_FUSE_CONCAT);
   if (h->has_post_proj) ok &= pack_linear(pk, "post_extract_proj", &h->post_proj);
@@ -693,6 +740,8 @@ bool pack_all(Packer& pk) {
       h->pos_w = pk.pack(p, D, kpad, kpad);
       h->pos_bias = pk.upload_f(wb->v);
       h->pos_acol = pk.upload(acol);
+      pk.job("encoder.pos_conv.0.weight_v", RJ_POS, h->pos_w.w, D, cg, kpad);
+      pk.job_vec("encoder.pos_conv.0.bias", h->pos_bias, D);
       if (c.reserved[3] != 0) {
         // backward w.r.t. the input: dx[t, i] = sum_k sum_o dc[t + KT/2 - k, o] w[o, i, k] — row = input channel, the
         // window holds the OUTPUT channels of the same groups (groups cover the same channel range on both sides)
@@ -709,6 +758,10 @@ bool pack_all(Packer& pk) {
         h->pos_wT = pk.pack(pt, D, kpad, kpad);
         h->pos_v_raw = pk.upload_f(wv->v);
         h->pos_g_raw = pk.upload_f(wg->v);
+        h->pos_ratio = pk.upload_f(ratio);
+        pk.job("encoder.pos_conv.0.weight_v", RJ_POS_T, h->pos_wT.w, D, cg, kpad);
+        pk.job_vec("encoder.pos_conv.0.weight_v", h->pos_v_raw, (long long)wv->v.size());
+        pk.job_vec("encoder.pos_conv.0.weight_g", h->pos_g_raw, (long long)wg->v.size());
       }
     } else ok = false;
   }
@@ -734,6 +787,13 @@ bool pack_all(Packer& pk) {
       for (int i = 0; i < D; ++i) { b[i] = qb->v[i] * qscale; b[D + i] = kb->v[i]; b[2 * D + i] = vb->v[i]; }
       lw.qkv.w = pk.pack(w, 3 * D, D, D);
       lw.qkv.bias = pk.upload_f(b);
+      {
+        const char* nm[3] = {"self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"};
+        for (int t = 0; t < 3; ++t) {
+          pk.job(pre + nm[t] + ".weight", RJ_MATRIX, lw.qkv.w.w, D, D, D, (long long)t * D, t == 0 ? qscale : 1.f);
+          pk.job(pre + nm[t] + ".bias", RJ_VEC_OFF, lw.qkv.bias, D, 0, 0, (long long)t * D, t == 0 ? qscale : 1.f);
+        }
+      }
       const HostTensor* g1 = pk.get(pre + "self_attn_layer_norm.weight");
       const HostTensor* b1 = pk.get(pre + "self_attn_layer_norm.bias");
       if (g1 && b1 && c.layer_norm_first && h->P == 1) pack_ln_folded(pk, w, b, 3 * D, D, g1->v, b1->v, &lw.qkv_ln, &lw.qkv_csum);
@@ -763,12 +823,20 @@ bool pack_all(Packer& pk) {
     if (g1 && b1 && g2 && b2) {
       lw.ln1_g = pk.upload_f(g1->v); lw.ln1_b = pk.upload_f(b1->v);
       lw.ln2_g = pk.upload_f(g2->v); lw.ln2_b = pk.upload_f(b2->v);
+      pk.job_vec(pre + "self_attn_layer_norm.weight", lw.ln1_g, D);
+      pk.job_vec(pre + "self_attn_layer_norm.bias", lw.ln1_b, D);
+      pk.job_vec(pre + "final_layer_norm.weight", lw.ln2_g, D);
+      pk.job_vec(pre + "final_layer_norm.bias", lw.ln2_b, D);
     } else ok = false;
   }
   {
     const HostTensor* g = pk.get("encoder.layer_norm.weight");
     const HostTensor* b = pk.get("encoder.layer_norm.bias");
-    if (g && b) { h->enc_ln_g = pk.upload_f(g->v); h->enc_ln_b = pk.upload_f(b->v); } else ok = false;
+    if (g && b) {
+      h->enc_ln_g = pk.upload_f(g->v); h->enc_ln_b = pk.upload_f(b->v);
+      pk.job_vec("encoder.layer_norm.weight", h->enc_ln_g, D);
+      pk.job_vec("encoder.layer_norm.bias", h->enc_ln_b, D);
+    } else ok = false;
   }
   return ok;
 }
@@ -2792,6 +2860,7 @@ int avh_finalize_weights(avh_handle* h) {
   h->prof_plan = nullptr;
   h->warena.release();
   h->warena = avh::Arena();
+  h->refresh_jobs.clear();
   avh::Packer sizer{h, nullptr, avh::Sizer(), ""};
   const bool ok = avh::pack_all(sizer);
   AVH_CHECK(ok, "missing state-dict key: " + sizer.missing);
@@ -3276,6 +3345,70 @@ int avh_encoder_backward_buckets(avh_handle* h, const void* dout, int dout_dtype
   if (rc) return 1;
   if (dx != nullptr && avh::launch_convert(p->dx_out, avh::DT_F32, dx, dx_dtype, N * D, s)) return 1;
   p->fwd_done = false;
+  return 0;
+}
+
+int avh_refresh_weights_device(avh_handle* h, const char* const* names, const void* const* ptrs, const int32_t* dtypes,
+                               const int64_t* numels, int32_t count, void* stream) {
+  AVH_CHECK(h != nullptr && names != nullptr && ptrs != nullptr && dtypes != nullptr && numels != nullptr, "null argument");
+  AVH_CHECK(h->finalized, "weights not finalized (call avh_finalize_weights once; this call refreshes them in place)");
+  AVH_CHECK(h->cfg.reserved[3] != 0, "only trainable handles (avh_config.reserved[3] = 1) record how to refresh their weights");
+  AVH_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  std::map<std::string, int> idx;
+  for (int i = 0; i < count; ++i) {
+    AVH_CHECK(names[i] != nullptr && ptrs[i] != nullptr, "null tensor in the parameter list");
+    AVH_CHECK(dtypes[i] == AVH_F32 || dtypes[i] == AVH_F16 || dtypes[i] == AVH_BF16, "bad parameter dtype");
+    idx[names[i]] = i;
+  }
+  const int P = h->P;
+  const int KT = h->cfg.conv_pos;
+  bool ratio_done = false;
+  for (const avh_handle::RefreshJob& j : h->refresh_jobs) {
+    auto it = idx.find(j.src);
+    AVH_CHECK(it != idx.end(), "parameter missing from the refresh list: " + j.src);
+    const int i = it->second;
+    const void* src = ptrs[i];
+    const int dt = dtypes[i];
+    const long long ne = numels[i];
+    switch (j.form) {
+      case avh::RJ_MATRIX:
+      case avh::RJ_MATRIX_T:
+        AVH_CHECK(ne == j.n * j.k, "parameter size changed: " + j.src);
+        if (avh::launch_refresh_matrix(src, dt, j.n, j.k, j.scale, j.dst, j.ld, P, j.off, j.form == avh::RJ_MATRIX_T, s)) return 1;
+        break;
+      case avh::RJ_VEC:
+      case avh::RJ_VEC_OFF:
+        AVH_CHECK(ne == j.n || ne == 1, "parameter size changed: " + j.src);
+        if (avh::launch_refresh_vec(src, dt, j.n, ne, j.scale, reinterpret_cast<float*>(j.dst) + j.off, s)) return 1;
+        break;
+      case avh::RJ_CONV:
+      case avh::RJ_CONV_T:
+        AVH_CHECK(ne == j.n * j.k * j.ks * j.ks, "parameter size changed: " + j.src);
+        if (avh::launch_refresh_conv(src, dt, (int)j.n, (int)j.k, j.ks * j.ks, j.dst, j.ld, P, j.form == avh::RJ_CONV_T, s)) return 1;
+        break;
+      case avh::RJ_STEM:
+        AVH_CHECK(ne == 64 * 245, "parameter size changed: " + j.src);
+        if (avh::launch_refresh_stem(src, dt, j.dst, P, s)) return 1;
+        break;
+      case avh::RJ_POS:
+      case avh::RJ_POS_T: {
+        AVH_CHECK(ne == j.n * j.k * KT && h->pos_ratio != nullptr, "parameter size changed: " + j.src);
+        if (!ratio_done) {
+          auto ig = idx.find("encoder.pos_conv.0.weight_g");
+          AVH_CHECK(ig != idx.end() && numels[ig->second] == KT, "parameter missing from the refresh list: encoder.pos_conv.0.weight_g");
+          if (avh::launch_posconv_ratio(src, dt, ptrs[ig->second], dtypes[ig->second], j.n * j.k, KT, h->pos_ratio, s)) return 1;
+          ratio_done = true;
+        }
+        if (avh::launch_refresh_pos(src, dt, h->pos_ratio, h->pos_acol, (int)j.n, (int)j.k, KT, h->pos_window, j.dst, P,
+                                    j.form == avh::RJ_POS_T, s))
+          return 1;
+        break;
+      }
+      default:
+        AVH_CHECK(false, "unknown refresh job");
+    }
+  }
   return 0;
 }
 

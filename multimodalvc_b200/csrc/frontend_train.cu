@@ -339,7 +339,7 @@ im2colT_kernel(const __nv_bfloat16* __restrict__ x, long long n, int H, int C, i
 template <bool F32>
 __global__ void __launch_bounds__(256)
 transposeT_kernel(const void* __restrict__ in, long long ld, long long rows, int C, __nv_bfloat16* __restrict__ out,
-                  long long out_ld) {
+                  long long out_ld, float scale) {
   __shared__ __align__(16) __nv_bfloat16 tile[64][72];
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
@@ -351,11 +351,19 @@ transposeT_kernel(const void* __restrict__ in, long long ld, long long rows, int
       if (F32) {
         const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + r * ld + c0 + j * 8);
         const float4 a = __ldg(src), b2 = __ldg(src + 1);
-        __nv_bfloat162 h[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
-                               __floats2bfloat162_rn(b2.x, b2.y), __floats2bfloat162_rn(b2.z, b2.w)};
+        __nv_bfloat162 h[4] = {__floats2bfloat162_rn(a.x * scale, a.y * scale), __floats2bfloat162_rn(a.z * scale, a.w * scale),
+                               __floats2bfloat162_rn(b2.x * scale, b2.y * scale), __floats2bfloat162_rn(b2.z * scale, b2.w * scale)};
         val = *reinterpret_cast<const uint4*>(h);
       } else {
         val = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + r * ld + c0) + j);
+        if (scale != 1.0f) {
+          float t[8];
+          bf16x8_to_float(val, t);
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(t[2 * e] * scale, t[2 * e + 1] * scale);
+          val = *reinterpret_cast<const uint4*>(h);
+        }
       }
     }
     *reinterpret_cast<uint4*>(&tile[i][(j ^ ((i >> 3) & 7)) << 3]) = val;
@@ -811,14 +819,14 @@ int launch_im2colT(const void* x, long long n, int H, int C, int ks, int stride,
   return 0;
 }
 int launch_transposeT(const void* in, int dt, long long ld, long long rows, int C, void* out, long long kp, long long out_ld,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, float scale) {
   AVH_CHECK((dt == DT_BF16 || dt == DT_F32) && C % 8 == 0 && ld % 8 == 0 && kp % 64 == 0 && kp >= rows && out_ld % 8 == 0,
             "tile transpose: bf16 / fp32 input, channel count and strides multiples of 8");
   dim3 grid((unsigned)(kp / 64), (unsigned)((C + 63) / 64));
   if (dt == DT_F32)
-    transposeT_kernel<true><<<grid, 256, 0, stream>>>(in, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), out_ld);
+    transposeT_kernel<true><<<grid, 256, 0, stream>>>(in, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), out_ld, scale);
   else
-    transposeT_kernel<false><<<grid, 256, 0, stream>>>(in, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), out_ld);
+    transposeT_kernel<false><<<grid, 256, 0, stream>>>(in, ld, rows, C, reinterpret_cast<__nv_bfloat16*>(out), out_ld, scale);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
   return 0;

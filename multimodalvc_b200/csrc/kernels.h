@@ -133,10 +133,21 @@ int launch_attention_bwd(const void* Q, long long ldq, const void* K, long long 
 int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int planes, cudaStream_t stream);
 int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* col, int planes,
                     cudaStream_t stream);
+// ---- refresh.cu: packed weights rewritten in place from device-resident parameters (index maps of api.cu's packers)
+int launch_refresh_matrix(const void* src, int dt, long long n, long long k, float scale, void* dst, long long ld, int planes,
+                          long long off, int transposed, cudaStream_t stream);
+int launch_refresh_vec(const void* src, int dt, long long n, long long n_src, float scale, float* dst, cudaStream_t stream);
+int launch_refresh_conv(const void* src, int dt, int cout, int cin, int ksq, void* dst, long long ld, int planes, int transposed,
+                        cudaStream_t stream);
+int launch_refresh_stem(const void* src, int dt, void* dst, int planes, cudaStream_t stream);
+int launch_posconv_ratio(const void* v, int v_dt, const void* g, int g_dt, long long per_tap, int KT, float* ratio,
+                         cudaStream_t stream);
+int launch_refresh_pos(const void* v, int dt, const float* ratio, const int* acol, int D, int cg, int KT, int window, void* dst,
+                       int planes, int transposed, cudaStream_t stream);
 int launch_im2colT(const void* x, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* colT, long long kp,
                    cudaStream_t stream);          // bf16 x -> bf16 colT [ks*ks*C, kp] (transposed patches)
 int launch_transposeT(const void* in, int dt, long long ld, long long rows, int C, void* out, long long kp, long long out_ld,
-                      cudaStream_t stream);       // [rows, C] bf16 / fp32 -> bf16 [C, out_ld] (64 x 64 tiles)
+                      cudaStream_t stream, float scale = 1.0f);       // [rows, C] bf16 / fp32 -> bf16 [C, out_ld] (64 x 64 tiles)
 int launch_col2im2d(const void* dcol, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, float* dx,
                     int accumulate, cudaStream_t stream);
 int launch_maxpool_dense(const void* x, void* y, int dt, long long n, int H, int C, int Ho, cudaStream_t stream,

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, masking
-from ._train import backward_flat
+from ._train import backward_flat, refresh_weights_device
 
 _DTYPES = {torch.float32: _lib.AVH_F32, torch.float16: _lib.AVH_F16, torch.bfloat16: _lib.AVH_BF16}
 _U8 = _lib.AVH_U8        # raw uint8 video frames (normalised + centre-cropped on the device)
@@ -379,6 +379,20 @@ class AVHubertModel(nn.Module):
         """Call after modifying parameters in place (optimizer step, manual edits)."""
         self._dirty = True
 
+    def _sync_trained_weights(self):
+        """Training steps: when an optimizer step changed the parameters since the last forward, refresh the packed
+        copies the training plans read — on the device, in place (a few ms; the full re-pack through the host takes
+        seconds for Large).  The eval-only packed forms are left stale: the next eval forward re-packs everything."""
+        versions = [p._version for p in self.parameters()]
+        if self._param_versions == versions:
+            return
+        if self._handle is not None and not self._dirty and self._param_versions is not None:
+            refresh_weights_device(self._handle, self)
+            self._eval_stale = True
+        else:
+            self._dirty = True
+        self._param_versions = versions
+
     def _destroy_handle(self):
         if self._handle is not None:
             _lib.load().avh_destroy(self._handle)
@@ -409,6 +423,9 @@ class AVHubertModel(nn.Module):
                                "device (there is no CPU path)")
         key = (p.device.index if p.device.index is not None else torch.cuda.current_device(),
                self._compute_mode(p.dtype))
+        if not self.training and getattr(self, "_eval_stale", False):
+            # training moved the BatchNorm running statistics / a device-side refresh skipped the eval-only packed forms
+            self._dirty, self._eval_stale = True, False
         if self._handle is not None and key == self._handle_key and not self._dirty:
             return self._handle
         lib = _lib.load()
@@ -606,8 +623,7 @@ class AVHubertModel(nn.Module):
                 v, _ = self.apply_input_mask(source["video"], padding_mask, None)
                 a, _ = self.apply_input_mask(source["audio"], padding_mask, None)
             source = {"audio": a, "video": v}
-        if self._param_versions != [p._version for p in self.parameters()]:
-            self._dirty = True
+        self._sync_trained_weights()
         handle = self._ensure_handle()
         self._param_versions = [p._version for p in self.parameters()]
         dev = self.encoder.layer_norm.weight.device
@@ -649,8 +665,7 @@ class AVHubertModel(nn.Module):
                 raise NotImplementedError(f"{name} must be 0 for the device training step (BASELINE config 5)")
         if c.feature_grad_mult > 0:
             return self._extract_finetune_full(source, padding_mask, mask)
-        if self._param_versions != [p._version for p in self.parameters()]:
-            self._dirty = True                                   # an optimizer step changed the weights: re-pack
+        self._sync_trained_weights()                             # an optimizer step changed the weights: refresh
         with torch.no_grad():
             y1, pm = self._extract_finetune_nograd(source, padding_mask, mask=mask, output_layer=1)
             B, T, _ = y1.shape

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._train import backward_flat
+from ._train import backward_flat, refresh_weights_device
 from .hubert import _DTYPES, _EncoderParams
 from .hubert_asr import _project
 
@@ -120,6 +120,8 @@ class TransformerEncoder(nn.Module):
             raise RuntimeError("multimodalvc_b200.TransformerEncoder computes on a B200 only (there is no CPU path)")
         mode = _lib.AVH_COMPUTE_FP32 if p.dtype == torch.float32 else _lib.AVH_COMPUTE_BF16
         key = (p.device.index if p.device.index is not None else torch.cuda.current_device(), mode)
+        if not self.training and getattr(self, "_eval_stale", False):
+            self._dirty, self._eval_stale = True, False      # the device-side refresh skipped the eval-only packed forms
         if self._handle is not None and key == self._handle_key and not self._dirty:
             return self._handle
         lib = _lib.load()
@@ -190,8 +192,14 @@ class TransformerEncoder(nn.Module):
             if tuple(padding_mask.shape) != (B, T):
                 raise ValueError(f"padding_mask must be [{B},{T}]")
             pm = padding_mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
-        if any(p._version != v for p, v in zip(self.parameters(), getattr(self, "_versions", []))) or not hasattr(self, "_versions"):
-            self._dirty = True                                   # an optimizer step changed the weights: re-pack
+        if not hasattr(self, "_versions"):
+            self._dirty = True
+        elif any(p._version != v for p, v in zip(self.parameters(), self._versions)):
+            if self._handle is not None and not self._dirty:     # an optimizer step changed the weights: refresh the packed
+                refresh_weights_device(self._handle, self, "encoder.")   # copies in place on the device (eval forms go stale)
+                self._eval_stale = True
+            else:
+                self._dirty = True
         self._ensure_handle()
         self._versions = [p._version for p in self.parameters()]
         return _EncoderTrainFn.apply(self, x, pm, *self.grad_parameters()), []

@@ -461,3 +461,51 @@ def test_overlapped_gradient_allreduce_two_gpus():
            "--master-port", "29547", os.path.join(here, "dist_overlap_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("fgm", [0.0, 1.0])
+def test_device_weight_refresh_matches_full_repack(fgm):
+    """After an optimizer step the packed weights are refreshed on the device, in place (avh_refresh_weights_device): the
+    next training forward equals the one of a fresh model that loaded the updated state dict through the host packers,
+    and an eval forward afterwards (full re-pack of the eval-only forms) equals that model's too."""
+    import copy
+    from multimodalvc_b200 import AVHubertConfig, AVHubertModel
+    o = ao.build_oracle("tiny", seed=1234)
+    B, T = 2, 18
+    src, pm = ao.synthetic_inputs(B, T, lengths=[18, 13], seed=29)
+    cfg = AVHubertConfig.named("tiny", feature_grad_mult=fgm, trainable=True, dropout=0.0, attention_dropout=0.0,
+                               activation_dropout=0.0, encoder_layerdrop=0.0, dropout_input=0.0)
+    m = AVHubertModel(cfg)
+    m.remove_pretraining_modules()
+    m.load_state_dict(o.state_dict(), strict=False)
+    m = m.cuda().train()
+    dsrc = {k: v.cuda() for k, v in src.items()}
+    opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+    for _ in range(2):
+        opt.zero_grad()
+        y, _ = m.extract_finetune(dsrc, pm.cuda())
+        (y[~pm.cuda()] ** 2).mean().backward()
+        opt.step()
+    handle = m._handle
+    sd = copy.deepcopy(m.state_dict())
+    y_dev, _ = m.extract_finetune(dsrc, pm.cuda())              # refreshes on the device
+    assert m._handle is handle and not m._dirty
+    m2 = AVHubertModel(cfg)
+    m2.remove_pretraining_modules()
+    m2.load_state_dict(sd, strict=False)
+    m2 = m2.cuda().train()
+    y_full, _ = m2.extract_finetune(dsrc, pm.cuda())            # packed through the host
+    assert rel_err(y_dev.detach().cpu()[~pm], y_full.detach().cpu()[~pm]) < 1e-5
+    assert rel_err(y_dev.detach().cpu()[~pm], y.detach().cpu()[~pm]) > 1e-4      # and the step did move the output
+    # gradients from the refreshed weights too
+    opt.zero_grad()
+    (y_dev[~pm.cuda()] ** 2).mean().backward()
+    (y_full[~pm.cuda()] ** 2).mean().backward()
+    g1 = dict(m.named_parameters())["encoder.layers.1.fc2.weight"].grad
+    g2 = dict(m2.named_parameters())["encoder.layers.1.fc2.weight"].grad
+    assert rel_err(g1.cpu(), g2.cpu()) < 1e-4
+    m.eval(); m2.eval()
+    with torch.no_grad():
+        e1, _ = m.extract_finetune(dsrc, pm.cuda())
+        e2, _ = m2.extract_finetune(dsrc, pm.cuda())
+    assert rel_err(e1.cpu()[~pm], e2.cpu()[~pm]) < 1e-5
