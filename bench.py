@@ -620,9 +620,13 @@ def main():
             torch.cuda.empty_cache()
             return out
 
-        cfg5 = config5_leg(0.1)
-        cfg5_opt = config5_leg(0.1, with_optimizer=True)
-        cfg5_frozen = config5_leg(0.0)
+        s5 = torch.cuda.Stream(device=dev)       # a real stream: the library replays its launch lists as CUDA graphs there
+        s5.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s5):
+            cfg5 = config5_leg(0.1)
+            cfg5_opt = config5_leg(0.1, with_optimizer=True)
+            cfg5_frozen = config5_leg(0.0)
+        torch.cuda.current_stream(dev).wait_stream(s5)
 
     # ---- max over ranks
     ms_sus = sustained[1] if sustained else 0.0

@@ -324,6 +324,10 @@ struct avh_handle {
     int ks = 0;                   // conv: taps per side
   };
   std::vector<RefreshJob> refresh_jobs;
+  // the job list captured as one CUDA graph for the parameter pointers it was last called with (an optimizer updates the
+  // same tensors in place every step: ~650 small launches become one graph launch)
+  std::vector<long long> refresh_key;
+  cudaGraphExec_t refresh_exec = nullptr;
   std::vector<LayerW> layers;
   // Q-Former handles (cfg.reserved[0] == 2): reserved[1] = encoder_width, reserved[2] = rows of query_tokens
   std::vector<QfLayerW> qf_layers;
@@ -2819,6 +2823,7 @@ int avh_destroy(avh_handle* h) {
     if (kv.second.video_pp) cudaFree(kv.second.video_pp);
   }
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  if (h->refresh_exec) cudaGraphExecDestroy(h->refresh_exec);
   delete h;
   return 0;
 }
@@ -2861,6 +2866,8 @@ int avh_finalize_weights(avh_handle* h) {
   h->warena.release();
   h->warena = avh::Arena();
   h->refresh_jobs.clear();
+  if (h->refresh_exec) { cudaGraphExecDestroy(h->refresh_exec); h->refresh_exec = nullptr; }
+  h->refresh_key.clear();
   avh::Packer sizer{h, nullptr, avh::Sizer(), ""};
   const bool ok = avh::pack_all(sizer);
   AVH_CHECK(ok, "missing state-dict key: " + sizer.missing);
@@ -3361,6 +3368,19 @@ int avh_refresh_weights_device(avh_handle* h, const char* const* names, const vo
     AVH_CHECK(dtypes[i] == AVH_F32 || dtypes[i] == AVH_F16 || dtypes[i] == AVH_BF16, "bad parameter dtype");
     idx[names[i]] = i;
   }
+  // same parameter tensors as last time: replay the captured graph
+  std::vector<long long> key;
+  key.reserve(3 * (size_t)count);
+  for (int i = 0; i < count; ++i) {
+    key.push_back((long long)reinterpret_cast<uintptr_t>(ptrs[i]));
+    key.push_back(dtypes[i]);
+    key.push_back(numels[i]);
+  }
+  if (h->refresh_exec != nullptr && key == h->refresh_key) {
+    AVH_CUDA_OK(cudaGraphLaunch(h->refresh_exec, s));
+    return 0;
+  }
+  auto run_jobs = [&]() -> int {
   const int P = h->P;
   const int KT = h->cfg.conv_pos;
   bool ratio_done = false;
@@ -3410,6 +3430,31 @@ int avh_refresh_weights_device(avh_handle* h, const char* const* names, const vo
     }
   }
   return 0;
+  };
+  if (h->refresh_exec) { cudaGraphExecDestroy(h->refresh_exec); h->refresh_exec = nullptr; }
+  h->refresh_key.clear();
+  read_graphs_env();
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  const bool real_stream = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  if (real_stream) cudaStreamIsCapturing(s, &cap_status);
+  if (graphs_env == 1 && real_stream && cap_status == cudaStreamCaptureStatusNone &&
+      cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    const int rc = run_jobs();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    cudaGraphExec_t exec = nullptr;
+    const bool ok = rc == 0 && e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (rc != 0) return 1;                         // a real error (missing / resized parameter): reported as is
+    if (ok) {
+      h->refresh_exec = exec;
+      h->refresh_key = key;
+      AVH_CUDA_OK(cudaGraphLaunch(exec, s));
+      return 0;
+    }
+  }
+  cudaGetLastError();                              // capture not possible on this stream (legacy default stream): direct
+  return run_jobs();
 }
 
 int avh_grad_bucket_count(avh_handle* h, int32_t* count) {

@@ -463,13 +463,25 @@ def test_overlapped_gradient_allreduce_two_gpus():
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
-@pytest.mark.parametrize("fgm", [0.0, 1.0])
-def test_device_weight_refresh_matches_full_repack(fgm):
+@pytest.mark.parametrize("fgm,side_stream", [(0.0, False), (1.0, False), (1.0, True)])
+def test_device_weight_refresh_matches_full_repack(fgm, side_stream):
     """After an optimizer step the packed weights are refreshed on the device, in place (avh_refresh_weights_device): the
     next training forward equals the one of a fresh model that loaded the updated state dict through the host packers,
     and an eval forward afterwards (full re-pack of the eval-only forms) equals that model's too."""
+    import contextlib
     import copy
     from multimodalvc_b200 import AVHubertConfig, AVHubertModel
+    # on a real stream the library replays its launch lists — the refresh job list included — as CUDA graphs
+    stream = torch.cuda.Stream() if side_stream else None
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream())
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        _refresh_case(fgm, copy, AVHubertConfig, AVHubertModel, 5 if side_stream else 2)
+    if stream is not None:
+        torch.cuda.current_stream().wait_stream(stream)
+
+
+def _refresh_case(fgm, copy, AVHubertConfig, AVHubertModel, steps):
     o = ao.build_oracle("tiny", seed=1234)
     B, T = 2, 18
     src, pm = ao.synthetic_inputs(B, T, lengths=[18, 13], seed=29)
@@ -481,7 +493,7 @@ def test_device_weight_refresh_matches_full_repack(fgm):
     m = m.cuda().train()
     dsrc = {k: v.cuda() for k, v in src.items()}
     opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
-    for _ in range(2):
+    for _ in range(steps):
         opt.zero_grad()
         y, _ = m.extract_finetune(dsrc, pm.cuda())
         (y[~pm.cuda()] ** 2).mean().backward()
