@@ -2304,15 +2304,15 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
         void* ftB = b.alloc((size_t)max_b * P * 2);
         // x_mode: 0 = xv [rows, n_in] values (x_dt), 1 = xv operand planes (bf16 [rows, P * n_in]), 2 = ftB already holds
         // the transposed operand (im2colT)
-        auto wgrad_rows = [&](const float* dyv, long long ld_dy, int n_out, const void* xv, int x_dt, long long ld_x, int x_mode,
-                              int n_in, long long rows, float* dW, float* db, const char* tag) -> bool {
+        auto wgrad_rows = [&](const void* dyv, long long ld_dy, int n_out, const void* xv, int x_dt, long long ld_x, int x_mode,
+                              int n_in, long long rows, float* dW, float* db, const char* tag, int dy_dt = DT_F32) -> bool {
           const long long kp = (rows + 63) / 64 * 64;
           const int planes = P;
           b.tag = "transpose";
           if (!f32 && n_out % 8 == 0 && ld_dy % 8 == 0) {
-            b.push([=](cudaStream_t s) { return launch_transposeT(dyv, DT_F32, ld_dy, rows, n_out, ftA, kp, kp, s); });
+            b.push([=](cudaStream_t s) { return launch_transposeT(dyv, dy_dt, ld_dy, rows, n_out, ftA, kp, kp, s); });
           } else {
-            b.push([=](cudaStream_t s) { return launch_transpose_split(dyv, DT_F32, ld_dy, rows, n_out, ftA, planes, kp, 1.0f, s); });
+            b.push([=](cudaStream_t s) { return launch_transpose_split(dyv, dy_dt, ld_dy, rows, n_out, ftA, planes, kp, 1.0f, s); });
           }
           if (x_mode == 1) {
             for (int pp = 0; pp < P; ++pp) {
@@ -2360,7 +2360,7 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
           }
           if (db != nullptr) {
             b.tag = "bias_grad";
-            b.push([=](cudaStream_t s) { return launch_colsum(dyv, DT_F32, ld_dy, rows, n_out, db, 1.0f, s); });
+            b.push([=](cudaStream_t s) { return launch_colsum(dyv, dy_dt, ld_dy, rows, n_out, db, 1.0f, s); });
           }
           return true;
         };
@@ -2417,21 +2417,23 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
           float* dcol = f32buf((long long)dcol_elems);
           void* dop = b.alloc(dop_elems * P * 2);
           // BatchNorm (+ residual) (+ PReLU) backward of one saved conv: dz -> d_raw (returned), d_res, parameter gradients
+          const int graw_dt = f32 ? DT_F32 : DT_BF16;     // bf16 mode: d(raw conv output) is only ever a GEMM operand
           auto bn_bwd = [&](const ConvSave& cs, const float* dz, float* d_res, int res_acc, float* g_bn, float* g_slope) {
             const long long rows = nfr * cs.Ho * cs.Ho;
             const int Cc = cs.cu->cout;
-            float* d_raw = f32buf(rows * Cc);
+            float* d_raw = f32buf(f32 ? rows * Cc : (rows * Cc + 1) / 2);
             const void* rawp = cs.raw.data;
             const void* resp = cs.res.data;
             const float* st = cs.stat; const float* gm = cs.cu->gamma; const float* bt = cs.cu->beta; const float* sl = cs.slope;
             b.tag = "bn_bwd";
             b.push([=](cudaStream_t s) {
               return launch_bn_act_bwd(rawp, act_dt, resp, dz, st, gm, bt, sl, rows, Cc, bn_sums, tot, d_raw, d_res, res_acc,
-                                       g_bn, g_bn + Cc, g_slope, s);
+                                       g_bn, g_bn + Cc, g_slope, s, graw_dt);
             });
             return d_raw;
           };
           // conv backward: dW = d_raw^T col(x); dx (+)= col2im(d_raw W)
+          // d_raw: fp32 [rows, cout] in fp32 mode, bf16 in bf16 mode (graw_dt)
           auto conv_bwd = [&](const ConvSave& cs, const float* d_raw, float* dW, float* dx, int dx_acc) -> bool {
             const ConvUnit& cu = *cs.cu;
             const int K = cu.ks * cu.ks * cu.cin, Cc = cu.cout;
@@ -2443,18 +2445,23 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
               // bf16 mode: the patches are written transposed straight from the map (no patch matrix, no transpose pass)
               const long long kp = (rows + 63) / 64 * 64;
               b.push([=](cudaStream_t s) { return launch_im2colT(xin, nfr, H, cin, ks, st, pad, Ho, ftB, kp, s); });
-              if (!wgrad_rows(d_raw, Cc, Cc, nullptr, DT_BF16, 0, 2, K, rows, dW, nullptr, "conv_wgrad")) return false;
+              if (!wgrad_rows(d_raw, Cc, Cc, nullptr, DT_BF16, 0, 2, K, rows, dW, nullptr, "conv_wgrad", graw_dt)) return false;
             } else {
               b.push([=](cudaStream_t s) { return launch_im2col2d(xin, act_dt, nfr, H, cin, ks, st, pad, Ho, colbuf, planes, s); });
               if (!wgrad_rows(d_raw, Cc, Cc, colbuf, DT_BF16, (long long)P * K, 1, K, rows, dW, nullptr, "conv_wgrad")) return false;
             }
             if (dx == nullptr) return true;
-            b.tag = "split";
-            b.push([=](cudaStream_t s) { return launch_split_rows(d_raw, Cc, dop, planes, rows, Cc, 0, 0, s); });
+            const void* dopv = dop;
+            if (f32) {
+              b.tag = "split";
+              b.push([=](cudaStream_t s) { return launch_split_rows(d_raw, Cc, dop, planes, rows, Cc, 0, 0, s); });
+            } else {
+              dopv = d_raw;                                          // already the bf16 operand
+            }
             Epilogue ep;
             ep.C = dcol; ep.ldc = K; ep.c_fp32 = f32 ? 1 : 0;        // bf16 mode: patch gradients in bf16 (half the traffic)
             b.tag = "conv_dgrad";
-            if (!b.gemm(dop, rows, P * Cc, cu.wT, rows, {Tap{0, 0, 0}}, cu.wT.kpad / 64, Cc, ep)) return false;
+            if (!b.gemm(dopv, rows, P * Cc, cu.wT, rows, {Tap{0, 0, 0}}, cu.wT.kpad / 64, Cc, ep)) return false;
             b.tag = "col2im";
             b.push([=](cudaStream_t s) { return launch_col2im2d(dcol, act_dt, nfr, H, cin, ks, st, pad, Ho, dx, dx_acc, s); });
             return true;
@@ -2508,7 +2515,8 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
             b.tag = "maxpool_bwd";
             b.push([=](cudaStream_t s) { return launch_maxpool_bwd(a0, act_dt, dp0, d_act0, nfr, 44, 64, 22, s, pool_arg); });
             float* d_raw0 = bn_bwd(cs, d_act0, nullptr, 0, g_stem_bn, g_stem_slope);
-            if (!wgrad_rows(d_raw0, 64, 64, stemcol, DT_BF16, (long long)P * 320, 1, 320, nfr * 1936, g_stem_w, nullptr, "stem_wgrad"))
+            if (!wgrad_rows(d_raw0, 64, 64, stemcol, DT_BF16, (long long)P * 320, 1, 320, nfr * 1936, g_stem_w, nullptr, "stem_wgrad",
+                            graw_dt))
               return false;
           }
         }

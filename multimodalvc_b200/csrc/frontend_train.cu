@@ -279,55 +279,73 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float* f) {
     f[2 * i] = t.x; f[2 * i + 1] = t.y;
   }
 }
-// im2col2d, one 16-byte vector (8 channels of one tap) per thread
+// im2col2d: one thread per (patch row, 8-channel group), the taps in an unrolled loop — the row is decoded once (32-bit
+// arithmetic) for KS * KS 16-byte copies.  (One thread per (row, tap, group) with 64-bit index arithmetic was instruction
+// bound: 309 us for a layer1 map, 27 % of the HBM rate under ncu.)
+template <int KS>
 __global__ void __launch_bounds__(256)
-im2col2d_vec_kernel(const __nv_bfloat16* __restrict__ x, long long n, int H, int C, int ks, int stride, int pad, int Ho,
-                    __nv_bfloat16* __restrict__ col) {
-  const int C8 = C / 8, K8 = ks * ks * C8;
-  const long long total = n * Ho * Ho * K8;
-  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const long long row = idx / K8;
-    const int k8 = (int)(idx % K8), tap = k8 / C8, c8 = k8 % C8, kh = tap / ks, kw = tap % ks;
-    const int pix = (int)(row % (Ho * Ho)), oy = pix / Ho, ox = pix % Ho;
-    const long long f = row / (Ho * Ho);
-    const int y = oy * stride + kh - pad, xx = ox * stride + kw - pad;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < H && xx >= 0 && xx < H) v = __ldg(reinterpret_cast<const uint4*>(x + ((f * H + y) * H + xx) * C) + c8);
-    reinterpret_cast<uint4*>(col)[idx] = v;
+im2col2d_vec_kernel(const uint4* __restrict__ x, unsigned rows, int H, int c8_shift, int stride, int pad, int Ho,
+                    uint4* __restrict__ col) {
+  const unsigned C8 = 1u << c8_shift, HoHo = (unsigned)(Ho * Ho);
+  const unsigned total = rows << c8_shift;
+  for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const unsigned row = idx >> c8_shift, c8 = idx & (C8 - 1);
+    const unsigned f = row / HoHo, pix = row - f * HoHo, oy = pix / (unsigned)Ho, ox = pix - oy * (unsigned)Ho;
+    const uint4* img = x + ((size_t)f * H * H << c8_shift) + c8;
+    uint4* out = col + ((size_t)row * (KS * KS) << c8_shift) + c8;
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+      const int y = (int)oy * stride + kh - pad;
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) {
+        const int xx = (int)ox * stride + kw - pad;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < H && xx >= 0 && xx < H) v = __ldg(img + ((size_t)(y * H + xx) << c8_shift));
+        out[(size_t)(kh * KS + kw) << c8_shift] = v;
+      }
+    }
   }
 }
 // the 64 x 64 tile store shared by the transposing kernels: tile[i][(j ^ (i/8 % 8)) * 8 + e] holds element (row i, column
 // 8 j + e); output row (c0 + c) receives the 8 consecutive K indices r0 + 8 g .. + 7 as one 16-byte store
 __device__ __forceinline__ void store_tile_T(const __nv_bfloat16 (*tile)[72], __nv_bfloat16* __restrict__ out, long long out_row0,
                                              int c_lim, long long out_ld, long long r0) {
-  for (int v = threadIdx.x; v < 512; v += 256) {
-    const int c = v / 8, g = v % 8;
-    if (c >= c_lim) continue;
-    __align__(16) __nv_bfloat16 w[8];
+  // one thread per (channel pair, 8-row group): eight 32-bit shared loads (conflict-free: bank = 4 q + 4 (vec ^ g) + pair)
+  // give the 8 consecutive K indices of TWO output rows
+  const int cp = threadIdx.x / 8, g = threadIdx.x % 8, c = 2 * cp;
+  if (c >= c_lim) return;
+  uint32_t w[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) w[q] = tile[g * 8 + q][(((c >> 3) ^ g) << 3) + (c & 7)];
-    *reinterpret_cast<uint4*>(out + (out_row0 + c) * out_ld + r0 + g * 8) = *reinterpret_cast<const uint4*>(w);
-  }
+  for (int q = 0; q < 8; ++q)
+    w[q] = *reinterpret_cast<const uint32_t*>(&tile[g * 8 + q][(((c >> 3) ^ g) << 3) + (c & 7)]);
+  uint4 lo, hi;
+  lo.x = __byte_perm(w[0], w[1], 0x5410); hi.x = __byte_perm(w[0], w[1], 0x7632);
+  lo.y = __byte_perm(w[2], w[3], 0x5410); hi.y = __byte_perm(w[2], w[3], 0x7632);
+  lo.z = __byte_perm(w[4], w[5], 0x5410); hi.z = __byte_perm(w[4], w[5], 0x7632);
+  lo.w = __byte_perm(w[6], w[7], 0x5410); hi.w = __byte_perm(w[6], w[7], 0x7632);
+  *reinterpret_cast<uint4*>(out + (out_row0 + c) * out_ld + r0 + g * 8) = lo;
+  if (c + 1 < c_lim) *reinterpret_cast<uint4*>(out + (out_row0 + c + 1) * out_ld + r0 + g * 8) = hi;
 }
 // patches written TRANSPOSED for the weight-gradient GEMM (K = pixels): colT[(tap * C + c), r] = x[patch r, tap, c], columns
-// r in [rows, kp) zero.  grid (kp / 64, C / 64, ks * ks)
+// r in [rows, kp) zero.  grid (ks * ks * C / 64, kp / 64): the taps and channel blocks of one 64-row block are neighbours in
+// the launch order, so the map is read from DRAM once (tap-major order re-read it per tap: 620 MB instead of 75 MB)
 __global__ void __launch_bounds__(256)
-im2colT_kernel(const __nv_bfloat16* __restrict__ x, long long n, int H, int C, int ks, int stride, int pad, int Ho,
+im2colT_kernel(const __nv_bfloat16* __restrict__ x, unsigned rows, int H, int C, int ks, int stride, int pad, int Ho,
                __nv_bfloat16* __restrict__ colT, long long kp) {
   __shared__ __align__(16) __nv_bfloat16 tile[64][72];
-  const long long rows = n * Ho * Ho;
-  const long long r0 = (long long)blockIdx.x * 64;
-  const int c0 = blockIdx.y * 64, tap = blockIdx.z, kh = tap / ks, kw = tap % ks;
+  const unsigned HoHo = (unsigned)(Ho * Ho);
+  const unsigned r0 = blockIdx.y * 64u;
+  const int cblocks = C / 64;
+  const int tap = blockIdx.x / cblocks, c0 = (blockIdx.x - tap * cblocks) * 64, kh = tap / ks, kw = tap - kh * ks;
   for (int v = threadIdx.x; v < 512; v += 256) {
     const int i = v / 8, j = v % 8;
-    const long long r = r0 + i;
+    const unsigned r = r0 + i;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (r < rows) {
-      const int pix = (int)(r % (Ho * Ho)), oy = pix / Ho, ox = pix % Ho;
-      const long long f = r / (Ho * Ho);
-      const int y = oy * stride + kh - pad, xx = ox * stride + kw - pad;
+      const unsigned f = r / HoHo, pix = r - f * HoHo, oy = pix / (unsigned)Ho, ox = pix - oy * (unsigned)Ho;
+      const int y = (int)oy * stride + kh - pad, xx = (int)ox * stride + kw - pad;
       if (y >= 0 && y < H && xx >= 0 && xx < H)
-        val = __ldg(reinterpret_cast<const uint4*>(x + ((f * H + y) * H + xx) * C + c0) + j);
+        val = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)f * H + y) * H + xx) * C + c0) + j);
     }
     *reinterpret_cast<uint4*>(&tile[i][(j ^ ((i >> 3) & 7)) << 3]) = val;
   }
@@ -371,34 +389,33 @@ transposeT_kernel(const void* __restrict__ in, long long ld, long long rows, int
   __syncthreads();
   store_tile_T(tile, out, c0, C - c0 < 64 ? C - c0 : 64, out_ld, r0);
 }
-// col2im as a gather, vectors along the channel axis (dcol bf16: 8 channels, fp32: 4 channels per thread)
+// col2im as a gather, vectors along the channel axis (dcol bf16: 8 channels, fp32: 4 channels per thread); 32-bit
+// index arithmetic, stride 1 or 2
 template <bool F32>
 __global__ void __launch_bounds__(256)
-col2im2d_vec_kernel(const void* __restrict__ dcol, long long n, int H, int C, int ks, int stride, int pad, int Ho,
+col2im2d_vec_kernel(const void* __restrict__ dcol, unsigned pixels, int H, int C, int cv_shift, int ks, int stride, int pad, int Ho,
                     float* __restrict__ dx, int accumulate) {
   constexpr int V = F32 ? 4 : 8;
-  const int CV = C / V;
-  const long long K = (long long)ks * ks * C;
-  const long long total = n * H * H * CV;
-  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const int cv = (int)(idx % CV);
-    const long long p = idx / CV;
-    const int xx = (int)(p % H), y = (int)((p / H) % H);
-    const long long f = p / ((long long)H * H);
+  const unsigned CV = 1u << cv_shift, HH = (unsigned)(H * H);
+  const size_t K = (size_t)ks * ks * C;
+  const unsigned total = pixels << cv_shift;
+  for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const unsigned p = idx >> cv_shift, cv = idx & (CV - 1);
+    const unsigned f = p / HH, rem = p - f * HH, y = rem / (unsigned)H, xx = rem - y * (unsigned)H;
     float s[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) s[e] = 0.f;
     for (int kh = 0; kh < ks; ++kh) {
-      const int ny = y + pad - kh;
-      if (ny < 0 || ny % stride != 0) continue;
-      const int oy = ny / stride;
+      const int ny = (int)y + pad - kh;
+      if (ny < 0 || (stride == 2 && (ny & 1))) continue;
+      const int oy = stride == 2 ? ny >> 1 : ny;
       if (oy >= Ho) continue;
       for (int kw = 0; kw < ks; ++kw) {
-        const int nx = xx + pad - kw;
-        if (nx < 0 || nx % stride != 0) continue;
-        const int ox = nx / stride;
+        const int nx = (int)xx + pad - kw;
+        if (nx < 0 || (stride == 2 && (nx & 1))) continue;
+        const int ox = stride == 2 ? nx >> 1 : nx;
         if (ox >= Ho) continue;
-        const long long off = ((f * Ho + oy) * Ho + ox) * K + (long long)(kh * ks + kw) * C + cv * V;
+        const size_t off = (((size_t)f * Ho + oy) * Ho + ox) * K + (size_t)(kh * ks + kw) * C + cv * V;
         if (F32) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dcol) + off));
           s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
@@ -410,7 +427,7 @@ col2im2d_vec_kernel(const void* __restrict__ dcol, long long n, int H, int C, in
         }
       }
     }
-    float4* o = reinterpret_cast<float4*>(dx + p * C + cv * V);
+    float4* o = reinterpret_cast<float4*>(dx + (size_t)p * C + cv * V);
 #pragma unroll
     for (int q = 0; q < V / 4; ++q) {
       float4 w = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
@@ -629,7 +646,8 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ res,
                             const float* __restrict__ dz, const float* __restrict__ stat, const float* __restrict__ gamma,
                             const float* __restrict__ beta, const float* __restrict__ slope, const float* __restrict__ tot,
-                            long long rows, int C, float* __restrict__ d_raw, float* __restrict__ d_res, int res_accumulate) {
+                            long long rows, int C, void* __restrict__ d_raw, int d_raw_bf16, float* __restrict__ d_res,
+                            int res_accumulate) {
   const int C8 = C / 8;
   const long long total = rows * C8;
   const float inv_rows = 1.0f / (float)rows;
@@ -647,9 +665,15 @@ bn_act_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bf
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       o[e] = gm[e] * rstd[e] * (dv[e] - tot[c0 + e] * inv_rows - xh[e] * tot[C + c0 + e] * inv_rows);
-    float4* dst = reinterpret_cast<float4*>(d_raw + off);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    if (d_raw_bf16) {       // bf16 mode: the only readers are GEMM operands (weight / input gradient), which are bf16 anyway
+      __nv_bfloat162 h[4] = {__floats2bfloat162_rn(o[0], o[1]), __floats2bfloat162_rn(o[2], o[3]),
+                             __floats2bfloat162_rn(o[4], o[5]), __floats2bfloat162_rn(o[6], o[7])};
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d_raw) + off) = *reinterpret_cast<const uint4*>(h);
+    } else {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(d_raw) + off);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
     if (d_res != nullptr) {
       float4* dr = reinterpret_cast<float4*>(d_res + off);
       if (res_accumulate) {
@@ -687,12 +711,23 @@ int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int p
 }
 int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* col, int planes,
                     cudaStream_t stream) {
-  if (dt == DT_BF16 && planes == 1 && C % 8 == 0) {
-    im2col2d_vec_kernel<<<grid_for(n * Ho * Ho * ks * ks * (C / 8)), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), n, H, C, ks, stride, pad, Ho, reinterpret_cast<__nv_bfloat16*>(col));
-    AVH_CUDA_OK(cudaGetLastError());
-    count_launch(1);
-    return 0;
+  {
+    const int C8 = C / 8;
+    const bool pow2 = C % 8 == 0 && (C8 & (C8 - 1)) == 0;
+    const long long rows = n * Ho * Ho;
+    if (dt == DT_BF16 && planes == 1 && pow2 && (ks == 3 || ks == 1) && rows * C8 < (1ll << 32) && n * H * H < (1ll << 31)) {
+      int sh = 0;
+      while ((1 << sh) < C8) ++sh;
+      const uint4* xi = reinterpret_cast<const uint4*>(x);
+      uint4* co = reinterpret_cast<uint4*>(col);
+      if (ks == 3)
+        im2col2d_vec_kernel<3><<<grid_for(rows * C8), 256, 0, stream>>>(xi, (unsigned)rows, H, sh, stride, pad, Ho, co);
+      else
+        im2col2d_vec_kernel<1><<<grid_for(rows * C8), 256, 0, stream>>>(xi, (unsigned)rows, H, sh, stride, pad, Ho, co);
+      AVH_CUDA_OK(cudaGetLastError());
+      count_launch(1);
+      return 0;
+    }
   }
   im2col2d_kernel<<<grid_for(n * Ho * Ho * ks * ks * C), 256, 0, stream>>>(x, dt, n, H, C, ks, stride, pad, Ho,
                                                                           reinterpret_cast<__nv_bfloat16*>(col), planes);
@@ -702,11 +737,25 @@ int launch_im2col2d(const void* x, int dt, long long n, int H, int C, int ks, in
 }
 int launch_col2im2d(const void* dcol, int dt, long long n, int H, int C, int ks, int stride, int pad, int Ho, float* dx,
                     int accumulate, cudaStream_t stream) {
-  if (dt == DT_BF16 && C % 8 == 0)
-    col2im2d_vec_kernel<false><<<grid_for(n * H * H * (C / 8)), 256, 0, stream>>>(dcol, n, H, C, ks, stride, pad, Ho, dx, accumulate);
-  else if (dt == DT_F32 && C % 4 == 0)
-    col2im2d_vec_kernel<true><<<grid_for(n * H * H * (C / 4)), 256, 0, stream>>>(dcol, n, H, C, ks, stride, pad, Ho, dx, accumulate);
-  else
+  {
+    const int V = dt == DT_BF16 ? 8 : 4;
+    const int CV = C / V;
+    const bool pow2 = C % V == 0 && CV > 0 && (CV & (CV - 1)) == 0;
+    const long long pixels = n * H * H;
+    if ((dt == DT_BF16 || dt == DT_F32) && pow2 && (stride == 1 || stride == 2) && pixels * CV < (1ll << 32)) {
+      int sh = 0;
+      while ((1 << sh) < CV) ++sh;
+      if (dt == DT_BF16)
+        col2im2d_vec_kernel<false><<<grid_for(pixels * CV), 256, 0, stream>>>(dcol, (unsigned)pixels, H, C, sh, ks, stride, pad, Ho, dx,
+                                                                             accumulate);
+      else
+        col2im2d_vec_kernel<true><<<grid_for(pixels * CV), 256, 0, stream>>>(dcol, (unsigned)pixels, H, C, sh, ks, stride, pad, Ho, dx,
+                                                                            accumulate);
+      AVH_CUDA_OK(cudaGetLastError());
+      count_launch(1);
+      return 0;
+    }
+  }
   col2im2d_kernel<<<grid_for(n * H * H * C), 256, 0, stream>>>(dcol, dt, n, H, C, ks, stride, pad, Ho, dx, accumulate);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);
@@ -758,8 +807,9 @@ int launch_bn_stat_from_affine(const float* scale, const float* bias, const floa
   return 0;
 }
 int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz, const float* stat, const float* gamma,
-                      const float* beta, const float* slope, long long rows, int C, double* sums, float* tot, float* d_raw,
-                      float* d_res, int res_accumulate, float* dgamma, float* dbeta, float* dslope, cudaStream_t stream) {
+                      const float* beta, const float* slope, long long rows, int C, double* sums, float* tot, void* d_raw,
+                      float* d_res, int res_accumulate, float* dgamma, float* dbeta, float* dslope, cudaStream_t stream,
+                      int d_raw_dt) {
   AVH_CHECK(C >= 32 && C <= 512 && (C <= 256 ? 256 % C == 0 : C % 256 == 0), "bn backward: channel count must divide or double 256");
   if (rows <= 0) return 0;
   if (dt == DT_BF16) {
@@ -777,7 +827,7 @@ int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz,
     bn_act_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, tot, dgamma, dbeta, dslope);
     AVH_CUDA_OK(cudaGetLastError());
     bn_act_bwd_apply_vec_kernel<<<grid_for(rows * (C / 8)), 256, 0, stream>>>(rw, rs, dz, stat, gamma, beta, slope, tot, rows, C,
-                                                                            d_raw, d_res, res_accumulate);
+                                                                            d_raw, d_raw_dt == DT_BF16, d_res, res_accumulate);
     AVH_CUDA_OK(cudaGetLastError());
     count_launch(3);
     return 0;
@@ -794,8 +844,9 @@ int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz,
   AVH_CUDA_OK(cudaGetLastError());
   bn_act_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, tot, dgamma, dbeta, dslope);
   AVH_CUDA_OK(cudaGetLastError());
-  bn_act_bwd_apply_kernel<<<grid_for(rows * C), 256, 0, stream>>>(raw, dt, res, dz, stat, gamma, beta, slope, tot, rows, C, d_raw,
-                                                                  d_res, res_accumulate);
+  AVH_CHECK(d_raw_dt == DT_F32, "bf16 gradient maps need bf16 activations");
+  bn_act_bwd_apply_kernel<<<grid_for(rows * C), 256, 0, stream>>>(raw, dt, res, dz, stat, gamma, beta, slope, tot, rows, C,
+                                                                  reinterpret_cast<float*>(d_raw), d_res, res_accumulate);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(3);
   return 0;
@@ -811,8 +862,9 @@ int launch_add_f32(float* a, const float* b, long long n, cudaStream_t stream) {
 int launch_im2colT(const void* x, long long n, int H, int C, int ks, int stride, int pad, int Ho, void* colT, long long kp,
                    cudaStream_t stream) {
   AVH_CHECK(C % 64 == 0 && kp % 64 == 0 && kp >= n * Ho * Ho, "transposed patches: channels / K padding must be multiples of 64");
-  dim3 grid((unsigned)(kp / 64), (unsigned)(C / 64), (unsigned)(ks * ks));
-  im2colT_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, H, C, ks, stride, pad, Ho,
+  AVH_CHECK(kp / 64 <= 65535 && n * Ho * Ho < (1ll << 31), "transposed patches: too many rows for one launch");
+  dim3 grid((unsigned)(ks * ks * (C / 64)), (unsigned)(kp / 64));
+  im2colT_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), (unsigned)(n * Ho * Ho), H, C, ks, stride, pad, Ho,
                                            reinterpret_cast<__nv_bfloat16*>(colT), kp);
   AVH_CUDA_OK(cudaGetLastError());
   count_launch(1);

@@ -162,8 +162,9 @@ int launch_bn_stat_from_affine(const float* scale, const float* bias, const floa
 // BatchNorm(batch stats) [+ residual] [+ PReLU] backward on [rows, C]: d_raw, d_res (optional, = or +=), dgamma, dbeta, dslope;
 // sums = BN_SLOTS x 3 x C doubles (zero before the first use), tot = 3 x C floats scratch
 int launch_bn_act_bwd(const void* raw, int dt, const void* res, const float* dz, const float* stat, const float* gamma,
-                      const float* beta, const float* slope, long long rows, int C, double* sums, float* tot, float* d_raw,
-                      float* d_res, int res_accumulate, float* dgamma, float* dbeta, float* dslope, cudaStream_t stream);
+                      const float* beta, const float* slope, long long rows, int C, double* sums, float* tot, void* d_raw,
+                      float* d_res, int res_accumulate, float* dgamma, float* dbeta, float* dslope, cudaStream_t stream,
+                      int d_raw_dt = DT_F32);       // d_raw_dt = DT_BF16 (bf16 maps only): the map gradient as a GEMM operand
 int launch_add_f32(float* a, const float* b, long long n, cudaStream_t stream);
 
 // ---- audio frontend ---------------------------------------------------------------------------------
