@@ -391,23 +391,26 @@ def test_full_finetune_step_matches_autograd(case):
         assert (bn_m.running_var.cpu() - bn_o.running_var).abs().max().item() < 1e-4
 
 
-def test_full_finetune_step_bf16_and_sgd():
-    """The whole-model step in bf16 mode (BASELINE config 5's precision): gradient directions against float64 autograd
-    (cosine per tensor), and an SGD step on the library's gradients lowers the loss (weights re-packed after the update,
-    BatchNorm running statistics carried)."""
+@pytest.mark.parametrize("B,T,lengths,f64", [(2, 20, [20, 14], True), (4, 150, [150, 97, 150, 121], False)])
+def test_full_finetune_step_bf16_and_sgd(B, T, lengths, f64):
+    """The whole-model step in bf16 mode (BASELINE config 5's precision): gradient directions against autograd on the
+    oracle (cosine per tensor; float64 for the small case, fp32 for the 600-frame one), and an SGD step on the library's
+    gradients lowers the loss (weights refreshed after the update, BatchNorm running statistics carried).  The
+    600-frame case runs the lip ResNet at the depth of the real workload: 290 400 patch rows in layer1, i.e. the
+    single-launch stream-K weight-gradient GEMMs over 4 537 K blocks and the 32-bit patch kernels."""
     import copy
     from multimodalvc_b200 import AVHubertConfig, AVHubertModel
     o32 = ao.build_oracle("tiny", seed=1234).train()
-    B, T = 2, 20
-    src32, pm = ao.synthetic_inputs(B, T, lengths=[20, 14], seed=23)
+    src32, pm = ao.synthetic_inputs(B, T, lengths=lengths, seed=23)
     g = torch.Generator().manual_seed(8)
     w32 = torch.randn(B, T, 128, generator=g)
-    o = copy.deepcopy(o32).double()
-    fv = o.feature_extractor_video(src32["video"].double())
-    fa = o.feature_extractor_audio(src32["audio"].double())
+    o = copy.deepcopy(o32).double() if f64 else copy.deepcopy(o32)
+    rdt = torch.float64 if f64 else torch.float32
+    fv = o.feature_extractor_video(src32["video"].to(rdt))
+    fa = o.feature_extractor_audio(src32["audio"].to(rdt))
     feats = o.post_extract_proj(o.layer_norm(torch.cat([fa, fv], dim=1).transpose(1, 2)))
-    _loss(o.encoder(feats, pm), w32.double(), pm).backward()
-    ref = {n: p.grad for n, p in o.named_parameters()}
+    _loss(o.encoder(feats, pm), w32.to(rdt), pm).backward()
+    ref = {n: p.grad.double() for n, p in o.named_parameters() if p.grad is not None}
     cfg = AVHubertConfig.named("tiny", feature_grad_mult=1.0, trainable=True, dropout=0.0, attention_dropout=0.0,
                                activation_dropout=0.0, encoder_layerdrop=0.0, dropout_input=0.0)
     m = AVHubertModel(cfg)
