@@ -1773,9 +1773,15 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
   const bool hm = plan->has_mask;
   const int tail = plan->tail;
   const bool full = tail == 2;
-  if (full && !f32) {
-    // stream-K workspace for the weight-gradient GEMMs of the lip ResNet (a handful of output tiles, K = pixels): one
-    // fp32 partial tile per SM + flags (zero from the arena's initial fill; the kernels hand the flags back as zeros)
+  // AVH_WGRAD_SK=1: stream-K also for the ENCODER's weight-gradient GEMMs (64-256 tiles of 19 K blocks at 8 x 150 tokens).
+  // Off by default: measured slower on one box, 16.96 vs 15.96 ms per frozen-extractor step (73 launches at 24.5 us against
+  // ~13 us as whole tiles — the partial-tile round trip through the workspace costs more than the idle SMs)
+  static int wgrad_sk_env = -1;
+  if (wgrad_sk_env < 0) { const char* ev = std::getenv("AVH_WGRAD_SK"); wgrad_sk_env = (ev != nullptr && ev[0] == '1') ? 1 : 0; }
+  if (!f32 && (full || wgrad_sk_env == 1)) {
+    // stream-K workspace for the weight-gradient GEMMs (lip ResNet: a handful of output tiles, K = pixels; encoder: 64-256
+    // tiles of 19 K blocks at 8 x 150 tokens, i.e. 0.4-1.7 waves of the 148 SMs): one fp32 partial tile per SM + flags
+    // (zero from the arena's initial fill; the kernels hand the flags back as zeros)
     b.sk_bytes = (size_t)device_sm_count() * 128 * 256 * 4;
     b.sk_ws = reinterpret_cast<float*>(b.alloc(b.sk_bytes));
     b.sk_flags = reinterpret_cast<int*>(b.alloc(4096));
@@ -2138,7 +2144,10 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
     Epilogue ep;
     ep.C = dW; ep.ldc = n_in; ep.c_fp32 = 1;
     b.tag = tag;
-    if (!b.gemm(tA, n_out, P * (int)Kp, xw, n_out, {Tap{0, 0, 0}}, (int)(Kp / 64), (int)Kp, ep)) return false;
+    b.force_sk = (!f32 && wgrad_sk_env == 1) ? 1 : 0;      // few tiles x short K: cut the k-block space evenly over the SMs
+    const bool ok = b.gemm(tA, n_out, P * (int)Kp, xw, n_out, {Tap{0, 0, 0}}, (int)(Kp / 64), (int)Kp, ep);
+    b.force_sk = 0;
+    if (!ok) return false;
     if (db != nullptr) {
       b.tag = "bias_grad";
       b.push([=](cudaStream_t s) { return launch_colsum(dyv, dy_dt, n_out, N, n_out, db, 1.0f, s); });
