@@ -233,7 +233,7 @@ AVH_API int avh_tail_train_forward(avh_handle* h, const void* fused, int dtype, 
  * feature_extractor_video.proj.{weight, bias}, frontend3D.0.weight as [64, 5, 64] (dt, kh*7+kw zero-padded to 64),
  * frontend3D.1.{weight,bias}, frontend3D.2.weight, and per BasicBlock conv1.weight as [C, kh, kw, Cin], bn1.{weight,
  * bias}, relu1.weight, conv2.weight, bn2.{weight,bias}, relu2.weight, downsample.0.weight [C, Cin], downsample.1.{weight,
- * bias} (first block of layers 2-4).  Correctness-first path: every convolution is explicit patches -> one GEMM.
+ * bias} (first block of layers 2-4).  Every convolution of this path is explicit patches -> one GEMM (dense NHWC maps).
  * video [B,1,T,88,88] float (or NULL), audio [B,F,T] + strides (or NULL).  Its dx output is not defined (pass NULL). */
 AVH_API int avh_full_grad_count(avh_handle* h, int has_video, int has_audio, int64_t* n_floats);
 AVH_API int avh_full_train_forward(avh_handle* h, const void* video, int video_dtype, const void* audio, int audio_dtype,

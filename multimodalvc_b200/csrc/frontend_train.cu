@@ -1,9 +1,13 @@
-// Training step of the lip ResNet (`feature_grad_mult > 0`): element-wise / gather kernels of a
-// correctness-first path in which every convolution is "explicit patches -> one GEMM" on DENSE NHWC maps:
+// Training step of the lip ResNet (`feature_grad_mult > 0`): the element-wise / gather / transpose
+// kernels of a path in which every convolution is "explicit patches -> one GEMM" on DENSE NHWC maps:
 //   forward   col = im2col(x);  raw = col W^T (tcgen05 GEMM);  BatchNorm with batch statistics + PReLU (+ residual)
-//   backward  dW = d_raw^T col (GEMM over K = pixels);  d_col = d_raw W (GEMM);  dx = col2im(d_col) (gather, no atomics)
+//   backward  dW = d_raw^T col (GEMM over K = pixels, operands written transposed: im2colT / transposeT);
+//             d_col = d_raw W (GEMM);  dx = col2im(d_col) (gather, no atomics)
 // avhubert/resnet.py:35-74 (BasicBlock), :131-169 (ResEncoder: Conv3d stem, BatchNorm3d, PReLU, MaxPool3d, trunk, avgpool).
-// The inference path keeps its fused kernels; this file only serves avh_train_forward / avh_encoder_backward.
+// Two sets of kernels: generic scalar ones (any dtype, hi / mid operand planes: the fp32-faithful mode the parity tests
+// run) and the bf16 fast paths (16-byte vectors along the channel axis, 32-bit index arithmetic, 64 x 64 smem-tile
+// transposes; ncu record: profiles/r2_full_train_ncu_full.txt).  The inference path keeps its fused implicit-GEMM kernels;
+// this file only serves avh_full_train_forward / avh_encoder_backward.
 #include "common.cuh"
 #include "kernels.h"
 
