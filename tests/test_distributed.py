@@ -90,3 +90,48 @@ def test_single_process_is_identity_and_fills_missing_grads():
     for p, g in zip(params[:-1], grads[:-1]):
         assert torch.equal(p.grad, g)
     assert params[-1].grad is not None and not params[-1].grad.any()     # reference :124-125: zeros_like
+
+
+def _worker_presynced(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = _make_params()
+    grads = _grads_for(rank, params)
+    for p, g in zip(params, grads):
+        p.grad = g.clone()
+    red = GradientAllReducer(params)
+    # the device backward reports what it already averaged (mark_reduced): those gradients must not be reduced twice
+    red.mark_reduced([params[0], params[2]])
+    n1 = red.all_reduce_grads()
+    first = [p.grad.clone() for p in params]
+    n2 = red.all_reduce_grads()                           # the mark is per step: the next call reduces everything again
+    second = [p.grad.clone() for p in params]
+    # off an NCCL group (gloo here) the bucketed overlap declines and leaves the work to all_reduce_grads
+    declined = red.reduce_buckets(None, None, torch.zeros(4)) is False
+    if rank == 0:
+        q.put((n1, n2, first, second, declined))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradients_reduced_during_the_backward_are_skipped_once():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_presynced, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n1, n2, first, second, declined = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params = _make_params()
+    g0, g1 = _grads_for(0, params), _grads_for(1, params)
+    assert declined and n1 >= 1 and n2 >= 1
+    for i in (0, 2):
+        assert torch.equal(first[i], g0[i])                                  # skipped in the first call ...
+        torch.testing.assert_close(second[i], (g0[i] + g1[i]) / 2)           # ... reduced by the second
+    for i in (1, 3, 4, 5):
+        torch.testing.assert_close(first[i], (g0[i] + g1[i]) / 2)
+        torch.testing.assert_close(second[i], (g0[i] + g1[i]) / 2)           # averages of identical values stay put
