@@ -230,7 +230,7 @@ AVH_API int avh_tail_train_forward(avh_handle* h, const void* fused, int dtype, 
  * projections, fusion, encoder, with saved activations; avh_encoder_backward then also returns, after the tail's
  * gradients, those of the feature extractors (scaled by feature_grad_mult as fairseq's GradMultiply does,
  * avhubert/hubert.py:538-547): feature_extractor_audio.proj.{weight [D, round_up(F,64)], bias} (when audio is given),
- * feature_extractor_video.proj.{weight, bias}, frontend3D.0.weight as [64, 5, 64] (dt, kh*7+kw zero-padded to 64),
+ * feature_extractor_video.proj.{weight, bias}, frontend3D.0.weight as [64, 5, 8, 8] (dt, kh, kw; kh = 7 / kw = 7 zero),
  * frontend3D.1.{weight,bias}, frontend3D.2.weight, and per BasicBlock conv1.weight as [C, kh, kw, Cin], bn1.{weight,
  * bias}, relu1.weight, conv2.weight, bn2.{weight,bias}, relu2.weight, downsample.0.weight [C, Cin], downsample.1.{weight,
  * bias} (first block of layers 2-4).  Every convolution of this path is explicit patches -> one GEMM (dense NHWC maps).

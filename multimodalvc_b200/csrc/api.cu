@@ -622,6 +622,7 @@ bool pack_all(Packer& pk) {
             for (int kw = 0; kw < 7; ++kw)
               pf[(size_t)o * 320 + dt * 64 + kh * 8 + kw] = w->v[(size_t)o * 245 + dt * 49 + kh * 7 + kw];
       h->stem_wf = pk.pack(pf, 64, 320, 320);
+      pk.job(R + "frontend3D.0.weight", RJ_STEM, h->stem_wf.w, 64, 245, 320, 0, 1.f, 8);      // ks = 8: the kh*8 + kw order
       h->stem.cin = 1; h->stem.cout = 64;
       std::vector<float> sc(64), bi(64), sl(64);
       for (int o = 0; o < 64; ++o) {
@@ -1916,7 +1917,7 @@ bool build_encoder_train_plan(avh_handle* h, Plan* plan, bool sizing, size_t* by
         Epilogue ep;
         ep.C = cs.raw.data; ep.ldc = 64; ep.c_fp32 = f32 ? 1 : 0;
         b.tag = "stem_gemm";
-        if (!b.gemm(stemcol, rows, P * 320, h->stem.w, rows, {Tap{0, 0, 0}}, 5, 320, ep)) return false;
+        if (!b.gemm(stemcol, rows, P * 320, h->stem_wf, rows, {Tap{0, 0, 0}}, 5, 320, ep)) return false;      // K = dt*64 + kh*8 + kw
         act0 = new_act(rows, 64);
         bn_fwd(cs, rows, h->stem.slope, nullptr, nullptr, act0);
         convs.push_back(cs);
@@ -3426,7 +3427,7 @@ int avh_refresh_weights_device(avh_handle* h, const char* const* names, const vo
         break;
       case avh::RJ_STEM:
         AVH_CHECK(ne == 64 * 245, "parameter size changed: " + j.src);
-        if (avh::launch_refresh_stem(src, dt, j.dst, P, s)) return 1;
+        if (avh::launch_refresh_stem(src, dt, j.dst, P, j.ks == 8 ? 1 : 0, s)) return 1;
         break;
       case avh::RJ_POS:
       case avh::RJ_POS_T: {

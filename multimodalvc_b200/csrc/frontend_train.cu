@@ -33,7 +33,8 @@ __device__ __forceinline__ void st_op(__nv_bfloat16* out, long long i, long long
   if (planes > 1) out[i + ps] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// ---- stem patches: video [B,1,T,88,88] -> col [B*T*1936, planes*320]; column dt*64 + kh*7 + kw (49..63 of a block zero)
+// ---- stem patches: video [B,1,T,88,88] -> col [B*T*1936, planes*320]; column dt*64 + kh*8 + kw (kw = 7 and kh = 7 zero:
+// the K order of the fused inference stem, whose packed weights the training GEMM shares)
 // = video[b, t+dt-2, 2*oy+kh-3, 2*ox+kw-3] (Conv3d(1,64,(5,7,7),stride (1,2,2),pad (2,3,3)), resnet.py:137)
 __global__ void __launch_bounds__(256)
 im2col_stem_kernel(const void* __restrict__ video, int dt_in, int B, int T, __nv_bfloat16* __restrict__ col, int planes) {
@@ -43,8 +44,8 @@ im2col_stem_kernel(const void* __restrict__ video, int dt_in, int B, int T, __nv
   const long long row = idx / 320;
   const int c = (int)(idx % 320), d = c / 64, j = c % 64;
   float v = 0.f;
-  if (j < 49) {
-    const int kh = j / 7, kw = j % 7;
+  const int kh = j / 8, kw = j % 8;
+  if (kh < 7 && kw < 7) {
     const int pix = (int)(row % 1936), oy = pix / 44, ox = pix % 44;
     const long long f = row / 1936;
     const int t = (int)(f % T) + d - 2, y = 2 * oy + kh - 3, x = 2 * ox + kw - 3;
@@ -440,32 +441,31 @@ col2im2d_vec_kernel(const void* __restrict__ dcol, unsigned pixels, int H, int C
     }
   }
 }
-// stem patches, bf16 video: one 16-byte vector (8 consecutive patch columns) per thread
+// stem patches, bf16 video: one 16-byte vector = one (dt, kh) row of the patch per thread — the 7 pixels 2 ox - 3 .. 2 ox + 3
+// come from four aligned 32-bit loads (pixels 2 ox - 4 .. 2 ox + 3; out-of-image pixels fall in whole words) shifted by one
 __global__ void __launch_bounds__(256)
 im2col_stem_vec_kernel(const __nv_bfloat16* __restrict__ video, int B, int T, __nv_bfloat16* __restrict__ col) {
-  const long long total = (long long)B * T * 1936 * 40;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const unsigned total = (unsigned)B * T * 1936u * 40u;
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
   if (idx >= total) return;
-  const long long row = idx / 40;
-  const int v = (int)(idx % 40), d = v / 8, jv = v % 8;
-  const int pix = (int)(row % 1936), oy = pix / 44, ox = pix % 44;
-  const long long f = row / 1936;
-  const int t = (int)(f % T) + d - 2;
-  __align__(16) __nv_bfloat16 w[8];
+  const unsigned row = idx / 40u, v = idx - row * 40u;
+  const int d = (int)(v >> 3), kh = (int)(v & 7u);
+  const unsigned f = row / 1936u, pix = row - f * 1936u;
+  const int oy = (int)(pix / 44u), ox = (int)(pix - (pix / 44u) * 44u);
+  const int t = (int)(f % (unsigned)T) + d - 2, y = 2 * oy + kh - 3;
+  uint4 out = make_uint4(0u, 0u, 0u, 0u);
+  if (kh < 7 && t >= 0 && t < T && y >= 0 && y < 88) {
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(video + ((size_t)(f / (unsigned)T) * T + t) * 7744 + y * 88);
+    const int w0 = ox - 2;                       // word of pixels (2 ox - 4, 2 ox - 3)
+    uint32_t w[4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) w[q] = __float2bfloat16_rn(0.f);
-  if (t >= 0 && t < T && jv < 7) {
-    const __nv_bfloat16* img = video + ((f / T) * T + t) * 7744;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = jv * 8 + q;
-      if (j < 49) {
-        const int kh = j / 7, kw = j % 7, y = 2 * oy + kh - 3, x = 2 * ox + kw - 3;
-        if (y >= 0 && y < 88 && x >= 0 && x < 88) w[q] = img[y * 88 + x];
-      }
-    }
+    for (int k = 0; k < 4; ++k) w[k] = (w0 + k >= 0 && w0 + k < 44) ? __ldg(rowp + w0 + k) : 0u;
+    out.x = __byte_perm(w[0], w[1], 0x5432);
+    out.y = __byte_perm(w[1], w[2], 0x5432);
+    out.z = __byte_perm(w[2], w[3], 0x5432);
+    out.w = w[3] >> 16;
   }
-  reinterpret_cast<uint4*>(col)[idx] = *reinterpret_cast<const uint4*>(w);
+  reinterpret_cast<uint4*>(col)[idx] = out;
 }
 // max-pool backward, bf16 maps, 8 channels per thread
 __global__ void __launch_bounds__(256)
@@ -700,7 +700,7 @@ inline unsigned grid_for(long long n) {
 int launch_im2col_stem(const void* video, int dt, int B, int T, void* col, int planes, cudaStream_t stream) {
   const long long total = (long long)B * T * 1936 * 320;
   AVH_CHECK((total + 255) / 256 < (1ll << 31), "stem patch matrix too large");
-  if (dt == DT_BF16 && planes == 1) {
+  if (dt == DT_BF16 && planes == 1 && total / 8 < (1ll << 32) && (reinterpret_cast<uintptr_t>(video) & 3) == 0) {
     im2col_stem_vec_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(video), B, T, reinterpret_cast<__nv_bfloat16*>(col));
     AVH_CUDA_OK(cudaGetLastError());

@@ -139,7 +139,7 @@ int launch_refresh_matrix(const void* src, int dt, long long n, long long k, flo
 int launch_refresh_vec(const void* src, int dt, long long n, long long n_src, float scale, float* dst, cudaStream_t stream);
 int launch_refresh_conv(const void* src, int dt, int cout, int cin, int ksq, void* dst, long long ld, int planes, int transposed,
                         cudaStream_t stream);
-int launch_refresh_stem(const void* src, int dt, void* dst, int planes, cudaStream_t stream);
+int launch_refresh_stem(const void* src, int dt, void* dst, int planes, int pitch8, cudaStream_t stream);
 int launch_posconv_ratio(const void* v, int v_dt, const void* g, int g_dt, long long per_tap, int KT, float* ratio,
                          cudaStream_t stream);
 int launch_refresh_pos(const void* v, int dt, const float* ratio, const int* acol, int D, int cg, int KT, int window, void* dst,

@@ -56,12 +56,14 @@ refresh_conv_kernel(const void* __restrict__ src, int dt, int cout, int cin, int
     st_planes(dst, d, ld, planes, ldw(src, dt, i));
   }
 }
-// stem Conv3d weight [64, 1, 5, 7, 7] -> [64, planes*320], column dt*64 + kh*7 + kw
-__global__ void refresh_stem_kernel(const void* __restrict__ src, int dt, __nv_bfloat16* __restrict__ dst, int planes) {
+// stem Conv3d weight [64, 1, 5, 7, 7] -> [64, planes*320], column dt*64 + kh*7 + kw (pitch8 = 0: the row-shift GEMM
+// form) or dt*64 + kh*8 + kw (pitch8 = 1: the fused inference stem and the training patches)
+__global__ void refresh_stem_kernel(const void* __restrict__ src, int dt, __nv_bfloat16* __restrict__ dst, int planes, int pitch8) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 245) return;
   const int o = i / 245, rem = i % 245, d = rem / 49, j = rem % 49;
-  st_planes(dst, (long long)o * planes * 320 + d * 64 + j, 320, planes, ldw(src, dt, i));
+  const int col = pitch8 ? (j / 7) * 8 + j % 7 : j;
+  st_planes(dst, (long long)o * planes * 320 + d * 64 + col, 320, planes, ldw(src, dt, i));
 }
 // weight_norm(dim=2): ratio[k] = g[k] / || v[:, :, k] ||   (one CTA per tap, fixed summation order)
 __global__ void __launch_bounds__(256)
@@ -133,8 +135,8 @@ int launch_refresh_conv(const void* src, int dt, int cout, int cin, int ksq, voi
   AVH_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_refresh_stem(const void* src, int dt, void* dst, int planes, cudaStream_t stream) {
-  refresh_stem_kernel<<<(64 * 245 + 255) / 256, 256, 0, stream>>>(src, dt, reinterpret_cast<__nv_bfloat16*>(dst), planes);
+int launch_refresh_stem(const void* src, int dt, void* dst, int planes, int pitch8, cudaStream_t stream) {
+  refresh_stem_kernel<<<(64 * 245 + 255) / 256, 256, 0, stream>>>(src, dt, reinterpret_cast<__nv_bfloat16*>(dst), planes, pitch8);
   AVH_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -599,7 +599,7 @@ class AVHubertModel(nn.Module):
             spec += [((D, 512), same), ((D,), same)]
             st = fe.resnet.frontend3D
             params += [st[0].weight, st[1].weight, st[1].bias, st[2].weight]
-            spec += [((64, 5, 64), lambda g: g[:, :, :49].reshape(64, 1, 5, 7, 7)), ((64,), same), ((64,), same), ((64,), same)]
+            spec += [((64, 5, 8, 8), lambda g: g[:, :, :7, :7].reshape(64, 1, 5, 7, 7)), ((64,), same), ((64,), same), ((64,), same)]
             cin = 64
             for i in range(1, 5):
                 C = 64 << (i - 1)
