@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_DTYPES = {torch.float32: _lib.AVH_F32, torch.float16: _lib.AVH_F16, torch.bfloat16: _lib.AVH_BF16}
 
 
 def backward_flat(handle, dout, dx, n_floats, dtypes, fwd_stream, owner):
