@@ -114,3 +114,41 @@ def test_token_buckets_partition_and_respect_the_budget():
                 assert [lengths[i] for i in b] == sorted((lengths[i] for i in b), reverse=True)
     assert sharding.token_buckets([], lengths) == []
     assert sharding.token_buckets([3], [10, 10, 10, 9000]) == [[3]]          # a clip longer than the budget runs alone
+
+
+@pytest.mark.parametrize("fuse", ["concat", "add"])
+def test_full_parameters_spec_maps_the_flat_gradient_onto_every_parameter(fuse):
+    """AVHubertModel.full_parameters: the (buffer shape, map) pairs that cut the library's flat gradient buffer
+    (include/avh_b200.h, avh_full_train_forward) must cover every trainable parameter once, and each map must land on
+    the parameter's own shape with the element it names — checked with index-valued buffers, no device needed."""
+    from multimodalvc_b200 import AVHubertConfig, AVHubertModel
+    m = AVHubertModel(AVHubertConfig.named("tiny", modality_fuse=fuse, trainable=True))
+    m.remove_pretraining_modules()
+    params, spec = m.full_parameters(True, True)
+    assert len(params) == len(spec)
+    named = {id(p): n for n, p in m.named_parameters()}
+    seen = set()
+    for p, (shape, to_param) in zip(params, spec):
+        assert id(p) in named and id(p) not in seen, "unknown or repeated parameter"
+        seen.add(id(p))
+        n = 1
+        for d in shape:
+            n *= d
+        buf = torch.arange(n, dtype=torch.float64).view(shape)
+        g = to_param(buf)
+        assert tuple(g.shape) == tuple(p.shape), (named[id(p)], tuple(g.shape), tuple(p.shape))
+        assert g.numel() <= n and torch.unique(g).numel() == g.numel()          # a selection / permutation, nothing repeated
+    missing = [n for n, p in m.named_parameters() if id(p) not in seen and n != "mask_emb"]
+    assert not missing, missing
+    # spot checks of the layouts the header documents
+    name_of = {named[id(p)]: (p, s) for p, s in zip(params, spec)}
+    p, (shape, f) = name_of["feature_extractor_video.resnet.trunk.layer2.0.conv1.weight"]
+    assert shape == (128, 3, 3, 64)                                              # [C, kh, kw, Cin] in the buffer
+    buf = torch.arange(128 * 9 * 64, dtype=torch.float64).view(shape)
+    assert f(buf)[5, 7, 2, 1].item() == buf[5, 2, 1, 7].item()                   # -> [C, Cin, kh, kw]
+    p, (shape, f) = name_of["feature_extractor_video.resnet.frontend3D.0.weight"]
+    assert shape == (64, 5, 8, 8)                                                # (dt, kh, kw) with the 8th row / column zero
+    buf = torch.arange(64 * 320, dtype=torch.float64).view(shape)
+    assert f(buf)[3, 0, 4, 6, 5].item() == buf[3, 4, 6, 5].item()
+    p, (shape, f) = name_of["feature_extractor_audio.proj.weight"]
+    assert shape == (128, 128) and tuple(f(torch.zeros(shape)).shape) == (128, 104)   # K padded to 64 in the buffer
