@@ -1,4 +1,7 @@
-"""Debug probe: backward intermediates of the full training step vs autograd on the oracle (fp32 mode)."""
+"""Debug probe: backward intermediates of the whole-model training step vs float64 autograd on the oracle (fp32 mode).
+This is the tool that attributed the ResNet gradient differences to PReLU kink flips: the gradient entering
+layer4.1.bn1 matches to 1e-5, the one leaving it differs in exactly the channels that hold a unit with |v| < 1e-5.
+  python tools/full_train_probe.py        (needs a B200)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -25,7 +28,6 @@ def hook(name):
     return f
 blk.conv2.register_full_backward_hook(hook("conv2"))
 blk.conv1.register_full_backward_hook(hook("conv1"))
-blk.bn2.register_full_backward_hook(hook("bn2"))
 fv = o.feature_extractor_video(src["video"].double())
 fa = o.feature_extractor_audio(src["audio"].double())
 feats = o.layer_norm(torch.cat([fa, fv], dim=1).transpose(1, 2))
@@ -40,14 +42,12 @@ def dev(name, C=512):
     return m.read_stage(name, N * 9 * C).view(N, 3, 3, C).permute(0, 3, 1, 2).cpu().double()
 def rel(a, b):
     return ((a - b).abs().max() / b.abs().max()).item()
-print("dz      (bn2 grad_out)", rel(dev("dbg_dz"), got["bn2_out"]))
-print("d_raw2  (conv2 grad_out)", rel(dev("dbg_d_raw2"), got["conv2_out"]))
-print("d_a1    (conv2 grad_in)", rel(dev("dbg_d_a1"), got["conv2_in"]))
-print("d_raw1  (conv1 grad_out)", rel(dev("dbg_d_raw1"), got["conv1_out"]))
-d = dev("dbg_d_a1") - got["conv2_in"]
+print("d_a1    (conv2 grad_in)", rel(dev("grad_layer4_1_conv2_in"), got["conv2_in"]))
+print("d_raw1  (conv1 grad_out)", rel(dev("grad_layer4_1_conv1_out"), got["conv1_out"]))
+d = dev("grad_layer4_1_conv2_in") - got["conv2_in"]
 print("d_a1 err by pixel", d.abs().amax(dim=(0, 1)) / got["conv2_in"].abs().max())
 print("d_a1 err by frame", d.abs().amax(dim=(1, 2, 3)) / got["conv2_in"].abs().max())
-dr = dev("dbg_d_raw1"); rr = got["conv1_out"]
+dr = dev("grad_layer4_1_conv1_out"); rr = got["conv1_out"]
 d = dr - rr
 print("d_raw1: per-channel mean of diff (abs max)", d.mean(dim=(0, 2, 3)).abs().max().item(), "per-channel std of diff max",
       d.std(dim=(0, 2, 3)).max().item(), "ref absmax", rr.abs().max().item())
