@@ -93,3 +93,44 @@ def make_pretrain_device_model(c, dtype, device="cuda"):
     missing = m.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys and not missing.missing_keys, missing
     return m.to(device=device, dtype=dtype).eval()
+
+
+class _GradMultiply(torch.autograd.Function):
+    """fairseq/modules/grad_multiply.py: identity forward, gradient scaled."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.s, None
+
+
+def oracle_finetune_graph(o, src, pm, fgm, fuse):
+    """extract_finetune of the reference in .train() as a differentiable graph on the ORACLE's modules
+    (avhubert/hubert.py:538-547,694-745): feature_grad_mult > 0 -> the extractors differentiate and GradMultiply scales the
+    gradient entering them; <= 0 -> extractors under no_grad; missing modality -> zeros; concat / add fusion; LayerNorm;
+    post_extract_proj; encoder.  Pinned to the REAL model's autograd by tests/golden/train_grads_tiny.npz
+    (oracle/make_golden_grads.py, tests/test_oracle_vs_reference.py)."""
+    def features(extractor, x):
+        if x is None:
+            return None
+        if fgm > 0:
+            f = extractor(x)
+            return _GradMultiply.apply(f, fgm) if fgm != 1.0 else f
+        with torch.no_grad():
+            return extractor(x)
+
+    fv = features(o.feature_extractor_video, src.get("video"))
+    fa = features(o.feature_extractor_audio, src.get("audio"))
+    if fv is None:
+        fv = torch.zeros_like(fa)
+    if fa is None:
+        fa = torch.zeros_like(fv)
+    fused = (torch.cat([fa, fv], dim=1) if fuse == "concat" else fa + fv).transpose(1, 2)
+    feats = o.layer_norm(fused)
+    if o.post_extract_proj is not None:
+        feats = o.post_extract_proj(feats)
+    return o.encoder(feats, pm)

@@ -10,7 +10,7 @@ import torch
 
 from oracle import avhubert_oracle as ao
 
-from helpers import cosine, rel_err
+from helpers import cosine, oracle_finetune_graph, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -316,27 +316,9 @@ def test_full_finetune_step_matches_autograd(case):
     m.remove_pretraining_modules()
     m.load_state_dict(o32.state_dict(), strict=False)
     m = m.cuda().train()
-    # reference: GradMultiply = identity forward, gradient scaled
-    class GM(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, x, s):
-            ctx.s = s
-            return x.clone()
-        @staticmethod
-        def backward(ctx, gr):
-            return gr * ctx.s, None
-    D = 128
-    fv = GM.apply(o.feature_extractor_video(src["video"]), case["fgm"]) if case["video"] else None
-    fa = GM.apply(o.feature_extractor_audio(src["audio"]), case["fgm"]) if case["audio"] else None
-    if fv is None:
-        fv = fa.new_zeros(B, D, T)
-    if fa is None:
-        fa = fv.new_zeros(B, D, T)
-    fused = (torch.cat([fa, fv], dim=1) if case["fuse"] == "concat" else fa + fv).transpose(1, 2)
-    feats = o.layer_norm(fused)
-    if o.post_extract_proj is not None:
-        feats = o.post_extract_proj(feats)
-    y_ref = o.encoder(feats, pm)
+    # the reference graph (GradMultiply on the extractor outputs, fusion, LayerNorm, post_extract_proj, encoder): pinned to
+    # the REAL model's autograd by tests/golden/train_grads_tiny.npz (tests/test_oracle_vs_reference.py)
+    y_ref = oracle_finetune_graph(o, src, pm, case["fgm"], case["fuse"])
     o.zero_grad()
     _loss(y_ref, w32.double(), pm).backward()
     dsrc = {k: (v.cuda() if v is not None else None) for k, v in src32.items()}
@@ -406,10 +388,8 @@ def test_full_finetune_step_bf16_and_sgd(B, T, lengths, f64):
     w32 = torch.randn(B, T, 128, generator=g)
     o = copy.deepcopy(o32).double() if f64 else copy.deepcopy(o32)
     rdt = torch.float64 if f64 else torch.float32
-    fv = o.feature_extractor_video(src32["video"].to(rdt))
-    fa = o.feature_extractor_audio(src32["audio"].to(rdt))
-    feats = o.post_extract_proj(o.layer_norm(torch.cat([fa, fv], dim=1).transpose(1, 2)))
-    _loss(o.encoder(feats, pm), w32.to(rdt), pm).backward()
+    y_ref = oracle_finetune_graph(o, {k: v.to(rdt) for k, v in src32.items()}, pm, 1.0, "concat")
+    _loss(y_ref, w32.to(rdt), pm).backward()
     ref = {n: p.grad.double() for n, p in o.named_parameters() if p.grad is not None}
     cfg = AVHubertConfig.named("tiny", feature_grad_mult=1.0, trainable=True, dropout=0.0, attention_dropout=0.0,
                                activation_dropout=0.0, encoder_layerdrop=0.0, dropout_input=0.0)

@@ -72,3 +72,46 @@ def test_sr_predictor_oracle_matches_golden_of_the_real_class(golden_dir):
         ref.load_state_dict(oracle.state_dict(), strict=True)
         with torch.no_grad():
             assert (ref(x) - y).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("case", ["fgm05_concat", "fgm1_add", "frozen_concat"])
+def test_training_graph_gradients_match_the_reference(case):
+    """The graph the GPU training tests differentiate (helpers.oracle_finetune_graph, built from the oracle's modules)
+    gives the gradients torch.autograd computes for the REAL AVHubertModel.extract_finetune in .train()
+    (feature_grad_mult 0.5 / 1 / 0, concat / add fusion, ragged masks): signatures of every parameter gradient from
+    oracle/make_golden_grads.py (sum, L2 norm, seeded random projection, first 8 values).  Runs without /root/reference."""
+    import ast
+    import os
+    import zlib
+    import numpy as np
+    from helpers import oracle_finetune_graph
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_grads_tiny.npz"))
+    fgm, fuse, B, T, lengths = [z[f"{case}_meta"][i] for i in range(5)]
+    fgm, B, T, lengths = float(fgm), int(B), int(T), ast.literal_eval(str(lengths))
+    o = ao.build_oracle("tiny", seed=1234, modality_fuse=str(fuse)).train()
+    src, pm = ao.synthetic_inputs(B, T, lengths=lengths, seed=41)
+    if pm is None:
+        pm = torch.zeros(B, T, dtype=torch.bool)
+    y = oracle_finetune_graph(o, src, pm, fgm, str(fuse))
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float32)
+    ((y * w) * (~pm).unsqueeze(-1)).sum().backward()
+    names = [str(n) for n in z[f"{case}_names"]]
+    sigs = torch.from_numpy(z[f"{case}_sigs"])
+    ref_index = {n: i for i, n in enumerate(names)}
+    got = {n: p.grad for n, p in o.named_parameters() if p.grad is not None}
+    assert sorted(got) == sorted(names), set(got) ^ set(names)
+    for n in names:
+        i = ref_index[n]
+        g = got[n].detach().double().flatten()
+        if n.endswith("k_proj.bias"):          # exactly 0 in exact arithmetic (softmax is shift-invariant): rounding noise only
+            q = sigs[ref_index[n.replace("k_proj", "q_proj")]][1].item()
+            assert g.norm().item() < 1e-4 * q and sigs[i][1].item() < 1e-4 * q, n
+            continue
+        r = torch.randn(g.numel(), generator=torch.Generator().manual_seed(zlib.crc32(n.encode())), dtype=torch.float64)
+        head = torch.zeros(8, dtype=torch.float64)
+        head[:min(8, g.numel())] = g[:8]
+        mine = torch.cat([torch.stack([g.sum(), g.norm(), torch.dot(g, r)]), head])
+        scale = sigs[i][1].abs().item() + 1e-12                 # the gradient's norm
+        # fp32 autograd on both sides, same modules: differences are summation-order noise (BatchNorm backward on ~30 frames)
+        assert (mine - sigs[i]).abs().max().item() <= 2e-3 * scale * max(1.0, g.numel() ** 0.5 / 8), (n, mine, sigs[i])
+
